@@ -1,0 +1,259 @@
+"""ctypes binding of the C ABI declared in ``include/despawn_b200.h``.
+
+This is the only way Python reaches the GPU path; there is no torch extension and no fallback.
+If the shared library is missing the import of ``lib()`` raises -- nothing silently degrades to a
+CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libdespawn_b200.so")
+
+# dsp_status
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ARENA_FULL, ERR_STORE_FULL, ERR_NOT_RESIDENT, ERR_INTERNAL = range(8)
+# dsp_gen_kind
+GEN_REFERENCE, GEN_NOISE, GEN_RANDOM, GEN_CHECKER = 0, 1, 2, 3
+# mesh modes
+MESH_PARITY, MESH_HALO = 0, 1
+NO_SLOT = 0xFFFFFFFF
+
+MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("reserved", np.uint32)])
+EDIT_DTYPE = np.dtype([("wx", np.int32), ("wy", np.int32), ("wz", np.int32), ("block", np.uint32)])
+VERTEX_DTYPE = np.dtype([("position", np.float32, 3), ("tex_coords", np.float32, 2)])  # vertex.rs:5-12
+assert MESH_ENTRY_DTYPE.itemsize == 16 and EDIT_DTYPE.itemsize == 16 and VERTEX_DTYPE.itemsize == 20
+
+# Every symbol include/despawn_b200.h declares: name -> (restype, argtypes)
+_vp, _u64, _u32, _i32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c_int
+_P = C.POINTER
+SYMBOLS = {
+    "dsp_create": (_int, [_int, _u64, _u64, _P(_vp)]),
+    "dsp_destroy": (_int, [_vp]),
+    "dsp_last_error": (C.c_char_p, [_vp]),
+    "dsp_status_string": (C.c_char_p, [_int]),
+    "dsp_abi_version": (_int, []),
+    "dsp_set_uv_table": (_int, [_vp, _u32, _P(C.c_float)]),
+    "dsp_generate_chunks": (_int, [_vp, _u64, _P(_i32), _int, _u32, _P(_u32)]),
+    "dsp_generate_region": (_int, [_vp, _P(_i32), _P(_u32), _int, _u32, _P(_u32)]),
+    "dsp_load_chunks": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _P(C.c_uint16), _P(_u32), _P(_u32)]),
+    "dsp_unload_chunks": (_int, [_vp, _u64, _P(_u32)]),
+    "dsp_find_chunk": (_int, [_vp, _P(_i32), _P(_u32)]),
+    "dsp_resident_chunks": (_u64, [_vp]),
+    "dsp_mesh_chunks": (_int, [_vp, _u64, _P(_u32), _u32, _u64, _vp, _P(_u64)]),
+    "dsp_mesh_range": (_int, [_vp, _u32, _u64, _u32, _u64, _vp, _P(_u64)]),
+    "dsp_mesh_range_async": (_int, [_vp, _u32, _u64, _u32, _u64]),
+    "dsp_mesh_chunks_async": (_int, [_vp, _u64, _P(_u32), _u32, _u64]),
+    "dsp_sync": (_int, [_vp]),
+    "dsp_mesh_result": (_int, [_vp, _vp, _P(_u64)]),
+    "dsp_apply_edits": (_int, [_vp, _u64, _vp, _P(_u32), _u64, _P(_u64)]),
+    "dsp_download_arena": (_int, [_vp, _u64, _u64, _vp]),
+    "dsp_download_chunk": (_int, [_vp, _u32, _P(C.c_uint16), _P(_i32)]),
+    "dsp_arena_device_ptr": (_vp, [_vp]),
+    "dsp_arena_bytes": (_u64, [_vp]),
+    "dsp_voxel_device_ptr": (_vp, [_vp]),
+    "dsp_entries_device_ptr": (_vp, [_vp]),
+    "dsp_stream": (_vp, [_vp]),
+    "dsp_max_chunks": (_u64, [_vp]),
+    "dsp_kernel_launches": (_u64, [_vp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads libdespawn_b200.so (built by ``despawnengine_b200.build``); raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m despawnengine_b200.build` "
+                "(there is no CPU fallback for the mesh path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.dsp_abi_version() != 1:
+            raise RuntimeError("ABI version mismatch between capi.py and libdespawn_b200.so")
+        _lib = L
+    return _lib
+
+
+class DspError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[{status}: {lib().dsp_status_string(status).decode()}] {message}")
+        self.status = status
+
+
+def _ptr(a: np.ndarray, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Context:
+    """Thin RAII wrapper: one context per GPU, single caller (SURVEY.md section 8b 'Threading')."""
+
+    def __init__(self, device: int = 0, max_chunks: int = 4096, arena_bytes: int = 1 << 30):
+        self._h = C.c_void_p()
+        rc = lib().dsp_create(device, max_chunks, arena_bytes, C.byref(self._h))
+        if rc != OK:
+            raise DspError(rc, lib().dsp_last_error(None).decode())
+        self.device = device
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != OK:
+            raise DspError(rc, lib().dsp_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().dsp_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- block_uvs -----------------------------------------------------------------------------------
+    def set_uv_table(self, uv_rows):
+        uv = np.ascontiguousarray(uv_rows, dtype=np.float32).reshape(-1, 4)
+        self._check(lib().dsp_set_uv_table(self._h, uv.shape[0], _ptr(uv, C.c_float)))
+
+    # -- residency -------------------------------------------------------------------------------------
+    def generate_chunks(self, pos, kind: int = GEN_REFERENCE, seed: int = 0) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        slots = np.empty(pos.shape[0], dtype=np.uint32)
+        self._check(lib().dsp_generate_chunks(self._h, pos.shape[0], _ptr(pos, C.c_int32), kind, seed & 0xFFFFFFFF, _ptr(slots, C.c_uint32)))
+        return slots
+
+    def generate_region(self, origin, dims, kind: int = GEN_NOISE, seed: int = 0) -> int:
+        o = np.ascontiguousarray(origin, dtype=np.int32).reshape(3)
+        d = np.ascontiguousarray(dims, dtype=np.uint32).reshape(3)
+        first = C.c_uint32(0)
+        self._check(lib().dsp_generate_region(self._h, _ptr(o, C.c_int32), _ptr(d, C.c_uint32), kind, seed & 0xFFFFFFFF, C.byref(first)))
+        return int(first.value)
+
+    def load_chunks(self, pos, blocks, palette_ids=None, palette_offsets=None) -> np.ndarray:
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        n = pos.shape[0]
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(n, 4096)
+        slots = np.empty(n, dtype=np.uint32)
+        if palette_ids is not None:
+            pal = np.ascontiguousarray(palette_ids, dtype=np.uint16).reshape(-1)
+            off = np.ascontiguousarray(palette_offsets, dtype=np.uint32).reshape(n + 1)
+            pp, po = _ptr(pal, C.c_uint16), _ptr(off, C.c_uint32)
+        else:
+            pp, po = None, None
+        self._check(lib().dsp_load_chunks(self._h, n, _ptr(pos, C.c_int32), _ptr(blocks, C.c_uint16), pp, po, _ptr(slots, C.c_uint32)))
+        return slots
+
+    def load_chunks_ptr(self, n: int, pos: np.ndarray, blocks_host_ptr: int, slots_out: np.ndarray):
+        """Raw-pointer form used by the bench (pinned host memory owned by the caller)."""
+        self._check(lib().dsp_load_chunks(self._h, n, _ptr(pos, C.c_int32), C.cast(blocks_host_ptr, C.POINTER(C.c_uint16)), None, None,
+                                          _ptr(slots_out, C.c_uint32)))
+
+    def unload_chunks(self, slots):
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        self._check(lib().dsp_unload_chunks(self._h, s.shape[0], _ptr(s, C.c_uint32)))
+
+    def find_chunk(self, pos):
+        p = np.ascontiguousarray(pos, dtype=np.int32).reshape(3)
+        s = C.c_uint32(0)
+        rc = lib().dsp_find_chunk(self._h, _ptr(p, C.c_int32), C.byref(s))
+        return int(s.value) if rc == OK else None
+
+    @property
+    def resident_chunks(self) -> int:
+        return int(lib().dsp_resident_chunks(self._h))
+
+    # -- meshing ---------------------------------------------------------------------------------------
+    def mesh_chunks(self, slots, mode: int = MESH_PARITY, arena_offset: int = 0):
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        entries = np.zeros(s.shape[0], dtype=MESH_ENTRY_DTYPE)
+        total = C.c_uint64(0)
+        self._check(lib().dsp_mesh_chunks(self._h, s.shape[0], _ptr(s, C.c_uint32), mode, arena_offset, entries.ctypes.data_as(C.c_void_p), C.byref(total)))
+        return entries, int(total.value)
+
+    def mesh_range(self, first_slot: int, n: int, mode: int = MESH_PARITY, arena_offset: int = 0, entries_out=None):
+        entries = np.zeros(n, dtype=MESH_ENTRY_DTYPE) if entries_out is None else entries_out
+        total = C.c_uint64(0)
+        self._check(lib().dsp_mesh_range(self._h, first_slot, n, mode, arena_offset, entries.ctypes.data_as(C.c_void_p), C.byref(total)))
+        return entries, int(total.value)
+
+    def mesh_range_async(self, first_slot: int, n: int, mode: int = MESH_PARITY, arena_offset: int = 0):
+        self._check(lib().dsp_mesh_range_async(self._h, first_slot, n, mode, arena_offset))
+
+    def mesh_chunks_async(self, slots, mode: int = MESH_PARITY, arena_offset: int = 0):
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        self._check(lib().dsp_mesh_chunks_async(self._h, s.shape[0], _ptr(s, C.c_uint32), mode, arena_offset))
+
+    def sync(self):
+        self._check(lib().dsp_sync(self._h))
+
+    def mesh_result(self, n: int, entries_ptr: int | None = None):
+        total = C.c_uint64(0)
+        if entries_ptr is None:
+            entries = np.zeros(n, dtype=MESH_ENTRY_DTYPE)
+            self._check(lib().dsp_mesh_result(self._h, entries.ctypes.data_as(C.c_void_p), C.byref(total)))
+            return entries, int(total.value)
+        self._check(lib().dsp_mesh_result(self._h, C.c_void_p(entries_ptr), C.byref(total)))
+        return None, int(total.value)
+
+    # -- edits -----------------------------------------------------------------------------------------
+    def apply_edits(self, edits) -> np.ndarray:
+        e = np.ascontiguousarray(edits, dtype=EDIT_DTYPE).reshape(-1)
+        dirty = np.empty(max(1, e.shape[0]), dtype=np.uint32)
+        nd = C.c_uint64(0)
+        self._check(lib().dsp_apply_edits(self._h, e.shape[0], e.ctypes.data_as(C.c_void_p), _ptr(dirty, C.c_uint32), dirty.shape[0], C.byref(nd)))
+        return dirty[: int(nd.value)].copy()
+
+    # -- data access -------------------------------------------------------------------------------------
+    def download_arena(self, offset: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        if nbytes:
+            self._check(lib().dsp_download_arena(self._h, offset, nbytes, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def download_arena_into(self, offset: int, nbytes: int, host_ptr: int):
+        self._check(lib().dsp_download_arena(self._h, offset, nbytes, C.c_void_p(host_ptr)))
+
+    def download_vertices(self, entry) -> np.ndarray:
+        """The vertex stream of one mesh entry as a structured array (empty <=> the reference's None)."""
+        n = int(entry["vertex_count"])
+        return self.download_arena(int(entry["offset_bytes"]), n * 20).view(VERTEX_DTYPE)
+
+    def download_chunk(self, slot: int):
+        ids = np.empty(4096, dtype=np.uint16)
+        pos = np.zeros(3, dtype=np.int32)
+        self._check(lib().dsp_download_chunk(self._h, slot, _ptr(ids, C.c_uint16), _ptr(pos, C.c_int32)))
+        return ids, pos
+
+    @property
+    def arena_device_ptr(self) -> int:
+        return int(lib().dsp_arena_device_ptr(self._h) or 0)
+
+    @property
+    def arena_bytes(self) -> int:
+        return int(lib().dsp_arena_bytes(self._h))
+
+    @property
+    def voxel_device_ptr(self) -> int:
+        return int(lib().dsp_voxel_device_ptr(self._h) or 0)
+
+    @property
+    def stream(self) -> int:
+        return int(lib().dsp_stream(self._h) or 0)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().dsp_kernel_launches(self._h))

@@ -1,0 +1,615 @@
+// libdespawn_b200.so -- C ABI (include/despawn_b200.h) over the sm_100a kernels.
+//
+// Host side of the context: the chunk map that World keeps (world.rs:10-14: pos -> chunk) becomes
+// pos -> slot of a device-resident voxel store; everything that touches voxels or vertices runs on
+// the GPU.  There is deliberately no CPU implementation of any operation in this file.
+#include "../../include/despawn_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mesh_kernels.cuh"
+#include "terrain_kernels.cuh"
+
+namespace {
+
+struct PosKey {
+    int32_t x, y, z;
+    bool operator==(const PosKey& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct PosHash {
+    size_t operator()(const PosKey& k) const {
+        uint64_t h = static_cast<uint32_t>(k.x) * 0x9E3779B97F4A7C15ull;
+        h ^= (static_cast<uint64_t>(static_cast<uint32_t>(k.y)) + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+        h ^= (static_cast<uint64_t>(static_cast<uint32_t>(k.z)) + 0x165667B1ull) * 0x9FB21C651E98DF25ull;
+        h ^= h >> 29;
+        return static_cast<size_t>(h * 0xBF58476D1CE4E5B9ull);
+    }
+};
+struct Region {
+    int32_t origin[3];
+    uint32_t dims[3];
+    uint32_t first_slot;
+};
+
+thread_local std::string g_create_error = "";
+
+}  // namespace
+
+struct dsp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t max_chunks = 0, arena_bytes = 0;
+    int num_sms = 0;
+    int mesh_nstage = 1;
+    int mesh_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [nstage-1][halo]
+
+    uint16_t* d_voxels = nullptr;
+    int4* d_pos = nullptr;
+    uint32_t* d_nbr = nullptr;  // [max_chunks][6], allocated on first halo mesh
+    uint8_t* d_arena = nullptr;
+    dsp::MeshEntry* d_entries = nullptr;
+    uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
+    uint32_t* d_slots = nullptr;
+    float4* d_uv_rows = nullptr;
+    float4* d_uvmap = nullptr;
+    uint32_t n_blocks = 0, uv_cap = 0;
+    uint8_t* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    uint8_t* h_pinned = nullptr;  // 4 KiB of pinned host memory for small read-backs
+
+    std::unordered_map<PosKey, uint32_t, PosHash> map;
+    std::vector<Region> regions;
+    std::vector<uint32_t> free_slots;
+    std::vector<uint8_t> resident;
+    uint64_t next_unused = 0, n_resident = 0;
+    bool nbr_dirty = true;
+
+    uint64_t last_mesh_n = 0;
+    uint64_t launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(dsp_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define DSP_CUDA(ctx, call)                                                                                         \
+    do {                                                                                                            \
+        cudaError_t e_ = (call);                                                                                    \
+        if (e_ != cudaSuccess) return fail(ctx, DSP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure_scratch(dsp_ctx* ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return DSP_OK;
+    if (ctx->d_scratch) { DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); DSP_CUDA(ctx, cudaFree(ctx->d_scratch)); ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; }
+    size_t cap = std::max<size_t>(bytes, 1u << 20);
+    DSP_CUDA(ctx, cudaMalloc(&ctx->d_scratch, cap));
+    ctx->scratch_bytes = cap;
+    return DSP_OK;
+}
+
+bool find_slot(const dsp_ctx* ctx, const int32_t p[3], uint32_t* out) {
+    auto it = ctx->map.find(PosKey{p[0], p[1], p[2]});
+    if (it != ctx->map.end()) { *out = it->second; return true; }
+    for (const Region& r : ctx->regions) {
+        const int64_t a = static_cast<int64_t>(p[0]) - r.origin[0], b = static_cast<int64_t>(p[1]) - r.origin[1],
+                      c = static_cast<int64_t>(p[2]) - r.origin[2];
+        if (a < 0 || b < 0 || c < 0 || a >= r.dims[0] || b >= r.dims[1] || c >= r.dims[2]) continue;
+        const uint64_t s = r.first_slot + static_cast<uint64_t>(a) + r.dims[0] * (static_cast<uint64_t>(b) + static_cast<uint64_t>(r.dims[1]) * c);
+        if (ctx->resident[s]) { *out = static_cast<uint32_t>(s); return true; }
+    }
+    return false;
+}
+
+// World::get_chunk's "insert if absent" (world.rs:29-31, 44-46) on slots.
+int acquire_slot(dsp_ctx* ctx, const int32_t p[3], uint32_t* out) {
+    if (find_slot(ctx, p, out)) return DSP_OK;
+    uint32_t s;
+    if (!ctx->free_slots.empty()) { s = ctx->free_slots.back(); ctx->free_slots.pop_back(); }
+    else if (ctx->next_unused < ctx->max_chunks) { s = static_cast<uint32_t>(ctx->next_unused++); }
+    else return fail(ctx, DSP_ERR_STORE_FULL, "voxel store full: %llu chunks resident of %llu",
+                     (unsigned long long)ctx->n_resident, (unsigned long long)ctx->max_chunks);
+    ctx->map.emplace(PosKey{p[0], p[1], p[2]}, s);
+    ctx->resident[s] = 1;
+    ctx->n_resident++;
+    ctx->nbr_dirty = true;
+    *out = s;
+    return DSP_OK;
+}
+
+// Copies n elements of elem_bytes each from host `src` to dst_base[slot[i]], one cudaMemcpyAsync per
+// run of consecutive slots (a fresh context hands out consecutive slots, so usually one copy).
+int upload_by_runs(dsp_ctx* ctx, uint8_t* dst_base, size_t elem_bytes, const uint32_t* slots, uint64_t n, const uint8_t* src) {
+    uint64_t i = 0;
+    while (i < n) {
+        uint64_t j = i + 1;
+        while (j < n && slots[j] == slots[j - 1] + 1) ++j;
+        DSP_CUDA(ctx, cudaMemcpyAsync(dst_base + static_cast<size_t>(slots[i]) * elem_bytes, src + i * elem_bytes, (j - i) * elem_bytes,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        i = j;
+    }
+    return DSP_OK;
+}
+
+int upload_positions(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint32_t* slots) {
+    std::vector<int4> p4(n);
+    for (uint64_t i = 0; i < n; ++i) p4[i] = make_int4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0);
+    return upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_pos), sizeof(int4), slots, n, reinterpret_cast<const uint8_t*>(p4.data()));
+}
+
+// returns device pointer to the slot list, or nullptr when the slots are one consecutive run
+int stage_slot_list(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, const uint32_t** d_list, uint32_t* first) {
+    bool consecutive = true;
+    for (uint64_t i = 1; i < n && consecutive; ++i) consecutive = slots[i] == slots[i - 1] + 1;
+    *first = n ? slots[0] : 0;
+    if (consecutive) { *d_list = nullptr; return DSP_OK; }
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots, slots, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    *d_list = ctx->d_slots;
+    return DSP_OK;
+}
+
+template <int NSTAGE, bool HALO>
+int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
+    auto kern = dsp::mesh_chunks_kernel<NSTAGE, HALO>;
+    constexpr int smem = dsp::MeshSmem<NSTAGE>::kBytes;
+    int& occ = ctx->mesh_ctas_per_sm[NSTAGE - 1][HALO ? 1 : 0];
+    if (occ == 0) {
+        DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        if (occ < 1) return fail(ctx, DSP_ERR_INTERNAL, "mesh kernel does not fit on an SM (smem %d)", smem);
+    }
+    const uint64_t resident_ctas = static_cast<uint64_t>(ctx->num_sms) * occ;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, resident_ctas));
+    kern<<<grid, 256, smem, ctx->stream>>>(p);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return DSP_OK;
+}
+
+int build_neighbour_table(dsp_ctx* ctx);
+
+int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset) {
+    if (mode & ~DSP_MESH_HALO) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
+    if (arena_offset % DSP_SLOT_ALIGN != 0 || arena_offset > ctx->arena_bytes)
+        return fail(ctx, DSP_ERR_BAD_ARG, "arena_offset %llu must be a multiple of 128 and <= arena size", (unsigned long long)arena_offset);
+    if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_BAD_ARG, "n = %llu exceeds max_chunks", (unsigned long long)n);
+    if (ctx->n_blocks == 0) return fail(ctx, DSP_ERR_BAD_ARG, "dsp_set_uv_table has not been called");
+    ctx->last_mesh_n = n;
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + 8 * n, ctx->stream));
+    if (n == 0) return DSP_OK;
+    const bool halo = (mode & DSP_MESH_HALO) != 0;
+    if (halo) { int rc = build_neighbour_table(ctx); if (rc != DSP_OK) return rc; }
+    dsp::MeshParams p{};
+    p.voxels = ctx->d_voxels;
+    p.chunk_pos = ctx->d_pos;
+    p.slot_list = d_list;
+    p.nbr_slots = ctx->d_nbr;
+    p.uvmap = ctx->d_uvmap;
+    p.n_blocks = ctx->n_blocks;
+    p.first_slot = first_slot;
+    p.n = static_cast<uint32_t>(n);
+    p.arena = ctx->d_arena + arena_offset;
+    p.arena_offset = arena_offset;
+    p.arena_room = ctx->arena_bytes - arena_offset;
+    p.entries = ctx->d_entries;
+    p.ctrl = reinterpret_cast<uint32_t*>(ctx->d_ctl);
+    p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
+    p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
+    if (ctx->mesh_nstage == 2) return halo ? launch_mesh_t<2, true>(ctx, p) : launch_mesh_t<2, false>(ctx, p);
+    return halo ? launch_mesh_t<1, true>(ctx, p) : launch_mesh_t<1, false>(ctx, p);
+}
+
+int validate_slots(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
+    for (uint64_t i = 0; i < n; ++i)
+        if (slots[i] >= ctx->next_unused || !ctx->resident[slots[i]])
+            return fail(ctx, DSP_ERR_NOT_RESIDENT, "slot %u (entry %llu) is not resident", slots[i], (unsigned long long)i);
+    return DSP_OK;
+}
+int validate_range(dsp_ctx* ctx, uint32_t first, uint64_t n) {
+    if (first + n > ctx->next_unused) return fail(ctx, DSP_ERR_NOT_RESIDENT, "slot range [%u, %llu) is not resident", first, (unsigned long long)(first + n));
+    for (uint64_t i = 0; i < n; ++i)
+        if (!ctx->resident[first + i]) return fail(ctx, DSP_ERR_NOT_RESIDENT, "slot %llu is not resident", (unsigned long long)(first + i));
+    return DSP_OK;
+}
+
+// Neighbour slots for halo culling: order top(+Y), bottom(-Y), rear(-Z), front(+Z), right(-X), left(+X)
+// (the reference's face order, chunk_mesh.rs:46-51).  Resolved on the host from the chunk map.
+int build_neighbour_table(dsp_ctx* ctx) {
+    if (!ctx->d_nbr) DSP_CUDA(ctx, cudaMalloc(&ctx->d_nbr, ctx->max_chunks * 6 * sizeof(uint32_t)));
+    if (!ctx->nbr_dirty) return DSP_OK;
+    static const int dirs[6][3] = {{0, 1, 0}, {0, -1, 0}, {0, 0, -1}, {0, 0, 1}, {-1, 0, 0}, {1, 0, 0}};
+    std::vector<uint32_t> nbr(ctx->next_unused * 6, DSP_NO_SLOT);
+    auto fill = [&](uint32_t slot, const int32_t p[3]) {
+        for (int f = 0; f < 6; ++f) {
+            const int32_t q[3] = {p[0] + dirs[f][0], p[1] + dirs[f][1], p[2] + dirs[f][2]};
+            uint32_t s;
+            if (find_slot(ctx, q, &s)) nbr[static_cast<size_t>(slot) * 6 + f] = s;
+        }
+    };
+    for (const auto& kv : ctx->map) { const int32_t p[3] = {kv.first.x, kv.first.y, kv.first.z}; fill(kv.second, p); }
+    for (const Region& r : ctx->regions)
+        for (uint32_t c = 0; c < r.dims[2]; ++c)
+            for (uint32_t b = 0; b < r.dims[1]; ++b)
+                for (uint32_t a = 0; a < r.dims[0]; ++a) {
+                    const uint64_t s = r.first_slot + a + static_cast<uint64_t>(r.dims[0]) * (b + static_cast<uint64_t>(r.dims[1]) * c);
+                    if (!ctx->resident[s]) continue;
+                    const int32_t p[3] = {r.origin[0] + static_cast<int32_t>(a), r.origin[1] + static_cast<int32_t>(b), r.origin[2] + static_cast<int32_t>(c)};
+                    fill(static_cast<uint32_t>(s), p);
+                }
+    if (!nbr.empty()) {
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr, nbr.data(), nbr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->nbr_dirty = false;
+    return DSP_OK;
+}
+
+int finish_mesh(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total) {
+    const uint64_t n = ctx->last_mesh_n;
+    if (out_total) *out_total = 0;
+    if (n && out_entries)
+        DSP_CUDA(ctx, cudaMemcpyAsync(out_entries, ctx->d_entries, n * sizeof(dsp_mesh_entry), cudaMemcpyDeviceToHost, ctx->stream));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_ctl, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint32_t status = reinterpret_cast<uint32_t*>(ctx->h_pinned)[1];
+    const uint64_t total = *reinterpret_cast<uint64_t*>(ctx->h_pinned + 16);
+    if (out_total) *out_total = total;
+    if (status & dsp::kStatusSpin) return fail(ctx, DSP_ERR_INTERNAL, "mesh kernel look-back timed out");
+    if (status & dsp::kStatusOverflow)
+        return fail(ctx, DSP_ERR_ARENA_FULL, "vertex arena too small: need %llu bytes from the given offset", (unsigned long long)total);
+    return DSP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dsp_abi_version(void) { return DSP_ABI_VERSION; }
+
+const char* dsp_status_string(int s) {
+    switch (s) {
+        case DSP_OK: return "ok";
+        case DSP_ERR_BAD_ARG: return "bad argument";
+        case DSP_ERR_CUDA: return "CUDA error";
+        case DSP_ERR_NO_DEVICE: return "no CUDA device";
+        case DSP_ERR_ARENA_FULL: return "vertex arena full";
+        case DSP_ERR_STORE_FULL: return "voxel store full";
+        case DSP_ERR_NOT_RESIDENT: return "chunk not resident";
+        case DSP_ERR_INTERNAL: return "internal error";
+        default: return "unknown status";
+    }
+}
+
+const char* dsp_last_error(const dsp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** out_ctx) {
+    if (!out_ctx) return fail(nullptr, DSP_ERR_BAD_ARG, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    if (max_chunks == 0 || max_chunks >= 0xFFFFFFFFull) return fail(nullptr, DSP_ERR_BAD_ARG, "max_chunks must be in [1, 2^32-2]");
+    if (arena_bytes % DSP_SLOT_ALIGN != 0) return fail(nullptr, DSP_ERR_BAD_ARG, "arena_bytes must be a multiple of 128");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, DSP_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, DSP_ERR_BAD_ARG, "device %d out of range [0,%d)", device, count);
+    cudaDeviceProp prop{};
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, DSP_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, DSP_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    dsp_ctx* ctx = new dsp_ctx();
+    ctx->device = device;
+    ctx->max_chunks = max_chunks;
+    ctx->arena_bytes = arena_bytes;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (const char* s = getenv("DSP_MESH_NSTAGE")) ctx->mesh_nstage = atoi(s) == 2 ? 2 : 1;
+    auto bail = [&](const char* what, cudaError_t err) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(err);
+        dsp_destroy(ctx);
+        return fail(nullptr, DSP_ERR_CUDA, "%s", msg.c_str());
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&ctx->d_voxels, max_chunks * dsp::kChunkBytes)) != cudaSuccess) return bail("cudaMalloc(voxel store)", e);
+    if ((e = cudaMalloc(&ctx->d_pos, max_chunks * sizeof(int4))) != cudaSuccess) return bail("cudaMalloc(chunk positions)", e);
+    if ((e = cudaMalloc(&ctx->d_arena, std::max<uint64_t>(arena_bytes, 128))) != cudaSuccess) return bail("cudaMalloc(vertex arena)", e);
+    if ((e = cudaMalloc(&ctx->d_entries, max_chunks * sizeof(dsp::MeshEntry))) != cudaSuccess) return bail("cudaMalloc(entries)", e);
+    if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks)) != cudaSuccess) return bail("cudaMalloc(control)", e);
+    if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
+    if ((e = cudaMallocHost(&ctx->h_pinned, 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
+    ctx->resident.assign(max_chunks, 0);
+    *out_ctx = ctx;
+    return DSP_OK;
+}
+
+int dsp_destroy(dsp_ctx* ctx) {
+    if (!ctx) return DSP_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
+    cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DSP_OK;
+}
+
+int dsp_set_uv_table(dsp_ctx* ctx, uint32_t n_blocks, const float* uv_rows) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (n_blocks == 0 || n_blocks > 65536 || !uv_rows) return fail(ctx, DSP_ERR_BAD_ARG, "n_blocks must be in [1,65536] and uv_rows non-NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n_blocks > ctx->uv_cap) {
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap);
+        ctx->d_uv_rows = ctx->d_uvmap = nullptr;
+        DSP_CUDA(ctx, cudaMalloc(&ctx->d_uv_rows, n_blocks * sizeof(float4)));
+        DSP_CUDA(ctx, cudaMalloc(&ctx->d_uvmap, (n_blocks + 1) * sizeof(float4)));
+        ctx->uv_cap = n_blocks;
+    }
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_uv_rows, uv_rows, n_blocks * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    dsp::uv_map_kernel<<<(n_blocks + 1 + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_uv_rows, ctx->d_uvmap, n_blocks);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    ctx->n_blocks = n_blocks;
+    return DSP_OK;
+}
+
+int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (gen_kind < 0 || gen_kind > 3) return fail(ctx, DSP_ERR_BAD_ARG, "unknown gen_kind %d", gen_kind);
+    if (n == 0) return DSP_OK;
+    if (!pos) return fail(ctx, DSP_ERR_BAD_ARG, "pos is NULL");
+    if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "n exceeds max_chunks");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> slots(n);
+    for (uint64_t i = 0; i < n; ++i) { int rc = acquire_slot(ctx, pos + 3 * i, &slots[i]); if (rc != DSP_OK) return rc; }
+    int rc = upload_positions(ctx, n, pos, slots.data());
+    if (rc != DSP_OK) return rc;
+    const uint32_t* d_list; uint32_t first;
+    if ((rc = stage_slot_list(ctx, n, slots.data(), &d_list, &first)) != DSP_OK) return rc;
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed};
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
+    dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (out_slots) std::memcpy(out_slots, slots.data(), n * sizeof(uint32_t));
+    return DSP_OK;
+}
+
+int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t dims[3], int gen_kind, uint32_t seed, uint32_t* out_first_slot) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (!origin || !dims || !out_first_slot) return fail(ctx, DSP_ERR_BAD_ARG, "NULL argument");
+    if (gen_kind < 0 || gen_kind > 3) return fail(ctx, DSP_ERR_BAD_ARG, "unknown gen_kind %d", gen_kind);
+    const uint64_t n = static_cast<uint64_t>(dims[0]) * dims[1] * dims[2];
+    if (n == 0) return fail(ctx, DSP_ERR_BAD_ARG, "empty region");
+    if (ctx->next_unused + n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "region of %llu chunks does not fit (%llu unused slots)",
+                                                            (unsigned long long)n, (unsigned long long)(ctx->max_chunks - ctx->next_unused));
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t first = static_cast<uint32_t>(ctx->next_unused);
+    ctx->next_unused += n;
+    Region r{{origin[0], origin[1], origin[2]}, {dims[0], dims[1], dims[2]}, first};
+    ctx->regions.push_back(r);
+    std::fill(ctx->resident.begin() + first, ctx->resident.begin() + first + n, 1);
+    ctx->n_resident += n;
+    ctx->nbr_dirty = true;
+    dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
+        ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), n);
+    DSP_CUDA(ctx, cudaGetLastError());
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed};
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
+    dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    *out_first_slot = first;
+    return DSP_OK;
+}
+
+int dsp_load_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint16_t* palette_ids,
+                    const uint32_t* palette_offsets, uint32_t* out_slots) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (n == 0) return DSP_OK;
+    if (!pos || !blocks) return fail(ctx, DSP_ERR_BAD_ARG, "pos/blocks is NULL");
+    if ((palette_ids == nullptr) != (palette_offsets == nullptr)) return fail(ctx, DSP_ERR_BAD_ARG, "palette_ids and palette_offsets go together");
+    if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "n exceeds max_chunks");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> slots(n);
+    for (uint64_t i = 0; i < n; ++i) { int rc = acquire_slot(ctx, pos + 3 * i, &slots[i]); if (rc != DSP_OK) return rc; }
+    int rc = upload_positions(ctx, n, pos, slots.data());
+    if (rc != DSP_OK) return rc;
+    if ((rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, slots.data(), n,
+                             reinterpret_cast<const uint8_t*>(blocks))) != DSP_OK) return rc;
+    if (palette_ids) {
+        const size_t pal_n = palette_offsets[n];
+        const size_t off_bytes = (n + 1) * sizeof(uint32_t), list_bytes = n * sizeof(uint32_t);
+        const size_t pal_off = (off_bytes + list_bytes + 15) & ~size_t(15);
+        if ((rc = ensure_scratch(ctx, pal_off + pal_n * sizeof(uint16_t))) != DSP_OK) return rc;
+        uint32_t* d_off = reinterpret_cast<uint32_t*>(ctx->d_scratch);
+        uint32_t* d_list = d_off + (n + 1);
+        uint16_t* d_pal = reinterpret_cast<uint16_t*>(ctx->d_scratch + pal_off);
+        DSP_CUDA(ctx, cudaMemcpyAsync(d_off, palette_offsets, off_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        DSP_CUDA(ctx, cudaMemcpyAsync(d_list, slots.data(), list_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        DSP_CUDA(ctx, cudaMemcpyAsync(d_pal, palette_ids, pal_n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 32));
+        dsp::palette_remap_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_voxels, d_list, d_pal, d_off, static_cast<uint32_t>(n));
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `slots` (pageable) must outlive the copy
+    }
+    if (out_slots) std::memcpy(out_slots, slots.data(), n * sizeof(uint32_t));
+    return DSP_OK;
+}
+
+int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (n && !slots) return fail(ctx, DSP_ERR_BAD_ARG, "slots is NULL");
+    int rc = validate_slots(ctx, n, slots);
+    if (rc != DSP_OK) return rc;
+    // positions of map-resident chunks are needed to erase them: read them back from the device
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint32_t s = slots[i];
+        if (!ctx->resident[s]) continue;  // duplicate in the list
+        bool in_region = false;
+        for (const Region& r : ctx->regions) {
+            const uint64_t cnt = static_cast<uint64_t>(r.dims[0]) * r.dims[1] * r.dims[2];
+            if (s >= r.first_slot && s < r.first_slot + cnt) { in_region = true; break; }
+        }
+        if (!in_region) {
+            int4 p;
+            DSP_CUDA(ctx, cudaMemcpy(&p, ctx->d_pos + s, sizeof p, cudaMemcpyDeviceToHost));
+            ctx->map.erase(PosKey{p.x, p.y, p.z});
+            ctx->free_slots.push_back(s);  // region slots are not recycled (their addresses are arithmetic)
+        }
+        ctx->resident[s] = 0;
+        ctx->n_resident--;
+    }
+    ctx->nbr_dirty = true;
+    return DSP_OK;
+}
+
+int dsp_find_chunk(const dsp_ctx* ctx, const int32_t pos[3], uint32_t* out_slot) {
+    if (!ctx || !pos || !out_slot) return DSP_ERR_BAD_ARG;
+    return find_slot(ctx, pos, out_slot) ? DSP_OK : DSP_ERR_NOT_RESIDENT;
+}
+
+uint64_t dsp_resident_chunks(const dsp_ctx* ctx) { return ctx ? ctx->n_resident : 0; }
+uint64_t dsp_max_chunks(const dsp_ctx* ctx) { return ctx ? ctx->max_chunks : 0; }
+
+int dsp_mesh_chunks_async(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint32_t mode, uint64_t arena_offset) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (n && !slots) return fail(ctx, DSP_ERR_BAD_ARG, "slots is NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_slots(ctx, n, slots);
+    if (rc != DSP_OK) return rc;
+    if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_BAD_ARG, "n exceeds max_chunks");
+    const uint32_t* d_list; uint32_t first;
+    if ((rc = stage_slot_list(ctx, n, slots, &d_list, &first)) != DSP_OK) return rc;
+    return enqueue_mesh(ctx, n, d_list, first, mode, arena_offset);
+}
+
+int dsp_mesh_range_async(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode, uint64_t arena_offset) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_range(ctx, first_slot, n);
+    if (rc != DSP_OK) return rc;
+    return enqueue_mesh(ctx, n, nullptr, first_slot, mode, arena_offset);
+}
+
+int dsp_sync(dsp_ctx* ctx) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DSP_OK;
+}
+
+int dsp_mesh_result(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    return finish_mesh(ctx, out_entries, out_total_bytes);
+}
+
+int dsp_mesh_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint32_t mode, uint64_t arena_offset, dsp_mesh_entry* out_entries,
+                    uint64_t* out_total_bytes) {
+    int rc = dsp_mesh_chunks_async(ctx, n, slots, mode, arena_offset);
+    if (rc != DSP_OK) return rc;
+    return finish_mesh(ctx, out_entries, out_total_bytes);
+}
+
+int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode, uint64_t arena_offset, dsp_mesh_entry* out_entries,
+                   uint64_t* out_total_bytes) {
+    int rc = dsp_mesh_range_async(ctx, first_slot, n, mode, arena_offset);
+    if (rc != DSP_OK) return rc;
+    return finish_mesh(ctx, out_entries, out_total_bytes);
+}
+
+int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (out_n_dirty) *out_n_dirty = 0;
+    if (n == 0) return DSP_OK;
+    if (!edits) return fail(ctx, DSP_ERR_BAD_ARG, "edits is NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    // world.rs:69-74 to_chunk_coord: chunk = div_euclid(w, 16), local = rem_euclid(w, 16)
+    std::unordered_map<uint64_t, uint32_t> last;  // (slot << 12 | voxel index) -> position in `packed`
+    std::vector<uint2> packed;
+    packed.reserve(n);
+    std::vector<uint32_t> dirty;
+    PosKey cached{0x7FFFFFFF, 0x7FFFFFFF, 0x7FFFFFFF};
+    uint32_t cached_slot = DSP_NO_SLOT;
+    for (uint64_t i = 0; i < n; ++i) {
+        const dsp_edit& e = edits[i];
+        if (e.block > 0xFFFFu) return fail(ctx, DSP_ERR_BAD_ARG, "edit %llu: block id %u does not fit u16", (unsigned long long)i, e.block);
+        const int32_t c[3] = {e.wx >> 4, e.wy >> 4, e.wz >> 4};
+        uint32_t slot;
+        if (cached.x == c[0] && cached.y == c[1] && cached.z == c[2]) slot = cached_slot;
+        else { if (!find_slot(ctx, c, &slot)) slot = DSP_NO_SLOT; cached = PosKey{c[0], c[1], c[2]}; cached_slot = slot; }
+        if (slot == DSP_NO_SLOT) continue;
+        const uint32_t idx = static_cast<uint32_t>(e.wx & 15) + 16u * static_cast<uint32_t>(e.wy & 15) + 256u * static_cast<uint32_t>(e.wz & 15);
+        const uint64_t key = (static_cast<uint64_t>(slot) << 12) | idx;
+        const uint2 rec = make_uint2(slot, idx | (e.block << 16));
+        auto it = last.find(key);
+        if (it == last.end()) { last.emplace(key, static_cast<uint32_t>(packed.size())); packed.push_back(rec); dirty.push_back(slot); }
+        else packed[it->second] = rec;  // later edit to the same voxel wins
+    }
+    std::sort(dirty.begin(), dirty.end());
+    dirty.erase(std::unique(dirty.begin(), dirty.end()), dirty.end());
+    if (!packed.empty()) {
+        int rc = ensure_scratch(ctx, packed.size() * sizeof(uint2));
+        if (rc != DSP_OK) return rc;
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, packed.data(), packed.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+        dsp::edit_scatter_kernel<<<static_cast<unsigned>((packed.size() + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_voxels, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(packed.size()));
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    if (out_n_dirty) *out_n_dirty = dirty.size();
+    if (out_dirty_slots) {
+        if (dirty.size() > cap_dirty) return fail(ctx, DSP_ERR_BAD_ARG, "dirty list needs %llu entries, capacity %llu",
+                                                  (unsigned long long)dirty.size(), (unsigned long long)cap_dirty);
+        std::memcpy(out_dirty_slots, dirty.data(), dirty.size() * sizeof(uint32_t));
+    }
+    return DSP_OK;
+}
+
+int dsp_download_arena(dsp_ctx* ctx, uint64_t offset_bytes, uint64_t bytes, void* host_dst) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (offset_bytes + bytes > ctx->arena_bytes) return fail(ctx, DSP_ERR_BAD_ARG, "arena read [%llu,+%llu) out of range", (unsigned long long)offset_bytes, (unsigned long long)bytes);
+    if (bytes == 0) return DSP_OK;
+    if (!host_dst) return fail(ctx, DSP_ERR_BAD_ARG, "host_dst is NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DSP_CUDA(ctx, cudaMemcpyAsync(host_dst, ctx->d_arena + offset_bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return DSP_OK;
+}
+
+int dsp_download_chunk(dsp_ctx* ctx, uint32_t slot, uint16_t* host_dst, int32_t* out_pos) {
+    if (!ctx || !host_dst) return DSP_ERR_BAD_ARG;
+    if (slot >= ctx->next_unused || !ctx->resident[slot]) return fail(ctx, DSP_ERR_NOT_RESIDENT, "slot %u is not resident", slot);
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DSP_CUDA(ctx, cudaMemcpyAsync(host_dst, ctx->d_voxels + static_cast<size_t>(slot) * dsp::kChunkVoxels, dsp::kChunkBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    int4 p = make_int4(0, 0, 0, 0);
+    if (out_pos) DSP_CUDA(ctx, cudaMemcpyAsync(&p, ctx->d_pos + slot, sizeof p, cudaMemcpyDeviceToHost, ctx->stream));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_pos) { out_pos[0] = p.x; out_pos[1] = p.y; out_pos[2] = p.z; }
+    return DSP_OK;
+}
+
+void* dsp_arena_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_arena : nullptr; }
+uint64_t dsp_arena_bytes(const dsp_ctx* ctx) { return ctx ? ctx->arena_bytes : 0; }
+void* dsp_voxel_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_voxels : nullptr; }
+void* dsp_entries_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_entries : nullptr; }
+void* dsp_stream(dsp_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
+uint64_t dsp_kernel_launches(const dsp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

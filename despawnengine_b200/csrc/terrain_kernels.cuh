@@ -1,0 +1,161 @@
+// Terrain fill, palette remap, edit scatter and bookkeeping kernels (sm_100a).
+//
+// Reference behaviour being replaced (paths under /root/reference/src):
+//   content/world/world.rs:35-42          generator chosen by chunk Y
+//   content/world/chunks/chunk.rs:86-120  generate_flat / generate_full / generate_empty
+// The NOISE / RANDOM / CHECKER kinds are builder-defined integer specs (DESIGN.md "Terrain spec").
+//
+// Roofline: HBM write bound, 8,192 algorithmic bytes per chunk (one u16 per voxel) plus 16 B of
+// position read.  One CTA of 256 threads per chunk; thread t owns x-row r = t (y = r & 15,
+// z = r >> 4) and stores its 32 bytes with two 128-bit stores, so a warp writes 1 KiB contiguous.
+#pragma once
+#include "dsp_common.cuh"
+
+namespace dsp {
+
+struct TerrainParams {
+    uint16_t* voxels;           // [max_chunks][4096]
+    const int4* chunk_pos;      // per slot (x,y,z,_)
+    const uint32_t* slot_list;  // nullable: chunk i -> slot_list[i], else first_slot + i
+    uint32_t first_slot;
+    uint32_t n;
+    int kind;
+    uint32_t seed;
+};
+
+// smoothstep-weighted bilinear value noise on a lattice whose values were hashed once per chunk
+// into `lat` (3x3 per octave, [dz][dx]); identical arithmetic to oracle/mesher_oracle.cpp.
+__device__ __forceinline__ uint32_t octave_from_lattice(const uint32_t* lat, int32_t wx, int32_t wz, int32_t ix0, int32_t iz0, int o) {
+    const int s = 5 - o;
+    const int dx = (wx >> s) - ix0, dz = (wz >> s) - iz0;
+    const uint32_t tx = static_cast<uint32_t>(wx & ((1 << s) - 1)) << (8 - s);
+    const uint32_t tz = static_cast<uint32_t>(wz & ((1 << s) - 1)) << (8 - s);
+    const uint32_t sx = (tx * tx * (768U - 2U * tx)) >> 16;
+    const uint32_t sz = (tz * tz * (768U - 2U * tz)) >> 16;
+    const uint32_t v00 = lat[dz * 3 + dx], v10 = lat[dz * 3 + dx + 1];
+    const uint32_t v01 = lat[(dz + 1) * 3 + dx], v11 = lat[(dz + 1) * 3 + dx + 1];
+    const uint32_t a = v00 * (256U - sx) + v10 * sx;
+    const uint32_t b = v01 * (256U - sx) + v11 * sx;
+    return (a * (256U - sz) + b * sz) >> 16;
+}
+
+__global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p) {
+    __shared__ uint32_t s_lat[3][9];
+    __shared__ int32_t s_h[256];  // [z][x] column heights
+    const int tid = threadIdx.x;
+    for (uint32_t i = blockIdx.x; i < p.n; i += gridDim.x) {
+        const uint32_t slot = p.slot_list ? p.slot_list[i] : p.first_slot + i;
+        const int4 cp = p.chunk_pos[slot];
+        const int y = tid & 15, z = tid >> 4;
+        const int32_t wy = cp.y * 16 + y, wz = cp.z * 16 + z, wx0 = cp.x * 16;
+        uint32_t w[8];  // 16 voxels, two per word, x ascending
+        if (p.kind == 0) {
+            // world.rs:35-42: Y > 0 empty, Y == 0 bottom half dirt (y < 8), Y < 0 full.
+            const uint32_t id = cp.y > 0 ? 0u : (cp.y == 0 ? (y < 8 ? 1u : 0u) : 1u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = id | (id << 16);
+        } else if (p.kind == 1) {
+            if (tid < 27) {  // lattice values for the three octaves, hashed once per chunk
+                const int o = tid / 9, q = tid % 9, s = 5 - o;
+                s_lat[o][q] = hash2(p.seed + static_cast<uint32_t>(o), (wx0 >> s) + q % 3, ((cp.z * 16) >> s) + q / 3) & 0xFFU;
+            }
+            __syncthreads();
+            {
+                const int x = tid & 15, zc = tid >> 4;
+                const int32_t cwx = wx0 + x, cwz = cp.z * 16 + zc;
+                uint32_t n = 0;
+#pragma unroll
+                for (int o = 0; o < 3; ++o) {
+                    const int s = 5 - o;
+                    n += octave_from_lattice(s_lat[o], cwx, cwz, wx0 >> s, (cp.z * 16) >> s, o) << (2 - o);
+                }
+                s_h[tid] = 16 + static_cast<int32_t>(n >> 3);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int32_t h0 = s_h[z * 16 + 2 * k], h1 = s_h[z * 16 + 2 * k + 1];
+                const uint32_t a = wy < h0 - 1 ? 1u : (wy == h0 - 1 ? 2u : 0u);
+                const uint32_t b = wy < h1 - 1 ? 1u : (wy == h1 - 1 ? 2u : 0u);
+                w[k] = a | (b << 16);
+            }
+            __syncthreads();  // s_h / s_lat reused by the next chunk of this CTA
+        } else if (p.kind == 2) {
+            const uint32_t hzy = 0;  // (kept explicit: hash3 = mix32(hash2(seed,wx,wy) + wz*K))
+            (void)hzy;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t r0 = hash3(p.seed, wx0 + 2 * k, wy, wz), r1 = hash3(p.seed, wx0 + 2 * k + 1, wy, wz);
+                const uint32_t a = (r0 & 1U) ? 1U + ((r0 >> 1) & 1U) : 0U;
+                const uint32_t b = (r1 & 1U) ? 1U + ((r1 >> 1) & 1U) : 0U;
+                w[k] = a | (b << 16);
+            }
+        } else {
+            // checkerboard: (wx+wy+wz) even -> 1.  wx0 is a multiple of 16, so parity is local.
+            const uint32_t even_first = ((wy + wz) & 1) == 0 ? 1u : 0u;  // voxel at even x
+            const uint32_t word = even_first | ((even_first ^ 1u) << 16);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w[k] = word;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// chunk_pos[first_slot + i] for a dims box: i = a + dims.x*(b + dims.y*c) -> origin + (a,b,c)
+__global__ void region_positions_kernel(int4* chunk_pos, uint32_t first_slot, int3 origin, uint3 dims, uint64_t n) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t a = static_cast<uint32_t>(i % dims.x);
+        const uint64_t t = i / dims.x;
+        const uint32_t b = static_cast<uint32_t>(t % dims.y), c = static_cast<uint32_t>(t / dims.y);
+        chunk_pos[first_slot + i] = make_int4(origin.x + static_cast<int>(a), origin.y + static_cast<int>(b), origin.z + static_cast<int>(c), 0);
+    }
+}
+
+// chunk.rs:58-65: a chunk's voxels are indices into its own palette; the device store holds global
+// ids, so after the raw host->device copy each voxel is replaced by palette_ids[off[i] + voxel].
+__global__ void __launch_bounds__(256) palette_remap_kernel(uint16_t* voxels, const uint32_t* slot_list, const uint16_t* palette_ids,
+                                                           const uint32_t* palette_offsets, uint32_t n) {
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t slot = slot_list[i], off = palette_offsets[i], len = palette_offsets[i + 1] - off;
+        uint4* row = reinterpret_cast<uint4*>(voxels + static_cast<size_t>(slot) * kChunkVoxels) + threadIdx.x * 2;
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+            uint4 q = row[hlf];
+            uint32_t* wq = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t lo = wq[k] & 0xFFFFu, hi = wq[k] >> 16;
+                const uint32_t a = lo < len ? palette_ids[off + lo] : 0u;  // out-of-range palette index -> air
+                const uint32_t b = hi < len ? palette_ids[off + hi] : 0u;
+                wq[k] = a | (b << 16);
+            }
+            row[hlf] = q;
+        }
+    }
+}
+
+// Chunk::set_block on resident chunks (chunk.rs:49-68).  The host has already resolved world
+// coordinates to (slot, voxel index) and kept only the last edit per voxel, so the scatter is
+// race-free.  packed = slot (u32), idx | block << 16 (u32).
+__global__ void edit_scatter_kernel(uint16_t* voxels, const uint2* edits, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 e = edits[i];
+    voxels[static_cast<size_t>(e.x) * kChunkVoxels + (e.y & 0xFFFu)] = static_cast<uint16_t>(e.y >> 16);
+}
+
+// map_uv of chunk_mesh.rs:23-28 evaluated once per block id instead of once per vertex:
+// out[id] = (map(0).x, map(0).y, map(1).x, map(1).y) with map(o) = uv_min + o * (uv_max - uv_min),
+// each operation rounded separately (no FMA contraction) like the rustc-compiled reference.
+__global__ void uv_map_kernel(const float4* uv_rows, float4* uvmap, uint32_t n_blocks) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_blocks) return;
+    const float4 a = i < n_blocks ? uv_rows[i] : make_float4(0.0f, 0.0f, 1.0f, 1.0f);  // row n_blocks = fallback (chunk_mesh.rs:53-56)
+    const float dx = __fsub_rn(a.z, a.x), dy = __fsub_rn(a.w, a.y);
+    uvmap[i] = make_float4(__fadd_rn(a.x, __fmul_rn(0.0f, dx)), __fadd_rn(a.y, __fmul_rn(0.0f, dy)),
+                           __fadd_rn(a.x, __fmul_rn(1.0f, dx)), __fadd_rn(a.y, __fmul_rn(1.0f, dy)));
+}
+
+}  // namespace dsp

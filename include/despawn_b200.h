@@ -1,0 +1,169 @@
+/* despawn_b200.h -- C ABI of the B200-native chunk terrain -> cull -> mesh path.
+ *
+ * One shared library (libdespawn_b200.so), plain pointers and sizes, no C++/torch types.  The
+ * reference engine has no FFI boundary today: the seam this library replaces
+ * is three Rust items, cited per entry point below as file:line under /root/reference/src.
+ *
+ *   World::get_chunk / load_chunk / unload_chunk     content/world/world.rs:28-47, 80-87
+ *   Chunk { position, blocks: Vec<u16>, palette }    content/world/chunks/chunk.rs:15-20
+ *   build_chunk_mesh(allocator, &Chunk, &block_uvs)  content/world/chunks/chunk_mesh.rs:13-129
+ *   BlockVertex { position: Vec3, tex_coords }       engine/rendering/vertex.rs:5-12   (20 bytes)
+ *
+ * Data contract
+ *   voxels    u16 per voxel, 4096 per chunk, index x + 16*y + 256*z (chunk.rs:44-46); 0 = air
+ *             (chunk.rs:39-41).  The device store holds GLOBAL block ids: the host shim resolves each
+ *             chunk's string palette (chunk.rs:58-65) to registry ids before upload, or passes the
+ *             palette so that dsp_load_chunks remaps on the device.
+ *   uv table  row id = (uv_min.x, uv_min.y, uv_max.x, uv_max.y) of AtlasUV
+ *             (engine/rendering/texture_atlas.rs:15-19); row 0 (air) is never read; ids >= n_blocks get the
+ *             reference's fallback (0,0)-(1,1) (chunk_mesh.rs:53-56).
+ *   vertices  tightly packed BlockVertex, 6 per face, in exactly the reference's emission order (voxel
+ *             index ascending; TOP, BOTTOM, REAR, FRONT, RIGHT, LEFT per voxel, chunk_mesh.rs:32,65-106).
+ *             Each chunk's stream starts at a 128-byte aligned offset of the arena.
+ *             vertex_count == 0  <=>  the reference returns None (chunk_mesh.rs:18-20,109-128).
+ *
+ * Threading: a context is single-caller (the reference meshes on the winit thread only,
+ * engine/scenes/scene_game.rs:39-82); one context per GPU.  No function panics or aborts; every
+ * function returns a dsp_status and dsp_last_error() explains the last failure.
+ * There is no CPU fallback: without a CUDA device dsp_create fails with DSP_ERR_NO_DEVICE.
+ */
+#ifndef DESPAWN_B200_H
+#define DESPAWN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSP_ABI_VERSION 1
+
+typedef enum dsp_status {
+    DSP_OK = 0,
+    DSP_ERR_BAD_ARG = 1,
+    DSP_ERR_CUDA = 2,         /* a CUDA call failed; see dsp_last_error */
+    DSP_ERR_NO_DEVICE = 3,    /* no usable CUDA device / driver */
+    DSP_ERR_ARENA_FULL = 4,   /* vertex arena too small: nothing is truncated, *total_bytes = bytes needed */
+    DSP_ERR_STORE_FULL = 5,   /* no free chunk slot (max_chunks reached) */
+    DSP_ERR_NOT_RESIDENT = 6, /* chunk position / slot not loaded */
+    DSP_ERR_INTERNAL = 7
+} dsp_status;
+
+/* Terrain generators.  REFERENCE is world.rs:35-42 (chunk Y > 0 empty, == 0 flat, < 0 full, all
+ * "template:dirt" = id 1).  The others are builder-defined integer specs (DESIGN.md "Terrain spec");
+ * the reference declares the `noise` crate but never calls it. */
+typedef enum dsp_gen_kind {
+    DSP_GEN_REFERENCE = 0,
+    DSP_GEN_NOISE = 1,   /* 3-octave integer value-noise heightmap, ids 1 (body) and 2 (surface) */
+    DSP_GEN_RANDOM = 2,  /* Bernoulli(0.5) per voxel from a 32-bit hash, ids 1 and 2 */
+    DSP_GEN_CHECKER = 3  /* (wx+wy+wz) even -> id 1: the 12,288-face maximum */
+} dsp_gen_kind;
+
+/* Mesh modes (bit flags).  0 is the reference's behaviour and the only bit-exact-to-reference mode. */
+#define DSP_MESH_PARITY 0u /* chunk-local cull, border faces always emitted (chunk_mesh.rs:46-51) */
+#define DSP_MESH_HALO 1u   /* extension: border faces tested against resident neighbour chunks */
+
+#define DSP_NO_SLOT 0xFFFFFFFFu
+#define DSP_CHUNK_VOXELS 4096
+#define DSP_VERTEX_BYTES 20
+#define DSP_FACE_BYTES 120
+#define DSP_SLOT_ALIGN 128
+
+typedef struct dsp_ctx dsp_ctx;
+
+/* Result of meshing one chunk: where its vertex stream lives in the arena.  16 bytes. */
+typedef struct dsp_mesh_entry {
+    uint64_t offset_bytes;  /* from the start of the arena; multiple of DSP_SLOT_ALIGN */
+    uint32_t vertex_count;  /* 6 * faces; 0 <=> None */
+    uint32_t reserved;
+} dsp_mesh_entry;
+
+/* One block edit in world voxel coordinates (world.rs:50-74 addressing: chunk = div_euclid(w,16),
+ * local = rem_euclid(w,16)); block is a global id, 0 destroys. */
+typedef struct dsp_edit {
+    int32_t wx, wy, wz;
+    uint32_t block;
+} dsp_edit;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`: a voxel store of max_chunks slots (8 KiB each) and a
+ * vertex arena of arena_bytes.  Replaces World::new + World::set_allocator (world.rs:18-25, 76-78). */
+int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** out_ctx);
+int dsp_destroy(dsp_ctx* ctx);
+const char* dsp_last_error(const dsp_ctx* ctx); /* never NULL; ctx may be NULL for create failures */
+const char* dsp_status_string(int status);
+int dsp_abi_version(void);
+
+/* ---- block_uvs ----------------------------------------------------------------------------------- */
+/* Replaces the &RapidHashMap<String,AtlasUV> argument of build_chunk_mesh (chunk_mesh.rs:16). */
+int dsp_set_uv_table(dsp_ctx* ctx, uint32_t n_blocks, const float* uv_rows /* n_blocks x 4 */);
+
+/* ---- chunk residency (World) ----------------------------------------------------------------------- */
+/* World::get_chunk + load_chunk with on-device generation (world.rs:28-47, 80-84; chunk.rs:86-120).
+ * pos: n x 3 chunk coordinates.  Positions already resident are regenerated in place.
+ * out_slots (n, may be NULL) receives the slot of each chunk. */
+int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots);
+
+/* Bulk form: a dims[0] x dims[1] x dims[2] box of chunks with minimum corner `origin`, generated into
+ * consecutive slots; chunk (i,j,k) of the box gets slot *out_first_slot + i + dims[0]*(j + dims[1]*k). */
+int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t dims[3], int gen_kind, uint32_t seed,
+                        uint32_t* out_first_slot);
+
+/* World::load_chunk for host-resident Chunk data (the reference's Chunk.blocks, chunk.rs:17).
+ * blocks: n x 4096 u16 in host memory.  If palette_ids != NULL the values are per-chunk palette
+ * indices and chunk i's palette is palette_ids[palette_offsets[i] .. palette_offsets[i+1]) (global id
+ * per palette index, entry 0 = air = 0); the remap runs on the device.  If NULL, values are global ids. */
+int dsp_load_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint16_t* palette_ids,
+                    const uint32_t* palette_offsets, uint32_t* out_slots);
+
+/* World::unload_chunk (world.rs:85-87): frees the slots. */
+int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots);
+int dsp_find_chunk(const dsp_ctx* ctx, const int32_t pos[3], uint32_t* out_slot); /* DSP_ERR_NOT_RESIDENT if absent */
+uint64_t dsp_resident_chunks(const dsp_ctx* ctx);
+
+/* ---- meshing (build_chunk_mesh) ---------------------------------------------------------------------- */
+/* Batched build_chunk_mesh (chunk_mesh.rs:13-129); n = 1 is the reference call.  Meshes the chunks in
+ * `slots` (n entries) into the arena starting at arena_offset (multiple of 128), packed in the order
+ * given.  out_entries (host, n entries, may be NULL) and *out_total_bytes (may be NULL) are filled
+ * when the call returns; the vertex data stays on the device (the reference's result is a device
+ * buffer too, chunk_mesh.rs:111-124).  Blocking. */
+int dsp_mesh_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint32_t mode, uint64_t arena_offset,
+                    dsp_mesh_entry* out_entries, uint64_t* out_total_bytes);
+/* Same for the consecutive slots first_slot .. first_slot+n-1 (no slot list crosses the bus). */
+int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode, uint64_t arena_offset,
+                   dsp_mesh_entry* out_entries, uint64_t* out_total_bytes);
+/* Asynchronous forms: enqueue on the context's stream and return; results are read with
+ * dsp_mesh_result after dsp_sync.  Let a caller overlap meshing with its own work (the reference is
+ * synchronous inside GameScene::update, scene_game.rs:56-64). */
+int dsp_mesh_range_async(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode, uint64_t arena_offset);
+int dsp_mesh_chunks_async(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint32_t mode, uint64_t arena_offset);
+int dsp_sync(dsp_ctx* ctx);
+int dsp_mesh_result(dsp_ctx* ctx, dsp_mesh_entry* out_entries /* n of the last mesh call, may be NULL */,
+                    uint64_t* out_total_bytes);
+
+/* ---- edits (Chunk::set_block on resident chunks, chunk.rs:49-68) ---------------------------------- */
+/* Applies n edits in order to the device voxel store.  Edits that fall in non-resident chunks are
+ * ignored.  out_dirty_slots (capacity cap_dirty, may be NULL) receives the distinct slots touched, in
+ * ascending slot order, and *out_n_dirty their number. */
+int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty,
+                    uint64_t* out_n_dirty);
+
+/* ---- data access ------------------------------------------------------------------------------------ */
+int dsp_download_arena(dsp_ctx* ctx, uint64_t offset_bytes, uint64_t bytes, void* host_dst);
+int dsp_download_chunk(dsp_ctx* ctx, uint32_t slot, uint16_t* host_dst /* 4096 */, int32_t* out_pos /* 3, may be NULL */);
+/* Raw device pointers for zero-copy consumers (CUDA/Vulkan external-memory interop, NCCL halo
+ * exchange, torch tensors over the same memory).  Valid until dsp_destroy. */
+void* dsp_arena_device_ptr(dsp_ctx* ctx);
+uint64_t dsp_arena_bytes(const dsp_ctx* ctx);
+void* dsp_voxel_device_ptr(dsp_ctx* ctx);   /* max_chunks x 4096 u16 */
+void* dsp_entries_device_ptr(dsp_ctx* ctx); /* dsp_mesh_entry[n] of the last mesh call */
+void* dsp_stream(dsp_ctx* ctx);             /* cudaStream_t all work of this context is enqueued on */
+uint64_t dsp_max_chunks(const dsp_ctx* ctx);
+
+/* Number of kernel launches this context has enqueued since creation (bench accounting). */
+uint64_t dsp_kernel_launches(const dsp_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DESPAWN_B200_H */
