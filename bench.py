@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- chunks meshed/s on BASELINE.json's configs[1] (16x16x16-chunk region of seeded noise
+terrain, 4,096 chunks = 256^3 voxels per GPU), device-resident (`value`), end to end from host buffers
+through the C ABI (`e2e`), against the kernel's HBM roofline (`roofline`) and with the CPU
+restatement of the reference timed beside it (`cpu_baseline`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by the driver through torch.distributed.run (one rank per GPU, NCCL); started
+without it, this script re-executes itself under torch.distributed.run.  Weak scaling: every rank
+meshes its own 16^3-chunk region (regions abut along X); chunks are independent in the reference's
+mesher (chunk_mesh.rs:46-51 never looks outside the chunk), so there is no data-path collective.
+
+A "step" is one pass of the hot path over the batch: the fused cull + scan + emit kernel over all
+4,096 resident chunks of the rank (one launch), writing the full vertex stream into the HBM arena.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 0xD5E50001
+DIMS = (16, 16, 16)
+N_CHUNKS = DIMS[0] * DIMS[1] * DIMS[2]
+UV = np.array([[0, 0, 0, 0], [0.0, 0.0, 0.5, 1.0], [0.5, 0.0, 1.0, 1.0]], dtype=np.float32)
+WORKLOAD = "configs[1]: 16x16x16-chunk region (256^3 voxels) of seeded integer value-noise terrain, reference cull semantics, unit quads"
+METRIC = "chunks meshed/sec"
+
+
+def region_positions(origin):
+    return np.array([(origin[0] + a, origin[1] + b, origin[2] + c) for c in range(DIMS[2]) for b in range(DIMS[1]) for a in range(DIMS[0])],
+                    dtype=np.int32)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.power = [], set(), []
+        self.stop_flag = threading.Event()
+        self.sm_max = None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def summary(self, note=""):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": [], "note": "NVML unavailable or no samples " + note}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples), "power_w_max": round(max(self.power), 1), "note": note}
+
+
+def reference_arm(args, rank):
+    """The reference's own CPU path.  Its Rust sources cannot be built in this image (no rustc/cargo), so this
+    arm times the C++ restatement of build_chunk_mesh (oracle/, kind = "port") on all host threads."""
+    if rank != 0:
+        return
+    from oracle import loader as orc
+    threads = orc.hardware_threads()
+    pos = region_positions((0, 0, 0))
+    w = orc.Workload(pos, orc.GEN_NOISE, SEED, UV)
+    for _ in range(max(1, min(args.warmup, 3))):
+        w.mesh(orc.FAITHFUL, threads)
+    secs, verts = [], 0
+    budget_t0 = time.perf_counter()
+    steps_done = 0
+    for _ in range(args.steps):
+        s, verts = w.mesh(orc.FAITHFUL, threads)
+        secs.append(s)
+        steps_done += 1
+        if time.perf_counter() - budget_t0 > 150:  # keep the whole run within a few minutes
+            break
+    total = float(np.sum(secs))
+    value = N_CHUNKS * steps_done / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": args.gpus, "steps": steps_done,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / steps_done, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16 voxels -> f32 vertices", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "chunks_per_step": N_CHUNKS, "vertices_per_step": verts,
+                   "note": "C++ restatement of build_chunk_mesh (faithful flavour: per-voxel string-keyed lookups, unreserved Vec) over "
+                           "host-resident chunks + one memcpy per chunk for the Vulkan upload; the Rust reference itself cannot be built here"},
+        "voxels_per_s": value * 4096,
+        "cpu_baseline": {"value": value, "unit": "chunks/s", "cores": threads, "kind": "port",
+                         "sample": f"all {N_CHUNKS} chunks of the workload per step, {steps_done} steps"},
+        "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default min(steps, 40))")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        port = os.environ.get("MASTER_PORT", "29577")
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                  "--master-addr", "127.0.0.1", "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:])
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the mesh path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    from despawnengine_b200 import build as dsp_build
+    from despawnengine_b200 import capi
+    if local_rank == 0 and not os.path.exists(capi.LIB_PATH):
+        dsp_build.build()
+    if distributed:
+        dist.barrier()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = capi.Context(local_rank, N_CHUNKS, 1 << 30)
+    ctx.set_uv_table(UV)
+    origin = (DIMS[0] * rank, 0, 0)
+    first = ctx.generate_region(origin, DIMS, capi.GEN_NOISE, SEED)
+    entries, total_bytes = ctx.mesh_range(first, N_CHUNKS)
+    faces = int(entries["vertex_count"].astype(np.int64).sum()) // 6
+    # algorithmic bytes per launch: voxels read once + vertices written once + position + entry
+    algo_bytes = N_CHUNKS * (8192 + 16 + 16) + 120 * faces
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # ---- device-resident leg: `value` -----------------------------------------------------------------
+    for _ in range(args.warmup):
+        ctx.mesh_range_async(first, N_CHUNKS)
+        flush_l2()
+    ctx.sync()
+    n0, ms0, _ = ctx.mesh_kernel_stats()
+    launches0 = ctx.kernel_launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record(stream)
+        ctx.mesh_range_async(first, N_CHUNKS)
+        ev[k][1].record(stream)
+        flush_l2()  # untimed: between the stop event of step k and the start event of step k+1
+    torch.cuda.synchronize()
+    wall1 = time.perf_counter()
+    barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    n1, ms1, _ = ctx.mesh_kernel_stats()
+    launches = ctx.kernel_launches - launches0
+    # clocks: if the timed region was too short for NVML to see it, keep the same load running ~1.2 s more
+    note = "sampled during the timed region"
+    if len(sampler.samples) < 10:
+        t_end = time.perf_counter() + 1.2
+        while time.perf_counter() < t_end:
+            for _ in range(20):
+                ctx.mesh_range_async(first, N_CHUNKS)
+            ctx.sync()
+        note = "timed region too short for NVML; sampled over the timed region plus ~1.2 s of the same step repeated"
+    sampler.stop_flag.set()
+    sampler.join()
+    _ = ctx.mesh_kernel_stats()
+
+    dev_ms_total = max_over_ranks(float(np.sum(step_ms)))
+    value = world * N_CHUNKS * args.steps / (dev_ms_total * 1e-3)
+    kernel_ms_avg = (ms1 - ms0) / max(1, n1 - n0)
+    peak, peak_src = load_peaks()
+    achieved = algo_bytes / (kernel_ms_avg * 1e-3) / 1e9
+
+    # ---- end-to-end leg: host voxel buffers -> dsp_load_chunks -> dsp_mesh_chunks -> entries on host ----------
+    e2e_steps = args.e2e_steps or min(args.steps, 40)
+    pos = region_positions(origin)
+    host_vox = torch.empty((N_CHUNKS, 4096), dtype=torch.int16).pin_memory()
+    hv = host_vox.numpy().view(np.uint16)
+    for i in range(N_CHUNKS):  # setup, untimed: host copies of the chunks, as a host caller would hold them (Chunk.blocks)
+        hv[i] = ctx.download_chunk(first + i)[0]
+    slots_out = np.empty(N_CHUNKS, dtype=np.uint32)
+    entries_host = torch.empty(N_CHUNKS * 16, dtype=torch.uint8).pin_memory()
+    entries_np = entries_host.numpy().view(capi.MESH_ENTRY_DTYPE)
+    h2d = N_CHUNKS * (8192 + 16)
+    d2h = N_CHUNKS * 16 + 32
+
+    def e2e_step():
+        ctx.load_chunks_ptr(N_CHUNKS, pos, host_vox.data_ptr(), slots_out)                 # H2D: 32 MiB voxels + positions
+        ctx.mesh_range(int(slots_out[0]), N_CHUNKS, entries_out=entries_np)                 # kernel + D2H of the entry table; blocking
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    torch.cuda.synchronize()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s_ev.record(stream)
+    for _ in range(e2e_steps):
+        e2e_step()
+    e_ev.record(stream)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    barrier()
+    assert int(entries_np["vertex_count"].astype(np.int64).sum()) == faces * 6  # the result really came back
+    e2e_ms = max_over_ranks(max(s_ev.elapsed_time(e_ev), (t1 - t0) * 1e3))
+    e2e_value = world * N_CHUNKS * e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- full read-back variant (vertices copied to pinned host memory as well), reported separately -----
+    rb_host = torch.empty(total_bytes, dtype=torch.uint8).pin_memory()
+    ctx.download_arena_into(0, total_bytes, rb_host.data_ptr())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rb_steps = max(2, min(5, e2e_steps))
+    for _ in range(rb_steps):
+        e2e_step()
+        ctx.download_arena_into(0, total_bytes, rb_host.data_ptr())
+    torch.cuda.synchronize()
+    rb_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    rb_value = world * N_CHUNKS * rb_steps / (rb_ms * 1e-3)
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import loader as orc
+        threads = orc.hardware_threads()
+        w = orc.Workload(pos, orc.GEN_NOISE, SEED, UV)
+        w.mesh(orc.FAITHFUL, threads)
+        secs, reps, t_start = 0.0, 0, time.perf_counter()
+        while time.perf_counter() - t_start < 10.0 and reps < 200:
+            s, _ = w.mesh(orc.FAITHFUL, threads)
+            secs += s
+            reps += 1
+        one, _ = w.mesh(orc.FAITHFUL, 1)
+        fair, _ = w.mesh(orc.FAIR, threads)
+        cpu = {"value": N_CHUNKS * reps / secs, "unit": "chunks/s", "cores": threads, "kind": "port",
+               "sample": f"build_chunk_mesh restatement (faithful flavour) over all {N_CHUNKS} chunks of the workload, {reps} passes (~10 s), host-resident chunks",
+               "one_thread_chunks_per_s": N_CHUNKS / one, "fair_flavour_chunks_per_s": N_CHUNKS / fair,
+               "note": "C++ restatement of the reference mesher; the Rust reference cannot be built in this image (no rustc)"}
+
+    faces_all = sum_over_ranks(float(faces))
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "chunks/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u16 voxels -> f32 vertices", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "chunks_per_step_per_gpu": N_CHUNKS, "faces_per_step": int(faces_all),
+                       "vertex_bytes_per_step_per_gpu": int(total_bytes), "seed": hex(SEED), "parallelism": f"region-per-gpu x{world}",
+                       "l2": "flushed between timed steps (256 MiB memset on the same stream, outside the event pairs)",
+                       "timing": "CUDA events around each step on the context's stream, summed; max over ranks"},
+            "voxels_per_s": value * 4096,
+            "faces_per_s": world * faces * args.steps / (dev_ms_total * 1e-3),
+            "gpu_launches": int(launches),
+            "wall_s_timed_region": wall1 - wall0,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "mesh_chunks_kernel<1,false>", "kernel_ms_avg": kernel_ms_avg,
+                         "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
+                         "frac_of_8TBs_datasheet": achieved / 8000.0},
+            "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms / e2e_steps,
+                    "what": "dsp_load_chunks(host u16 voxels, pinned) + dsp_mesh_range -> dsp_mesh_entry table on the host; vertices stay in HBM "
+                            "(the reference's result is a device buffer too, chunk_mesh.rs:111-124)"},
+            "e2e_vertex_readback": {"value": rb_value, "unit": "chunks/s", "d2h_bytes_per_step": int(total_bytes) + d2h, "steps": rb_steps,
+                                    "what": "same, plus the whole vertex stream copied to pinned host memory"},
+            "clocks": sampler.summary(note),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,7 @@ SYMBOLS = {
     "dsp_stream": (_vp, [_vp]),
     "dsp_max_chunks": (_u64, [_vp]),
     "dsp_kernel_launches": (_u64, [_vp]),
+    "dsp_mesh_kernel_stats": (_int, [_vp, _P(_u64), _P(C.c_double), _P(C.c_float)]),
 }
 
 _lib = None
@@ -253,6 +254,12 @@ class Context:
     @property
     def stream(self) -> int:
         return int(lib().dsp_stream(self._h) or 0)
+
+    def mesh_kernel_stats(self):
+        """(launch count, summed device ms, newest launch ms) of the mesh kernel alone."""
+        n, tot, last = C.c_uint64(0), C.c_double(0), C.c_float(0)
+        self._check(lib().dsp_mesh_kernel_stats(self._h, C.byref(n), C.byref(tot), C.byref(last)))
+        return int(n.value), float(tot.value), float(last.value)
 
     @property
     def kernel_launches(self) -> int:

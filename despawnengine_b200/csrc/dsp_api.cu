@@ -63,6 +63,19 @@ struct dsp_ctx {
     uint8_t* d_scratch = nullptr;
     size_t scratch_bytes = 0;
     uint8_t* h_pinned = nullptr;  // 4 KiB of pinned host memory for small read-backs
+    uint8_t* h_stage = nullptr;   // pinned staging for positions / slot lists (async H2D without a pageable bounce)
+    size_t h_stage_bytes = 0;
+    cudaEvent_t ev_stage = nullptr;  // recorded after the last copy out of h_stage
+    bool stage_pending = false;
+    // CUDA events around every mesh kernel launch (ring of kEvRing pairs, drained lazily) so that the
+    // kernel's own device time can be reported separately from the memset / copies around it.
+    static constexpr int kEvRing = 16;
+    cudaEvent_t ev_k0[kEvRing] = {}, ev_k1[kEvRing] = {};
+    bool ev_pending[kEvRing] = {};
+    int ev_next = 0;
+    double kernel_ms_total = 0.0;
+    float kernel_ms_last = 0.0f;
+    uint64_t kernel_count = 0;
 
     std::unordered_map<PosKey, uint32_t, PosHash> map;
     std::vector<Region> regions;
@@ -100,6 +113,25 @@ int ensure_scratch(dsp_ctx* ctx, size_t bytes) {
     size_t cap = std::max<size_t>(bytes, 1u << 20);
     DSP_CUDA(ctx, cudaMalloc(&ctx->d_scratch, cap));
     ctx->scratch_bytes = cap;
+    return DSP_OK;
+}
+
+// Pinned staging: returns `bytes` of pinned host memory whose previous contents have been consumed.
+int stage_host(dsp_ctx* ctx, size_t bytes, uint8_t** out) {
+    if (ctx->stage_pending) { DSP_CUDA(ctx, cudaEventSynchronize(ctx->ev_stage)); ctx->stage_pending = false; }
+    if (bytes > ctx->h_stage_bytes) {
+        if (ctx->h_stage) DSP_CUDA(ctx, cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 2, 1u << 20);
+        DSP_CUDA(ctx, cudaMallocHost(&ctx->h_stage, cap));
+        ctx->h_stage_bytes = cap;
+    }
+    *out = ctx->h_stage;
+    return DSP_OK;
+}
+int stage_release(dsp_ctx* ctx) {
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_stage, ctx->stream));
+    ctx->stage_pending = true;
     return DSP_OK;
 }
 
@@ -146,20 +178,39 @@ int upload_by_runs(dsp_ctx* ctx, uint8_t* dst_base, size_t elem_bytes, const uin
     return DSP_OK;
 }
 
-int upload_positions(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint32_t* slots) {
-    std::vector<int4> p4(n);
-    for (uint64_t i = 0; i < n; ++i) p4[i] = make_int4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0);
-    return upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_pos), sizeof(int4), slots, n, reinterpret_cast<const uint8_t*>(p4.data()));
-}
-
-// returns device pointer to the slot list, or nullptr when the slots are one consecutive run
-int stage_slot_list(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, const uint32_t** d_list, uint32_t* first) {
+// Positions (as int4) and, when the slots are not one consecutive run, the slot list go through one
+// pinned staging block: [int4 x n][u32 x n].  *d_list is nullptr for a consecutive run.
+int upload_positions_and_slots(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint32_t* slots, const uint32_t** d_list, uint32_t* first) {
     bool consecutive = true;
     for (uint64_t i = 1; i < n && consecutive; ++i) consecutive = slots[i] == slots[i - 1] + 1;
     *first = n ? slots[0] : 0;
-    if (consecutive) { *d_list = nullptr; return DSP_OK; }
-    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots, slots, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    *d_list = ctx->d_slots;
+    *d_list = nullptr;
+    uint8_t* h;
+    int rc = stage_host(ctx, n * (sizeof(int4) + sizeof(uint32_t)), &h);
+    if (rc != DSP_OK) return rc;
+    if (pos) {
+        int4* p4 = reinterpret_cast<int4*>(h);
+        for (uint64_t i = 0; i < n; ++i) p4[i] = make_int4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0);
+        if ((rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_pos), sizeof(int4), slots, n, h)) != DSP_OK) return rc;
+    }
+    if (!consecutive) {
+        uint32_t* hl = reinterpret_cast<uint32_t*>(h + n * sizeof(int4));
+        std::memcpy(hl, slots, n * sizeof(uint32_t));
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots, hl, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        *d_list = ctx->d_slots;
+    }
+    return stage_release(ctx);
+}
+
+int drain_kernel_event(dsp_ctx* ctx, int e) {
+    if (!ctx->ev_pending[e]) return DSP_OK;
+    float ms = 0.0f;
+    DSP_CUDA(ctx, cudaEventSynchronize(ctx->ev_k1[e]));
+    DSP_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_k0[e], ctx->ev_k1[e]));
+    ctx->kernel_ms_total += ms;
+    ctx->kernel_ms_last = ms;
+    ctx->kernel_count++;
+    ctx->ev_pending[e] = false;
     return DSP_OK;
 }
 
@@ -175,8 +226,15 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
     }
     const uint64_t resident_ctas = static_cast<uint64_t>(ctx->num_sms) * occ;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, resident_ctas));
+    const int e = ctx->ev_next;
+    int rc = drain_kernel_event(ctx, e);  // the pair from kEvRing launches ago: long finished
+    if (rc != DSP_OK) return rc;
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k0[e], ctx->stream));
     kern<<<grid, 256, smem, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k1[e], ctx->stream));
+    ctx->ev_pending[e] = true;
+    ctx->ev_next = (e + 1) % dsp_ctx::kEvRing;
     ctx->launches++;
     return DSP_OK;
 }
@@ -330,6 +388,9 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks)) != cudaSuccess) return bail("cudaMalloc(control)", e);
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
     if ((e = cudaMallocHost(&ctx->h_pinned, 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int i = 0; i < dsp_ctx::kEvRing; ++i)
+        if ((e = cudaEventCreate(&ctx->ev_k0[i])) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_k1[i])) != cudaSuccess) return bail("cudaEventCreate", e);
     ctx->resident.assign(max_chunks, 0);
     *out_ctx = ctx;
     return DSP_OK;
@@ -342,6 +403,12 @@ int dsp_destroy(dsp_ctx* ctx) {
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
     cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+    for (int i = 0; i < dsp_ctx::kEvRing; ++i) {
+        if (ctx->ev_k0[i]) cudaEventDestroy(ctx->ev_k0[i]);
+        if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]);
+    }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return DSP_OK;
@@ -376,10 +443,9 @@ int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_ki
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint32_t> slots(n);
     for (uint64_t i = 0; i < n; ++i) { int rc = acquire_slot(ctx, pos + 3 * i, &slots[i]); if (rc != DSP_OK) return rc; }
-    int rc = upload_positions(ctx, n, pos, slots.data());
-    if (rc != DSP_OK) return rc;
     const uint32_t* d_list; uint32_t first;
-    if ((rc = stage_slot_list(ctx, n, slots.data(), &d_list, &first)) != DSP_OK) return rc;
+    int rc = upload_positions_and_slots(ctx, n, pos, slots.data(), &d_list, &first);
+    if (rc != DSP_OK) return rc;
     dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed};
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
     dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
@@ -427,7 +493,8 @@ int dsp_load_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     std::vector<uint32_t> slots(n);
     for (uint64_t i = 0; i < n; ++i) { int rc = acquire_slot(ctx, pos + 3 * i, &slots[i]); if (rc != DSP_OK) return rc; }
-    int rc = upload_positions(ctx, n, pos, slots.data());
+    const uint32_t* d_unused; uint32_t first_unused;
+    int rc = upload_positions_and_slots(ctx, n, pos, slots.data(), &d_unused, &first_unused);
     if (rc != DSP_OK) return rc;
     if ((rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, slots.data(), n,
                              reinterpret_cast<const uint8_t*>(blocks))) != DSP_OK) return rc;
@@ -497,7 +564,7 @@ int dsp_mesh_chunks_async(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint3
     if (rc != DSP_OK) return rc;
     if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_BAD_ARG, "n exceeds max_chunks");
     const uint32_t* d_list; uint32_t first;
-    if ((rc = stage_slot_list(ctx, n, slots, &d_list, &first)) != DSP_OK) return rc;
+    if ((rc = upload_positions_and_slots(ctx, n, nullptr, slots, &d_list, &first)) != DSP_OK) return rc;
     return enqueue_mesh(ctx, n, d_list, first, mode, arena_offset);
 }
 
@@ -611,5 +678,17 @@ void* dsp_voxel_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_voxels : nullptr;
 void* dsp_entries_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_entries : nullptr; }
 void* dsp_stream(dsp_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 uint64_t dsp_kernel_launches(const dsp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_ms, float* out_last_ms) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    for (int i = 0; i < dsp_ctx::kEvRing; ++i) {  // oldest first so that `last` is the newest launch
+        int rc = drain_kernel_event(ctx, (ctx->ev_next + i) % dsp_ctx::kEvRing);
+        if (rc != DSP_OK) return rc;
+    }
+    if (out_count) *out_count = ctx->kernel_count;
+    if (out_total_ms) *out_total_ms = ctx->kernel_ms_total;
+    if (out_last_ms) *out_last_ms = ctx->kernel_ms_last;
+    return DSP_OK;
+}
 
 }  // extern "C"

@@ -162,6 +162,10 @@ uint64_t dsp_max_chunks(const dsp_ctx* ctx);
 
 /* Number of kernel launches this context has enqueued since creation (bench accounting). */
 uint64_t dsp_kernel_launches(const dsp_ctx* ctx);
+/* Device time of the mesh kernel launches alone, from CUDA events the library records around every
+ * launch on the context's stream: number of launches, their summed duration, and the newest one.
+ * Waits for outstanding launches. */
+int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_ms, float* out_last_ms);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,12 @@ def lib() -> C.CDLL:
         L.orc_mesh_batch.restype = C.c_int64
         L.orc_time_pipeline.argtypes = [C.c_int64, i32p, C.c_int, C.c_uint32, f32p, C.c_uint32, C.c_int, C.c_int, C.c_int, i64p]
         L.orc_time_pipeline.restype = C.c_double
+        L.orc_workload_create.argtypes = [C.c_int64, i32p, C.c_int, C.c_uint32, f32p, C.c_uint32]
+        L.orc_workload_create.restype = C.c_void_p
+        L.orc_workload_destroy.argtypes = [C.c_void_p]
+        L.orc_workload_destroy.restype = None
+        L.orc_workload_mesh.argtypes = [C.c_void_p, C.c_int, C.c_int, i64p]
+        L.orc_workload_mesh.restype = C.c_double
         L.orc_hardware_threads.argtypes = []
         L.orc_hardware_threads.restype = C.c_int
         _lib = L
@@ -131,6 +137,29 @@ def time_pipeline(pos: np.ndarray, kind: int, seed: int, uv: np.ndarray, flavour
     s = lib().orc_time_pipeline(pos.shape[0], _p(pos, C.c_int32), kind, seed & 0xFFFFFFFF, _p(uv, C.c_float), uv.shape[0],
                                 flavour, threads, 1 if include_generation else 0, C.byref(tot))
     return float(s), int(tot.value)
+
+
+class Workload:
+    """Chunks prepared once (outside timing); ``mesh`` times one pass of build_chunk_mesh over all of them."""
+
+    def __init__(self, pos: np.ndarray, kind: int, seed: int, uv: np.ndarray):
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 4)
+        self.n = pos.shape[0]
+        self._h = lib().orc_workload_create(self.n, _p(pos, C.c_int32), kind, seed & 0xFFFFFFFF, _p(uv, C.c_float), uv.shape[0])
+
+    def mesh(self, flavour: int = FAITHFUL, threads: int = 1):
+        tot = C.c_int64(0)
+        s = lib().orc_workload_mesh(self._h, flavour, threads, C.byref(tot))
+        return float(s), int(tot.value)
+
+    def close(self):
+        if self._h:
+            lib().orc_workload_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 def hardware_threads() -> int:

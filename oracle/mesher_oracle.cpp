@@ -523,6 +523,59 @@ double orc_time_pipeline(int64_t n, const int32_t* pos, int kind, uint32_t seed,
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Prepared workload for repeated timing (bench.py): the Chunk objects (string palettes and all) are
+// built once, outside any timed region, the way World keeps Arc<Chunk>s around (world.rs:11-12).
+struct OrcWorkload {
+    std::vector<Chunk> chunks;
+    BlockUvMap uv;
+};
+
+void* orc_workload_create(int64_t n, const int32_t* pos, int kind, uint32_t seed, const float* uv, uint32_t n_blocks) {
+    auto* w = new OrcWorkload();
+    w->uv = uv_map_from_table(uv, n_blocks);
+    w->chunks.reserve(static_cast<size_t>(n));
+    std::vector<uint16_t> ids(4096);
+    for (int64_t i = 0; i < n; ++i) {
+        if (kind == GEN_REFERENCE) w->chunks.push_back(world_get_chunk(pos + 3 * i));
+        else { generate_ids(kind, seed, pos + 3 * i, ids.data()); w->chunks.push_back(chunk_from_global_ids(pos + 3 * i, ids.data())); }
+    }
+    return w;
+}
+void orc_workload_destroy(void* h) { delete static_cast<OrcWorkload*>(h); }
+
+// One pass of build_chunk_mesh over every chunk of the workload on `threads` host threads, each
+// result followed by one memcpy standing in for the Vulkan upload (chunk_mesh.rs:111-124).
+// Returns seconds; *out_vertices receives the vertex total.
+double orc_workload_mesh(void* h, int flavour, int threads, int64_t* out_vertices) {
+    auto* w = static_cast<OrcWorkload*>(h);
+    const int64_t n = static_cast<int64_t>(w->chunks.size());
+    std::atomic<int64_t> next{0}, total{0};
+    if (threads < 1) threads = 1;
+    auto work = [&]() {
+        std::vector<BlockVertex> upload(12288 * 6);
+        int64_t local = 0;
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            std::vector<BlockVertex> verts;  // Vec::new() per call, chunk_mesh.rs:21
+            const bool some = flavour == 0 ? build_chunk_mesh(w->chunks[i], w->uv, verts) : build_chunk_mesh_fair(w->chunks[i], w->uv, verts);
+            if (some) {
+                std::memcpy(upload.data(), verts.data(), verts.size() * sizeof(BlockVertex));
+                local += static_cast<int64_t>(verts.size());
+            }
+        }
+        total.fetch_add(local);
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (out_vertices) *out_vertices = total.load();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 int orc_hardware_threads() { return static_cast<int>(std::thread::hardware_concurrency()); }
 
 }  // extern "C"
