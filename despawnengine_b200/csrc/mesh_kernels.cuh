@@ -15,9 +15,11 @@
 //   2. thread r builds the occupancy mask of x-row r, derives the six face masks and its face
 //      count; a warp-shuffle + 8-way scan gives every row its first face ordinal and the CTA the
 //      chunk's face total F;
-//   3. warp 0 publishes align128(120*F) and resolves the chunk's arena offset with a decoupled
-//      look-back over the tickets before it (single pass: voxels are read from HBM exactly once);
-//      meanwhile all rows write 16-bit face records (voxel index, direction) in stream order;
+//   3. thread 0 publishes align128(120*F) right after the count; the count phase of chunk k+1 runs BEFORE the
+//      emission of chunk k, so every ticket's size is published early and nobody's look-back waits on a CTA
+//      that is busy writing vertices.  Warp 0 then resolves the chunk's arena offset with a decoupled
+//      look-back over the earlier tickets (single pass: voxels are read from HBM exactly once);
+//      all rows write 16-bit face records (voxel index, direction) in stream order;
 //   4. faces are expanded 256 at a time, one thread per face, into a 30 KiB staging tile and each
 //      tile leaves with ONE bulk shared->global copy (cp.async.bulk), i.e. full-line writes only.
 // Algorithmic HBM bytes per chunk: 8,192 (voxels) + 120*F (vertices) + 16 (position) + 16 (entry).
@@ -129,6 +131,20 @@ struct MeshSmem {
     static constexpr int kBytes = kNext + 8;
 };
 
+// Per-thread result of the count phase for one chunk (thread r owns x-row r = y + 16 z).
+struct RowFaces {
+    uint32_t top, bot, rear, front, right, left;  // 16-bit face masks of this row
+    uint32_t cnt;                                  // faces in this row
+    uint32_t first;                                // ordinal of this row's first face within the chunk
+    uint32_t total;                                // faces in the chunk (same in every thread)
+};
+
+__device__ __forceinline__ uint64_t slot_bytes_of(uint32_t faces) {
+    return (static_cast<uint64_t>(faces) * kFaceBytes + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1);
+}
+
+constexpr uint64_t kLbAgg = 1ull << 62, kLbPrefix = 2ull << 62, kLbVal = (1ull << 62) - 1;
+
 template <int NSTAGE, bool HALO>
 __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(const MeshParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -143,39 +159,18 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
     uint32_t* s_next = reinterpret_cast<uint32_t*>(smem + L::kNext);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = tid, y = r & 15, z = r >> 4;
 
+    auto slot_of = [&](uint32_t ticket) { return p.slot_list ? __ldg(p.slot_list + ticket) : p.first_slot + ticket; };
     auto issue_load = [&](uint32_t ticket, int buf) {  // thread 0 only
-        const uint32_t slot = p.slot_list ? p.slot_list[ticket] : p.first_slot + ticket;
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
-        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
+        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(ticket)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
     };
 
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        fence_mbar_init();
-        const uint32_t t = atomicAdd(&p.ctrl[0], 1u);
-        s_next[0] = t;
-        if (t < p.n) issue_load(t, 0);
-    }
-    __syncthreads();
-    uint32_t cur = s_next[0];
-    uint32_t it = 0, stage_ctr = 0;
-
-    while (cur < p.n) {
-        const int buf = it & 1;
-        if (tid == 0) {  // take the next ticket now and start its voxel tile moving
-            const uint32_t t = atomicAdd(&p.ctrl[0], 1u);
-            s_next[(it + 1) & 1] = t;
-            if (t < p.n) issue_load(t, buf ^ 1);
-        }
-        const uint32_t slot = p.slot_list ? p.slot_list[cur] : p.first_slot + cur;
-        const int4 cp = __ldg(&p.chunk_pos[slot]);
-        mbar_wait(&s_bar[buf], (it >> 1) & 1);
+    // ---- count phase: row occupancy -> six face masks -> per-row count -> block scan; publishes the
+    //      chunk's byte size for the look-back of later tickets as early as possible.  2 barriers.
+    auto count_phase = [&](uint32_t ticket, int buf) -> RowFaces {
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
-
-        // ---- 2. row occupancy, face masks, counts ------------------------------------------------
-        const int r = tid, y = r & 15, z = r >> 4;
         uint32_t m;
         {
             const uint4* rowp = reinterpret_cast<const uint4*>(vox + r * 16);
@@ -193,7 +188,7 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
         uint32_t xm = 0u, xp = 0u;  // occupancy of the voxel beyond x = 0 / x = 15
         if (HALO) {
             // extension: consult the resident neighbour across each border (DSP_MESH_HALO)
-            const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot) * 6;
+            const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot_of(ticket)) * 6;
             auto row_mask_of = [&](uint32_t nslot, int nr) -> uint32_t {
                 const uint4* q = reinterpret_cast<const uint4*>(p.voxels + static_cast<size_t>(nslot) * kChunkVoxels + nr * 16);
                 return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
@@ -205,10 +200,12 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
             { const uint32_t s = __ldg(nb + 4); if (s != 0xFFFFFFFFu) xm = __ldg(p.voxels + static_cast<size_t>(s) * kChunkVoxels + r * 16 + 15) != 0; }
             { const uint32_t s = __ldg(nb + 5); if (s != 0xFFFFFFFFu) xp = __ldg(p.voxels + static_cast<size_t>(s) * kChunkVoxels + r * 16) != 0; }
         }
-        const uint32_t f_top = m & ~up, f_bot = m & ~dn, f_rear = m & ~re, f_front = m & ~fr;
-        const uint32_t f_right = m & ~((m << 1) | xm), f_left = m & ~((m >> 1) | (xp << 15));
-        const uint32_t cnt = __popc(f_top) + __popc(f_bot) + __popc(f_rear) + __popc(f_front) + __popc(f_right) + __popc(f_left);
-        uint32_t incl = cnt;
+        RowFaces f;
+        f.top = m & ~up; f.bot = m & ~dn; f.rear = m & ~re; f.front = m & ~fr;
+        f.right = m & ~((m << 1) | xm);
+        f.left = m & ~((m >> 1) | (xp << 15));
+        f.cnt = __popc(f.top) + __popc(f.bot) + __popc(f.rear) + __popc(f.front) + __popc(f.right) + __popc(f.left);
+        uint32_t incl = f.cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
@@ -223,69 +220,107 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
             wpre += w < warp ? v : 0u;
             total += v;
         }
-        const uint32_t F = total;
-        const uint64_t slot_bytes = (static_cast<uint64_t>(F) * kFaceBytes + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1);
+        f.first = wpre + incl - f.cnt;
+        f.total = total;
+        if (tid == 0) st_volatile_u64(&p.lookback[ticket], (ticket == 0 ? kLbPrefix : kLbAgg) | slot_bytes_of(total));
+        return f;
+    };
 
-        // ---- 3a. arena offset: decoupled look-back over earlier tickets (warp 0) --------------------
-        if (warp == 0) {
-            constexpr uint64_t kAgg = 1ull << 62, kPrefix = 2ull << 62, kVal = (1ull << 62) - 1;
-            if (lane == 0) st_volatile_u64(&p.lookback[cur], (cur == 0 ? kPrefix : kAgg) | slot_bytes);
-            uint64_t excl = 0;
-            if (cur > 0) {
-                int64_t j = static_cast<int64_t>(cur) - 1;
-                uint32_t spins = 0;
-                for (;;) {
-                    const int64_t q = j - lane;
-                    const uint64_t v = q >= 0 ? ld_volatile_u64(&p.lookback[q]) : kPrefix;
-                    const uint32_t flag = static_cast<uint32_t>(v >> 62);
-                    const uint32_t pref = __ballot_sync(0xFFFFFFFFu, flag == 2u);
-                    const uint32_t inval = __ballot_sync(0xFFFFFFFFu, flag == 0u);
-                    const int first = pref ? __ffs(pref) - 1 : 31;          // lanes 0..first are needed
-                    const uint32_t need = first == 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
-                    if (inval & need) {                                     // a predecessor has not published yet
-                        if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&p.ctrl[1], kStatusSpin); break; }
-                        __nanosleep(20);
-                        continue;
-                    }
-                    uint64_t part = (need >> lane) & 1u ? (v & kVal) : 0ull;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-                    excl += part;
-                    if (pref) break;
-                    j -= 32;
+    // ---- decoupled look-back (warp 0): exclusive prefix of the byte sizes of all earlier tickets ----------
+    auto look_back = [&](uint32_t ticket, uint32_t faces) {
+        const uint64_t bytes = slot_bytes_of(faces);
+        uint64_t excl = 0;
+        if (ticket > 0) {
+            int64_t j = static_cast<int64_t>(ticket) - 1;
+            uint32_t spins = 0;
+            for (;;) {
+                const int64_t q = j - lane;
+                const uint64_t v = q >= 0 ? ld_volatile_u64(&p.lookback[q]) : kLbPrefix;
+                const uint32_t flag = static_cast<uint32_t>(v >> 62);
+                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, flag == 2u);
+                const uint32_t inval = __ballot_sync(0xFFFFFFFFu, flag == 0u);
+                const int first = pref ? __ffs(pref) - 1 : 31;  // lanes 0..first are needed
+                const uint32_t need = first == 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
+                if (inval & need) {  // a predecessor has not published yet
+                    if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&p.ctrl[1], kStatusSpin); break; }
+                    __nanosleep(20);
+                    continue;
                 }
-                if (lane == 0) st_volatile_u64(&p.lookback[cur], kPrefix | (excl + slot_bytes));
+                uint64_t part = (need >> lane) & 1u ? (v & kLbVal) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+                excl += part;
+                if (pref) break;
+                j -= 32;
             }
-            if (lane == 0) {
-                *s_base = excl;
-                const bool fits = excl + slot_bytes <= p.arena_room;
-                if (!fits) atomicOr(&p.ctrl[1], kStatusOverflow);
-                p.entries[cur] = MeshEntry{p.arena_offset + excl, F * 6u, 0u};
-                if (cur == p.n - 1) *p.total_bytes = excl + slot_bytes;
-            }
+            if (lane == 0) st_volatile_u64(&p.lookback[ticket], kLbPrefix | (excl + bytes));
         }
+        if (lane == 0) {
+            *s_base = excl;
+            if (excl + bytes > p.arena_room) atomicOr(&p.ctrl[1], kStatusOverflow);
+            p.entries[ticket] = MeshEntry{p.arena_offset + excl, faces * 6u, 0u};
+            if (ticket == p.n - 1) *p.total_bytes = excl + bytes;
+        }
+    };
 
-        // ---- 3b. face records in stream order: rec = (voxel index << 3) | direction ------------------
-        if (cnt) {
-            uint16_t* rp = s_rec + (wpre + incl - cnt);
+    // ---- prologue: first two tickets, first count phase ------------------------------------------------------
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+        const uint32_t t0 = atomicAdd(&p.ctrl[0], 1u);
+        s_next[0] = t0;
+        if (t0 < p.n) issue_load(t0, 0);
+        uint32_t t1 = 0xFFFFFFFFu;
+        if (t0 < p.n) { t1 = atomicAdd(&p.ctrl[0], 1u); if (t1 < p.n) issue_load(t1, 1); }
+        s_next[1] = t1;
+    }
+    __syncthreads();
+    uint32_t cur = s_next[0];
+    if (cur >= p.n) return;
+    mbar_wait(&s_bar[0], 0);
+    RowFaces fc = count_phase(cur, 0);
+    uint32_t it = 0, stage_ctr = 0;
+
+    // Invariant at the top of iteration `it`: chunk `cur` is in voxel buffer it&1 with its count phase done and
+    // its size published; the ticket after it is in s_next[(it+1)&1] and its tile is in flight to the other buffer.
+    for (;;) {
+        const int buf = it & 1;
+        const uint16_t* vox = s_vox + buf * kChunkVoxels;
+        const uint32_t nxt = s_next[(it + 1) & 1];
+        const uint32_t F = fc.total;
+
+        // face records in stream order: rec = (voxel index << 3) | direction (chunk_mesh.rs:32, 65-106)
+        if (fc.cnt) {
+            uint16_t* rp = s_rec + fc.first;
             const uint32_t rbase = static_cast<uint32_t>(r) << 7;
 #pragma unroll
             for (int x = 0; x < 16; ++x) {
                 const uint32_t bit = 1u << x, v = rbase | (x << 3);
-                if (f_top & bit) *rp++ = static_cast<uint16_t>(v | 0u);
-                if (f_bot & bit) *rp++ = static_cast<uint16_t>(v | 1u);
-                if (f_rear & bit) *rp++ = static_cast<uint16_t>(v | 2u);
-                if (f_front & bit) *rp++ = static_cast<uint16_t>(v | 3u);
-                if (f_right & bit) *rp++ = static_cast<uint16_t>(v | 4u);
-                if (f_left & bit) *rp++ = static_cast<uint16_t>(v | 5u);
+                if (fc.top & bit) *rp++ = static_cast<uint16_t>(v | 0u);
+                if (fc.bot & bit) *rp++ = static_cast<uint16_t>(v | 1u);
+                if (fc.rear & bit) *rp++ = static_cast<uint16_t>(v | 2u);
+                if (fc.front & bit) *rp++ = static_cast<uint16_t>(v | 3u);
+                if (fc.right & bit) *rp++ = static_cast<uint16_t>(v | 4u);
+                if (fc.left & bit) *rp++ = static_cast<uint16_t>(v | 5u);
             }
         }
-        __syncthreads();
 
-        // ---- 4. expand + bulk store, 256 faces per tile -------------------------------------------------
+        // count the NEXT chunk before emitting this one, so that its size is published before the long
+        // emission phase and nobody's look-back ever waits on a CTA that is busy writing vertices
+        RowFaces fn{};
+        if (nxt < p.n) {
+            mbar_wait(&s_bar[buf ^ 1], ((it + 1) >> 1) & 1);
+            fn = count_phase(nxt, buf ^ 1);
+        }
+        if (warp == 0) look_back(cur, F);
+        __syncthreads();  // s_rec, s_base visible
+
+        // expand + bulk store, 256 faces per tile
         const uint64_t base = *s_base;
-        const bool fits = base + slot_bytes <= p.arena_room;
+        const bool fits = base + slot_bytes_of(F) <= p.arena_room;
         uint8_t* gout = p.arena + base;
+        const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
         const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
         const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
@@ -308,9 +343,14 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
             }
             ++stage_ctr;
         }
-        __syncthreads();  // all reads of vox / s_rec / s_next done before they are overwritten
+        if (nxt >= p.n) break;
+        uint32_t t2 = 0;
+        if (tid == 0) { t2 = atomicAdd(&p.ctrl[0], 1u); s_next[it & 1] = t2; }
+        __syncthreads();  // everyone is done with vox(buf), s_rec and s_base; s_next visible
+        if (tid == 0 && t2 < p.n) issue_load(t2, buf);
+        cur = nxt;
+        fc = fn;
         ++it;
-        cur = s_next[it & 1];
     }
     if (tid == 0) bulk_wait<0>();
 }
