@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end leg (default min(steps, 40))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ordered", action="store_true", help="use DSP_MESH_ORDERED (slots packed in call order); default is completion order")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -205,7 +206,8 @@ def main():
     ctx.set_uv_table(UV)
     origin = (DIMS[0] * rank, 0, 0)
     first = ctx.generate_region(origin, DIMS, capi.GEN_NOISE, SEED)
-    entries, total_bytes = ctx.mesh_range(first, N_CHUNKS)
+    mode = capi.MESH_ORDERED if args.ordered else capi.MESH_PARITY
+    entries, total_bytes = ctx.mesh_range(first, N_CHUNKS, mode)
     faces = int(entries["vertex_count"].astype(np.int64).sum()) // 6
     # algorithmic bytes per launch: voxels read once + vertices written once + position + entry
     algo_bytes = N_CHUNKS * (8192 + 16 + 16) + 120 * faces
@@ -219,7 +221,7 @@ def main():
 
     # ---- device-resident leg: `value` -----------------------------------------------------------------
     for _ in range(args.warmup):
-        ctx.mesh_range_async(first, N_CHUNKS)
+        ctx.mesh_range_async(first, N_CHUNKS, mode)
         flush_l2()
     ctx.sync()
     n0, ms0, _ = ctx.mesh_kernel_stats()
@@ -232,7 +234,7 @@ def main():
     wall0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record(stream)
-        ctx.mesh_range_async(first, N_CHUNKS)
+        ctx.mesh_range_async(first, N_CHUNKS, mode)
         ev[k][1].record(stream)
         flush_l2()  # untimed: between the stop event of step k and the start event of step k+1
     torch.cuda.synchronize()
@@ -247,7 +249,7 @@ def main():
         t_end = time.perf_counter() + 1.2
         while time.perf_counter() < t_end:
             for _ in range(20):
-                ctx.mesh_range_async(first, N_CHUNKS)
+                ctx.mesh_range_async(first, N_CHUNKS, mode)
             ctx.sync()
         note = "timed region too short for NVML; sampled over the timed region plus ~1.2 s of the same step repeated"
     sampler.stop_flag.set()
@@ -275,7 +277,7 @@ def main():
 
     def e2e_step():
         ctx.load_chunks_ptr(N_CHUNKS, pos, host_vox.data_ptr(), slots_out)                 # H2D: 32 MiB voxels + positions
-        ctx.mesh_range(int(slots_out[0]), N_CHUNKS, entries_out=entries_np)                 # kernel + D2H of the entry table; blocking
+        ctx.mesh_range(int(slots_out[0]), N_CHUNKS, mode, entries_out=entries_np)                 # kernel + D2H of the entry table; blocking
 
     for _ in range(3):
         e2e_step()
@@ -333,7 +335,7 @@ def main():
             "ms_per_step": dev_ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16 voxels -> f32 vertices", "data": "synthetic",
             "config": {"workload": WORKLOAD, "chunks_per_step_per_gpu": N_CHUNKS, "faces_per_step": int(faces_all),
-                       "vertex_bytes_per_step_per_gpu": int(total_bytes), "seed": hex(SEED), "parallelism": f"region-per-gpu x{world}",
+                       "vertex_bytes_per_step_per_gpu": int(total_bytes), "seed": hex(SEED), "slot_order": "call order (DSP_MESH_ORDERED)" if args.ordered else "completion order", "parallelism": f"region-per-gpu x{world}",
                        "l2": "flushed between timed steps (256 MiB memset on the same stream, outside the event pairs)",
                        "timing": "CUDA events around each step on the context's stream, summed; max over ranks"},
             "voxels_per_s": value * 4096,
@@ -341,7 +343,7 @@ def main():
             "gpu_launches": int(launches),
             "wall_s_timed_region": wall1 - wall0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "mesh_chunks_kernel<1,false>", "kernel_ms_avg": kernel_ms_avg,
+                         "traffic": None, "kernel": "mesh_chunks_kernel (look-back, DSP_MESH_ORDERED)" if args.ordered else "mesh_chunks_bump_kernel", "kernel_ms_avg": kernel_ms_avg,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                          "frac_of_8TBs_datasheet": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,

@@ -12,14 +12,14 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libdespawn_b200.so")
+LIB_PATH = os.environ.get("DSP_LIB_PATH") or os.path.join(_PKG, "lib", "libdespawn_b200.so")  # override: A/B builds
 
 # dsp_status
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ARENA_FULL, ERR_STORE_FULL, ERR_NOT_RESIDENT, ERR_INTERNAL = range(8)
 # dsp_gen_kind
 GEN_REFERENCE, GEN_NOISE, GEN_RANDOM, GEN_CHECKER = 0, 1, 2, 3
 # mesh modes
-MESH_PARITY, MESH_HALO = 0, 1
+MESH_PARITY, MESH_HALO, MESH_ORDERED = 0, 1, 2
 NO_SLOT = 0xFFFFFFFF
 
 MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("reserved", np.uint32)])
@@ -59,6 +59,7 @@ SYMBOLS = {
     "dsp_stream": (_vp, [_vp]),
     "dsp_max_chunks": (_u64, [_vp]),
     "dsp_kernel_launches": (_u64, [_vp]),
+    "dsp_debug_phase_cycles": (_int, [_vp, _P(_u64)]),
     "dsp_mesh_kernel_stats": (_int, [_vp, _P(_u64), _P(C.c_double), _P(C.c_float)]),
 }
 
@@ -254,6 +255,11 @@ class Context:
     @property
     def stream(self) -> int:
         return int(lib().dsp_stream(self._h) or 0)
+
+    def debug_phase_cycles(self) -> np.ndarray:
+        out = np.zeros(16, dtype=np.uint64)
+        self._check(lib().dsp_debug_phase_cycles(self._h, _ptr(out, C.c_uint64)))
+        return out
 
     def mesh_kernel_stats(self):
         """(launch count, summed device ms, newest launch ms) of the mesh kernel alone."""

@@ -47,8 +47,9 @@ struct dsp_ctx {
     cudaStream_t stream = nullptr;
     uint64_t max_chunks = 0, arena_bytes = 0;
     int num_sms = 0;
-    int mesh_nstage = 1;
-    int mesh_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};  // [nstage-1][halo]
+    int mesh_variant = 0;
+    unsigned mesh_prefetch_mult = 2;  // L2 prefetch distance in units of the grid size (0 = off)
+    int mesh_ctas_per_sm[4][4] = {};  // [variant][halo], filled on first launch
 
     uint16_t* d_voxels = nullptr;
     int4* d_pos = nullptr;
@@ -61,6 +62,7 @@ struct dsp_ctx {
     float4* d_uvmap = nullptr;
     uint32_t n_blocks = 0, uv_cap = 0;
     uint8_t* d_scratch = nullptr;
+    unsigned long long* d_phase = nullptr;  // debug phase timers (16 counters)
     size_t scratch_bytes = 0;
     uint8_t* h_pinned = nullptr;  // 4 KiB of pinned host memory for small read-backs
     uint8_t* h_stage = nullptr;   // pinned staging for positions / slot lists (async H2D without a pageable bounce)
@@ -214,11 +216,12 @@ int drain_kernel_event(dsp_ctx* ctx, int e) {
     return DSP_OK;
 }
 
-template <int NSTAGE, bool HALO>
-int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
-    auto kern = dsp::mesh_chunks_kernel<NSTAGE, HALO>;
-    constexpr int smem = dsp::MeshSmem<NSTAGE>::kBytes;
-    int& occ = ctx->mesh_ctas_per_sm[NSTAGE - 1][HALO ? 1 : 0];
+template <class Cfg, bool HALO, bool ORDERED>
+int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
+    void (*kern)(const dsp::MeshParams);
+    if constexpr (ORDERED) kern = dsp::mesh_chunks_kernel<Cfg, HALO>; else kern = dsp::mesh_chunks_bump_kernel<Cfg, HALO>;
+    constexpr int smem = Cfg::kBytes;
+    int& occ = ctx->mesh_ctas_per_sm[variant][(HALO ? 1 : 0) + (ORDERED ? 2 : 0)];
     if (occ == 0) {
         DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
@@ -226,11 +229,14 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
     }
     const uint64_t resident_ctas = static_cast<uint64_t>(ctx->num_sms) * occ;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, resident_ctas));
+    dsp::MeshParams pp = p;
+    pp.phase_cycles = ctx->d_phase;
+    pp.prefetch_ahead = ctx->mesh_prefetch_mult * grid;
     const int e = ctx->ev_next;
     int rc = drain_kernel_event(ctx, e);  // the pair from kEvRing launches ago: long finished
     if (rc != DSP_OK) return rc;
     DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k0[e], ctx->stream));
-    kern<<<grid, 256, smem, ctx->stream>>>(p);
+    kern<<<grid, 256, smem, ctx->stream>>>(pp);
     DSP_CUDA(ctx, cudaGetLastError());
     DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k1[e], ctx->stream));
     ctx->ev_pending[e] = true;
@@ -239,10 +245,24 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
     return DSP_OK;
 }
 
+// Kernel shapes.  0 is what ships (and what bench.py reports); DSP_MESH_VARIANT=1..3 selects the others for A/B runs:
+//   0: 3 CTAs/SM, one bulk store per 256-face tile     1: 3 CTAs/SM, one bulk store per warp (32 faces)
+//   2: 4 CTAs/SM (8 KiB record window), tile           3: 4 CTAs/SM, warp
+constexpr int kMeshVariants = 4;
+template <bool HALO, bool ORDERED>
+int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
+    switch (ctx->mesh_variant) {
+        case 1: return launch_mesh_t<dsp::MeshCfg<3, 1, true>, HALO, ORDERED>(ctx, p, 1);
+        case 2: return launch_mesh_t<dsp::MeshCfg<4, 1, false>, HALO, ORDERED>(ctx, p, 2);
+        case 3: return launch_mesh_t<dsp::MeshCfg<4, 1, true>, HALO, ORDERED>(ctx, p, 3);
+        default: return launch_mesh_t<dsp::MeshCfg<3, 1, false>, HALO, ORDERED>(ctx, p, 0);
+    }
+}
+
 int build_neighbour_table(dsp_ctx* ctx);
 
 int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset) {
-    if (mode & ~DSP_MESH_HALO) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
+    if (mode & ~(DSP_MESH_HALO | DSP_MESH_ORDERED)) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
     if (arena_offset % DSP_SLOT_ALIGN != 0 || arena_offset > ctx->arena_bytes)
         return fail(ctx, DSP_ERR_BAD_ARG, "arena_offset %llu must be a multiple of 128 and <= arena size", (unsigned long long)arena_offset);
     if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_BAD_ARG, "n = %llu exceeds max_chunks", (unsigned long long)n);
@@ -268,8 +288,8 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     p.ctrl = reinterpret_cast<uint32_t*>(ctx->d_ctl);
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
     p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
-    if (ctx->mesh_nstage == 2) return halo ? launch_mesh_t<2, true>(ctx, p) : launch_mesh_t<2, false>(ctx, p);
-    return halo ? launch_mesh_t<1, true>(ctx, p) : launch_mesh_t<1, false>(ctx, p);
+    if (mode & DSP_MESH_ORDERED) return halo ? launch_mesh_variant<true, true>(ctx, p) : launch_mesh_variant<false, true>(ctx, p);
+    return halo ? launch_mesh_variant<true, false>(ctx, p) : launch_mesh_variant<false, false>(ctx, p);
 }
 
 int validate_slots(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
@@ -373,7 +393,8 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     ctx->max_chunks = max_chunks;
     ctx->arena_bytes = arena_bytes;
     ctx->num_sms = prop.multiProcessorCount;
-    if (const char* s = getenv("DSP_MESH_NSTAGE")) ctx->mesh_nstage = atoi(s) == 2 ? 2 : 1;
+    if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
+    if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) ctx->mesh_variant = v; }
     auto bail = [&](const char* what, cudaError_t err) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(err);
         dsp_destroy(ctx);
@@ -385,8 +406,10 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     if ((e = cudaMalloc(&ctx->d_pos, max_chunks * sizeof(int4))) != cudaSuccess) return bail("cudaMalloc(chunk positions)", e);
     if ((e = cudaMalloc(&ctx->d_arena, std::max<uint64_t>(arena_bytes, 128))) != cudaSuccess) return bail("cudaMalloc(vertex arena)", e);
     if ((e = cudaMalloc(&ctx->d_entries, max_chunks * sizeof(dsp::MeshEntry))) != cudaSuccess) return bail("cudaMalloc(entries)", e);
-    if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks)) != cudaSuccess) return bail("cudaMalloc(control)", e);
+    if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks + 64)) != cudaSuccess) return bail("cudaMalloc(control)", e);
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
+    if ((e = cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
+    cudaMemset(ctx->d_phase, 0, 16 * sizeof(unsigned long long));
     if ((e = cudaMallocHost(&ctx->h_pinned, 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < dsp_ctx::kEvRing; ++i)
@@ -401,7 +424,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
-    cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
+    cudaFree(ctx->d_phase); cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
@@ -678,6 +701,15 @@ void* dsp_voxel_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_voxels : nullptr;
 void* dsp_entries_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_entries : nullptr; }
 void* dsp_stream(dsp_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 uint64_t dsp_kernel_launches(const dsp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// debug: reads and clears the 16 phase counters (all zero unless the library was built with -DDSP_PHASE_TIMERS)
+int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16) {
+    if (!ctx || !out16) return DSP_ERR_BAD_ARG;
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DSP_CUDA(ctx, cudaMemcpy(out16, ctx->d_phase, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    DSP_CUDA(ctx, cudaMemset(ctx->d_phase, 0, 16 * sizeof(uint64_t)));
+    return DSP_OK;
+}
 
 int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_ms, float* out_last_ms) {
     if (!ctx) return DSP_ERR_BAD_ARG;

@@ -52,6 +52,10 @@ __device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src,
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                  : "memory");
 }
+// global -> L2 bulk prefetch (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {  // <= N groups still reading their smem source
@@ -68,6 +72,11 @@ __device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
     uint64_t v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+// four consecutive u64 (32-byte aligned group) with two 128-bit volatile loads
+__device__ __forceinline__ void ld_volatile_u64x4(const uint64_t* p, uint64_t (&v)[4]) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[2]), "=l"(v[3]) : "l"(p + 2) : "memory");
 }
 __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

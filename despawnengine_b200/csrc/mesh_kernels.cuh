@@ -20,8 +20,9 @@
 //      that is busy writing vertices.  Warp 0 then resolves the chunk's arena offset with a decoupled
 //      look-back over the earlier tickets (single pass: voxels are read from HBM exactly once);
 //      all rows write 16-bit face records (voxel index, direction) in stream order;
-//   4. faces are expanded 256 at a time, one thread per face, into a 30 KiB staging tile and each
-//      tile leaves with ONE bulk shared->global copy (cp.async.bulk), i.e. full-line writes only.
+//   4. faces are expanded one thread per face; each warp stages its 32 faces (3,840 B = 30 full lines) in a
+//      private shared-memory slot and sends it with ONE bulk shared->global copy (cp.async.bulk), so only
+//      full-line writes reach L2/HBM and the emission loop has no CTA-wide barrier.
 // Algorithmic HBM bytes per chunk: 8,192 (voxels) + 120*F (vertices) + 16 (position) + 16 (entry).
 #pragma once
 #include "dsp_common.cuh"
@@ -50,6 +51,8 @@ struct MeshParams {
     uint64_t* lookback;         // [n], zeroed before launch
     uint32_t* ctrl;             // [0] ticket counter, [1] status bits; zeroed before launch
     uint64_t* total_bytes;      // out
+    unsigned long long* phase_cycles;  // [16] debug: per-phase SM cycles of thread 0 summed over CTAs (DSP_PHASE_TIMERS builds)
+    uint32_t prefetch_ahead;    // L2-prefetch the tile of ticket + prefetch_ahead when a tile load is issued (0 = off)
 };
 
 constexpr uint32_t kStatusOverflow = 1u;
@@ -57,6 +60,7 @@ constexpr uint32_t kStatusSpin = 2u;
 
 constexpr int kTileFaces = 256;
 constexpr int kTileBytes = kTileFaces * kFaceBytes;  // 30,720
+constexpr int kWarpSlotWords = 32 * kFaceWords;      // 3,840 bytes: one warp's 32 faces
 
 // Corner codes.  Hand-typed from /root/reference/src/engine/rendering/cube.rs:156-312.  Each face is
 // 4 corners (c0,c1,c2,c3) emitted as c0,c1,c2,c2,c3,c0; a corner is 5 bits:
@@ -117,13 +121,21 @@ __device__ __forceinline__ void emit_face(float* dst, uint32_t rec, const uint16
     o[12] = make_float2(cv[3], cx[0]);  o[13] = make_float2(cy[0], cz[0]);  o[14] = make_float2(cu[0], cv[0]);
 }
 
-// Shared-memory carve-up (dynamic).  NSTAGE staging tiles of 30,720 B.
-template <int NSTAGE>
-struct MeshSmem {
+// Kernel variant: how many CTAs share an SM (sets the shared-memory budget), how many 30,720-byte staging
+// tiles each CTA owns, and whether emission is per CTA tile (one bulk store per 256 faces, two CTA barriers per
+// tile) or per warp (one bulk store per 32 faces, no CTA barrier in the emission loop).
+template <int CTAS, int NSTAGE_, bool WARP_EMIT_>
+struct MeshCfg {
+    static constexpr int kCtasPerSm = CTAS;
+    static constexpr int NSTAGE = NSTAGE_;
+    static constexpr bool WARP_EMIT = WARP_EMIT_;
+    // Face records are produced in windows of kRecCap faces; 4 CTAs/SM only fit with an 8 KiB window.  A chunk with
+    // more faces than the window (dense noise, > 1/3 of the 12,288 maximum) takes several record/emit rounds.
+    static constexpr int kRecCap = CTAS >= 4 ? 4096 : kMaxFaces;
     static constexpr int kVox = 0;                                   // 2 x 8192
     static constexpr int kStage = 2 * kChunkBytes;                   // NSTAGE x 30720
-    static constexpr int kRec = kStage + NSTAGE * kTileBytes;        // 12288 x u16
-    static constexpr int kRowMask = kRec + kMaxFaces * 2;            // 256 x u16
+    static constexpr int kRec = kStage + NSTAGE * kTileBytes;        // kRecCap x u16
+    static constexpr int kRowMask = kRec + kRecCap * 2;              // 256 x u16
     static constexpr int kWarpTot = kRowMask + kRows * 2;            // 8 x u32 (+8 pad)
     static constexpr int kBar = kWarpTot + 64;                       // 2 x u64
     static constexpr int kBase = kBar + 16;                          // u64
@@ -145,31 +157,52 @@ __device__ __forceinline__ uint64_t slot_bytes_of(uint32_t faces) {
 
 constexpr uint64_t kLbAgg = 1ull << 62, kLbPrefix = 2ull << 62, kLbVal = (1ull << 62) - 1;
 
-template <int NSTAGE, bool HALO>
-__global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(const MeshParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    using L = MeshSmem<NSTAGE>;
-    uint16_t* s_vox = reinterpret_cast<uint16_t*>(smem + L::kVox);
-    float* s_stage = reinterpret_cast<float*>(smem + L::kStage);
-    uint16_t* s_rec = reinterpret_cast<uint16_t*>(smem + L::kRec);
-    uint16_t* s_rowmask = reinterpret_cast<uint16_t*>(smem + L::kRowMask);
-    uint32_t* s_warp = reinterpret_cast<uint32_t*>(smem + L::kWarpTot);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
-    uint64_t* s_base = reinterpret_cast<uint64_t*>(smem + L::kBase);
-    uint32_t* s_next = reinterpret_cast<uint32_t*>(smem + L::kNext);
+// Per-CTA working set shared by the two kernel organisations below.
+template <class Cfg, bool HALO>
+struct MeshCta {
+    static constexpr int NSTAGE = Cfg::NSTAGE;
+    static constexpr uint32_t kRecCap = Cfg::kRecCap;
+    const MeshParams& p;
+    uint16_t* s_vox;
+    float* s_stage;
+    uint16_t* s_rec;
+    uint16_t* s_rowmask;
+    uint32_t* s_warp;
+    uint64_t* s_bar;
+    uint64_t* s_base;
+    uint32_t* s_next;
+    int tid, lane, warp, r, y, z;
+    uint32_t stage_ctr = 0;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r = tid, y = r & 15, z = r >> 4;
+    __device__ __forceinline__ MeshCta(const MeshParams& params, uint8_t* smem) : p(params) {
+        s_vox = reinterpret_cast<uint16_t*>(smem + Cfg::kVox);
+        s_stage = reinterpret_cast<float*>(smem + Cfg::kStage);
+        s_rec = reinterpret_cast<uint16_t*>(smem + Cfg::kRec);
+        s_rowmask = reinterpret_cast<uint16_t*>(smem + Cfg::kRowMask);
+        s_warp = reinterpret_cast<uint32_t*>(smem + Cfg::kWarpTot);
+        s_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBar);
+        s_base = reinterpret_cast<uint64_t*>(smem + Cfg::kBase);
+        s_next = reinterpret_cast<uint32_t*>(smem + Cfg::kNext);
+        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+        r = tid; y = r & 15; z = r >> 4;
+    }
 
-    auto slot_of = [&](uint32_t ticket) { return p.slot_list ? __ldg(p.slot_list + ticket) : p.first_slot + ticket; };
-    auto issue_load = [&](uint32_t ticket, int buf) {  // thread 0 only
+    __device__ __forceinline__ uint32_t slot_of(uint32_t chunk) const { return p.slot_list ? __ldg(p.slot_list + chunk) : p.first_slot + chunk; }
+
+    // thread 0 only: 8 KiB voxel tile of `chunk` -> voxel buffer `buf`, completion on s_bar[buf]
+    __device__ __forceinline__ void issue_load(uint32_t chunk, int buf) const {
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
-        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(ticket)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
-    };
+        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
+#ifdef DSP_L2_PREFETCH
+        // tickets are handed out in order, so the tile of chunk + prefetch_ahead will be wanted by some CTA soon: pull it into L2
+        const uint64_t ahead = static_cast<uint64_t>(chunk) + p.prefetch_ahead;
+        if (p.prefetch_ahead && ahead < p.n) bulk_prefetch_l2(p.voxels + static_cast<size_t>(slot_of(static_cast<uint32_t>(ahead))) * kChunkVoxels, kChunkBytes);
+#endif
+    }
 
-    // ---- count phase: row occupancy -> six face masks -> per-row count -> block scan; publishes the
-    //      chunk's byte size for the look-back of later tickets as early as possible.  2 barriers.
-    auto count_phase = [&](uint32_t ticket, int buf) -> RowFaces {
+    // ---- count phase: row occupancy -> six face masks -> per-row count -> block scan.  2 CTA barriers.
+    //      With `publish`, thread 0 posts the chunk's byte size for the look-back of later chunks.
+    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish) const {
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
         uint32_t m;
         {
@@ -188,7 +221,7 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
         uint32_t xm = 0u, xp = 0u;  // occupancy of the voxel beyond x = 0 / x = 15
         if (HALO) {
             // extension: consult the resident neighbour across each border (DSP_MESH_HALO)
-            const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot_of(ticket)) * 6;
+            const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot_of(chunk)) * 6;
             auto row_mask_of = [&](uint32_t nslot, int nr) -> uint32_t {
                 const uint4* q = reinterpret_cast<const uint4*>(p.voxels + static_cast<size_t>(nslot) * kChunkVoxels + nr * 16);
                 return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
@@ -222,23 +255,43 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
         }
         f.first = wpre + incl - f.cnt;
         f.total = total;
-        if (tid == 0) st_volatile_u64(&p.lookback[ticket], (ticket == 0 ? kLbPrefix : kLbAgg) | slot_bytes_of(total));
+        if (publish && tid == 0) st_volatile_u64(&p.lookback[chunk], (chunk == 0 ? kLbPrefix : kLbAgg) | slot_bytes_of(total));
         return f;
-    };
+    }
 
-    // ---- decoupled look-back (warp 0): exclusive prefix of the byte sizes of all earlier tickets ----------
-    auto look_back = [&](uint32_t ticket, uint32_t faces) {
+    // ---- decoupled look-back (one warp): exclusive prefix of the byte sizes of all earlier chunks; also writes the
+    //      chunk's mesh entry, the overflow flag and (last chunk) the batch total.  Result in *s_base.
+    //      Each probe covers 128 predecessors (lane l reads the aligned quad of entries (j >> 2) - l with two 128-bit
+    //      loads): with ~500 chunks in flight the walk back to the nearest resolved prefix must be a couple of L2 round
+    //      trips, not a dozen -- at 32 entries per probe the look-back chain itself capped the whole kernel.
+    __device__ __forceinline__ void look_back(uint32_t chunk, uint32_t faces) const {
         const uint64_t bytes = slot_bytes_of(faces);
         uint64_t excl = 0;
-        if (ticket > 0) {
-            int64_t j = static_cast<int64_t>(ticket) - 1;
+        if (chunk > 0) {
+            int64_t j = static_cast<int64_t>(chunk) - 1;  // nearest predecessor not yet accounted for
             uint32_t spins = 0;
             for (;;) {
-                const int64_t q = j - lane;
-                const uint64_t v = q >= 0 ? ld_volatile_u64(&p.lookback[q]) : kLbPrefix;
-                const uint32_t flag = static_cast<uint32_t>(v >> 62);
-                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, flag == 2u);
-                const uint32_t inval = __ballot_sync(0xFFFFFFFFu, flag == 0u);
+                const int64_t quad = (j >> 2) - lane;  // entries 4*quad .. 4*quad+3
+                uint64_t e[4];
+                if (quad >= 0) ld_volatile_u64x4(&p.lookback[quad * 4], e);
+                // walk this lane's entries from the highest index down, stopping at the first resolved prefix
+                uint64_t sum = 0;
+                bool has_pref = quad < 0, invalid = false;  // below index 0: an implicit prefix of 0
+                if (quad >= 0) {
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) {
+                        const int64_t idx = quad * 4 + k;
+                        const uint32_t flag = static_cast<uint32_t>(e[k] >> 62);
+                        const bool take = idx <= j && !has_pref;
+                        if (take) {
+                            invalid |= flag == 0u;
+                            sum += e[k] & kLbVal;
+                            has_pref = flag == 2u;
+                        }
+                    }
+                }
+                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, has_pref);
+                const uint32_t inval = __ballot_sync(0xFFFFFFFFu, invalid);
                 const int first = pref ? __ffs(pref) - 1 : 31;  // lanes 0..first are needed
                 const uint32_t need = first == 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
                 if (inval & need) {  // a predecessor has not published yet
@@ -246,54 +299,30 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
                     __nanosleep(20);
                     continue;
                 }
-                uint64_t part = (need >> lane) & 1u ? (v & kLbVal) : 0ull;
+                uint64_t part = (need >> lane) & 1u ? sum : 0ull;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
                 excl += part;
                 if (pref) break;
-                j -= 32;
+                j = ((j >> 2) - 32) * 4 + 3;  // continue below the 32 quads just covered
             }
-            if (lane == 0) st_volatile_u64(&p.lookback[ticket], kLbPrefix | (excl + bytes));
+            if (lane == 0) st_volatile_u64(&p.lookback[chunk], kLbPrefix | (excl + bytes));
         }
         if (lane == 0) {
             *s_base = excl;
             if (excl + bytes > p.arena_room) atomicOr(&p.ctrl[1], kStatusOverflow);
-            p.entries[ticket] = MeshEntry{p.arena_offset + excl, faces * 6u, 0u};
-            if (ticket == p.n - 1) *p.total_bytes = excl + bytes;
+            p.entries[chunk] = MeshEntry{p.arena_offset + excl, faces * 6u, 0u};
+            if (chunk == p.n - 1) *p.total_bytes = excl + bytes;
         }
-    };
-
-    // ---- prologue: first two tickets, first count phase ------------------------------------------------------
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        fence_mbar_init();
-        const uint32_t t0 = atomicAdd(&p.ctrl[0], 1u);
-        s_next[0] = t0;
-        if (t0 < p.n) issue_load(t0, 0);
-        uint32_t t1 = 0xFFFFFFFFu;
-        if (t0 < p.n) { t1 = atomicAdd(&p.ctrl[0], 1u); if (t1 < p.n) issue_load(t1, 1); }
-        s_next[1] = t1;
     }
-    __syncthreads();
-    uint32_t cur = s_next[0];
-    if (cur >= p.n) return;
-    mbar_wait(&s_bar[0], 0);
-    RowFaces fc = count_phase(cur, 0);
-    uint32_t it = 0, stage_ctr = 0;
 
-    // Invariant at the top of iteration `it`: chunk `cur` is in voxel buffer it&1 with its count phase done and
-    // its size published; the ticket after it is in s_next[(it+1)&1] and its tile is in flight to the other buffer.
-    for (;;) {
-        const int buf = it & 1;
-        const uint16_t* vox = s_vox + buf * kChunkVoxels;
-        const uint32_t nxt = s_next[(it + 1) & 1];
-        const uint32_t F = fc.total;
-
-        // face records in stream order: rec = (voxel index << 3) | direction (chunk_mesh.rs:32, 65-106)
-        if (fc.cnt) {
+    // ---- face records in stream order for the window [q0, q0 + kRecCap): rec = (voxel index << 3) | direction
+    //      (chunk_mesh.rs:32, 65-106: voxel ascending; TOP, BOTTOM, REAR, FRONT, RIGHT, LEFT per voxel)
+    __device__ __forceinline__ void write_records(const RowFaces& fc, uint32_t q0) const {
+        if (!fc.cnt) return;
+        const uint32_t rbase = static_cast<uint32_t>(r) << 7;
+        if (kRecCap >= kMaxFaces || fc.total <= kRecCap) {
             uint16_t* rp = s_rec + fc.first;
-            const uint32_t rbase = static_cast<uint32_t>(r) << 7;
 #pragma unroll
             for (int x = 0; x < 16; ++x) {
                 const uint32_t bit = 1u << x, v = rbase | (x << 3);
@@ -304,55 +333,241 @@ __global__ void __launch_bounds__(256, NSTAGE == 1 ? 3 : 2) mesh_chunks_kernel(c
                 if (fc.right & bit) *rp++ = static_cast<uint16_t>(v | 4u);
                 if (fc.left & bit) *rp++ = static_cast<uint16_t>(v | 5u);
             }
+        } else {  // windowed: only ordinals in [q0, q0 + kRecCap) are recorded this round
+            uint32_t ord = fc.first - q0;  // wraps below the window; the unsigned compare rejects those
+#pragma unroll 1
+            for (int x = 0; x < 16; ++x) {
+                const uint32_t v = rbase | (x << 3);
+                const uint32_t six = ((fc.top >> x) & 1u) | (((fc.bot >> x) & 1u) << 1) | (((fc.rear >> x) & 1u) << 2) |
+                                     (((fc.front >> x) & 1u) << 3) | (((fc.right >> x) & 1u) << 4) | (((fc.left >> x) & 1u) << 5);
+#pragma unroll
+                for (uint32_t d = 0; d < 6; ++d)
+                    if ((six >> d) & 1u) { if (ord < kRecCap) s_rec[ord] = static_cast<uint16_t>(v | d); ++ord; }
+            }
         }
+    }
 
-        // count the NEXT chunk before emitting this one, so that its size is published before the long
-        // emission phase and nobody's look-back ever waits on a CTA that is busy writing vertices
-        RowFaces fn{};
-        if (nxt < p.n) {
-            mbar_wait(&s_bar[buf ^ 1], ((it + 1) >> 1) & 1);
-            fn = count_phase(nxt, buf ^ 1);
+    // ---- expand the records of faces [q0, q1) into vertices and send them to the arena at gout (chunk base)
+    __device__ __forceinline__ void emit_window(uint32_t q0, uint32_t q1, uint32_t F, const uint16_t* vox, float cbx, float cby, float cbz,
+                                                uint8_t* gout, bool fits) {
+        if (Cfg::WARP_EMIT) {
+            // warp w expands faces [256 j + 32 w, +32) of every 256-face tile j into its own 3,840-byte slot(s) and
+            // sends each slot with one bulk copy (30 full 128-byte lines, line-aligned in the arena); a warp only
+            // ever waits for the drain of its own previous store -- no CTA-wide barrier in this loop
+            float* wstage = s_stage + warp * (NSTAGE * kWarpSlotWords);
+            for (uint32_t f0 = q0 + warp * 32u; f0 < q1; f0 += kTileFaces) {
+                float* slot = wstage + (stage_ctr % NSTAGE) * kWarpSlotWords;
+                if (lane == 0) bulk_wait_read<NSTAGE - 1>();
+                __syncwarp();
+                const uint32_t f = f0 + lane;
+                if (f < F) {
+                    emit_face(slot + lane * kFaceWords, s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
+                } else if (f == F && (F & 1u)) {  // odd face count: pad the last 16-byte unit with zeros
+                    *reinterpret_cast<float2*>(slot + lane * kFaceWords) = make_float2(0.0f, 0.0f);
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && fits) {
+                    const uint32_t nf = min(32u, F - f0);
+                    bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, slot, (nf * kFaceBytes + 15u) & ~15u);
+                    bulk_commit();
+                }
+                ++stage_ctr;
+            }
+        } else {
+            // 256 faces per tile, one thread per face, one bulk copy of up to 30,720 bytes per tile
+            for (uint32_t f0 = q0; f0 < q1; f0 += kTileFaces) {
+                float* stage = s_stage + (stage_ctr % NSTAGE) * (kTileBytes / 4);
+                if (tid == 0) bulk_wait_read<NSTAGE - 1>();  // the store that last used this tile has drained it
+                __syncthreads();
+                const uint32_t f = f0 + tid;
+                if (f < F) {
+                    emit_face(stage + tid * kFaceWords, s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
+                } else if (f == F && (F & 1u)) {
+                    *reinterpret_cast<float2*>(stage + tid * kFaceWords) = make_float2(0.0f, 0.0f);
+                }
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0 && fits) {
+                    const uint32_t nf = min(static_cast<uint32_t>(kTileFaces), F - f0);
+                    bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, stage, (nf * kFaceBytes + 15u) & ~15u);
+                    bulk_commit();
+                }
+                ++stage_ctr;
+            }
         }
-        if (warp == 0) look_back(cur, F);
+    }
+
+    // records + emission of one counted chunk; `between` runs once after the (first round of) records and before the
+    // barrier that publishes them (the single-pass kernel counts the next chunk and does its look-back there)
+#ifdef DSP_PHASE_TIMERS
+    long long ph[16] = {};
+    long long tlast = 0;
+    __device__ __forceinline__ void tick(int k) { const long long t = clock64(); ph[k] += t - tlast; tlast = t; }
+#else
+    __device__ __forceinline__ void tick(int) {}
+#endif
+
+    template <class Between>
+    __device__ __forceinline__ void records_and_emit(uint32_t chunk, const RowFaces& fc, const uint16_t* vox, Between between) {
+        const uint32_t F = fc.total;
+        tick(0);
+        // issued first so that its global-memory latency hides behind the record phase (it used to sit right after the
+        // barrier, where ncu showed a quarter of all stall samples)
+        const int4 cp = __ldg(&p.chunk_pos[slot_of(chunk)]);
+        write_records(fc, 0);
+        tick(1);
+        between();
+        tick(4);
         __syncthreads();  // s_rec, s_base visible
-
-        // expand + bulk store, 256 faces per tile
+        tick(5);
         const uint64_t base = *s_base;
         const bool fits = base + slot_bytes_of(F) <= p.arena_room;
         uint8_t* gout = p.arena + base;
-        const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
         const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
         const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
-        for (uint32_t f0 = 0; f0 < F; f0 += kTileFaces) {
-            float* stage = s_stage + (stage_ctr % NSTAGE) * (kTileBytes / 4);
-            if (tid == 0) bulk_wait_read<NSTAGE - 1>();  // the store that last used this tile has drained it
+        emit_window(0, min(F, kRecCap), F, vox, cbx, cby, cbz, gout, fits);
+        if (kRecCap < kMaxFaces && F > kRecCap) more_rounds(fc, vox, cbx, cby, cbz, gout, fits);
+        tick(6);
+    }
+
+    // rare: a chunk with more faces than the record window takes further record/emit rounds
+    __device__ __forceinline__ void more_rounds(const RowFaces& fc, const uint16_t* vox, float cbx, float cby, float cbz, uint8_t* gout, bool fits) {
+        const uint32_t F = fc.total;
+        for (uint32_t q0 = kRecCap; q0 < F; q0 += kRecCap) {
+            __syncthreads();  // the previous round's records are consumed before they are overwritten
+            write_records(fc, q0);
             __syncthreads();
-            const uint32_t f = f0 + tid;
-            if (f < F) {
-                emit_face(stage + tid * kFaceWords, s_rec[f], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
-            } else if (f == F && (F & 1u)) {  // odd face count: pad the last 16-byte unit with zeros
-                *reinterpret_cast<float2*>(stage + tid * kFaceWords) = make_float2(0.0f, 0.0f);
-            }
-            fence_proxy_async_smem();
-            __syncthreads();
-            if (tid == 0 && fits) {
-                const uint32_t nf = min(static_cast<uint32_t>(kTileFaces), F - f0);
-                bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, stage, (nf * kFaceBytes + 15u) & ~15u);
-                bulk_commit();
-            }
-            ++stage_ctr;
+            emit_window(q0, min(F, q0 + kRecCap), F, vox, cbx, cby, cbz, gout, fits);
         }
+    }
+};
+
+// ===== organisation A (DSP_MESH_ORDERED): single pass, slots packed in call order by decoupled look-back ================
+// Voxels are read from HBM exactly once.  The count phase of chunk k+1 runs before the emission of chunk k, so every
+// ticket's size is published within (tile latency + count) of the ticket being taken.  The price of the reproducible
+// layout is the look-back itself: ~1.3 us per chunk on the critical path of the CTA (profiles/README.md).
+template <class Cfg, bool HALO>
+__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const MeshParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    MeshCta<Cfg, HALO> c(p, smem);
+    const int tid = c.tid;
+
+    if (tid == 0) {
+        mbar_init(&c.s_bar[0], 1);
+        mbar_init(&c.s_bar[1], 1);
+        fence_mbar_init();
+        const uint32_t t0 = atomicAdd(&p.ctrl[0], 1u);
+        c.s_next[0] = t0;
+        if (t0 < p.n) c.issue_load(t0, 0);
+        uint32_t t1 = 0xFFFFFFFFu;
+        if (t0 < p.n) { t1 = atomicAdd(&p.ctrl[0], 1u); if (t1 < p.n) c.issue_load(t1, 1); }
+        c.s_next[1] = t1;
+    }
+    __syncthreads();
+    uint32_t cur = c.s_next[0];
+    if (cur >= p.n) return;
+    mbar_wait(&c.s_bar[0], 0);
+    RowFaces fc = c.count_phase(cur, 0, true);
+    uint32_t it = 0;
+#ifdef DSP_PHASE_TIMERS
+    c.tlast = clock64();
+#endif
+
+    // Invariant at the top of iteration `it`: chunk `cur` is in voxel buffer it&1 with its count phase done and
+    // its size published; the ticket after it is in s_next[(it+1)&1] and its tile is in flight to the other buffer.
+    for (;;) {
+        const int buf = it & 1;
+        const uint32_t nxt = c.s_next[(it + 1) & 1];
+        RowFaces fn{};
+        c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
+            if (nxt < p.n) {
+                mbar_wait(&c.s_bar[buf ^ 1], ((it + 1) >> 1) & 1);
+                c.tick(2);
+                fn = c.count_phase(nxt, buf ^ 1, true);
+                c.tick(3);
+            }
+            if (c.warp == 0) c.look_back(cur, fc.total);
+        });
         if (nxt >= p.n) break;
         uint32_t t2 = 0;
-        if (tid == 0) { t2 = atomicAdd(&p.ctrl[0], 1u); s_next[it & 1] = t2; }
+        if (tid == 0) { t2 = atomicAdd(&p.ctrl[0], 1u); c.s_next[it & 1] = t2; }
+        c.tick(7);
         __syncthreads();  // everyone is done with vox(buf), s_rec and s_base; s_next visible
-        if (tid == 0 && t2 < p.n) issue_load(t2, buf);
+        c.tick(8);
+        if (tid == 0 && t2 < p.n) c.issue_load(t2, buf);
         cur = nxt;
         fc = fn;
         ++it;
     }
-    if (tid == 0) bulk_wait<0>();
+    if (c.lane == 0) bulk_wait<0>();  // lane 0 of every warp may own bulk stores
+#ifdef DSP_PHASE_TIMERS
+    c.tick(9);
+    if (tid == 0 && p.phase_cycles) for (int k = 0; k < 16; ++k) atomicAdd(&p.phase_cycles[k], static_cast<unsigned long long>(c.ph[k]));
+    if (tid == 255 && p.phase_cycles) atomicAdd(&p.phase_cycles[15], 1ull);
+#endif
+}
+
+// ===== organisation B: single pass, arena space claimed with one atomic per chunk ========================================
+// No ordering between chunks at all: thread 0 claims align128(120*F) bytes from a global cursor as soon as the chunk
+// is counted, so there is no look-back, tickets can be taken a whole chunk early (deep tile prefetch) and nothing ever
+// waits on another CTA.  Every chunk's stream is still byte-exact and the entry table says where it landed; only the
+// ORDER of the slots in the arena follows completion order instead of call order (DSP_MESH_ORDERED selects the
+// look-back organisation when a reproducible layout matters).
+template <class Cfg, bool HALO>
+__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    MeshCta<Cfg, HALO> c(p, smem);
+    const int tid = c.tid;
+    if (tid == 0) {
+        mbar_init(&c.s_bar[0], 1);
+        mbar_init(&c.s_bar[1], 1);
+        fence_mbar_init();
+        const uint32_t t0 = atomicAdd(&p.ctrl[0], 1u);
+        c.s_next[0] = t0;
+        if (t0 < p.n) c.issue_load(t0, 0);
+    }
+    __syncthreads();
+    uint32_t cur = c.s_next[0];
+    uint32_t it = 0;
+#ifdef DSP_PHASE_TIMERS
+    c.tlast = clock64();
+#endif
+    // (Measured alternatives that were NOT faster on B200: consuming the ticket atomic only after the record phase, and
+    // running tickets two chunks ahead of the tiles; see profiles/README.md.)
+    while (cur < p.n) {
+        const int buf = it & 1;
+        if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
+            const uint32_t t = atomicAdd(&p.ctrl[0], 1u);
+            c.s_next[(it + 1) & 1] = t;
+            if (t < p.n) c.issue_load(t, buf ^ 1);  // buf^1 was released by the barrier that ended the previous iteration
+        }
+        c.tick(7);
+        mbar_wait(&c.s_bar[buf], (it >> 1) & 1);
+        c.tick(2);
+        const RowFaces fc = c.count_phase(cur, buf, false);
+        c.tick(3);
+        c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
+            if (tid == 0) {  // claim the chunk's arena slot
+                const uint64_t bytes = slot_bytes_of(fc.total);
+                const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
+                *c.s_base = base;
+                if (base + bytes > p.arena_room) atomicOr(&p.ctrl[1], kStatusOverflow);
+                p.entries[cur] = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
+            }
+        });
+        __syncthreads();  // all reads of vox(buf), s_rec, s_next done before they are overwritten
+        c.tick(8);
+        ++it;
+        cur = c.s_next[it & 1];
+    }
+    if (c.lane == 0) bulk_wait<0>();
+#ifdef DSP_PHASE_TIMERS
+    c.tick(9);
+    if (tid == 0 && p.phase_cycles) for (int k = 0; k < 16; ++k) atomicAdd(&p.phase_cycles[k], static_cast<unsigned long long>(c.ph[k]));
+    if (tid == 255 && p.phase_cycles) atomicAdd(&p.phase_cycles[15], 1ull);
+#endif
 }
 
 }  // namespace dsp

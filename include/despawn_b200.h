@@ -62,6 +62,8 @@ typedef enum dsp_gen_kind {
 /* Mesh modes (bit flags).  0 is the reference's behaviour and the only bit-exact-to-reference mode. */
 #define DSP_MESH_PARITY 0u /* chunk-local cull, border faces always emitted (chunk_mesh.rs:46-51) */
 #define DSP_MESH_HALO 1u   /* extension: border faces tested against resident neighbour chunks */
+#define DSP_MESH_ORDERED 2u /* pack the chunks' arena slots back to back in the order of the call (reproducible
+                             * layout, ~10 % slower); without it slots are claimed in completion order */
 
 #define DSP_NO_SLOT 0xFFFFFFFFu
 #define DSP_CHUNK_VOXELS 4096
@@ -123,8 +125,11 @@ uint64_t dsp_resident_chunks(const dsp_ctx* ctx);
 
 /* ---- meshing (build_chunk_mesh) ---------------------------------------------------------------------- */
 /* Batched build_chunk_mesh (chunk_mesh.rs:13-129); n = 1 is the reference call.  Meshes the chunks in
- * `slots` (n entries) into the arena starting at arena_offset (multiple of 128), packed in the order
- * given.  out_entries (host, n entries, may be NULL) and *out_total_bytes (may be NULL) are filled
+ * `slots` (n entries) into the arena starting at arena_offset (multiple of 128).  Every chunk gets a
+ * 128-byte aligned slot of align128(20 * vertex_count) bytes; the slots are gap-free and together occupy
+ * exactly *out_total_bytes.  With DSP_MESH_ORDERED they follow each other in the order given, otherwise in
+ * completion order (the reference allocates one buffer per chunk, so slot order is not observable there).
+ * out_entries (host, n entries, may be NULL) and *out_total_bytes (may be NULL) are filled
  * when the call returns; the vertex data stays on the device (the reference's result is a device
  * buffer too, chunk_mesh.rs:111-124).  Blocking. */
 int dsp_mesh_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint32_t mode, uint64_t arena_offset,
@@ -166,6 +171,10 @@ uint64_t dsp_kernel_launches(const dsp_ctx* ctx);
  * launch on the context's stream: number of launches, their summed duration, and the newest one.
  * Waits for outstanding launches. */
 int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_ms, float* out_last_ms);
+
+/* Debug aid: per-phase SM-cycle counters of the mesh kernel, summed over CTAs, read and cleared.  All zero
+ * unless the library was built with -DDSP_PHASE_TIMERS (not the shipped build). */
+int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16);
 
 #ifdef __cplusplus
 }

@@ -32,12 +32,22 @@ def align128(n):
     return (n + 127) & ~127
 
 
-def check_entries_layout(entries, total, base=0):
-    off = base
-    for e in entries:
-        assert int(e["offset_bytes"]) == off and off % 128 == 0
-        off += align128(int(e["vertex_count"]) * 20)
-    assert total == off - base
+def check_entries_layout(entries, total, base=0, ordered=False):
+    """Slots are 128-byte aligned, gap-free and disjoint inside [base, base + total).  With DSP_MESH_ORDERED they
+    also follow each other in call order; otherwise their order is the kernel's completion order."""
+    sizes = np.array([align128(int(e["vertex_count"]) * 20) for e in entries], dtype=np.int64)
+    offs = entries["offset_bytes"].astype(np.int64)
+    assert total == int(sizes.sum())
+    assert (offs % 128 == 0).all()
+    if ordered:
+        assert np.array_equal(offs, base + np.concatenate([[0], np.cumsum(sizes)[:-1]]))
+        return
+    nz = sizes > 0
+    order = np.argsort(offs[nz], kind="stable")
+    o, z = offs[nz][order], sizes[nz][order]
+    if len(o):
+        assert o[0] == base and np.array_equal(o[1:], o[:-1] + z[:-1]) and o[-1] + z[-1] == base + total
+    assert ((offs[~nz] >= base) & (offs[~nz] <= base + total)).all()
 
 
 def compare_batch(ctx, pos, slots, entries, uv, kind=None, seed=None, ids=None):
@@ -153,6 +163,27 @@ def test_mixed_order_and_repeats_do_not_change_streams(ctx, uv_default):
         assert ctx.download_vertices(e2[j]).tobytes() == streams[i]
     e3, _ = ctx.mesh_chunks(slots)  # idempotent
     assert [ctx.download_vertices(e).tobytes() for e in e3] == streams
+
+
+@pytest.mark.parametrize("mode", [capi.MESH_ORDERED, capi.MESH_ORDERED | capi.MESH_HALO])
+def test_ordered_mode_packs_slots_in_call_order(ctx, uv_default, mode):
+    """DSP_MESH_ORDERED: same streams, slots back to back in the order of the call, bit-reproducible arena."""
+    dims = (5, 16, 4)
+    first = ctx.generate_region((0, 0, 0), dims, capi.GEN_NOISE, SEED_NOISE)
+    n = dims[0] * dims[1] * dims[2]
+    e_ord, t_ord = ctx.mesh_range(first, n, mode)
+    check_entries_layout(e_ord, t_ord, ordered=True)
+    blob1 = ctx.download_arena(0, t_ord).copy()
+    e_def, t_def = ctx.mesh_range(first, n, mode & ~capi.MESH_ORDERED, arena_offset=align128(t_ord))
+    check_entries_layout(e_def, t_def, base=align128(t_ord))
+    assert t_def == t_ord and np.array_equal(e_def["vertex_count"], e_ord["vertex_count"])
+    for a, b in zip(e_ord[::7], e_def[::7]):
+        assert ctx.download_vertices(a).tobytes() == ctx.download_vertices(b).tobytes()
+    e_again, _ = ctx.mesh_range(first, n, mode)
+    assert np.array_equal(e_again, e_ord) and np.array_equal(ctx.download_arena(0, t_ord), blob1)
+    if not (mode & capi.MESH_HALO):
+        pos = np.array([(a, b, c) for c in range(dims[2]) for b in range(dims[1]) for a in range(dims[0])], dtype=np.int32)
+        compare_batch(ctx, pos, None, e_ord, uv_default, orc.GEN_NOISE, SEED_NOISE)
 
 
 # ---- host chunk data with per-chunk palettes (chunk.rs:58-65) ---------------------------------------------
