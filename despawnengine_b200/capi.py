@@ -21,6 +21,8 @@ GEN_REFERENCE, GEN_NOISE, GEN_RANDOM, GEN_CHECKER = 0, 1, 2, 3
 # mesh modes
 MESH_PARITY, MESH_HALO, MESH_ORDERED = 0, 1, 2
 NO_SLOT = 0xFFFFFFFF
+FACE_TOP, FACE_BOTTOM, FACE_REAR, FACE_FRONT, FACE_RIGHT, FACE_LEFT = range(6)
+OPPOSITE_FACE = (1, 0, 3, 2, 5, 4)
 
 MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("reserved", np.uint32)])
 EDIT_DTYPE = np.dtype([("wx", np.int32), ("wy", np.int32), ("wz", np.int32), ("block", np.uint32)])
@@ -45,11 +47,15 @@ SYMBOLS = {
     "dsp_resident_chunks": (_u64, [_vp]),
     "dsp_mesh_chunks": (_int, [_vp, _u64, _P(_u32), _u32, _u64, _vp, _P(_u64)]),
     "dsp_mesh_range": (_int, [_vp, _u32, _u64, _u32, _u64, _vp, _P(_u64)]),
+    "dsp_mesh_host_chunks": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _u32, _u64, _P(_u32), _vp, _P(_u64)]),
     "dsp_mesh_range_async": (_int, [_vp, _u32, _u64, _u32, _u64]),
     "dsp_mesh_chunks_async": (_int, [_vp, _u64, _P(_u32), _u32, _u64]),
     "dsp_sync": (_int, [_vp]),
     "dsp_mesh_result": (_int, [_vp, _vp, _P(_u64)]),
     "dsp_apply_edits": (_int, [_vp, _u64, _vp, _P(_u32), _u64, _P(_u64)]),
+    "dsp_pack_border_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
+    "dsp_set_halo_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
+    "dsp_clear_halo_slabs": (_int, [_vp]),
     "dsp_download_arena": (_int, [_vp, _u64, _u64, _vp]),
     "dsp_download_chunk": (_int, [_vp, _u32, _P(C.c_uint16), _P(_i32)]),
     "dsp_arena_device_ptr": (_vp, [_vp]),
@@ -192,6 +198,25 @@ class Context:
         self._check(lib().dsp_mesh_range(self._h, first_slot, n, mode, arena_offset, entries.ctypes.data_as(C.c_void_p), C.byref(total)))
         return entries, int(total.value)
 
+    def mesh_host_chunks(self, pos, blocks, mode: int = MESH_PARITY, arena_offset: int = 0):
+        """Load host chunk data (global ids) and mesh it, pipelined; returns (slots, entries, total_bytes)."""
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        n = pos.shape[0]
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(n, 4096)
+        slots = np.empty(n, dtype=np.uint32)
+        entries = np.zeros(n, dtype=MESH_ENTRY_DTYPE)
+        total = C.c_uint64(0)
+        self._check(lib().dsp_mesh_host_chunks(self._h, n, _ptr(pos, C.c_int32), _ptr(blocks, C.c_uint16), mode, arena_offset,
+                                               _ptr(slots, C.c_uint32), entries.ctypes.data_as(C.c_void_p), C.byref(total)))
+        return slots, entries, int(total.value)
+
+    def mesh_host_chunks_ptr(self, n: int, pos: np.ndarray, blocks_host_ptr: int, entries_out: np.ndarray, mode: int = MESH_PARITY, arena_offset: int = 0) -> int:
+        """Raw-pointer form (pinned host voxels owned by the caller); returns total bytes."""
+        total = C.c_uint64(0)
+        self._check(lib().dsp_mesh_host_chunks(self._h, n, _ptr(pos, C.c_int32), C.cast(blocks_host_ptr, C.POINTER(C.c_uint16)), mode, arena_offset,
+                                               None, entries_out.ctypes.data_as(C.c_void_p), C.byref(total)))
+        return int(total.value)
+
     def mesh_range_async(self, first_slot: int, n: int, mode: int = MESH_PARITY, arena_offset: int = 0):
         self._check(lib().dsp_mesh_range_async(self._h, first_slot, n, mode, arena_offset))
 
@@ -210,6 +235,18 @@ class Context:
             return entries, int(total.value)
         self._check(lib().dsp_mesh_result(self._h, C.c_void_p(entries_ptr), C.byref(total)))
         return None, int(total.value)
+
+    # -- region seams ------------------------------------------------------------------------------------
+    def pack_border_slabs(self, slots, face: int, dst_device_ptr: int):
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        self._check(lib().dsp_pack_border_slabs(self._h, s.shape[0], _ptr(s, C.c_uint32), face, C.c_void_p(dst_device_ptr)))
+
+    def set_halo_slabs(self, slots, face: int, src_device_ptr: int):
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        self._check(lib().dsp_set_halo_slabs(self._h, s.shape[0], _ptr(s, C.c_uint32), face, C.c_void_p(src_device_ptr)))
+
+    def clear_halo_slabs(self):
+        self._check(lib().dsp_clear_halo_slabs(self._h))
 
     # -- edits -----------------------------------------------------------------------------------------
     def apply_edits(self, edits) -> np.ndarray:

@@ -45,6 +45,11 @@ thread_local std::string g_create_error = "";
 struct dsp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // H2D of dsp_mesh_host_chunks, overlapped with meshing on `stream`
+    static constexpr int kMaxSub = 64;   // sub-batches of one pipelined call
+    cudaEvent_t ev_sub[kMaxSub] = {};
+    cudaEvent_t ev_done = nullptr;
+    uint32_t* d_tickets = nullptr;       // kMaxSub ticket counters
     uint64_t max_chunks = 0, arena_bytes = 0;
     int num_sms = 0;
     int mesh_variant = 0;
@@ -54,6 +59,9 @@ struct dsp_ctx {
     uint16_t* d_voxels = nullptr;
     int4* d_pos = nullptr;
     uint32_t* d_nbr = nullptr;  // [max_chunks][6], allocated on first halo mesh
+    uint16_t* d_halo = nullptr; // [halo_cap][256] border slabs of neighbours that live on other devices
+    uint64_t halo_cap = 0, halo_n = 0;
+    std::unordered_map<uint64_t, uint32_t> halo_of;  // slot * 8 + face -> slab index
     uint8_t* d_arena = nullptr;
     dsp::MeshEntry* d_entries = nullptr;
     uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
@@ -261,22 +269,24 @@ int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
 
 int build_neighbour_table(dsp_ctx* ctx);
 
-int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset) {
+int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offset) {
     if (mode & ~(DSP_MESH_HALO | DSP_MESH_ORDERED)) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
     if (arena_offset % DSP_SLOT_ALIGN != 0 || arena_offset > ctx->arena_bytes)
         return fail(ctx, DSP_ERR_BAD_ARG, "arena_offset %llu must be a multiple of 128 and <= arena size", (unsigned long long)arena_offset);
     if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_BAD_ARG, "n = %llu exceeds max_chunks", (unsigned long long)n);
     if (ctx->n_blocks == 0) return fail(ctx, DSP_ERR_BAD_ARG, "dsp_set_uv_table has not been called");
-    ctx->last_mesh_n = n;
-    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + 8 * n, ctx->stream));
-    if (n == 0) return DSP_OK;
+    return DSP_OK;
+}
+
+// One mesh launch over `n` chunks whose entries start at entry index `entry0`; `sub` picks the ticket counter.
+int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub) {
     const bool halo = (mode & DSP_MESH_HALO) != 0;
-    if (halo) { int rc = build_neighbour_table(ctx); if (rc != DSP_OK) return rc; }
     dsp::MeshParams p{};
     p.voxels = ctx->d_voxels;
     p.chunk_pos = ctx->d_pos;
     p.slot_list = d_list;
     p.nbr_slots = ctx->d_nbr;
+    p.halo_slabs = ctx->d_halo;
     p.uvmap = ctx->d_uvmap;
     p.n_blocks = ctx->n_blocks;
     p.first_slot = first_slot;
@@ -284,12 +294,24 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     p.arena = ctx->d_arena + arena_offset;
     p.arena_offset = arena_offset;
     p.arena_room = ctx->arena_bytes - arena_offset;
-    p.entries = ctx->d_entries;
-    p.ctrl = reinterpret_cast<uint32_t*>(ctx->d_ctl);
+    p.entries = ctx->d_entries + entry0;
+    p.ticket = ctx->d_tickets + sub;
+    p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
     p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
     if (mode & DSP_MESH_ORDERED) return halo ? launch_mesh_variant<true, true>(ctx, p) : launch_mesh_variant<false, true>(ctx, p);
     return halo ? launch_mesh_variant<true, false>(ctx, p) : launch_mesh_variant<false, false>(ctx, p);
+}
+
+int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset) {
+    int rc = check_mesh_args(ctx, n, mode, arena_offset);
+    if (rc != DSP_OK) return rc;
+    ctx->last_mesh_n = n;
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + ((mode & DSP_MESH_ORDERED) ? 8 * n : 0), ctx->stream));
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t), ctx->stream));
+    if (n == 0) return DSP_OK;
+    if (mode & DSP_MESH_HALO) { if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc; }
+    return launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0);
 }
 
 int validate_slots(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
@@ -316,7 +338,11 @@ int build_neighbour_table(dsp_ctx* ctx) {
         for (int f = 0; f < 6; ++f) {
             const int32_t q[3] = {p[0] + dirs[f][0], p[1] + dirs[f][1], p[2] + dirs[f][2]};
             uint32_t s;
-            if (find_slot(ctx, q, &s)) nbr[static_cast<size_t>(slot) * 6 + f] = s;
+            if (find_slot(ctx, q, &s)) { nbr[static_cast<size_t>(slot) * 6 + f] = s; continue; }
+            if (!ctx->halo_of.empty()) {  // no resident neighbour: maybe its border layer was received from another device
+                auto it = ctx->halo_of.find(static_cast<uint64_t>(slot) * 8 + f);
+                if (it != ctx->halo_of.end()) nbr[static_cast<size_t>(slot) * 6 + f] = dsp::kNbrExternal | it->second;
+            }
         }
     };
     for (const auto& kv : ctx->map) { const int32_t p[3] = {kv.first.x, kv.first.y, kv.first.z}; fill(kv.second, p); }
@@ -378,7 +404,7 @@ const char* dsp_last_error(const dsp_ctx* ctx) { return ctx ? ctx->err.c_str() :
 int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** out_ctx) {
     if (!out_ctx) return fail(nullptr, DSP_ERR_BAD_ARG, "out_ctx is NULL");
     *out_ctx = nullptr;
-    if (max_chunks == 0 || max_chunks >= 0xFFFFFFFFull) return fail(nullptr, DSP_ERR_BAD_ARG, "max_chunks must be in [1, 2^32-2]");
+    if (max_chunks == 0 || max_chunks >= 0x80000000ull) return fail(nullptr, DSP_ERR_BAD_ARG, "max_chunks must be in [1, 2^31-1]");
     if (arena_bytes % DSP_SLOT_ALIGN != 0) return fail(nullptr, DSP_ERR_BAD_ARG, "arena_bytes must be a multiple of 128");
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -410,6 +436,11 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
     if ((e = cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
     cudaMemset(ctx->d_phase, 0, 16 * sizeof(unsigned long long));
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    for (int i = 0; i < dsp_ctx::kMaxSub; ++i)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_sub[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMalloc(&ctx->d_tickets, dsp_ctx::kMaxSub * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(tickets)", e);
     if ((e = cudaMallocHost(&ctx->h_pinned, 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < dsp_ctx::kEvRing; ++i)
@@ -423,7 +454,11 @@ int dsp_destroy(dsp_ctx* ctx) {
     if (!ctx) return DSP_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
+    cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_halo); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+    cudaFree(ctx->d_tickets);
     cudaFree(ctx->d_phase); cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -566,6 +601,7 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
         }
         ctx->resident[s] = 0;
         ctx->n_resident--;
+        for (int f = 0; f < 6 && !ctx->halo_of.empty(); ++f) ctx->halo_of.erase(static_cast<uint64_t>(s) * 8 + f);
     }
     ctx->nbr_dirty = true;
     return DSP_OK;
@@ -624,6 +660,65 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
     return finish_mesh(ctx, out_entries, out_total_bytes);
 }
 
+int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+                         uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (out_total_bytes) *out_total_bytes = 0;
+    if (n && (!pos || !blocks)) return fail(ctx, DSP_ERR_BAD_ARG, "pos/blocks is NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = check_mesh_args(ctx, n, mode, arena_offset);
+    if (rc != DSP_OK) return rc;
+    if (mode & (DSP_MESH_ORDERED | DSP_MESH_HALO)) {  // these need the whole batch resident first: plain load, then mesh
+        std::vector<uint32_t> slots(n);
+        if ((rc = dsp_load_chunks(ctx, n, pos, blocks, nullptr, nullptr, slots.data())) != DSP_OK) return rc;
+        if (out_slots) std::memcpy(out_slots, slots.data(), n * sizeof(uint32_t));
+        return dsp_mesh_chunks(ctx, n, slots.data(), mode, arena_offset, out_entries, out_total_bytes);
+    }
+    ctx->last_mesh_n = n;
+    // sub-batches: copy k+1 crosses PCIe while sub-batch k is meshed
+    uint64_t sub_n = 512;
+    while ((n + sub_n - 1) / sub_n > static_cast<uint64_t>(dsp_ctx::kMaxSub)) sub_n *= 2;
+    const int subs = static_cast<int>((n + sub_n - 1) / sub_n);
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32, ctx->stream));
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, dsp_ctx::kMaxSub * sizeof(uint32_t), ctx->stream));
+    if (n == 0) return finish_mesh(ctx, out_entries, out_total_bytes);
+    uint8_t* h;
+    if ((rc = stage_host(ctx, n * (sizeof(int4) + sizeof(uint32_t)), &h)) != DSP_OK) return rc;
+    int4* h_pos = reinterpret_cast<int4*>(h);
+    uint32_t* h_slots = reinterpret_cast<uint32_t*>(h + n * sizeof(int4));
+    // the copy stream must not overtake earlier work of the main stream that still reads the voxel store
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_done, ctx->stream));
+    DSP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
+    cudaStream_t main_stream = ctx->stream;
+    for (int j = 0; j < subs; ++j) {
+        const uint64_t i0 = j * sub_n, m = std::min<uint64_t>(sub_n, n - i0);
+        bool consecutive = true;
+        for (uint64_t i = 0; i < m; ++i) {
+            if ((rc = acquire_slot(ctx, pos + 3 * (i0 + i), &h_slots[i0 + i])) != DSP_OK) return rc;
+            h_pos[i0 + i] = make_int4(pos[3 * (i0 + i)], pos[3 * (i0 + i) + 1], pos[3 * (i0 + i) + 2], 0);
+            if (i && h_slots[i0 + i] != h_slots[i0 + i - 1] + 1) consecutive = false;
+        }
+        ctx->stream = ctx->copy_stream;  // upload_by_runs enqueues on ctx->stream
+        rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_pos), sizeof(int4), h_slots + i0, m, reinterpret_cast<const uint8_t*>(h_pos + i0));
+        if (rc == DSP_OK) rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, h_slots + i0, m,
+                                              reinterpret_cast<const uint8_t*>(blocks + (i0 * dsp::kChunkVoxels)));
+        const uint32_t* d_list = nullptr;
+        if (rc == DSP_OK && !consecutive) {
+            cudaError_t e_ = cudaMemcpyAsync(ctx->d_slots + i0, h_slots + i0, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e_ != cudaSuccess) rc = fail(ctx, DSP_ERR_CUDA, "cudaMemcpyAsync(slot list): %s", cudaGetErrorString(e_));
+            d_list = ctx->d_slots + i0;
+        }
+        ctx->stream = main_stream;
+        if (rc != DSP_OK) return rc;
+        DSP_CUDA(ctx, cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream));
+        DSP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0));
+        if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j)) != DSP_OK) return rc;
+    }
+    if (out_slots) std::memcpy(out_slots, h_slots, n * sizeof(uint32_t));
+    if ((rc = stage_release(ctx)) != DSP_OK) return rc;
+    return finish_mesh(ctx, out_entries, out_total_bytes);
+}
+
 int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty) {
     if (!ctx) return DSP_ERR_BAD_ARG;
     if (out_n_dirty) *out_n_dirty = 0;
@@ -669,6 +764,60 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
                                                   (unsigned long long)dirty.size(), (unsigned long long)cap_dirty);
         std::memcpy(out_dirty_slots, dirty.data(), dirty.size() * sizeof(uint32_t));
     }
+    return DSP_OK;
+}
+
+int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, void* dst_device) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (face < 0 || face > 5) return fail(ctx, DSP_ERR_BAD_ARG, "face %d out of range", face);
+    if (n == 0) return DSP_OK;
+    if (!slots || !dst_device) return fail(ctx, DSP_ERR_BAD_ARG, "NULL argument");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_slots(ctx, n, slots);
+    if (rc != DSP_OK) return rc;
+    uint8_t* h;
+    if ((rc = stage_host(ctx, n * sizeof(uint32_t), &h)) != DSP_OK) return rc;
+    std::memcpy(h, slots, n * sizeof(uint32_t));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = stage_release(ctx)) != DSP_OK) return rc;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 16));
+    dsp::pack_border_slabs_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_voxels, ctx->d_slots, static_cast<uint32_t>(n), face, static_cast<uint16_t*>(dst_device));
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return DSP_OK;
+}
+
+int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, const void* src_device) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (face < 0 || face > 5) return fail(ctx, DSP_ERR_BAD_ARG, "face %d out of range", face);
+    if (n == 0) return DSP_OK;
+    if (!slots || !src_device) return fail(ctx, DSP_ERR_BAD_ARG, "NULL argument");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_slots(ctx, n, slots);
+    if (rc != DSP_OK) return rc;
+    // slabs of one call are stored contiguously; a (slot, face) set again simply points at the newer slab
+    if (ctx->halo_n + n > ctx->halo_cap) {
+        const uint64_t cap = std::max<uint64_t>(ctx->halo_n + n, std::max<uint64_t>(1024, ctx->halo_cap * 2));
+        uint16_t* grown = nullptr;
+        DSP_CUDA(ctx, cudaMalloc(&grown, cap * 512));
+        if (ctx->halo_n) DSP_CUDA(ctx, cudaMemcpyAsync(grown, ctx->d_halo, ctx->halo_n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_halo);
+        ctx->d_halo = grown;
+        ctx->halo_cap = cap;
+    }
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo + ctx->halo_n * 256, src_device, n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+    for (uint64_t i = 0; i < n; ++i) ctx->halo_of[static_cast<uint64_t>(slots[i]) * 8 + face] = static_cast<uint32_t>(ctx->halo_n + i);
+    ctx->halo_n += n;
+    ctx->nbr_dirty = true;
+    return DSP_OK;
+}
+
+int dsp_clear_halo_slabs(dsp_ctx* ctx) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    ctx->halo_of.clear();
+    ctx->halo_n = 0;
+    ctx->nbr_dirty = true;
     return DSP_OK;
 }
 

@@ -39,7 +39,8 @@ struct MeshParams {
     const uint16_t* voxels;     // [max_chunks][4096]
     const int4* chunk_pos;      // per slot
     const uint32_t* slot_list;  // nullable
-    const uint32_t* nbr_slots;  // [max_chunks][6] (halo mode) or nullptr
+    const uint32_t* nbr_slots;  // [max_chunks][6] (halo mode) or nullptr: neighbour slot, kNbrExternal | slab index, or none
+    const uint16_t* halo_slabs; // [n_slabs][256] border layers received from other devices (halo mode)
     const float4* uvmap;        // [n_blocks + 1], last row = fallback
     uint32_t n_blocks;
     uint32_t first_slot;
@@ -49,12 +50,15 @@ struct MeshParams {
     uint64_t arena_room;        // bytes available from arena_offset
     MeshEntry* entries;         // [n]
     uint64_t* lookback;         // [n], zeroed before launch
-    uint32_t* ctrl;             // [0] ticket counter, [1] status bits; zeroed before launch
+    uint32_t* ticket;           // chunk ticket counter of this launch; zeroed before launch
+    uint32_t* status;           // status bits (kStatus*), shared by the launches of one call
     uint64_t* total_bytes;      // out
     unsigned long long* phase_cycles;  // [16] debug: per-phase SM cycles of thread 0 summed over CTAs (DSP_PHASE_TIMERS builds)
     uint32_t prefetch_ahead;    // L2-prefetch the tile of ticket + prefetch_ahead when a tile load is issued (0 = off)
 };
 
+constexpr uint32_t kNbrNone = 0xFFFFFFFFu;
+constexpr uint32_t kNbrExternal = 0x80000000u;  // neighbour lives on another device: low bits index halo_slabs
 constexpr uint32_t kStatusOverflow = 1u;
 constexpr uint32_t kStatusSpin = 2u;
 
@@ -222,16 +226,24 @@ struct MeshCta {
         if (HALO) {
             // extension: consult the resident neighbour across each border (DSP_MESH_HALO)
             const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot_of(chunk)) * 6;
-            auto row_mask_of = [&](uint32_t nslot, int nr) -> uint32_t {
-                const uint4* q = reinterpret_cast<const uint4*>(p.voxels + static_cast<size_t>(nslot) * kChunkVoxels + nr * 16);
+            // occupancy of 16 consecutive voxels: row `nr` of a resident neighbour chunk, or row `sr` of a received slab
+            auto row_mask_of = [&](uint32_t code, int nr, int sr) -> uint32_t {
+                const uint16_t* base = (code & kNbrExternal) ? p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sr * 16
+                                                             : p.voxels + static_cast<size_t>(code) * kChunkVoxels + nr * 16;
+                const uint4* q = reinterpret_cast<const uint4*>(base);
                 return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
             };
-            if (y == 15) { const uint32_t s = __ldg(nb + 0); if (s != 0xFFFFFFFFu) up = row_mask_of(s, 0 + 16 * z); }
-            if (y == 0) { const uint32_t s = __ldg(nb + 1); if (s != 0xFFFFFFFFu) dn = row_mask_of(s, 15 + 16 * z); }
-            if (z == 0) { const uint32_t s = __ldg(nb + 2); if (s != 0xFFFFFFFFu) re = row_mask_of(s, y + 16 * 15); }
-            if (z == 15) { const uint32_t s = __ldg(nb + 3); if (s != 0xFFFFFFFFu) fr = row_mask_of(s, y); }
-            { const uint32_t s = __ldg(nb + 4); if (s != 0xFFFFFFFFu) xm = __ldg(p.voxels + static_cast<size_t>(s) * kChunkVoxels + r * 16 + 15) != 0; }
-            { const uint32_t s = __ldg(nb + 5); if (s != 0xFFFFFFFFu) xp = __ldg(p.voxels + static_cast<size_t>(s) * kChunkVoxels + r * 16) != 0; }
+            auto voxel_of = [&](uint32_t code, int vidx, int sidx) -> uint32_t {
+                return (code & kNbrExternal) ? __ldg(p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sidx)
+                                             : __ldg(p.voxels + static_cast<size_t>(code) * kChunkVoxels + vidx);
+            };
+            // slab layouts: +-Y faces [z][x], +-Z faces [y][x], +-X faces [z][y] (== row index r)
+            if (y == 15) { const uint32_t s = __ldg(nb + 0); if (s != kNbrNone) up = row_mask_of(s, 0 + 16 * z, z); }
+            if (y == 0) { const uint32_t s = __ldg(nb + 1); if (s != kNbrNone) dn = row_mask_of(s, 15 + 16 * z, z); }
+            if (z == 0) { const uint32_t s = __ldg(nb + 2); if (s != kNbrNone) re = row_mask_of(s, y + 16 * 15, y); }
+            if (z == 15) { const uint32_t s = __ldg(nb + 3); if (s != kNbrNone) fr = row_mask_of(s, y, y); }
+            { const uint32_t s = __ldg(nb + 4); if (s != kNbrNone) xm = voxel_of(s, r * 16 + 15, r) != 0; }
+            { const uint32_t s = __ldg(nb + 5); if (s != kNbrNone) xp = voxel_of(s, r * 16, r) != 0; }
         }
         RowFaces f;
         f.top = m & ~up; f.bot = m & ~dn; f.rear = m & ~re; f.front = m & ~fr;
@@ -295,7 +307,7 @@ struct MeshCta {
                 const int first = pref ? __ffs(pref) - 1 : 31;  // lanes 0..first are needed
                 const uint32_t need = first == 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
                 if (inval & need) {  // a predecessor has not published yet
-                    if (++spins > (1u << 24)) { if (lane == 0) atomicOr(&p.ctrl[1], kStatusSpin); break; }
+                    if (++spins > (1u << 24)) { if (lane == 0) atomicOr(p.status, kStatusSpin); break; }
                     __nanosleep(20);
                     continue;
                 }
@@ -310,7 +322,7 @@ struct MeshCta {
         }
         if (lane == 0) {
             *s_base = excl;
-            if (excl + bytes > p.arena_room) atomicOr(&p.ctrl[1], kStatusOverflow);
+            if (excl + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
             p.entries[chunk] = MeshEntry{p.arena_offset + excl, faces * 6u, 0u};
             if (chunk == p.n - 1) *p.total_bytes = excl + bytes;
         }
@@ -458,11 +470,11 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const
         mbar_init(&c.s_bar[0], 1);
         mbar_init(&c.s_bar[1], 1);
         fence_mbar_init();
-        const uint32_t t0 = atomicAdd(&p.ctrl[0], 1u);
+        const uint32_t t0 = atomicAdd(p.ticket, 1u);
         c.s_next[0] = t0;
         if (t0 < p.n) c.issue_load(t0, 0);
         uint32_t t1 = 0xFFFFFFFFu;
-        if (t0 < p.n) { t1 = atomicAdd(&p.ctrl[0], 1u); if (t1 < p.n) c.issue_load(t1, 1); }
+        if (t0 < p.n) { t1 = atomicAdd(p.ticket, 1u); if (t1 < p.n) c.issue_load(t1, 1); }
         c.s_next[1] = t1;
     }
     __syncthreads();
@@ -492,7 +504,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const
         });
         if (nxt >= p.n) break;
         uint32_t t2 = 0;
-        if (tid == 0) { t2 = atomicAdd(&p.ctrl[0], 1u); c.s_next[it & 1] = t2; }
+        if (tid == 0) { t2 = atomicAdd(p.ticket, 1u); c.s_next[it & 1] = t2; }
         c.tick(7);
         __syncthreads();  // everyone is done with vox(buf), s_rec and s_base; s_next visible
         c.tick(8);
@@ -524,7 +536,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         mbar_init(&c.s_bar[0], 1);
         mbar_init(&c.s_bar[1], 1);
         fence_mbar_init();
-        const uint32_t t0 = atomicAdd(&p.ctrl[0], 1u);
+        const uint32_t t0 = atomicAdd(p.ticket, 1u);
         c.s_next[0] = t0;
         if (t0 < p.n) c.issue_load(t0, 0);
     }
@@ -539,7 +551,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
     while (cur < p.n) {
         const int buf = it & 1;
         if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
-            const uint32_t t = atomicAdd(&p.ctrl[0], 1u);
+            const uint32_t t = atomicAdd(p.ticket, 1u);
             c.s_next[(it + 1) & 1] = t;
             if (t < p.n) c.issue_load(t, buf ^ 1);  // buf^1 was released by the barrier that ended the previous iteration
         }
@@ -553,7 +565,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
                 const uint64_t bytes = slot_bytes_of(fc.total);
                 const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
                 *c.s_base = base;
-                if (base + bytes > p.arena_room) atomicOr(&p.ctrl[1], kStatusOverflow);
+                if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
                 p.entries[cur] = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
             }
         });

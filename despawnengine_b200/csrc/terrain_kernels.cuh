@@ -146,6 +146,24 @@ __global__ void edit_scatter_kernel(uint16_t* voxels, const uint2* edits, uint32
     voxels[static_cast<size_t>(e.x) * kChunkVoxels + (e.y & 0xFFFu)] = static_cast<uint16_t>(e.y >> 16);
 }
 
+// Border layer of each listed chunk at `face` (0 top y=15, 1 bottom y=0, 2 rear z=0, 3 front z=15, 4 right x=0, 5 left
+// x=15) as a 256-entry slab: +-Y faces [z][x], +-Z faces [y][x], +-X faces [z][y].  This is what crosses NVLink at a
+// region seam in halo mode: 512 bytes per chunk face instead of the 8 KiB chunk.
+__global__ void __launch_bounds__(256) pack_border_slabs_kernel(const uint16_t* voxels, const uint32_t* slots, uint32_t n, int face, uint16_t* out) {
+    const int t = threadIdx.x, a = t >> 4, b = t & 15;
+    int idx;
+    switch (face) {
+        case 0: idx = b + 16 * 15 + 256 * a; break;
+        case 1: idx = b + 256 * a; break;
+        case 2: idx = b + 16 * a; break;
+        case 3: idx = b + 16 * a + 256 * 15; break;
+        case 4: idx = 16 * b + 256 * a; break;
+        default: idx = 15 + 16 * b + 256 * a; break;
+    }
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x)
+        out[static_cast<size_t>(i) * 256 + t] = voxels[static_cast<size_t>(slots[i]) * kChunkVoxels + idx];
+}
+
 // map_uv of chunk_mesh.rs:23-28 evaluated once per block id instead of once per vertex:
 // out[id] = (map(0).x, map(0).y, map(1).x, map(1).y) with map(o) = uv_min + o * (uv_max - uv_min),
 // each operation rounded separately (no FMA contraction) like the rustc-compiled reference.

@@ -1,0 +1,45 @@
+"""GPU side of the region-seam exchange: border slabs are packed by a CUDA kernel into a torch tensor (device memory),
+moved between ranks by torch.distributed (NCCL over NVLink/NVSwitch) and registered with the receiving context.
+torch is plumbing here (device memory + the collective); the pack and the culling are libdespawn_b200's kernels."""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import numpy as np
+
+from . import capi
+from .partition import Region, SlabPartition, exchange_halos
+
+
+class RegionOnDevice:
+    """One rank's slab of the world, generated on its GPU into consecutive slots."""
+
+    def __init__(self, ctx: capi.Context, region: Region, gen_kind: int, seed: int):
+        self.ctx, self.region = ctx, region
+        self.first_slot = ctx.generate_region(region.origin, region.dims, gen_kind, seed)
+
+    def slots_of(self, positions: np.ndarray) -> np.ndarray:
+        return np.array([self.first_slot + self.region.index_of(p) for p in positions], dtype=np.uint32)
+
+
+def exchange_region_halos(dev: RegionOnDevice, partition: SlabPartition, rank: int, dist) -> int:
+    """One halo exchange for `rank`; afterwards DSP_MESH_HALO on this context culls seam faces against the neighbouring
+    ranks' border layers.  Returns bytes sent."""
+    import torch
+    ctx = dev.ctx
+    device = torch.device("cuda", ctx.device)
+
+    def pack(positions, face):
+        t = torch.empty((len(positions), 256), dtype=torch.int16, device=device)
+        ctx.pack_border_slabs(dev.slots_of(positions), face, t.data_ptr())
+        return t
+
+    def unpack(positions, face, t):
+        ctx.set_halo_slabs(dev.slots_of(positions), face, t.data_ptr())
+        ctx.sync()  # the copy out of `t` is enqueued on the context's stream; `t` may be freed after this returns
+
+    def sync():
+        ctx.sync()
+        torch.cuda.synchronize(device)
+
+    return exchange_halos(partition.seam_transfers(rank), pack, torch.empty_like, unpack, dist=dist, sync=sync)

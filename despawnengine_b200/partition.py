@@ -1,0 +1,148 @@
+"""World partitioning across the GPUs of one box and the region-seam (halo) exchange plan.
+
+The reference is single-process; its mesher never looks outside a chunk
+(/root/reference/src/content/world/chunks/chunk_mesh.rs:46-51), so in the reference's own mode the world
+shards by chunk region with no exchange at all.  The cross-chunk culling extension (DSP_MESH_HALO) needs, at
+each seam between two ranks, the one-voxel-thick border layer of the chunks on the other side: 512 bytes per
+chunk face (16x16 u16).  This module is pure host logic -- who owns what, who sends which slabs to whom, in which
+order -- shared by the GPU path (NCCL over NVLink through torch.distributed) and the CPU tests (gloo).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+FACE_TOP, FACE_BOTTOM, FACE_REAR, FACE_FRONT, FACE_RIGHT, FACE_LEFT = range(6)  # chunk_mesh.rs:46-51 order
+OPPOSITE_FACE = (FACE_BOTTOM, FACE_TOP, FACE_FRONT, FACE_REAR, FACE_LEFT, FACE_RIGHT)
+SLAB_ELEMS = 256  # 16 x 16 u16
+
+
+def split_extent(n: int, parts: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced split of range(n) into `parts` (start, count) pieces; earlier pieces get the remainder."""
+    if parts < 1:
+        raise ValueError("parts must be >= 1")
+    base, rem = divmod(n, parts)
+    out, start = [], 0
+    for r in range(parts):
+        cnt = base + (1 if r < rem else 0)
+        out.append((start, cnt))
+        start += cnt
+    return out
+
+
+@dataclass(frozen=True)
+class Region:
+    """A box of chunks: minimum corner `origin` (chunk coordinates) and `dims` chunks along x, y, z."""
+    origin: Tuple[int, int, int]
+    dims: Tuple[int, int, int]
+
+    @property
+    def n_chunks(self) -> int:
+        return self.dims[0] * self.dims[1] * self.dims[2]
+
+    def positions(self) -> np.ndarray:
+        """(n,3) int32 in the slot order of dsp_generate_region: x fastest, then y, then z."""
+        a, b, c = (np.arange(d, dtype=np.int32) for d in self.dims)
+        z, y, x = np.meshgrid(c, b, a, indexing="ij")
+        return np.stack([x.ravel() + self.origin[0], y.ravel() + self.origin[1], z.ravel() + self.origin[2]], axis=1).astype(np.int32)
+
+    def index_of(self, pos) -> int:
+        a, b, c = (int(pos[i]) - self.origin[i] for i in range(3))
+        if not (0 <= a < self.dims[0] and 0 <= b < self.dims[1] and 0 <= c < self.dims[2]):
+            raise KeyError(tuple(pos))
+        return a + self.dims[0] * (b + self.dims[1] * c)
+
+    def face_positions(self, face: int) -> np.ndarray:
+        """Positions of the chunks on the boundary layer of the region at `face`, in canonical order (z outer,
+        then y, then x over the two free axes) so that sender and receiver enumerate a seam identically."""
+        ox, oy, oz = self.origin
+        dx, dy, dz = self.dims
+        xs, ys, zs = np.arange(ox, ox + dx), np.arange(oy, oy + dy), np.arange(oz, oz + dz)
+        if face == FACE_RIGHT:
+            xs = xs[:1]
+        elif face == FACE_LEFT:
+            xs = xs[-1:]
+        elif face == FACE_BOTTOM:
+            ys = ys[:1]
+        elif face == FACE_TOP:
+            ys = ys[-1:]
+        elif face == FACE_REAR:
+            zs = zs[:1]
+        elif face == FACE_FRONT:
+            zs = zs[-1:]
+        else:
+            raise ValueError(face)
+        z, y, x = np.meshgrid(zs, ys, xs, indexing="ij")
+        return np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1).astype(np.int32)
+
+
+@dataclass(frozen=True)
+class SeamTransfer:
+    """One direction of one seam: this rank packs `send_face` of `send_positions` for `peer`, and registers what it
+    receives from `peer` as the neighbour layer across `send_face` of the same chunks (the peer packed the
+    opposite face of ITS boundary chunks, enumerated in the same canonical order)."""
+    peer: int
+    send_face: int
+    positions: np.ndarray  # this rank's boundary chunks at the seam, canonical order
+
+
+class SlabPartition:
+    """X-slab partition: the world's X extent is cut into `world_size` contiguous slabs;
+    rank r owns slab r, its seams are with r-1 (across its RIGHT/-X face) and r+1 (across its LEFT/+X face)."""
+
+    def __init__(self, world: Region, world_size: int):
+        if world.dims[0] < world_size:
+            raise ValueError(f"cannot cut {world.dims[0]} chunks of X extent into {world_size} slabs")
+        self.world, self.world_size = world, world_size
+        self._cuts = split_extent(world.dims[0], world_size)
+
+    def region(self, rank: int) -> Region:
+        start, cnt = self._cuts[rank]
+        return Region((self.world.origin[0] + start, self.world.origin[1], self.world.origin[2]), (cnt, self.world.dims[1], self.world.dims[2]))
+
+    def owner_of(self, pos) -> int:
+        a = int(pos[0]) - self.world.origin[0]
+        for r, (start, cnt) in enumerate(self._cuts):
+            if start <= a < start + cnt:
+                return r
+        raise KeyError(tuple(pos))
+
+    def seam_transfers(self, rank: int) -> List[SeamTransfer]:
+        reg, out = self.region(rank), []
+        if rank > 0:
+            out.append(SeamTransfer(rank - 1, FACE_RIGHT, reg.face_positions(FACE_RIGHT)))
+        if rank < self.world_size - 1:
+            out.append(SeamTransfer(rank + 1, FACE_LEFT, reg.face_positions(FACE_LEFT)))
+        return out
+
+    def seam_bytes(self, rank: int) -> int:
+        """Bytes this rank sends (== receives) per exchange."""
+        return sum(len(t.positions) * SLAB_ELEMS * 2 for t in self.seam_transfers(rank))
+
+
+def exchange_halos(transfers: Sequence[SeamTransfer], pack: Callable[[np.ndarray, int], "object"], alloc_like: Callable[["object"], "object"],
+                   unpack: Callable[[np.ndarray, int, "object"], None], dist=None, sync: Optional[Callable[[], None]] = None) -> int:
+    """Runs one halo exchange.  `pack(positions, face)` returns a tensor of border slabs (n x 256 int16) of this rank's
+    chunks; `alloc_like(t)` returns an empty tensor of the same shape/device; `unpack(positions, face, tensor)`
+    registers received slabs as the neighbour layer across `face`.  `dist` is torch.distributed (NCCL on GPUs, gloo in
+    the CPU tests).  All sends and receives of a rank are posted together (batch_isend_irecv), so neighbouring ranks
+    cannot deadlock on ordering.  Returns the bytes sent."""
+    if not transfers:
+        return 0
+    send_bufs = [pack(t.positions, t.send_face) for t in transfers]
+    if sync is not None:
+        sync()  # packing ran on the context's stream; the collective runs on torch's
+    recv_bufs = [alloc_like(b) for b in send_bufs]
+    ops = []
+    for t, sb, rb in zip(transfers, send_bufs, recv_bufs):
+        ops.append(dist.P2POp(dist.isend, sb, t.peer))
+        ops.append(dist.P2POp(dist.irecv, rb, t.peer))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    if sync is not None:
+        sync()
+    for t, rb in zip(transfers, recv_bufs):
+        unpack(t.positions, t.send_face, rb)
+    return sum(int(b.numel()) * 2 for b in send_bufs)

@@ -137,6 +137,14 @@ int dsp_mesh_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, uint32_t mo
 /* Same for the consecutive slots first_slot .. first_slot+n-1 (no slot list crosses the bus). */
 int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode, uint64_t arena_offset,
                    dsp_mesh_entry* out_entries, uint64_t* out_total_bytes);
+/* build_chunk_mesh for HOST-resident chunks in one call: World::load_chunk (host voxel data, global ids) followed
+ * by the mesh of the same chunks, pipelined in sub-batches so that the host->device copy of sub-batch k+1 overlaps
+ * the meshing of sub-batch k (pass pinned host memory for `blocks` to get a truly asynchronous copy).  This is the
+ * end-to-end entry point for a caller that, like the reference, holds Chunk.blocks in host memory
+ * (chunks/chunk.rs:17, scene_game.rs:56-64).  out_slots (n, may be NULL) receives the slot of each chunk.  Blocking. */
+int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+                         uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes);
+
 /* Asynchronous forms: enqueue on the context's stream and return; results are read with
  * dsp_mesh_result after dsp_sync.  Let a caller overlap meshing with its own work (the reference is
  * synchronous inside GameScene::update, scene_game.rs:56-64). */
@@ -152,6 +160,24 @@ int dsp_mesh_result(dsp_ctx* ctx, dsp_mesh_entry* out_entries /* n of the last m
  * ascending slot order, and *out_n_dirty their number. */
 int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty,
                     uint64_t* out_n_dirty);
+
+/* ---- region seams (multi-GPU halo mode) ----------------------------------------------------- */
+/* Faces are numbered in the reference's emission order (chunk_mesh.rs:46-51, 65-106). */
+#define DSP_FACE_TOP 0    /* +Y, layer y = 15 */
+#define DSP_FACE_BOTTOM 1 /* -Y, layer y = 0 */
+#define DSP_FACE_REAR 2   /* -Z, layer z = 0 */
+#define DSP_FACE_FRONT 3  /* +Z, layer z = 15 */
+#define DSP_FACE_RIGHT 4  /* -X, layer x = 0 */
+#define DSP_FACE_LEFT 5   /* +X, layer x = 15 */
+/* Extracts the one-voxel-thick border layer at `face` of each listed chunk into dst_device (device memory owned by
+ * the caller, n x 256 u16 = 512 bytes per chunk; layout +-Y: [z][x], +-Z: [y][x], +-X: [z][y]).  Asynchronous on the
+ * context's stream (dsp_sync before handing dst_device to NCCL / a peer copy on another stream). */
+int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, void* dst_device);
+/* Registers, for each listed resident chunk, the border layer of its NON-resident neighbour across `face` (as packed
+ * by the owning device with the opposite face).  DSP_MESH_HALO then culls against it exactly as against a resident
+ * neighbour.  src_device: n x 512 bytes of device memory, copied. */
+int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, const void* src_device);
+int dsp_clear_halo_slabs(dsp_ctx* ctx);
 
 /* ---- data access ------------------------------------------------------------------------------------ */
 int dsp_download_arena(dsp_ctx* ctx, uint64_t offset_bytes, uint64_t bytes, void* host_dst);

@@ -213,6 +213,27 @@ def test_load_chunks_with_palettes(ctx, uv_default):
     compare_batch(ctx, pos + 100, slots2, entries2, uv_default, ids=gids2)
 
 
+def test_mesh_host_chunks_pipelined(ctx, uv_default):
+    """dsp_mesh_host_chunks: host voxels in, sub-batched copy/mesh pipeline, same streams as load + mesh."""
+    dims = (16, 10, 10)  # 1,600 chunks -> 4 sub-batches of 512
+    pos = np.array([(a, 3 + b, c) for c in range(dims[2]) for b in range(dims[1]) for a in range(dims[0])], dtype=np.int32)
+    ids = orc.generate_batch(orc.GEN_NOISE, SEED_NOISE, pos)
+    slots, entries, total = ctx.mesh_host_chunks(pos, ids)
+    check_entries_layout(entries, total)
+    compare_batch(ctx, pos, slots, entries, uv_default, ids=ids)
+    assert ctx.resident_chunks == len(pos) and np.array_equal(ctx.download_chunk(int(slots[777]))[0], ids[777])
+    # again into a different part of the arena, after fragmenting the slot space so that slot runs are short
+    ctx.unload_chunks(slots[100:1500:3])
+    ids2 = ids[::-1].copy()
+    slots2, entries2, total2 = ctx.mesh_host_chunks(pos, ids2, arena_offset=align128(total))
+    check_entries_layout(entries2, total2, base=align128(total))
+    compare_batch(ctx, pos, slots2, entries2, uv_default, ids=ids2)
+    # ordered mode goes through the plain load + mesh path
+    slots3, entries3, total3 = ctx.mesh_host_chunks(pos[:700], ids[:700], capi.MESH_ORDERED)
+    check_entries_layout(entries3, total3, ordered=True)
+    compare_batch(ctx, pos[:700], slots3, entries3, uv_default, ids=ids[:700])
+
+
 # ---- edge cases ------------------------------------------------------------------------------------------------
 def test_empty_and_single_voxel_chunks(ctx, uv_default):
     ids = np.zeros((4, 4096), dtype=np.uint16)
@@ -350,6 +371,49 @@ def test_halo_mode_matches_extended_oracle(ctx, uv_default):
         fp = {bytes(r) for r in ctx.download_vertices(ep).view(np.uint8).reshape(-1, 120)}
         fh = {bytes(r) for r in ctx.download_vertices(eh).view(np.uint8).reshape(-1, 120)}
         assert fh <= fp
+
+
+def test_two_contexts_with_seam_exchange_equal_one_context(uv_default):
+    """Config-5 mechanics at a small size: the world is cut into two X-slabs held by two contexts (two 'ranks' on one
+    GPU); border slabs are packed on one, handed over in device memory, registered on the other; halo-mode meshes of
+    every chunk must equal those of a single context that holds the whole world."""
+    import torch
+    from despawnengine_b200 import partition as part
+    from despawnengine_b200.halo import RegionOnDevice
+    world = part.Region((3, 5, -2), (6, 4, 3))
+    sp = part.SlabPartition(world, 2)
+    with capi.Context(0, 256, 256 << 20) as whole, capi.Context(0, 128, 128 << 20) as c0, capi.Context(0, 128, 128 << 20) as c1:
+        for c in (whole, c0, c1):
+            c.set_uv_table(uv_default)
+        ref = RegionOnDevice(whole, world, capi.GEN_NOISE, SEED_NOISE)
+        devs = [RegionOnDevice(c0, sp.region(0), capi.GEN_NOISE, SEED_NOISE), RegionOnDevice(c1, sp.region(1), capi.GEN_NOISE, SEED_NOISE)]
+        # the exchange, done by hand instead of through torch.distributed (one process here)
+        for rank, dev in enumerate(devs):
+            for t in sp.seam_transfers(rank):
+                peer = devs[t.peer]
+                peer_positions = sp.region(t.peer).face_positions(part.OPPOSITE_FACE[t.send_face])
+                buf = torch.empty((len(peer_positions), 256), dtype=torch.int16, device="cuda")
+                peer.ctx.pack_border_slabs(peer.slots_of(peer_positions), part.OPPOSITE_FACE[t.send_face], buf.data_ptr())
+                peer.ctx.sync()
+                dev.ctx.set_halo_slabs(dev.slots_of(t.positions), t.send_face, buf.data_ptr())
+                dev.ctx.sync()
+        e_ref, _ = whole.mesh_range(ref.first_slot, world.n_chunks, capi.MESH_HALO)
+        fewer = 0
+        for rank, dev in enumerate(devs):
+            reg = sp.region(rank)
+            e, total = dev.ctx.mesh_range(dev.first_slot, reg.n_chunks, capi.MESH_HALO)
+            check_entries_layout(e, total)
+            e_par, _ = dev.ctx.mesh_range(dev.first_slot, reg.n_chunks, capi.MESH_PARITY, arena_offset=align128(total))
+            for i, p in enumerate(reg.positions()):
+                want = whole.download_vertices(e_ref[world.index_of(p)])
+                assert dev.ctx.download_vertices(e[i]).tobytes() == want.tobytes(), (rank, tuple(p))
+            fewer += int(e_par["vertex_count"].sum()) - int(e["vertex_count"].sum())
+        assert fewer > 0
+        # without the exchange the seam faces come back (reference behaviour at a non-resident neighbour)
+        c0.clear_halo_slabs()
+        e_no, _ = c0.mesh_range(devs[0].first_slot, sp.region(0).n_chunks, capi.MESH_HALO)
+        seam = [sp.region(0).index_of(p) for p in sp.region(0).face_positions(part.FACE_LEFT)]
+        assert int(e_no["vertex_count"][seam].sum()) > int(np.array([e_ref[world.index_of(p)]["vertex_count"] for p in sp.region(0).face_positions(part.FACE_LEFT)]).sum())
 
 
 # ---- full BASELINE config 2 size: 16x16x16 chunks ------------------------------------------------------------
