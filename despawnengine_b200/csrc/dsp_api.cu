@@ -332,6 +332,48 @@ int validate_range(dsp_ctx* ctx, uint32_t first, uint64_t n) {
 int build_neighbour_table(dsp_ctx* ctx) {
     if (!ctx->d_nbr) DSP_CUDA(ctx, cudaMalloc(&ctx->d_nbr, ctx->max_chunks * 6 * sizeof(uint32_t)));
     if (!ctx->nbr_dirty) return DSP_OK;
+    // Fast path: the world is one fully resident box (dsp_generate_region, nothing unloaded, no individually loaded
+    // chunks) -- neighbour slots are arithmetic, computed on the device; received halo slabs are scattered over the
+    // box-boundary entries.  Millions of chunks never touch the host.
+    if (ctx->map.empty() && ctx->regions.size() == 1) {
+        const Region& r = ctx->regions[0];
+        const uint64_t n = static_cast<uint64_t>(r.dims[0]) * r.dims[1] * r.dims[2];
+        if (ctx->n_resident == n) {
+            dsp::region_neighbours_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
+                ctx->d_nbr, r.first_slot, make_uint3(r.dims[0], r.dims[1], r.dims[2]), n);
+            DSP_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+            if (!ctx->halo_of.empty()) {
+                std::vector<uint2> ov;
+                ov.reserve(ctx->halo_of.size());
+                for (const auto& kv : ctx->halo_of)
+                    ov.push_back(make_uint2(static_cast<uint32_t>((kv.first >> 3) * 6 + (kv.first & 7)), dsp::kNbrExternal | kv.second));
+                // a halo slab only stands in for a neighbour that is NOT resident: inside the box the resident one wins
+                std::vector<uint2> keep;
+                keep.reserve(ov.size());
+                for (const uint2& e : ov) {
+                    const uint64_t slot = e.x / 6, i = slot - r.first_slot;
+                    const uint32_t f = e.x % 6, a = static_cast<uint32_t>(i % r.dims[0]), b = static_cast<uint32_t>((i / r.dims[0]) % r.dims[1]),
+                                   c = static_cast<uint32_t>(i / (static_cast<uint64_t>(r.dims[0]) * r.dims[1]));
+                    const bool on_boundary = (f == 0 && b + 1 == r.dims[1]) || (f == 1 && b == 0) || (f == 2 && c == 0) || (f == 3 && c + 1 == r.dims[2]) ||
+                                             (f == 4 && a == 0) || (f == 5 && a + 1 == r.dims[0]);
+                    if (on_boundary) keep.push_back(e);
+                }
+                if (!keep.empty()) {
+                    int rc = ensure_scratch(ctx, keep.size() * sizeof(uint2));
+                    if (rc != DSP_OK) return rc;
+                    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, keep.data(), keep.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
+                    dsp::scatter_u32_kernel<<<static_cast<unsigned>((keep.size() + 255) / 256), 256, 0, ctx->stream>>>(
+                        ctx->d_nbr, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(keep.size()));
+                    DSP_CUDA(ctx, cudaGetLastError());
+                    ctx->launches++;
+                    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `keep` is pageable
+                }
+            }
+            ctx->nbr_dirty = false;
+            return DSP_OK;
+        }
+    }
     static const int dirs[6][3] = {{0, 1, 0}, {0, -1, 0}, {0, 0, -1}, {0, 0, 1}, {-1, 0, 0}, {1, 0, 0}};
     std::vector<uint32_t> nbr(ctx->next_unused * 6, DSP_NO_SLOT);
     auto fill = [&](uint32_t slot, const int32_t p[3]) {

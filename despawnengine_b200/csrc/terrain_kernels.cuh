@@ -113,6 +113,29 @@ __global__ void region_positions_kernel(int4* chunk_pos, uint32_t first_slot, in
     }
 }
 
+// Neighbour slots of every chunk of a box-shaped region (order top +Y, bottom -Y, rear -Z, front +Z, right -X, left +X):
+// inside the box it is slot arithmetic; across the box boundary there is no resident neighbour (0xFFFFFFFF) unless a
+// received halo slab is scattered over it afterwards.
+__global__ void region_neighbours_kernel(uint32_t* nbr, uint32_t first_slot, uint3 dims, uint64_t n) {
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t a = static_cast<uint32_t>(i % dims.x);
+        const uint64_t t = i / dims.x;
+        const uint32_t b = static_cast<uint32_t>(t % dims.y), c = static_cast<uint32_t>(t / dims.y);
+        const uint32_t s = first_slot + static_cast<uint32_t>(i), sy = dims.x, sz = dims.x * dims.y;
+        uint32_t* o = nbr + static_cast<size_t>(s) * 6;
+        o[0] = b + 1 < dims.y ? s + sy : 0xFFFFFFFFu;
+        o[1] = b > 0 ? s - sy : 0xFFFFFFFFu;
+        o[2] = c > 0 ? s - sz : 0xFFFFFFFFu;
+        o[3] = c + 1 < dims.z ? s + sz : 0xFFFFFFFFu;
+        o[4] = a > 0 ? s - 1 : 0xFFFFFFFFu;
+        o[5] = a + 1 < dims.x ? s + 1 : 0xFFFFFFFFu;
+    }
+}
+__global__ void scatter_u32_kernel(uint32_t* dst, const uint2* idx_val, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[idx_val[i].x] = idx_val[i].y;
+}
+
 // chunk.rs:58-65: a chunk's voxels are indices into its own palette; the device store holds global
 // ids, so after the raw host->device copy each voxel is replaced by palette_ids[off[i] + voxel].
 __global__ void __launch_bounds__(256) palette_remap_kernel(uint16_t* voxels, const uint32_t* slot_list, const uint16_t* palette_ids,

@@ -19,7 +19,11 @@ class RegionOnDevice:
         self.first_slot = ctx.generate_region(region.origin, region.dims, gen_kind, seed)
 
     def slots_of(self, positions: np.ndarray) -> np.ndarray:
-        return np.array([self.first_slot + self.region.index_of(p) for p in positions], dtype=np.uint32)
+        p = np.asarray(positions, dtype=np.int64).reshape(-1, 3) - np.array(self.region.origin, dtype=np.int64)
+        d = self.region.dims
+        if len(p) and (p.min() < 0 or (p >= np.array(d)).any()):
+            raise KeyError("position outside the region")
+        return (self.first_slot + p[:, 0] + d[0] * (p[:, 1] + d[1] * p[:, 2])).astype(np.uint32)
 
 
 def exchange_region_halos(dev: RegionOnDevice, partition: SlabPartition, rank: int, dist) -> int:
@@ -30,7 +34,7 @@ def exchange_region_halos(dev: RegionOnDevice, partition: SlabPartition, rank: i
     device = torch.device("cuda", ctx.device)
 
     def pack(positions, face):
-        t = torch.empty((len(positions), 256), dtype=torch.int16, device=device)
+        t = torch.empty((len(positions), 512), dtype=torch.uint8, device=device)  # NCCL has no 16-bit integer type: ship bytes
         ctx.pack_border_slabs(dev.slots_of(positions), face, t.data_ptr())
         return t
 

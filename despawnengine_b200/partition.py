@@ -124,7 +124,7 @@ class SlabPartition:
 
 def exchange_halos(transfers: Sequence[SeamTransfer], pack: Callable[[np.ndarray, int], "object"], alloc_like: Callable[["object"], "object"],
                    unpack: Callable[[np.ndarray, int, "object"], None], dist=None, sync: Optional[Callable[[], None]] = None) -> int:
-    """Runs one halo exchange.  `pack(positions, face)` returns a tensor of border slabs (n x 256 int16) of this rank's
+    """Runs one halo exchange.  `pack(positions, face)` returns a tensor of border slabs (n x 512 uint8 = n x 256 u16) of this rank's
     chunks; `alloc_like(t)` returns an empty tensor of the same shape/device; `unpack(positions, face, tensor)`
     registers received slabs as the neighbour layer across `face`.  `dist` is torch.distributed (NCCL on GPUs, gloo in
     the CPU tests).  All sends and receives of a rank are posted together (batch_isend_irecv), so neighbouring ranks
@@ -145,4 +145,4 @@ def exchange_halos(transfers: Sequence[SeamTransfer], pack: Callable[[np.ndarray
         sync()
     for t, rb in zip(transfers, recv_bufs):
         unpack(t.positions, t.send_face, rb)
-    return sum(int(b.numel()) * 2 for b in send_bufs)
+    return sum(int(b.numel()) * int(b.element_size()) for b in send_bufs)

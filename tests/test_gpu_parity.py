@@ -392,7 +392,7 @@ def test_two_contexts_with_seam_exchange_equal_one_context(uv_default):
             for t in sp.seam_transfers(rank):
                 peer = devs[t.peer]
                 peer_positions = sp.region(t.peer).face_positions(part.OPPOSITE_FACE[t.send_face])
-                buf = torch.empty((len(peer_positions), 256), dtype=torch.int16, device="cuda")
+                buf = torch.empty((len(peer_positions), 512), dtype=torch.uint8, device="cuda")
                 peer.ctx.pack_border_slabs(peer.slots_of(peer_positions), part.OPPOSITE_FACE[t.send_face], buf.data_ptr())
                 peer.ctx.sync()
                 dev.ctx.set_halo_slabs(dev.slots_of(t.positions), t.send_face, buf.data_ptr())

@@ -63,10 +63,10 @@ def _rank_main(rank, world_size, port, out_dir):
         halo = {}
 
         def pack(positions, face):
-            return torch.from_numpy(np.stack([slab_of(chunks[tuple(p)], face) for p in positions.tolist()]).astype(np.int16))
+            return torch.from_numpy(np.stack([slab_of(chunks[tuple(p)], face) for p in positions.tolist()]).astype(np.uint16).view(np.uint8))
 
         def unpack(positions, face, t):
-            for p, row in zip(positions.tolist(), t.numpy().astype(np.uint16)):
+            for p, row in zip(positions.tolist(), t.numpy().view(np.uint16)):
                 halo[(tuple(p), face)] = row
 
         sent = part.exchange_halos(sp.seam_transfers(rank), pack, torch.empty_like, unpack, dist=dist)
