@@ -571,14 +571,28 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
     std::fill(ctx->resident.begin() + first, ctx->resident.begin() + first + n, 1);
     ctx->n_resident += n;
     ctx->nbr_dirty = true;
-    dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
-        ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), n);
-    DSP_CUDA(ctx, cudaGetLastError());
-    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed};
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
-    dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
-    DSP_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    if (gen_kind == DSP_GEN_NOISE) {
+        // heightmap computed once per chunk column and reused up the stack (terrain_fill_region_noise_kernel)
+        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed};
+        // enough CTAs to fill the machine a few times over, but as tall a run per CTA as that allows
+        const uint64_t columns = static_cast<uint64_t>(dims[0]) * dims[2], want = static_cast<uint64_t>(ctx->num_sms) * 16;
+        uint32_t pieces = static_cast<uint32_t>(std::min<uint64_t>(dims[1], std::max<uint64_t>(1, (want + columns - 1) / columns)));
+        rp.ny = (dims[1] + pieces - 1) / pieces;
+        pieces = (dims[1] + rp.ny - 1) / rp.ny;
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(columns * pieces, static_cast<uint64_t>(ctx->num_sms) * 32));
+        dsp::terrain_fill_region_noise_kernel<<<grid, 256, 0, ctx->stream>>>(rp);
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 1;
+    } else {
+        dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
+            ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), n);
+        DSP_CUDA(ctx, cudaGetLastError());
+        dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed};
+        const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
+        dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches += 2;
+    }
     *out_first_slot = first;
     return DSP_OK;
 }

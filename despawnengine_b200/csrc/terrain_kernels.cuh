@@ -81,8 +81,6 @@ __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p
             }
             __syncthreads();  // s_h / s_lat reused by the next chunk of this CTA
         } else if (p.kind == 2) {
-            const uint32_t hzy = 0;  // (kept explicit: hash3 = mix32(hash2(seed,wx,wy) + wz*K))
-            (void)hzy;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t r0 = hash3(p.seed, wx0 + 2 * k, wy, wz), r1 = hash3(p.seed, wx0 + 2 * k + 1, wy, wz);
@@ -100,6 +98,92 @@ __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p
         uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
         dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
         dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// NOISE terrain for a whole box of chunks (dsp_generate_region).  The heightmap depends on (x, z) only, so one CTA
+// takes a chunk column (a, c) and a run of `ny` vertically stacked chunks: the 27 lattice hashes and the 256 column
+// heights are computed ONCE and reused for every chunk of the run; per chunk only the row compare/pack and the two
+// 128-bit stores per thread remain, and rows entirely below / above the surface of their z-slice skip the per-voxel
+// compare.  (The per-chunk kernel above spends 2,500 warp-instructions per chunk on the heights and is issue-bound at
+// 2.2 TB/s; this one is bound by the 8,192 bytes it writes per chunk.)  Same integer arithmetic as the oracle.
+struct RegionFillParams {
+    uint16_t* voxels;
+    int4* chunk_pos;     // written here as well: slot -> position
+    uint32_t first_slot;
+    int3 origin;
+    uint3 dims;
+    uint32_t ny;         // chunks of a column handled by one CTA
+    uint32_t seed;
+};
+
+__global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const RegionFillParams p) {
+    __shared__ uint32_t s_lat[3][9];
+    __shared__ int32_t s_h[256];
+    __shared__ int32_t s_zmin[16], s_zmax[16];
+    const int tid = threadIdx.x;
+    const uint32_t ypieces = (p.dims.y + p.ny - 1) / p.ny;
+    const uint64_t n_items = static_cast<uint64_t>(p.dims.x) * p.dims.z * ypieces;
+    for (uint64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const uint32_t a = static_cast<uint32_t>(item % p.dims.x);
+        const uint64_t t = item / p.dims.x;
+        const uint32_t c = static_cast<uint32_t>(t % p.dims.z), piece = static_cast<uint32_t>(t / p.dims.z);
+        const int32_t cx = p.origin.x + static_cast<int32_t>(a), cz = p.origin.z + static_cast<int32_t>(c);
+        const int32_t wx0 = cx * 16, wz0 = cz * 16;
+        if (tid < 27) {
+            const int o = tid / 9, q = tid % 9, s = 5 - o;
+            s_lat[o][q] = hash2(p.seed + static_cast<uint32_t>(o), (wx0 >> s) + q % 3, (wz0 >> s) + q / 3) & 0xFFU;
+        }
+        __syncthreads();
+        {
+            const int x = tid & 15, zc = tid >> 4;
+            uint32_t n = 0;
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+                const int s = 5 - o;
+                n += octave_from_lattice(s_lat[o], wx0 + x, wz0 + zc, wx0 >> s, wz0 >> s, o) << (2 - o);
+            }
+            const int32_t h = 16 + static_cast<int32_t>(n >> 3);
+            s_h[tid] = h;
+            // min / max of the 16 heights of this z-slice: the 16 threads of a slice are half a warp
+            int32_t lo = h, hi = h;
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+                hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+            }
+            if (x == 0) { s_zmin[zc] = lo; s_zmax[zc] = hi; }
+        }
+        __syncthreads();
+        const int y = tid & 15, z = tid >> 4;
+        const int32_t zlo = s_zmin[z], zhi = s_zmax[z];
+        const uint32_t b0 = piece * p.ny, b1 = min(p.dims.y, b0 + p.ny);
+        for (uint32_t b = b0; b < b1; ++b) {
+            const int32_t cy = p.origin.y + static_cast<int32_t>(b);
+            const int32_t wy = cy * 16 + y;
+            const uint32_t slot = p.first_slot + a + p.dims.x * (b + p.dims.y * c);
+            uint32_t w[8];
+            if (wy < zlo - 1) {            // whole row below every surface voxel of the slice: body block
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = 0x00010001u;
+            } else if (wy > zhi - 1) {     // whole row above the surface: air
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = 0u;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int32_t h0 = s_h[z * 16 + 2 * k], h1 = s_h[z * 16 + 2 * k + 1];
+                    const uint32_t v0 = wy < h0 - 1 ? 1u : (wy == h0 - 1 ? 2u : 0u);
+                    const uint32_t v1 = wy < h1 - 1 ? 1u : (wy == h1 - 1 ? 2u : 0u);
+                    w[k] = v0 | (v1 << 16);
+                }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            if (tid == 0) p.chunk_pos[slot] = make_int4(cx, cy, cz, 0);
+        }
+        __syncthreads();  // s_h / s_lat are rewritten for the next column
     }
 }
 

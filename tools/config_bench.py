@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Side benches for the BASELINE.json configs that are not the bench.py headline (one GPU):
+  config 1  single default chunk (reference terrain), latency of one build_chunk_mesh call through the C ABI
+  config 3  worst-case density: 3-D checkerboard (12,288 faces/chunk) and Bernoulli(0.5), 4,096 chunks
+  config 4  incremental remesh: 10,000 random place/destroy edits per frame over a 64x64x16-chunk world
+Prints one JSON line per config.  python tools/config_bench.py [--frames 20]
+"""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from despawnengine_b200 import capi
+
+UV = np.array([[0, 0, 0, 0], [0.0, 0.0, 0.5, 1.0], [0.5, 0.0, 1.0, 1.0]], dtype=np.float32)
+PEAK = 6453.1
+
+
+def kernel_ms(ctx, fn, reps):
+    fn(); ctx.sync()
+    n0, t0, _ = ctx.mesh_kernel_stats()
+    for _ in range(reps):
+        fn()
+    ctx.sync()
+    n1, t1, _ = ctx.mesh_kernel_stats()
+    return (t1 - t0) / (n1 - n0)
+
+
+def splitmix64(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x, z ^ (z >> 31)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=20)
+    args = ap.parse_args()
+    # ---- config 1 -----------------------------------------------------------------------------------------
+    with capi.Context(0, 64, 64 << 20) as ctx:
+        ctx.set_uv_table(UV)
+        slots = ctx.generate_chunks([(0, 0, 0)], capi.GEN_REFERENCE)
+        for _ in range(20):
+            ctx.mesh_chunks(slots)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            e, _ = ctx.mesh_chunks(slots)
+        call_us = (time.perf_counter() - t0) / 200 * 1e6
+        kms = kernel_ms(ctx, lambda: ctx.mesh_chunks_async(slots), 50)
+        print(json.dumps({"config": 1, "workload": "single default chunk (0,0,0), reference terrain", "faces": int(e[0]["vertex_count"]) // 6,
+                          "blocking_call_us": call_us, "kernel_us": kms * 1e3,
+                          "note": "one chunk cannot fill 148 SMs: this is launch + one CTA's latency, the batched call is the design point"}), flush=True)
+    # ---- config 3 -----------------------------------------------------------------------------------------
+    for name, kind, seed in (("3a checkerboard (12,288 faces/chunk, the maximum)", capi.GEN_CHECKER, 0), ("3b Bernoulli(0.5)", capi.GEN_RANDOM, 0xD5E50003)):
+        with capi.Context(0, 4096, 7 << 30) as ctx:
+            ctx.set_uv_table(UV)
+            first = ctx.generate_region((0, 0, 0), (16, 16, 16), kind, seed)
+            entries, total = ctx.mesh_range(first, 4096)
+            faces = int(entries["vertex_count"].astype(np.int64).sum()) // 6
+            algo = 4096 * (8192 + 32) + 120 * faces
+            kms = kernel_ms(ctx, lambda: ctx.mesh_range_async(first, 4096), 10)
+            print(json.dumps({"config": 3, "workload": name + ", 4,096 chunks", "faces": faces, "vertex_bytes": total, "kernel_ms": kms,
+                              "chunks_per_s": 4096 / (kms * 1e-3), "achieved_GBps": algo / (kms * 1e-3) / 1e9, "frac_of_measured_peak": algo / (kms * 1e-3) / 1e9 / PEAK}), flush=True)
+    # ---- config 4 -----------------------------------------------------------------------------------------
+    dims = (64, 16, 64)
+    n = dims[0] * dims[1] * dims[2]
+    with capi.Context(0, n, 4 << 30) as ctx:
+        ctx.set_uv_table(UV)
+        first = ctx.generate_region((0, 0, 0), dims, capi.GEN_NOISE, 0xD5E50001)
+        ctx.mesh_range(first, 1024)
+        state = 0xD5E50004
+        frame_ms, dirty_counts, apply_ms, mesh_ms = [], [], [], []
+        for frame in range(args.frames + 2):
+            edits = np.zeros(10000, dtype=capi.EDIT_DTYPE)
+            r = np.empty(40000, dtype=np.uint64)
+            for i in range(40000):
+                state, r[i] = splitmix64(state)
+            r = r.reshape(10000, 4)
+            edits["wx"] = (r[:, 0] % (dims[0] * 16)).astype(np.int32)
+            edits["wy"] = (r[:, 1] % (dims[1] * 16)).astype(np.int32)
+            edits["wz"] = (r[:, 2] % (dims[2] * 16)).astype(np.int32)
+            edits["block"] = (r[:, 3] & 1).astype(np.uint32)  # 50 % destroy / 50 % place dirt
+            ctx.sync()
+            t0 = time.perf_counter()
+            dirty = ctx.apply_edits(edits)
+            t1 = time.perf_counter()
+            entries, total = ctx.mesh_chunks(dirty)   # whole-chunk remesh of the dirty set: the reference's only granularity
+            t2 = time.perf_counter()
+            if frame >= 2:
+                frame_ms.append((t2 - t0) * 1e3); apply_ms.append((t1 - t0) * 1e3); mesh_ms.append((t2 - t1) * 1e3); dirty_counts.append(len(dirty))
+        print(json.dumps({"config": 4, "workload": "10,000 random block edits per frame over a 64x64x16-chunk world (65,536 chunks, 512 MiB voxels resident)",
+                          "frames": args.frames, "dirty_chunks_per_frame": float(np.mean(dirty_counts)), "frame_ms": float(np.median(frame_ms)),
+                          "apply_edits_ms": float(np.median(apply_ms)), "remesh_ms": float(np.median(mesh_ms)),
+                          "edits_per_s": 10000 / (np.median(frame_ms) * 1e-3), "dirty_chunks_per_s": float(np.mean(dirty_counts)) / (np.median(frame_ms) * 1e-3),
+                          "timing": "host wall clock around dsp_apply_edits + dsp_mesh_chunks (both blocking), edits in pageable host memory"}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,11 +46,18 @@ def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 40
     csv_txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    rows = [r for r in csv.reader(csv_txt.splitlines()) if len(r) > 6 and r[2].isdigit()]
+    # the page is a sequence of per-launch sections, each opened by a ["Kernel Name", <demangled name>] row
+    sections, cur = [], None
+    for r in csv.reader(csv_txt.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = [r[1] if len(r) > 1 else "", []]
+            sections.append(cur)
+        elif cur is not None and len(r) > 6 and r[2].isdigit():
+            cur[1].append(r)
     dis = disasm_lines(kern)
     n = len(dis)
-    assert n and len(rows) % n == 0, (len(rows), n)
-    rows = rows[:n]  # first launch
+    rows = next((rs for name, rs in sections if len(rs) == n), None)  # first launch whose SASS length matches the cubin's
+    assert n and rows is not None, (n, [(name[:40], len(rs)) for name, rs in sections])
     by_line = defaultdict(lambda: [0, 0, 0])  # samples, warp-instr, sass count
     for (loc, _), r in zip(dis, rows):
         b = by_line[loc]
