@@ -35,6 +35,12 @@ N_CHUNKS = DIMS[0] * DIMS[1] * DIMS[2]
 UV = np.array([[0, 0, 0, 0], [0.0, 0.0, 0.5, 1.0], [0.5, 0.0, 1.0, 1.0]], dtype=np.float32)
 WORKLOAD = "configs[1]: 16x16x16-chunk region (256^3 voxels) of seeded integer value-noise terrain, reference cull semantics, unit quads"
 METRIC = "chunks meshed/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE mesh_chunks_bump_kernel launch of this exact workload, from the
+# `ncu --set full` capture summarised in profiles/r01_final_ncu_full_summary.csv (33.66 MB read + 338.16 MB written; the
+# remaining ~59 MB of the 397 MB vertex stream was still dirty in the 126 MB L2 when the kernel ended).  Below the
+# algorithmic 430.5 MB, i.e. no wasted re-reads.
+NCU_TRAFFIC_BYTES = 33_662_208 + 338_164_736
+NCU_TRAFFIC_SOURCE = "profiles/r01_final_ncu_full_summary.csv (ncu --set full, one launch, same workload)"
 
 
 def region_positions(origin):
@@ -356,7 +362,8 @@ def main():
             "gpu_launches": int(launches),
             "wall_s_timed_region": wall1 - wall0,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "mesh_chunks_kernel (look-back, DSP_MESH_ORDERED)" if args.ordered else "mesh_chunks_bump_kernel", "kernel_ms_avg": kernel_ms_avg,
+                         "traffic": None if args.ordered else NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
+                         "kernel": "mesh_chunks_kernel (look-back, DSP_MESH_ORDERED)" if args.ordered else "mesh_chunks_bump_kernel", "kernel_ms_avg": kernel_ms_avg,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
                          "frac_of_8TBs_datasheet": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
