@@ -19,12 +19,12 @@ OK, ERR_BAD_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_ARENA_FULL, ERR_STORE_FULL, ERR_NO
 # dsp_gen_kind
 GEN_REFERENCE, GEN_NOISE, GEN_RANDOM, GEN_CHECKER = 0, 1, 2, 3
 # mesh modes
-MESH_PARITY, MESH_HALO, MESH_ORDERED = 0, 1, 2
+MESH_PARITY, MESH_HALO, MESH_ORDERED, MESH_GREEDY, MESH_INDEXED = 0, 1, 2, 4, 8
 NO_SLOT = 0xFFFFFFFF
 FACE_TOP, FACE_BOTTOM, FACE_REAR, FACE_FRONT, FACE_RIGHT, FACE_LEFT = range(6)
 OPPOSITE_FACE = (1, 0, 3, 2, 5, 4)
 
-MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("reserved", np.uint32)])
+MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("index_count", np.uint32)])
 EDIT_DTYPE = np.dtype([("wx", np.int32), ("wy", np.int32), ("wz", np.int32), ("block", np.uint32)])
 VERTEX_DTYPE = np.dtype([("position", np.float32, 3), ("tex_coords", np.float32, 2)])  # vertex.rs:5-12
 assert MESH_ENTRY_DTYPE.itemsize == 16 and EDIT_DTYPE.itemsize == 16 and VERTEX_DTYPE.itemsize == 20
@@ -270,6 +270,12 @@ class Context:
         """The vertex stream of one mesh entry as a structured array (empty <=> the reference's None)."""
         n = int(entry["vertex_count"])
         return self.download_arena(int(entry["offset_bytes"]), n * 20).view(VERTEX_DTYPE)
+
+    def download_indices(self, entry) -> np.ndarray:
+        """DSP_MESH_INDEXED: the chunk-local u32 indices of one mesh entry (they follow the vertices, 128-byte aligned)."""
+        n = int(entry["index_count"])
+        off = int(entry["offset_bytes"]) + ((int(entry["vertex_count"]) * 20 + 127) & ~127)
+        return self.download_arena(off, n * 4).view(np.uint32)
 
     def download_chunk(self, slot: int):
         ids = np.empty(4096, dtype=np.uint16)

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "mesh_kernels.cuh"
+#include "quad_kernels.cuh"
 #include "terrain_kernels.cuh"
 
 namespace {
@@ -55,6 +56,7 @@ struct dsp_ctx {
     int mesh_variant = 0;
     unsigned mesh_prefetch_mult = 2;  // L2 prefetch distance in units of the grid size (0 = off)
     int mesh_ctas_per_sm[4][4] = {};  // [variant][halo], filled on first launch
+    int quad_ctas_per_sm[8] = {};     // [halo + 2 greedy + 4 indexed]
 
     uint16_t* d_voxels = nullptr;
     int4* d_pos = nullptr;
@@ -267,10 +269,43 @@ int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
     }
 }
 
+// Quad modes (DSP_MESH_GREEDY / DSP_MESH_INDEXED): mesh_chunks_quads_kernel, always the atomic slot claim.
+template <bool HALO, bool GREEDY, bool INDEXED>
+int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
+    void (*kern)(const dsp::MeshParams) = dsp::mesh_chunks_quads_kernel<HALO, GREEDY, INDEXED>;
+    constexpr int smem = dsp::QuadSmem::kBytes;
+    int& occ = ctx->quad_ctas_per_sm[(HALO ? 1 : 0) + (GREEDY ? 2 : 0) + (INDEXED ? 4 : 0)];
+    if (occ == 0) {
+        DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        if (occ < 1) return fail(ctx, DSP_ERR_INTERNAL, "quad mesh kernel does not fit on an SM (smem %d)", smem);
+    }
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, static_cast<uint64_t>(ctx->num_sms) * occ));
+    const int e = ctx->ev_next;
+    int rc = drain_kernel_event(ctx, e);
+    if (rc != DSP_OK) return rc;
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k0[e], ctx->stream));
+    kern<<<grid, 256, smem, ctx->stream>>>(p);
+    DSP_CUDA(ctx, cudaGetLastError());
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k1[e], ctx->stream));
+    ctx->ev_pending[e] = true;
+    ctx->ev_next = (e + 1) % dsp_ctx::kEvRing;
+    ctx->launches++;
+    return DSP_OK;
+}
+template <bool HALO>
+int launch_quads(dsp_ctx* ctx, const dsp::MeshParams& p, uint32_t mode) {
+    const bool g = (mode & DSP_MESH_GREEDY) != 0, i = (mode & DSP_MESH_INDEXED) != 0;
+    if (g) return i ? launch_quads_t<HALO, true, true>(ctx, p) : launch_quads_t<HALO, true, false>(ctx, p);
+    return launch_quads_t<HALO, false, true>(ctx, p);
+}
+
 int build_neighbour_table(dsp_ctx* ctx);
 
 int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offset) {
-    if (mode & ~(DSP_MESH_HALO | DSP_MESH_ORDERED)) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
+    if (mode & ~(DSP_MESH_HALO | DSP_MESH_ORDERED | DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
+    if ((mode & DSP_MESH_ORDERED) && (mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)))
+        return fail(ctx, DSP_ERR_BAD_ARG, "DSP_MESH_ORDERED is not available with DSP_MESH_GREEDY / DSP_MESH_INDEXED");
     if (arena_offset % DSP_SLOT_ALIGN != 0 || arena_offset > ctx->arena_bytes)
         return fail(ctx, DSP_ERR_BAD_ARG, "arena_offset %llu must be a multiple of 128 and <= arena size", (unsigned long long)arena_offset);
     if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_BAD_ARG, "n = %llu exceeds max_chunks", (unsigned long long)n);
@@ -299,6 +334,7 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
     p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
+    if (mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return halo ? launch_quads<true>(ctx, p, mode) : launch_quads<false>(ctx, p, mode);
     if (mode & DSP_MESH_ORDERED) return halo ? launch_mesh_variant<true, true>(ctx, p) : launch_mesh_variant<false, true>(ctx, p);
     return halo ? launch_mesh_variant<true, false>(ctx, p) : launch_mesh_variant<false, false>(ctx, p);
 }

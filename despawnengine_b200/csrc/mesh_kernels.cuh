@@ -32,7 +32,7 @@ namespace dsp {
 struct MeshEntry {  // == dsp_mesh_entry
     uint64_t offset_bytes;
     uint32_t vertex_count;
-    uint32_t reserved;
+    uint32_t index_count;
 };
 
 struct MeshParams {
@@ -147,6 +147,48 @@ struct MeshCfg {
     static constexpr int kBytes = kNext + 8;
 };
 
+// The six 16-bit face masks of x-row r = y + 16 z (bit x set: that face of voxel (x, y, z) is emitted), from the row
+// occupancy masks of the chunk in shared memory.  chunk_mesh.rs:46-51.
+struct FaceMasks {
+    uint32_t top, bot, rear, front, right, left;
+};
+template <bool HALO>
+__device__ __forceinline__ FaceMasks row_face_masks(const MeshParams& p, uint32_t slot, const uint16_t* s_rowmask, int r, int y, int z, uint32_t m) {
+    // chunk_mesh.rs:46-51: outside the chunk counts as air (mask 0) in parity mode
+    uint32_t up = y < 15 ? s_rowmask[r + 1] : 0u;
+    uint32_t dn = y > 0 ? s_rowmask[r - 1] : 0u;
+    uint32_t re = z > 0 ? s_rowmask[r - 16] : 0u;
+    uint32_t fr = z < 15 ? s_rowmask[r + 16] : 0u;
+    uint32_t xm = 0u, xp = 0u;  // occupancy of the voxel beyond x = 0 / x = 15
+    if (HALO) {
+        // extension: consult the resident neighbour across each border (DSP_MESH_HALO)
+        const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot) * 6;
+        // occupancy of 16 consecutive voxels: row `nr` of a resident neighbour chunk, or row `sr` of a received slab
+        auto row_mask_of = [&](uint32_t code, int nr, int sr) -> uint32_t {
+            const uint16_t* base = (code & kNbrExternal) ? p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sr * 16
+                                                         : p.voxels + static_cast<size_t>(code) * kChunkVoxels + nr * 16;
+            const uint4* q = reinterpret_cast<const uint4*>(base);
+            return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
+        };
+        auto voxel_of = [&](uint32_t code, int vidx, int sidx) -> uint32_t {
+            return (code & kNbrExternal) ? __ldg(p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sidx)
+                                         : __ldg(p.voxels + static_cast<size_t>(code) * kChunkVoxels + vidx);
+        };
+        // slab layouts: +-Y faces [z][x], +-Z faces [y][x], +-X faces [z][y] (== row index r)
+        if (y == 15) { const uint32_t s = __ldg(nb + 0); if (s != kNbrNone) up = row_mask_of(s, 0 + 16 * z, z); }
+        if (y == 0) { const uint32_t s = __ldg(nb + 1); if (s != kNbrNone) dn = row_mask_of(s, 15 + 16 * z, z); }
+        if (z == 0) { const uint32_t s = __ldg(nb + 2); if (s != kNbrNone) re = row_mask_of(s, y + 16 * 15, y); }
+        if (z == 15) { const uint32_t s = __ldg(nb + 3); if (s != kNbrNone) fr = row_mask_of(s, y, y); }
+        { const uint32_t s = __ldg(nb + 4); if (s != kNbrNone) xm = voxel_of(s, r * 16 + 15, r) != 0; }
+        { const uint32_t s = __ldg(nb + 5); if (s != kNbrNone) xp = voxel_of(s, r * 16, r) != 0; }
+    }
+    FaceMasks f;
+    f.top = m & ~up; f.bot = m & ~dn; f.rear = m & ~re; f.front = m & ~fr;
+    f.right = m & ~((m << 1) | xm);
+    f.left = m & ~((m >> 1) | (xp << 15));
+    return f;
+}
+
 // Per-thread result of the count phase for one chunk (thread r owns x-row r = y + 16 z).
 struct RowFaces {
     uint32_t top, bot, rear, front, right, left;  // 16-bit face masks of this row
@@ -217,38 +259,11 @@ struct MeshCta {
         }
         s_rowmask[r] = static_cast<uint16_t>(m);
         __syncthreads();
-        // chunk_mesh.rs:46-51: outside the chunk counts as air (mask 0) in parity mode
-        uint32_t up = y < 15 ? s_rowmask[r + 1] : 0u;
-        uint32_t dn = y > 0 ? s_rowmask[r - 1] : 0u;
-        uint32_t re = z > 0 ? s_rowmask[r - 16] : 0u;
-        uint32_t fr = z < 15 ? s_rowmask[r + 16] : 0u;
-        uint32_t xm = 0u, xp = 0u;  // occupancy of the voxel beyond x = 0 / x = 15
-        if (HALO) {
-            // extension: consult the resident neighbour across each border (DSP_MESH_HALO)
-            const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot_of(chunk)) * 6;
-            // occupancy of 16 consecutive voxels: row `nr` of a resident neighbour chunk, or row `sr` of a received slab
-            auto row_mask_of = [&](uint32_t code, int nr, int sr) -> uint32_t {
-                const uint16_t* base = (code & kNbrExternal) ? p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sr * 16
-                                                             : p.voxels + static_cast<size_t>(code) * kChunkVoxels + nr * 16;
-                const uint4* q = reinterpret_cast<const uint4*>(base);
-                return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
-            };
-            auto voxel_of = [&](uint32_t code, int vidx, int sidx) -> uint32_t {
-                return (code & kNbrExternal) ? __ldg(p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sidx)
-                                             : __ldg(p.voxels + static_cast<size_t>(code) * kChunkVoxels + vidx);
-            };
-            // slab layouts: +-Y faces [z][x], +-Z faces [y][x], +-X faces [z][y] (== row index r)
-            if (y == 15) { const uint32_t s = __ldg(nb + 0); if (s != kNbrNone) up = row_mask_of(s, 0 + 16 * z, z); }
-            if (y == 0) { const uint32_t s = __ldg(nb + 1); if (s != kNbrNone) dn = row_mask_of(s, 15 + 16 * z, z); }
-            if (z == 0) { const uint32_t s = __ldg(nb + 2); if (s != kNbrNone) re = row_mask_of(s, y + 16 * 15, y); }
-            if (z == 15) { const uint32_t s = __ldg(nb + 3); if (s != kNbrNone) fr = row_mask_of(s, y, y); }
-            { const uint32_t s = __ldg(nb + 4); if (s != kNbrNone) xm = voxel_of(s, r * 16 + 15, r) != 0; }
-            { const uint32_t s = __ldg(nb + 5); if (s != kNbrNone) xp = voxel_of(s, r * 16, r) != 0; }
-        }
         RowFaces f;
-        f.top = m & ~up; f.bot = m & ~dn; f.rear = m & ~re; f.front = m & ~fr;
-        f.right = m & ~((m << 1) | xm);
-        f.left = m & ~((m >> 1) | (xp << 15));
+        {
+            const FaceMasks fm = row_face_masks<HALO>(p, HALO ? slot_of(chunk) : 0u, s_rowmask, r, y, z, m);
+            f.top = fm.top; f.bot = fm.bot; f.rear = fm.rear; f.front = fm.front; f.right = fm.right; f.left = fm.left;
+        }
         f.cnt = __popc(f.top) + __popc(f.bot) + __popc(f.rear) + __popc(f.front) + __popc(f.right) + __popc(f.left);
         uint32_t incl = f.cnt;
 #pragma unroll

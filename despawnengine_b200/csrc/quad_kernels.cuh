@@ -1,0 +1,417 @@
+// Quad modes of the mesher (sm_100a): greedy run-stack merge (DSP_MESH_GREEDY) and/or the indexed layout
+// (DSP_MESH_INDEXED).  Extensions named by SURVEY.md section 8f-2; the reference emits one unit quad per visible face
+// as six vertices (/root/reference/src/content/world/chunks/chunk_mesh.rs:65-106) and draws non-indexed
+// (src/engine/scenes/scene_game.rs:118-122).  The spec lives with the oracle (oracle/mesher_oracle.cpp, "extension
+// oracle: greedy run-stack merge"); in short:
+//   * per direction the face plane has a run axis u and a stack axis v (TOP/BOTTOM: x,z; REAR/FRONT: x,y; RIGHT/LEFT: y,z);
+//   * a RUN is a maximal interval along u of visible faces with equal block id; a QUAD is a maximal chain of
+//     identical runs (same start, length, id) in consecutive rows along v;
+//   * quads leave in the reference's order applied to their anchor (smallest voxel index): anchor ascending, then
+//     TOP, BOTTOM, REAR, FRONT, RIGHT, LEFT; every corner uses the reference's arithmetic for the voxel under it.
+// No decision depends on an earlier one, so all 256 rows of a chunk decide at once:
+//   1. thread r (x-row r = y + 16 z) holds the six 16-bit face masks of its row and three id-equality masks
+//      (towards x-1, y-1, z-1);
+//   2. for RIGHT/LEFT the run axis is y: the 16 rows of a z-slice sit in 16 lanes of one warp, so the row masks are
+//      turned into column masks (bit = y) by a 4-step butterfly of warp shuffles, two 16-bit matrices per register;
+//   3. a run is a (start bit, end bit) pair of the row mask; comparing a row with its predecessor along v gives the
+//      mask of CONTINUED runs, anchors = starts & ~continued; height = how many following rows continue the run;
+//   4. anchors are counted, scanned (warp shuffle + 8-way), the slot is claimed with one atomic, records
+//      (anchor, direction, w, h) are written in stream order and expanded one thread per quad into a staging tile that
+//      leaves with one bulk (TMA) store -- the same back half as mesh_chunks_bump_kernel.
+// Algorithmic HBM bytes per chunk: 8,192 + 120 Q (stream) or 8,192 + 104 Q (indexed: 4 x 20-byte vertices + 6 u32) + 32.
+#pragma once
+#include "mesh_kernels.cuh"
+
+namespace dsp {
+
+constexpr int kQuadVertexBytesIdx = 80;   // 4 vertices
+constexpr int kQuadIndexBytes = 24;       // 6 x u32
+constexpr uint32_t kQuadRecCap = 4096;    // records per window (u32 each)
+
+struct QuadSmem {
+    static constexpr int kVox = 0;                               // 2 x 8192
+    static constexpr int kStage = 2 * kChunkBytes;               // 30720: 256 quads (stream) or 20480 + 6144 (indexed)
+    static constexpr int kRec = kStage + kTileBytes;             // kQuadRecCap x u32
+    static constexpr int kRowMask = kRec + kQuadRecCap * 4;      // 256 x u16
+    static constexpr int kF = kRowMask + kRows * 2;              // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
+    static constexpr int kEqx = kF + 4 * kRows * 2;              // [256] u16
+    static constexpr int kFT = kEqx + kRows * 2;                 // [2][256] u16: RIGHT, LEFT masks per column (bit = y)
+    static constexpr int kEqRunT = kFT + 2 * kRows * 2;          // [256] u16: id equality towards y-1, per column
+    static constexpr int kC = kEqRunT + kRows * 2;               // [4][256] u16 continued-run masks per row
+    static constexpr int kCT = kC + 4 * kRows * 2;               // [2][256] u16 continued-run masks per column
+    static constexpr int kA = kCT + 2 * kRows * 2;               // [6][256] u16 anchor masks per row
+    static constexpr int kFirst = kA + 6 * kRows * 2;            // [256] u16 ordinal of the row's first quad
+    static constexpr int kWarpTot = kFirst + kRows * 2;          // 8 x u32 (+ pad)
+    static constexpr int kBar = kWarpTot + 64;                   // 2 x u64
+    static constexpr int kBase = kBar + 16;                      // u64
+    static constexpr int kNext = kBase + 8;                      // 2 x u32
+    static constexpr int kBytes = kNext + 8;
+};
+static_assert(QuadSmem::kBytes <= 76800, "three CTAs per SM");
+
+// 16x16 bit-matrix transpose across the 16 lanes of a half warp, two matrices at once (low / high half of v):
+// lane i holds row i; afterwards lane i holds column i.  Four shuffle steps.
+__device__ __forceinline__ uint32_t transpose16x16_pair(uint32_t v, int lane) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int j = 8 >> s;
+        const uint32_t mk = s == 0 ? 0x00FF00FFu : s == 1 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
+        v = (lane & j) ? (((other >> j) & mk) | (v & ~mk)) : ((v & mk) | ((other & mk) << j));
+    }
+    return v;
+}
+
+// bit x = ids equal at position x of two rows of 16 u16 (held as 8 words each)
+__device__ __forceinline__ uint32_t eq_mask16(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+    const uint32_t d[8] = {a0.x ^ b0.x, a0.y ^ b0.y, a0.z ^ b0.z, a0.w ^ b0.w, a1.x ^ b1.x, a1.y ^ b1.y, a1.z ^ b1.z, a1.w ^ b1.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        m |= (d[k] & 0xFFFFu) ? 0u : (1u << (2 * k));
+        m |= (d[k] >> 16) ? 0u : (2u << (2 * k));
+    }
+    return m;
+}
+// bit x (x >= 1) = id[x] == id[x-1] within one row
+__device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 a0, const uint4 a1) {
+    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        m |= ((w[k] & 0xFFFFu) == (w[k] >> 16)) ? (2u << (2 * k)) : 0u;
+        if (k > 0) m |= ((w[k] & 0xFFFFu) == (w[k - 1] >> 16)) ? (1u << (2 * k)) : 0u;
+    }
+    return m;
+}
+
+__device__ __forceinline__ uint32_t run_starts(uint32_t f, uint32_t eq) { return f & ~((f << 1) & eq); }
+__device__ __forceinline__ uint32_t run_ends(uint32_t f, uint32_t eq) { return f & ~((f >> 1) & (eq >> 1)); }
+
+// start bits of row b whose run is identical (start, end, block id) to a run of the previous row a
+__device__ __forceinline__ uint32_t continued_runs(uint32_t fa, uint32_t eqa, uint32_t fb, uint32_t eqb, uint32_t eqv) {
+    const uint32_t eb = run_ends(fb, eqb);
+    uint32_t cand = run_starts(fa, eqa) & run_starts(fb, eqb) & eqv;
+    const uint32_t diff = run_ends(fa, eqa) ^ eb;
+    uint32_t out = 0;
+    while (cand) {
+        const int u0 = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const int len1 = __ffs(eb >> u0) - 1;  // run length - 1
+        if (((diff >> u0) & ((2u << len1) - 1u)) == 0u) out |= 1u << u0;
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint64_t quad_slot_bytes(uint32_t quads, bool indexed) {
+    const uint64_t a = kSlotAlign - 1;
+    if (!indexed) return (static_cast<uint64_t>(quads) * kFaceBytes + a) & ~a;
+    return ((static_cast<uint64_t>(quads) * kQuadVertexBytesIdx + a) & ~a) + ((static_cast<uint64_t>(quads) * kQuadIndexBytes + a) & ~a);
+}
+
+// Corners of one quad record: positions lo/hi per axis and the block's mapped uv row.
+struct QuadGeom {
+    float lx, hx, ly, hy, lz, hz;
+    float4 uv;
+    uint32_t code;
+};
+__device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox, float cbx, float cby, float cbz,
+                                              const float4* __restrict__ uvmap, uint32_t n_blocks) {
+    const uint32_t idx = rec & 0xFFFu, d = (rec >> 12) & 7u, w1 = (rec >> 15) & 15u, h1 = (rec >> 19) & 15u;
+    const uint32_t id = vox[idx];
+    QuadGeom g;
+    g.uv = __ldg(&uvmap[id < n_blocks ? id : n_blocks]);
+    const uint32_t ax = idx & 15u, ay = (idx >> 4) & 15u, az = idx >> 8;
+    // far cell per axis: TOP/BOTTOM run x, stack z; REAR/FRONT run x, stack y; RIGHT/LEFT run y, stack z
+    const uint32_t fx = ax + (d < 4u ? w1 : 0u);
+    const uint32_t fy = ay + (d >= 4u ? w1 : ((d & 6u) == 2u ? h1 : 0u));
+    const uint32_t fz = az + (d < 2u || d >= 4u ? h1 : 0u);
+    // chunk_mesh.rs:61-62,67: template +-0.5 added to ((local as f32) + (chunk as f32 * 16.0)) of the voxel under the corner
+    g.lx = __fadd_rn(-0.5f, __fadd_rn(__uint2float_rn(ax), cbx));  g.hx = __fadd_rn(0.5f, __fadd_rn(__uint2float_rn(fx), cbx));
+    g.ly = __fadd_rn(-0.5f, __fadd_rn(__uint2float_rn(ay), cby));  g.hy = __fadd_rn(0.5f, __fadd_rn(__uint2float_rn(fy), cby));
+    g.lz = __fadd_rn(-0.5f, __fadd_rn(__uint2float_rn(az), cbz));  g.hz = __fadd_rn(0.5f, __fadd_rn(__uint2float_rn(fz), cbz));
+    g.code = static_cast<uint32_t>((d < 3 ? kCodes0 >> (20 * d) : kCodes1 >> (20 * (d - 3))) & 0xFFFFFu);
+    return g;
+}
+
+template <bool HALO, bool GREEDY, bool INDEXED>
+__global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint16_t* const s_vox = reinterpret_cast<uint16_t*>(smem + QuadSmem::kVox);
+    float* const s_stage = reinterpret_cast<float*>(smem + QuadSmem::kStage);
+    uint32_t* const s_rec = reinterpret_cast<uint32_t*>(smem + QuadSmem::kRec);
+    uint16_t* const s_rowmask = reinterpret_cast<uint16_t*>(smem + QuadSmem::kRowMask);
+    uint16_t* const s_F = reinterpret_cast<uint16_t*>(smem + QuadSmem::kF);
+    uint16_t* const s_eqx = reinterpret_cast<uint16_t*>(smem + QuadSmem::kEqx);
+    uint16_t* const s_FT = reinterpret_cast<uint16_t*>(smem + QuadSmem::kFT);
+    uint16_t* const s_eqrunT = reinterpret_cast<uint16_t*>(smem + QuadSmem::kEqRunT);
+    uint16_t* const s_C = reinterpret_cast<uint16_t*>(smem + QuadSmem::kC);
+    uint16_t* const s_CT = reinterpret_cast<uint16_t*>(smem + QuadSmem::kCT);
+    uint16_t* const s_A = reinterpret_cast<uint16_t*>(smem + QuadSmem::kA);
+    uint16_t* const s_first = reinterpret_cast<uint16_t*>(smem + QuadSmem::kFirst);
+    uint32_t* const s_warp = reinterpret_cast<uint32_t*>(smem + QuadSmem::kWarpTot);
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + QuadSmem::kBar);
+    uint64_t* const s_base = reinterpret_cast<uint64_t*>(smem + QuadSmem::kBase);
+    uint32_t* const s_next = reinterpret_cast<uint32_t*>(smem + QuadSmem::kNext);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = tid, y = r & 15, z = r >> 4;   // as a row thread: x-row (y, z), masks over x
+    const int tx = tid & 15;                      // as a column thread: column (tx, z), masks over y
+    auto slot_of = [&](uint32_t chunk) -> uint32_t { return p.slot_list ? __ldg(p.slot_list + chunk) : p.first_slot + chunk; };
+    auto issue_load = [&](uint32_t chunk, int buf) {
+        mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
+        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
+    };
+
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+        const uint32_t t0 = atomicAdd(p.ticket, 1u);
+        s_next[0] = t0;
+        if (t0 < p.n) issue_load(t0, 0);
+    }
+    __syncthreads();
+    uint32_t cur = s_next[0];
+    uint32_t it = 0;
+    while (cur < p.n) {
+        const int buf = it & 1;
+        if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
+            const uint32_t t = atomicAdd(p.ticket, 1u);
+            s_next[(it + 1) & 1] = t;
+            if (t < p.n) issue_load(t, buf ^ 1);
+        }
+        const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
+        mbar_wait(&s_bar[buf], (it >> 1) & 1);
+        const uint16_t* vox = s_vox + buf * kChunkVoxels;
+
+        // ---- 1. row occupancy, id-equality towards x-1
+        uint4 qa, qb;
+        uint32_t m;
+        {
+            const uint4* rowp = reinterpret_cast<const uint4*>(vox + r * 16);
+            const int h = (r >> 2) & 1;  // alternate which half is read first: conflict-free LDS.128
+            const uint4 q0 = rowp[h], q1 = rowp[h ^ 1];
+            qa = h ? q1 : q0;
+            qb = h ? q0 : q1;
+            m = nonzero_mask8(qa) | (nonzero_mask8(qb) << 8);
+        }
+        s_rowmask[r] = static_cast<uint16_t>(m);
+        __syncthreads();
+
+        // ---- 2. face masks (chunk_mesh.rs:46-51); anchors = faces unless merging
+        const FaceMasks fm = row_face_masks<HALO>(p, HALO ? slot_of(cur) : 0u, s_rowmask, r, y, z, m);
+        uint32_t A[6] = {fm.top, fm.bot, fm.rear, fm.front, fm.right, fm.left};
+        uint32_t fT[2] = {0u, 0u}, AT[2] = {0u, 0u}, eqx = 0u, eqrunT = 0u;
+        if (GREEDY) {
+            eqx = eq_prev_mask16(qa, qb);
+            uint32_t eqy = 0u, eqz = 0u;
+            if (y > 0) { const uint4* q = reinterpret_cast<const uint4*>(vox + (r - 1) * 16); eqy = eq_mask16(qa, qb, q[0], q[1]); }
+            if (z > 0) { const uint4* q = reinterpret_cast<const uint4*>(vox + (r - 16) * 16); eqz = eq_mask16(qa, qb, q[0], q[1]); }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) s_F[d * kRows + r] = static_cast<uint16_t>(A[d]);
+            s_eqx[r] = static_cast<uint16_t>(eqx);
+            // RIGHT / LEFT run along y: rows -> columns (lane l of a half warp: row y = l  ->  column x = l, same z)
+            const uint32_t tf = transpose16x16_pair(A[4] | (A[5] << 16), lane);
+            const uint32_t te = transpose16x16_pair(eqy | (eqz << 16), lane);
+            fT[0] = tf & 0xFFFFu; fT[1] = tf >> 16;
+            eqrunT = te & 0xFFFFu;
+            const uint32_t eqstackT = te >> 16;
+            s_FT[tid] = static_cast<uint16_t>(fT[0]);
+            s_FT[kRows + tid] = static_cast<uint16_t>(fT[1]);
+            s_eqrunT[tid] = static_cast<uint16_t>(eqrunT);
+            __syncthreads();
+            // ---- 3. continued runs -> anchors
+            uint32_t Cm[4] = {0u, 0u, 0u, 0u};
+            if (z > 0) {
+                const uint32_t eqa = s_eqx[r - 16];
+                Cm[0] = continued_runs(s_F[0 * kRows + r - 16], eqa, A[0], eqx, eqz);
+                Cm[1] = continued_runs(s_F[1 * kRows + r - 16], eqa, A[1], eqx, eqz);
+            }
+            if (y > 0) {
+                const uint32_t eqa = s_eqx[r - 1];
+                Cm[2] = continued_runs(s_F[2 * kRows + r - 1], eqa, A[2], eqx, eqy);
+                Cm[3] = continued_runs(s_F[3 * kRows + r - 1], eqa, A[3], eqx, eqy);
+            }
+            uint32_t CT[2] = {0u, 0u};
+            if (z > 0) {
+                const uint32_t eqa = s_eqrunT[tid - 16];
+                CT[0] = continued_runs(s_FT[tid - 16], eqa, fT[0], eqrunT, eqstackT);
+                CT[1] = continued_runs(s_FT[kRows + tid - 16], eqa, fT[1], eqrunT, eqstackT);
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                s_C[d * kRows + r] = static_cast<uint16_t>(Cm[d]);
+                A[d] = run_starts(A[d], eqx) & ~Cm[d];
+            }
+            s_CT[tid] = static_cast<uint16_t>(CT[0]);
+            s_CT[kRows + tid] = static_cast<uint16_t>(CT[1]);
+            AT[0] = run_starts(fT[0], eqrunT) & ~CT[0];
+            AT[1] = run_starts(fT[1], eqrunT) & ~CT[1];
+            const uint32_t ta = transpose16x16_pair(AT[0] | (AT[1] << 16), lane);  // columns -> rows
+            A[4] = ta & 0xFFFFu;
+            A[5] = ta >> 16;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) s_A[d * kRows + r] = static_cast<uint16_t>(A[d]);
+        }
+
+        // ---- 4. count, scan
+        const uint32_t cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]) + __popc(A[4]) + __popc(A[5]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t wpre = 0, Q = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t v = s_warp[w];
+            wpre += w < warp ? v : 0u;
+            Q += v;
+        }
+        const uint32_t first = wpre + incl - cnt;
+        if (GREEDY) s_first[r] = static_cast<uint16_t>(first);
+        if (tid == 0) {  // claim the chunk's arena slot
+            const uint64_t bytes = quad_slot_bytes(Q, INDEXED);
+            const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
+            *s_base = base;
+            if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
+            p.entries[cur] = MeshEntry{p.arena_offset + base, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
+        }
+        const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
+        const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
+        const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
+
+        if (GREEDY) __syncthreads();  // s_first is read by the column threads below
+
+        // ---- 5./6. records of a window of quads, then their expansion
+        for (uint32_t q0 = 0; q0 == 0 || q0 < Q; q0 += kQuadRecCap) {
+            if (q0 > 0) __syncthreads();  // the previous window's records are consumed
+            if (cnt) {
+                uint32_t ord = first - q0;  // wraps below the window; the unsigned compare rejects those
+                const uint32_t rbase = static_cast<uint32_t>(r) << 4;
+#pragma unroll 1
+                for (int x = 0; x < 16; ++x) {
+                    const uint32_t six = ((A[0] >> x) & 1u) | (((A[1] >> x) & 1u) << 1) | (((A[2] >> x) & 1u) << 2) |
+                                         (((A[3] >> x) & 1u) << 3) | (((A[4] >> x) & 1u) << 4) | (((A[5] >> x) & 1u) << 5);
+                    if (!six) continue;
+#pragma unroll
+                    for (uint32_t d = 0; d < 6; ++d) {
+                        if (!((six >> d) & 1u)) continue;
+                        if (ord < kQuadRecCap && (!GREEDY || d < 4u)) {
+                            uint32_t rec = (rbase + x) | (d << 12);
+                            if (GREEDY) {
+                                // run length from the row's end mask; height = rows along the stack axis that continue it
+                                const uint32_t fmask = d == 0 ? fm.top : d == 1 ? fm.bot : d == 2 ? fm.rear : fm.front;
+                                const uint32_t w1 = __ffs(run_ends(fmask, eqx) >> x) - 1;
+                                const int stride = d < 2u ? 16 : 1;
+                                const int left = d < 2u ? 15 - z : 15 - y;
+                                int h1 = 0;
+                                while (h1 < left && ((s_C[d * kRows + r + (h1 + 1) * stride] >> x) & 1u)) ++h1;
+                                rec |= (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
+                            }
+                            s_rec[ord] = rec;
+                        }
+                        ++ord;
+                    }
+                }
+            }
+            if (GREEDY) {
+                // RIGHT / LEFT anchors are known to the column threads: column (tx, z), anchor bit = y
+#pragma unroll
+                for (int dd = 0; dd < 2; ++dd) {
+                    uint32_t am = AT[dd];
+                    while (am) {
+                        const int y0 = __ffs(am) - 1;
+                        am &= am - 1;
+                        const int row = y0 + 16 * z;
+                        // ordinal: first quad of the anchor's row + anchors of that row that precede (tx, direction)
+                        const uint32_t below = (1u << tx) - 1u;
+                        uint32_t ord = s_first[row];
+#pragma unroll
+                        for (int d = 0; d < 6; ++d) {
+                            const uint32_t a = s_A[d * kRows + row];
+                            ord += __popc(a & below) + ((d < 4 + dd) ? ((a >> tx) & 1u) : 0u);
+                        }
+                        ord -= q0;
+                        if (ord < kQuadRecCap) {
+                            const uint32_t w1 = __ffs(run_ends(fT[dd], eqrunT) >> y0) - 1;
+                            int h1 = 0;
+                            while (h1 < 15 - z && ((s_CT[dd * kRows + tid + (h1 + 1) * 16] >> y0) & 1u)) ++h1;
+                            s_rec[ord] = static_cast<uint32_t>(tx + 16 * y0 + 256 * z) | (static_cast<uint32_t>(4 + dd) << 12) | (w1 << 15) |
+                                         (static_cast<uint32_t>(h1) << 19);
+                        }
+                    }
+                }
+            }
+            __syncthreads();  // records and s_base visible
+            const uint64_t base = *s_base;
+            const bool fits = base + quad_slot_bytes(Q, INDEXED) <= p.arena_room;
+            uint8_t* const gout = p.arena + base;
+            uint8_t* const gidx = gout + ((static_cast<uint64_t>(Q) * kQuadVertexBytesIdx + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1));
+            const uint32_t q1 = min(Q, q0 + kQuadRecCap);
+            for (uint32_t f0 = q0; f0 < q1; f0 += kTileFaces) {
+                if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
+                __syncthreads();
+                const uint32_t f = f0 + tid;
+                if (f < Q) {
+                    const QuadGeom g = quad_geom(s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
+                    float cx[4], cy[4], cz[4], cu[4], cv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t c = g.code >> (5 * k);
+                        cx[k] = (c & 1u) ? g.hx : g.lx;
+                        cy[k] = (c & 2u) ? g.hy : g.ly;
+                        cz[k] = (c & 4u) ? g.hz : g.lz;
+                        cu[k] = (c & 8u) ? g.uv.z : g.uv.x;
+                        cv[k] = (c & 16u) ? g.uv.w : g.uv.y;
+                    }
+                    if (INDEXED) {
+                        float4* o = reinterpret_cast<float4*>(s_stage + tid * 20);  // 80 bytes: 5 conflict-free STS.128
+                        o[0] = make_float4(cx[0], cy[0], cz[0], cu[0]);
+                        o[1] = make_float4(cv[0], cx[1], cy[1], cz[1]);
+                        o[2] = make_float4(cu[1], cv[1], cx[2], cy[2]);
+                        o[3] = make_float4(cz[2], cu[2], cv[2], cx[3]);
+                        o[4] = make_float4(cy[3], cz[3], cu[3], cv[3]);
+                        uint2* io = reinterpret_cast<uint2*>(s_stage + 256 * 20 + tid * 6);  // 24 bytes: 3 conflict-free STS.64
+                        const uint32_t v0 = f * 4u;
+                        io[0] = make_uint2(v0, v0 + 1u);
+                        io[1] = make_uint2(v0 + 2u, v0 + 2u);
+                        io[2] = make_uint2(v0 + 3u, v0);
+                    } else {
+                        float2* o = reinterpret_cast<float2*>(s_stage + tid * kFaceWords);
+                        o[0] = make_float2(cx[0], cy[0]);   o[1] = make_float2(cz[0], cu[0]);   o[2] = make_float2(cv[0], cx[1]);
+                        o[3] = make_float2(cy[1], cz[1]);   o[4] = make_float2(cu[1], cv[1]);   o[5] = make_float2(cx[2], cy[2]);
+                        o[6] = make_float2(cz[2], cu[2]);   o[7] = make_float2(cv[2], cx[2]);   o[8] = make_float2(cy[2], cz[2]);
+                        o[9] = make_float2(cu[2], cv[2]);   o[10] = make_float2(cx[3], cy[3]);  o[11] = make_float2(cz[3], cu[3]);
+                        o[12] = make_float2(cv[3], cx[0]);  o[13] = make_float2(cy[0], cz[0]);  o[14] = make_float2(cu[0], cv[0]);
+                    }
+                } else if (f == Q && (Q & 1u)) {  // odd count: pad the last 16-byte unit with zeros (inside the slot's alignment gap)
+                    if (INDEXED) *reinterpret_cast<uint2*>(s_stage + 256 * 20 + tid * 6) = make_uint2(0u, 0u);
+                    else *reinterpret_cast<float2*>(s_stage + tid * kFaceWords) = make_float2(0.0f, 0.0f);
+                }
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0 && fits) {
+                    const uint32_t nq = min(static_cast<uint32_t>(kTileFaces), Q - f0);
+                    if (INDEXED) {
+                        bulk_store(gout + static_cast<size_t>(f0) * kQuadVertexBytesIdx, s_stage, nq * kQuadVertexBytesIdx);
+                        bulk_store(gidx + static_cast<size_t>(f0) * kQuadIndexBytes, s_stage + 256 * 20, (nq * kQuadIndexBytes + 15u) & ~15u);
+                    } else {
+                        bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, s_stage, (nq * kFaceBytes + 15u) & ~15u);
+                    }
+                    bulk_commit();
+                }
+            }
+        }
+        __syncthreads();  // all reads of vox(buf), tables, s_rec, s_next done before they are overwritten
+        ++it;
+        cur = s_next[it & 1];
+    }
+    if (lane == 0) bulk_wait<0>();
+}
+
+}  // namespace dsp

@@ -105,6 +105,7 @@ class ChunkMesh:
     world: "World"
     offset_bytes: int
     vertex_count: int
+    index_count: int = 0  # > 0 with MESH_INDEXED: draw_indexed(index_count, ...) instead of draw(vertex_count, ...)
 
     def __len__(self) -> int:  # mesh.len() as used by draw(), scene_game.rs:118-122
         return self.vertex_count
@@ -115,6 +116,13 @@ class ChunkMesh:
 
     def to_host(self) -> np.ndarray:
         return self.world.ctx.download_arena(self.offset_bytes, self.vertex_count * 20).view(capi.VERTEX_DTYPE)
+
+    @property
+    def index_offset_bytes(self) -> int:
+        return self.offset_bytes + ((self.vertex_count * 20 + 127) & ~127)
+
+    def indices_to_host(self) -> np.ndarray:
+        return self.world.ctx.download_arena(self.index_offset_bytes, self.index_count * 4).view(np.uint32)
 
 
 class World:
@@ -175,7 +183,7 @@ def build_chunk_meshes(world: World, positions: Sequence[Sequence[int]], block_u
     slots = world.get_chunks(positions)
     entries, total = world.ctx.mesh_chunks(slots, mode, world._arena_top)
     world._arena_top += total
-    return [ChunkMesh(world, int(e["offset_bytes"]), int(e["vertex_count"])) if e["vertex_count"] else None for e in entries]
+    return [ChunkMesh(world, int(e["offset_bytes"]), int(e["vertex_count"]), int(e["index_count"])) if e["vertex_count"] else None for e in entries]
 
 
 def build_chunk_mesh(world: World, chunk_pos, block_uvs: Dict[str, AtlasUV]) -> Optional[ChunkMesh]:

@@ -65,10 +65,21 @@ typedef enum dsp_gen_kind {
 #define DSP_MESH_ORDERED 2u /* pack the chunks' arena slots back to back in the order of the call (reproducible
                              * layout, ~10 % slower); without it slots are claimed in completion order */
 
+/* Quad modes (extensions; spec with the oracle, oracle/mesher_oracle.cpp).  Not available with
+ * DSP_MESH_ORDERED. */
+#define DSP_MESH_GREEDY 4u  /* greedy run-stack merge: maximal runs of equal-id visible faces along one in-plane axis, identical
+                             * runs stacked along the other; re-expanded cell by cell the quads are exactly the faces the
+                             * reference emits (chunk_mesh.rs:46-51,65-106).  Quads leave ordered by their anchor voxel. */
+#define DSP_MESH_INDEXED 8u /* 4 vertices (template corners c0..c3, cube.rs:156-312) + 6 u32 indices 4q+(0,1,2,2,3,0) per quad
+                             * instead of 6 vertices.  The chunk's slot holds the vertices, then (128-byte aligned) the indices:
+                             * index bytes start at offset_bytes + align128(20 * vertex_count); indices are chunk-local. */
+
 #define DSP_NO_SLOT 0xFFFFFFFFu
 #define DSP_CHUNK_VOXELS 4096
 #define DSP_VERTEX_BYTES 20
 #define DSP_FACE_BYTES 120
+#define DSP_QUAD_VERTEX_BYTES_INDEXED 80
+#define DSP_QUAD_INDEX_BYTES 24
 #define DSP_SLOT_ALIGN 128
 
 typedef struct dsp_ctx dsp_ctx;
@@ -76,8 +87,8 @@ typedef struct dsp_ctx dsp_ctx;
 /* Result of meshing one chunk: where its vertex stream lives in the arena.  16 bytes. */
 typedef struct dsp_mesh_entry {
     uint64_t offset_bytes;  /* from the start of the arena; multiple of DSP_SLOT_ALIGN */
-    uint32_t vertex_count;  /* 6 * faces; 0 <=> None */
-    uint32_t reserved;
+    uint32_t vertex_count;  /* 6 * faces (4 * quads with DSP_MESH_INDEXED); 0 <=> None */
+    uint32_t index_count;   /* 6 * quads with DSP_MESH_INDEXED, else 0 */
 } dsp_mesh_entry;
 
 /* One block edit in world voxel coordinates (world.rs:50-74 addressing: chunk = div_euclid(w,16),

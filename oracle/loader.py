@@ -43,6 +43,10 @@ def lib() -> C.CDLL:
         L.orc_mesh_chunk.restype = C.c_int64
         L.orc_mesh_chunk_halo.argtypes = [i32p, u16p, u16p, u8p, f32p, C.c_uint32, C.c_void_p, C.c_int64]
         L.orc_mesh_chunk_halo.restype = C.c_int64
+        u32p = C.POINTER(C.c_uint32)
+        L.orc_mesh_chunk_ext.argtypes = [i32p, u16p, u16p, u8p, f32p, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int64,
+                                         u32p, C.c_int64, i64p, u32p, C.c_int64, i64p]
+        L.orc_mesh_chunk_ext.restype = C.c_int64
         L.orc_mesh_batch.argtypes = [C.c_int64, i32p, u16p, f32p, C.c_uint32, C.c_int, C.c_int, i64p, C.c_void_p, C.c_int64]
         L.orc_mesh_batch.restype = C.c_int64
         L.orc_time_pipeline.argtypes = [C.c_int64, i32p, C.c_int, C.c_uint32, f32p, C.c_uint32, C.c_int, C.c_int, C.c_int, i64p]
@@ -105,6 +109,27 @@ def mesh_chunk_halo(pos, ids, nbr_slabs, nbr_present, uv) -> np.ndarray:
                                   _p(uv, C.c_float), uv.shape[0], out.ctypes.data_as(C.c_void_p), out.shape[0])
     assert n >= 0
     return out[:n].copy()
+
+
+def mesh_chunk_ext(pos, ids, uv, greedy: bool = False, indexed: bool = False, nbr_slabs=None, nbr_present=None):
+    """Extension modes (builder-defined, see mesher_oracle.cpp): returns (vertices, indices u32, quad records u32)."""
+    p = np.ascontiguousarray(pos, dtype=np.int32)
+    ids = np.ascontiguousarray(ids, dtype=np.uint16).reshape(4096)
+    uv = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 4)
+    slabs = present = None
+    if nbr_slabs is not None:
+        slabs = np.ascontiguousarray(nbr_slabs, dtype=np.uint16).reshape(6, 256)
+        present = np.ascontiguousarray(nbr_present, dtype=np.uint8).reshape(6)
+    verts = np.empty(12288 * 6, dtype=VERTEX_DTYPE)
+    inds = np.empty(12288 * 6, dtype=np.uint32)
+    quads = np.empty(12288, dtype=np.uint32)
+    n_i, n_q = C.c_int64(0), C.c_int64(0)
+    n = lib().orc_mesh_chunk_ext(_p(p, C.c_int32), _p(ids, C.c_uint16), None if slabs is None else _p(slabs, C.c_uint16),
+                                 None if present is None else _p(present, C.c_uint8), _p(uv, C.c_float), uv.shape[0],
+                                 1 if greedy else 0, 1 if indexed else 0, verts.ctypes.data_as(C.c_void_p), verts.shape[0],
+                                 _p(inds, C.c_uint32), inds.shape[0], C.byref(n_i), _p(quads, C.c_uint32), quads.shape[0], C.byref(n_q))
+    assert n >= 0
+    return verts[:n].copy(), inds[:n_i.value].copy(), quads[:n_q.value].copy()
 
 
 def mesh_batch(pos: np.ndarray, ids: np.ndarray, uv: np.ndarray, flavour: int = FAIR, threads: int = 0):

@@ -31,6 +31,7 @@
 #include <unordered_map>
 #include <vector>
 #include <atomic>
+#include <algorithm>
 #include <chrono>
 
 namespace {
@@ -391,6 +392,135 @@ bool build_chunk_mesh_halo(const Chunk& chunk, const BlockUvMap& block_uvs, cons
     return !vertices.empty();
 }
 
+
+// ---- extension oracle: greedy run-stack merge and indexed layout ----------------
+// NOT in the reference (it emits one unit quad per visible face, chunk_mesh.rs:65-106, and draws non-indexed,
+// scene_game.rs:118-122).  Builder-defined spec, pinned to the reference by two invariants that the tests check:
+//   (1) the merged quads, re-expanded cell by cell, are exactly the reference's visible-face set;
+//   (2) every corner of a merged quad is computed with the reference's own arithmetic for the voxel under that
+//       corner (chunk_mesh.rs:61-62,67), so an unmerged quad is byte-identical to the reference's face and a
+//       chunk in which nothing merges reproduces the reference stream.
+// Spec.  For direction d the face plane has a run axis u and a stack axis v:
+//       TOP/BOTTOM (normal y): u = x, v = z      REAR/FRONT (normal z): u = x, v = y      RIGHT/LEFT (normal x): u = y, v = z
+//   A RUN is a maximal interval of cells along u (fixed slice, fixed v) whose faces are all visible and whose block
+//   ids (palette entries, chunk.rs:58-65) are equal.  Two runs in adjacent rows v, v+1 of the same slice are IDENTICAL
+//   when they have the same start, length and block id.  A QUAD is a maximal chain of identical runs in consecutive
+//   rows: w = run length, h = chain length.  (Unlike the sequential "take the widest, then the tallest" greedy, no
+//   decision depends on an earlier one, so every row can decide independently -- that is what the CUDA kernel
+//   exploits with warp ballots.)  The quad's ANCHOR is its cell with the smallest voxel index; quads are emitted in
+//   the reference's order applied to anchors: anchor voxel index ascending, then TOP, BOTTOM, REAR, FRONT, RIGHT, LEFT.
+//   Corner k of the quad = template corner k of the unit face (cube.rs:156-312) placed on the quad's cell that lies
+//   furthest in the direction of the corner's sign on each axis; tex_coords are the template's, through map_uv
+//   (chunk_mesh.rs:23-28): the block's atlas tile stretches over the merged quad (the reference's fragment shader
+//   samples atlas UVs directly, assets/shaders/first_triangle/fragment.glsl:10-12, so tiling would need a shader change).
+//   Indexed layout: 4 vertices per quad (template corners c0,c1,c2,c3) and 6 u32 indices 4q + (0,1,2,2,3,0) -- the
+//   expansion pattern of every template, cube.rs:156-312 -- local to the chunk.
+struct Quad {
+    uint16_t idx;  // anchor voxel
+    uint8_t dir, w, h;
+};
+const int FACE_AXES[6][3] = {{1, 0, 2}, {1, 0, 2}, {2, 0, 1}, {2, 0, 1}, {0, 1, 2}, {0, 1, 2}};  // normal, u, v
+
+// vis[d][idx]: face d of voxel idx is emitted.  nbr == nullptr: reference cull (chunk_mesh.rs:46-51).
+void face_visibility(const Chunk& chunk, const uint16_t* const* nbr, std::vector<uint8_t>& vis) {
+    vis.assign(6 * 4096, 0);
+    for (size_t idx = 0; idx < 4096; ++idx) {
+        if (chunk.is_air_at_idx(idx)) continue;
+        const size_t x = idx % 16, y = (idx / 16) % 16, z = idx / 256;
+        auto slab_air = [&](int f, size_t a, size_t b) { return nbr == nullptr || nbr[f] == nullptr || nbr[f][a * 16 + b] == 0; };
+        vis[0 * 4096 + idx] = y == 15 ? slab_air(0, z, x) : chunk.is_air_at_idx(idx + 16);
+        vis[1 * 4096 + idx] = y == 0 ? slab_air(1, z, x) : chunk.is_air_at_idx(idx - 16);
+        vis[2 * 4096 + idx] = z == 0 ? slab_air(2, y, x) : chunk.is_air_at_idx(idx - 256);
+        vis[3 * 4096 + idx] = z == 15 ? slab_air(3, y, x) : chunk.is_air_at_idx(idx + 256);
+        vis[4 * 4096 + idx] = x == 0 ? slab_air(4, z, y) : chunk.is_air_at_idx(idx - 1);
+        vis[5 * 4096 + idx] = x == 15 ? slab_air(5, z, y) : chunk.is_air_at_idx(idx + 1);
+    }
+}
+
+std::vector<Quad> merge_quads(const Chunk& chunk, const std::vector<uint8_t>& vis, bool greedy) {
+    std::vector<Quad> quads;
+    for (int d = 0; d < 6; ++d) {
+        const int an = FACE_AXES[d][0], au = FACE_AXES[d][1], av = FACE_AXES[d][2];
+        auto at = [&](int s, int u, int v) {
+            int c[3];
+            c[an] = s; c[au] = u; c[av] = v;
+            return Chunk::index(static_cast<size_t>(c[0]), static_cast<size_t>(c[1]), static_cast<size_t>(c[2]));
+        };
+        auto face = [&](int s, int u, int v) { return vis[static_cast<size_t>(d) * 4096 + at(s, u, v)] != 0; };
+        auto id = [&](int s, int u, int v) { return chunk.blocks[at(s, u, v)]; };
+        // is there a run with exactly this start, length and block id in row v?
+        auto has_run = [&](int s, int v, int u0, int w, uint16_t bid) {
+            for (int u = u0; u < u0 + w; ++u)
+                if (!face(s, u, v) || id(s, u, v) != bid) return false;
+            if (u0 > 0 && face(s, u0 - 1, v) && id(s, u0 - 1, v) == bid) return false;            // would start earlier
+            if (u0 + w < 16 && face(s, u0 + w, v) && id(s, u0 + w, v) == bid) return false;        // would end later
+            return true;
+        };
+        for (int s = 0; s < 16; ++s)
+            for (int v = 0; v < 16; ++v)
+                for (int u = 0; u < 16;) {
+                    if (!face(s, u, v)) { ++u; continue; }
+                    if (!greedy) {
+                        quads.push_back(Quad{static_cast<uint16_t>(at(s, u, v)), static_cast<uint8_t>(d), 1, 1});
+                        ++u;
+                        continue;
+                    }
+                    const uint16_t bid = id(s, u, v);
+                    int w = 1;
+                    while (u + w < 16 && face(s, u + w, v) && id(s, u + w, v) == bid) ++w;
+                    if (!(v > 0 && has_run(s, v - 1, u, w, bid))) {  // not a continuation: this run opens a quad
+                        int h = 1;
+                        while (v + h < 16 && has_run(s, v + h, u, w, bid)) ++h;
+                        quads.push_back(Quad{static_cast<uint16_t>(at(s, u, v)), static_cast<uint8_t>(d), static_cast<uint8_t>(w), static_cast<uint8_t>(h)});
+                    }
+                    u += w;
+                }
+    }
+    std::stable_sort(quads.begin(), quads.end(), [](const Quad& a, const Quad& b) { return a.idx != b.idx ? a.idx < b.idx : a.dir < b.dir; });
+    return quads;
+}
+
+// Vertices (and indices) of the quads.  indexed == false: 6 vertices per quad, the reference's layout.
+void emit_quads(const Chunk& chunk, const BlockUvMap& block_uvs, const std::vector<Quad>& quads, bool indexed,
+                std::vector<BlockVertex>& vertices, std::vector<uint32_t>& indices) {
+    vertices.clear();
+    indices.clear();
+    static const int kExpand[6] = {0, 1, 2, 2, 3, 0};
+    static const int kCornerVertex[4] = {0, 1, 2, 4};  // template vertex that carries corner c0..c3
+    uint32_t q = 0;
+    for (const Quad& quad : quads) {
+        const size_t idx = quad.idx;
+        const std::string& block_id = chunk.palette[chunk.blocks[idx]];
+        AtlasUV atlas{{0.0f, 0.0f}, {1.0f, 1.0f}};  // chunk_mesh.rs:53-56
+        auto it = block_uvs.find(block_id);
+        if (it != block_uvs.end()) atlas = it->second;
+        const int anchor[3] = {static_cast<int>(idx % 16), static_cast<int>((idx / 16) % 16), static_cast<int>(idx / 256)};
+        int ext[3];
+        ext[FACE_AXES[quad.dir][0]] = 1;
+        ext[FACE_AXES[quad.dir][1]] = quad.w;
+        ext[FACE_AXES[quad.dir][2]] = quad.h;
+        auto corner = [&](int k) {
+            BlockVertex v = FACE_TEMPLATES[quad.dir][k];
+            Vec3 cell;
+            for (int a = 0; a < 3; ++a) cell.v[a] = static_cast<float>(anchor[a] + (v.position.v[a] > 0.0f ? ext[a] - 1 : 0));
+            const Vec3 pos_offset = vec3_add(cell, vec3_mul(vec3_from_i32(chunk.position), 16.0f));  // chunk_mesh.rs:61-62
+            v.position = vec3_add(v.position, pos_offset);
+            const float u = atlas.uv_min[0] + v.tex_coords[0] * (atlas.uv_max[0] - atlas.uv_min[0]);
+            const float w = atlas.uv_min[1] + v.tex_coords[1] * (atlas.uv_max[1] - atlas.uv_min[1]);
+            v.tex_coords[0] = u;
+            v.tex_coords[1] = w;
+            return v;
+        };
+        if (indexed) {
+            for (int c = 0; c < 4; ++c) vertices.push_back(corner(kCornerVertex[c]));
+            for (int k = 0; k < 6; ++k) indices.push_back(4 * q + static_cast<uint32_t>(kExpand[k]));
+        } else {
+            for (int k = 0; k < 6; ++k) vertices.push_back(corner(k));
+        }
+        ++q;
+    }
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -431,6 +561,39 @@ int64_t orc_mesh_chunk_halo(const int32_t* pos, const uint16_t* ids, const uint1
     if (!build_chunk_mesh_halo(c, m, nbr, verts)) return 0;
     if (static_cast<int64_t>(verts.size()) > cap_vertices) return -1;
     std::memcpy(out_vertices, verts.data(), verts.size() * sizeof(BlockVertex));
+    return static_cast<int64_t>(verts.size());
+}
+
+// Extension modes (greedy merge and/or indexed layout, optionally with halo culling).  nbr_slabs / nbr_present may be
+// NULL (reference cull).  out_quads (may be NULL, capacity = cap_quads) receives one record per quad:
+// anchor | dir << 12 | (w-1) << 15 | (h-1) << 19.  Returns the vertex count (-1: a capacity was too small);
+// *out_n_indices and *out_n_quads receive the other counts.
+int64_t orc_mesh_chunk_ext(const int32_t* pos, const uint16_t* ids, const uint16_t* nbr_slabs, const uint8_t* nbr_present,
+                           const float* uv, uint32_t n_blocks, int greedy, int indexed, void* out_vertices, int64_t cap_vertices,
+                           uint32_t* out_indices, int64_t cap_indices, int64_t* out_n_indices, uint32_t* out_quads, int64_t cap_quads,
+                           int64_t* out_n_quads) {
+    Chunk c = chunk_from_global_ids(pos, ids);
+    BlockUvMap m = uv_map_from_table(uv, n_blocks);
+    const uint16_t* nbr[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (nbr_slabs != nullptr && nbr_present != nullptr)
+        for (int f = 0; f < 6; ++f) nbr[f] = nbr_present[f] ? nbr_slabs + 256 * f : nullptr;
+    std::vector<uint8_t> vis;
+    face_visibility(c, nbr, vis);
+    const std::vector<Quad> quads = merge_quads(c, vis, greedy != 0);
+    std::vector<BlockVertex> verts;
+    std::vector<uint32_t> inds;
+    emit_quads(c, m, quads, indexed != 0, verts, inds);
+    if (out_n_indices) *out_n_indices = static_cast<int64_t>(inds.size());
+    if (out_n_quads) *out_n_quads = static_cast<int64_t>(quads.size());
+    if (static_cast<int64_t>(verts.size()) > cap_vertices || static_cast<int64_t>(inds.size()) > cap_indices) return -1;
+    if (out_quads != nullptr) {
+        if (static_cast<int64_t>(quads.size()) > cap_quads) return -1;
+        for (size_t i = 0; i < quads.size(); ++i)
+            out_quads[i] = quads[i].idx | (static_cast<uint32_t>(quads[i].dir) << 12) | (static_cast<uint32_t>(quads[i].w - 1) << 15) |
+                           (static_cast<uint32_t>(quads[i].h - 1) << 19);
+    }
+    if (!verts.empty()) std::memcpy(out_vertices, verts.data(), verts.size() * sizeof(BlockVertex));
+    if (!inds.empty()) std::memcpy(out_indices, inds.data(), inds.size() * sizeof(uint32_t));
     return static_cast<int64_t>(verts.size());
 }
 

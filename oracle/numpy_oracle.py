@@ -177,3 +177,105 @@ def generate(kind: int, seed: int, pos) -> np.ndarray:
     else:
         raise ValueError(kind)
     return ids.reshape(4096)
+
+
+# ---- extension: greedy run-stack merge, bit-mask formulation -------------------------------------------------
+# Independent of merge_quads() in mesher_oracle.cpp (which walks cells and compares runs cell by cell): here every
+# row is a 16-bit mask and a run is a (start bit, end bit) pair, the formulation the CUDA kernel uses.  Tests
+# require both to give the same quad records.  Spec: header comment of the extension block in mesher_oracle.cpp.
+def _starts_ends(f: int, eq: int):
+    """f: visible-face mask of a row along the run axis, eq: bit u = id[u] == id[u-1].  Returns (S, E) masks."""
+    s = f & ~((f << 1) & eq) & 0xFFFF
+    e = f & ~((f >> 1) & (eq >> 1)) & 0xFFFF
+    return s, e
+
+
+def _continued(f_a: int, eq_a: int, f_b: int, eq_b: int, eqv_b: int) -> int:
+    """Start bits of row b whose run is identical (start, end, id) to a run of the previous row a."""
+    s_a, e_a = _starts_ends(f_a, eq_a)
+    s_b, e_b = _starts_ends(f_b, eq_b)
+    cand = s_a & s_b & eqv_b
+    diff = e_a ^ e_b
+    out = 0
+    while cand:
+        u0 = (cand & -cand).bit_length() - 1
+        cand &= cand - 1
+        eb = ((e_b >> u0) & -(e_b >> u0)).bit_length() - 1  # run length - 1
+        if ((diff >> u0) & ((2 << eb) - 1)) == 0:
+            out |= 1 << u0
+    return out
+
+
+def greedy_records(ids: np.ndarray, masks: np.ndarray | None = None) -> np.ndarray:
+    """Quad records anchor | dir << 12 | (w-1) << 15 | (h-1) << 19 in emission order (anchor voxel ascending, then
+    direction).  masks: bool (6,16z,16y,16x) visible faces (default: the reference cull, face_masks)."""
+    ids = np.asarray(ids, dtype=np.uint16).reshape(4096)
+    if masks is None:
+        masks = face_masks(ids)
+    v = ids.reshape(256, 16).astype(np.int64)  # [row = y + 16 z][x]
+    rows = range(256)
+
+    def bits(b):  # bool[16] -> int, bit i = b[i]
+        return int(sum(1 << i for i in range(16) if b[i]))
+
+    f = [[bits(masks[d].reshape(256, 16)[r]) for r in rows] for d in range(6)]
+    eqx = [bits(np.concatenate([[False], v[r, 1:] == v[r, :-1]])) for r in rows]
+    eqy = [bits(v[r] == v[r - 1]) if (r & 15) > 0 else 0 for r in rows]
+    eqz = [bits(v[r] == v[r - 16]) if r >= 16 else 0 for r in rows]
+    recs = []
+    # directions whose run axis is x: thread-per-row masks are used as they are
+    for d, stride, eqv, has_prev in ((0, 16, eqz, lambda r: r >= 16), (1, 16, eqz, lambda r: r >= 16),
+                                     (2, 1, eqy, lambda r: (r & 15) > 0), (3, 1, eqy, lambda r: (r & 15) > 0)):
+        cont = [(_continued(f[d][r - stride], eqx[r - stride], f[d][r], eqx[r], eqv[r]) if has_prev(r) else 0) for r in rows]
+        for r in rows:
+            s, e = _starts_ends(f[d][r], eqx[r])
+            anchors = s & ~cont[r]
+            left = (15 - (r >> 4)) if stride == 16 else (15 - (r & 15))  # rows after this one along the stack axis
+            for u0 in range(16):
+                if not (anchors >> u0) & 1:
+                    continue
+                w = ((e >> u0) & -(e >> u0)).bit_length()
+                h = 1
+                while h <= left and (cont[r + h * stride] >> u0) & 1:
+                    h += 1
+                recs.append((r * 16 + u0) | (d << 12) | ((w - 1) << 15) | ((h - 1) << 19))
+    # RIGHT / LEFT: run axis y, stack axis z -> transposed masks, column t = x + 16 z, bit = y
+    def transpose(m):  # m[row = y + 16 z] bit x  ->  t[x + 16 z] bit y
+        return [sum(((m[y + 16 * (t >> 4)] >> (t & 15)) & 1) << y for y in range(16)) for t in range(256)]
+    eq_run, eq_stack = transpose(eqy), transpose(eqz)
+    for d in (4, 5):
+        ft = transpose(f[d])
+        cont = [(_continued(ft[t - 16], eq_run[t - 16], ft[t], eq_run[t], eq_stack[t]) if t >= 16 else 0) for t in range(256)]
+        for t in range(256):
+            s, e = _starts_ends(ft[t], eq_run[t])
+            anchors = s & ~cont[t]
+            x, z = t & 15, t >> 4
+            for u0 in range(16):
+                if not (anchors >> u0) & 1:
+                    continue
+                w = ((e >> u0) & -(e >> u0)).bit_length()
+                h = 1
+                while z + h <= 15 and (cont[t + 16 * h] >> u0) & 1:
+                    h += 1
+                recs.append((x + 16 * u0 + 256 * z) | (d << 12) | ((w - 1) << 15) | ((h - 1) << 19))
+    recs.sort(key=lambda q: ((q & 0xFFF) << 3) | ((q >> 12) & 7))
+    return np.array(recs, dtype=np.uint32)
+
+
+def expand_records_to_unit_faces(recs: np.ndarray) -> np.ndarray:
+    """bool (6, 4096): the unit faces covered by the quads (each must be covered exactly once)."""
+    axes = ((1, 0, 2), (1, 0, 2), (2, 0, 1), (2, 0, 1), (0, 1, 2), (0, 1, 2))  # normal, run, stack
+    cover = np.zeros((6, 4096), dtype=np.int32)
+    for q in np.asarray(recs, dtype=np.uint32).tolist():
+        idx, d, w, h = q & 0xFFF, (q >> 12) & 7, ((q >> 15) & 15) + 1, ((q >> 19) & 15) + 1
+        c0 = [idx & 15, (idx >> 4) & 15, idx >> 8]
+        _, au, av = axes[d]
+        for j in range(h):
+            for i in range(w):
+                c = list(c0)
+                c[au] += i
+                c[av] += j
+                assert c[au] < 16 and c[av] < 16
+                cover[d, c[0] + 16 * c[1] + 256 * c[2]] += 1
+    assert cover.max(initial=0) <= 1, "a unit face is covered by two quads"
+    return cover.astype(bool)
