@@ -273,7 +273,7 @@ int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
 template <bool HALO, bool GREEDY, bool INDEXED>
 int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
     void (*kern)(const dsp::MeshParams) = dsp::mesh_chunks_quads_kernel<HALO, GREEDY, INDEXED>;
-    constexpr int smem = dsp::QuadSmem::kBytes;
+    constexpr int smem = dsp::QuadSmem<GREEDY>::kBytes;
     int& occ = ctx->quad_ctas_per_sm[(HALO ? 1 : 0) + (GREEDY ? 2 : 0) + (INDEXED ? 4 : 0)];
     if (occ == 0) {
         DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -26,28 +26,36 @@ namespace dsp {
 
 constexpr int kQuadVertexBytesIdx = 80;   // 4 vertices
 constexpr int kQuadIndexBytes = 24;       // 6 x u32
-constexpr uint32_t kQuadRecCap = 4096;    // records per window (u32 each)
 
+// Shared-memory plan.  Greedy output is small (typically 10x fewer quads than faces), so the merge kernel trades
+// staging space for residency: 128-quad tiles and a 2,048-record window make room for 4 CTAs per SM, which is what
+// hides the per-chunk latencies (tile, barriers, the slot atomic) once there is little emission to hide them behind.
+// The unit-quad indexed kernel keeps the 256-quad tile / 4,096-record window of the parity kernel (3 CTAs per SM).
+template <bool GREEDY>
 struct QuadSmem {
-    static constexpr int kVox = 0;                               // 2 x 8192
-    static constexpr int kStage = 2 * kChunkBytes;               // 30720: 256 quads (stream) or 20480 + 6144 (indexed)
-    static constexpr int kRec = kStage + kTileBytes;             // kQuadRecCap x u32
-    static constexpr int kRowMask = kRec + kQuadRecCap * 4;      // 256 x u16
-    static constexpr int kF = kRowMask + kRows * 2;              // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
-    static constexpr int kEqx = kF + 4 * kRows * 2;              // [256] u16
-    static constexpr int kFT = kEqx + kRows * 2;                 // [2][256] u16: RIGHT, LEFT masks per column (bit = y)
-    static constexpr int kEqRunT = kFT + 2 * kRows * 2;          // [256] u16: id equality towards y-1, per column
-    static constexpr int kC = kEqRunT + kRows * 2;               // [4][256] u16 continued-run masks per row
-    static constexpr int kCT = kC + 4 * kRows * 2;               // [2][256] u16 continued-run masks per column
-    static constexpr int kA = kCT + 2 * kRows * 2;               // [6][256] u16 anchor masks per row
-    static constexpr int kFirst = kA + 6 * kRows * 2;            // [256] u16 ordinal of the row's first quad
-    static constexpr int kWarpTot = kFirst + kRows * 2;          // 8 x u32 (+ pad)
-    static constexpr int kBar = kWarpTot + 64;                   // 2 x u64
-    static constexpr int kBase = kBar + 16;                      // u64
-    static constexpr int kNext = kBase + 8;                      // 2 x u32
+    static constexpr int kCtasPerSm = GREEDY ? 4 : 3;
+    static constexpr int kTileQuads = GREEDY ? 128 : 256;
+    static constexpr uint32_t kRecCap = GREEDY ? 2048 : 4096;         // records per window (u32 each)
+    static constexpr int kT = GREEDY ? kRows * 2 : 0;                 // bytes of one [256] u16 table (none without merging)
+    static constexpr int kVox = 0;                                    // 2 x 8192
+    static constexpr int kStage = 2 * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
+    static constexpr int kRec = kStage + kTileQuads * kFaceBytes;     // kRecCap x u32
+    static constexpr int kRowMask = kRec + kRecCap * 4;               // 256 x u16
+    static constexpr int kF = kRowMask + kRows * 2;                   // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
+    static constexpr int kEqx = kF + 4 * kT;                          // [256] u16
+    static constexpr int kFT = kEqx + kT;                             // [2][256] u16: RIGHT, LEFT masks per column (bit = y)
+    static constexpr int kEqRunT = kFT + 2 * kT;                      // [256] u16: id equality towards y-1, per column
+    static constexpr int kC = kEqRunT + kT;                           // [4][256] u16 continued-run masks per row
+    static constexpr int kCT = kC + 4 * kT;                           // [2][256] u16 continued-run masks per column
+    static constexpr int kA = kCT + 2 * kT;                           // [6][256] u16 anchor masks per row
+    static constexpr int kFirst = kA + 6 * kT;                        // [256] u16 ordinal of the row's first quad
+    static constexpr int kWarpTot = kFirst + kT;                      // 8 x u32 (+ pad)
+    static constexpr int kBar = kWarpTot + 64;                        // 2 x u64
+    static constexpr int kBase = kBar + 16;                           // u64
+    static constexpr int kNext = kBase + 8;                           // 2 x u32
     static constexpr int kBytes = kNext + 8;
 };
-static_assert(QuadSmem::kBytes <= 76800, "three CTAs per SM");
+static_assert(QuadSmem<true>::kBytes <= 57344 && QuadSmem<false>::kBytes <= 76800, "4 / 3 CTAs per SM");
 
 // 16x16 bit-matrix transpose across the 16 lanes of a half warp, two matrices at once (low / high half of v):
 // lane i holds row i; afterwards lane i holds column i.  Four shuffle steps.
@@ -135,24 +143,28 @@ __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox,
 }
 
 template <bool HALO, bool GREEDY, bool INDEXED>
-__global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshParams p) {
+__global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p) {
+    using L = QuadSmem<GREEDY>;
+    constexpr uint32_t kRecCap = L::kRecCap;
+    constexpr int kTile = L::kTileQuads;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint16_t* const s_vox = reinterpret_cast<uint16_t*>(smem + QuadSmem::kVox);
-    float* const s_stage = reinterpret_cast<float*>(smem + QuadSmem::kStage);
-    uint32_t* const s_rec = reinterpret_cast<uint32_t*>(smem + QuadSmem::kRec);
-    uint16_t* const s_rowmask = reinterpret_cast<uint16_t*>(smem + QuadSmem::kRowMask);
-    uint16_t* const s_F = reinterpret_cast<uint16_t*>(smem + QuadSmem::kF);
-    uint16_t* const s_eqx = reinterpret_cast<uint16_t*>(smem + QuadSmem::kEqx);
-    uint16_t* const s_FT = reinterpret_cast<uint16_t*>(smem + QuadSmem::kFT);
-    uint16_t* const s_eqrunT = reinterpret_cast<uint16_t*>(smem + QuadSmem::kEqRunT);
-    uint16_t* const s_C = reinterpret_cast<uint16_t*>(smem + QuadSmem::kC);
-    uint16_t* const s_CT = reinterpret_cast<uint16_t*>(smem + QuadSmem::kCT);
-    uint16_t* const s_A = reinterpret_cast<uint16_t*>(smem + QuadSmem::kA);
-    uint16_t* const s_first = reinterpret_cast<uint16_t*>(smem + QuadSmem::kFirst);
-    uint32_t* const s_warp = reinterpret_cast<uint32_t*>(smem + QuadSmem::kWarpTot);
-    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + QuadSmem::kBar);
-    uint64_t* const s_base = reinterpret_cast<uint64_t*>(smem + QuadSmem::kBase);
-    uint32_t* const s_next = reinterpret_cast<uint32_t*>(smem + QuadSmem::kNext);
+    uint16_t* const s_vox = reinterpret_cast<uint16_t*>(smem + L::kVox);
+    float* const s_stage = reinterpret_cast<float*>(smem + L::kStage);
+    uint32_t* const s_rec = reinterpret_cast<uint32_t*>(smem + L::kRec);
+    uint16_t* const s_rowmask = reinterpret_cast<uint16_t*>(smem + L::kRowMask);
+    uint16_t* const s_F = reinterpret_cast<uint16_t*>(smem + L::kF);
+    uint16_t* const s_eqx = reinterpret_cast<uint16_t*>(smem + L::kEqx);
+    uint16_t* const s_FT = reinterpret_cast<uint16_t*>(smem + L::kFT);
+    uint16_t* const s_eqrunT = reinterpret_cast<uint16_t*>(smem + L::kEqRunT);
+    uint16_t* const s_C = reinterpret_cast<uint16_t*>(smem + L::kC);
+    uint16_t* const s_CT = reinterpret_cast<uint16_t*>(smem + L::kCT);
+    uint16_t* const s_A = reinterpret_cast<uint16_t*>(smem + L::kA);
+    uint16_t* const s_first = reinterpret_cast<uint16_t*>(smem + L::kFirst);
+    uint32_t* const s_warp = reinterpret_cast<uint32_t*>(smem + L::kWarpTot);
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
+    uint64_t* const s_base = reinterpret_cast<uint64_t*>(smem + L::kBase);
+    uint32_t* const s_next = reinterpret_cast<uint32_t*>(smem + L::kNext);
+    float* const s_istage = s_stage + kTile * 20;  // indexed layout: the tile's indices follow its vertices
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = tid, y = r & 15, z = r >> 4;   // as a row thread: x-row (y, z), masks over x
@@ -163,12 +175,17 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
         bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
     };
 
+    // Tickets run one chunk ahead of the tiles: the atomic that fetches the ticket after next is issued at the top of an
+    // iteration and its result is first touched at the top of the following one, so its round trip to L2 is never waited
+    // for (with little emission per chunk it would otherwise sit on the critical path of every chunk).
+    uint32_t pending = 0;  // thread 0: the ticket after s_next[(it + 1) & 1]
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
         fence_mbar_init();
-        const uint32_t t0 = atomicAdd(p.ticket, 1u);
+        const uint32_t t0 = atomicAdd(p.ticket, 2u);
         s_next[0] = t0;
+        pending = t0 + 1u;
         if (t0 < p.n) issue_load(t0, 0);
     }
     __syncthreads();
@@ -176,16 +193,17 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
     uint32_t it = 0;
     while (cur < p.n) {
         const int buf = it & 1;
-        if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
-            const uint32_t t = atomicAdd(p.ticket, 1u);
+        if (tid == 0) {
+            const uint32_t t = pending;
             s_next[(it + 1) & 1] = t;
-            if (t < p.n) issue_load(t, buf ^ 1);
+            if (t < p.n) issue_load(t, buf ^ 1);  // lands while this chunk is processed
+            pending = atomicAdd(p.ticket, 1u);
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         mbar_wait(&s_bar[buf], (it >> 1) & 1);
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
 
-        // ---- 1. row occupancy, id-equality towards x-1
+        // ---- 1. row occupancy; is the whole chunk one block id?
         uint4 qa, qb;
         uint32_t m;
         {
@@ -197,113 +215,157 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
             m = nonzero_mask8(qa) | (nonzero_mask8(qb) << 8);
         }
         s_rowmask[r] = static_cast<uint16_t>(m);
-        __syncthreads();
+        const uint32_t id0 = vox[0];
+        const uint32_t id0w = id0 * 0x00010001u;
+        const uint32_t differs = (qa.x ^ id0w) | (qa.y ^ id0w) | (qa.z ^ id0w) | (qa.w ^ id0w) | (qb.x ^ id0w) | (qb.y ^ id0w) | (qb.z ^ id0w) | (qb.w ^ id0w);
+        const bool uniform = __syncthreads_and(differs == 0u) != 0;  // also publishes s_rowmask
+        if (uniform && id0 == 0u) {
+            // all air: the reference's palette.len() == 1 early-out (chunk_mesh.rs:18-20)
+            if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+            ++it;
+            cur = s_next[it & 1];
+            continue;
+        }
+        // one solid block id throughout, chunk-local cull: exactly one 16x16 quad per side
+        const bool solid_uniform = GREEDY && !HALO && uniform;
 
-        // ---- 2. face masks (chunk_mesh.rs:46-51); anchors = faces unless merging
-        const FaceMasks fm = row_face_masks<HALO>(p, HALO ? slot_of(cur) : 0u, s_rowmask, r, y, z, m);
-        uint32_t A[6] = {fm.top, fm.bot, fm.rear, fm.front, fm.right, fm.left};
+        uint32_t A[6] = {0u, 0u, 0u, 0u, 0u, 0u};
         uint32_t fT[2] = {0u, 0u}, AT[2] = {0u, 0u}, eqx = 0u, eqrunT = 0u;
-        if (GREEDY) {
-            eqx = eq_prev_mask16(qa, qb);
-            uint32_t eqy = 0u, eqz = 0u;
-            if (y > 0) { const uint4* q = reinterpret_cast<const uint4*>(vox + (r - 1) * 16); eqy = eq_mask16(qa, qb, q[0], q[1]); }
-            if (z > 0) { const uint4* q = reinterpret_cast<const uint4*>(vox + (r - 16) * 16); eqz = eq_mask16(qa, qb, q[0], q[1]); }
+        FaceMasks fm{};
+        uint32_t cnt = 0, first = 0, Q;
+        if (solid_uniform) {
+            Q = 6u;
+            if (tid < 6) {
+                // anchors (x,y,z): BOTTOM, REAR, RIGHT at voxel 0; LEFT at (15,0,0); TOP at (0,15,0); FRONT at (0,0,15)
+                const uint32_t rec = tid == 0 ? (0u | (1u << 12)) : tid == 1 ? (0u | (2u << 12)) : tid == 2 ? (0u | (4u << 12))
+                                   : tid == 3 ? (15u | (5u << 12)) : tid == 4 ? (240u | (0u << 12)) : (3840u | (3u << 12));
+                s_rec[tid] = rec | (15u << 15) | (15u << 19);
+            }
+        } else {
+            // ---- 2. face masks (chunk_mesh.rs:46-51); anchors = faces unless merging
+            fm = row_face_masks<HALO>(p, HALO ? slot_of(cur) : 0u, s_rowmask, r, y, z, m);
+            A[0] = fm.top; A[1] = fm.bot; A[2] = fm.rear; A[3] = fm.front; A[4] = fm.right; A[5] = fm.left;
+            if (GREEDY) {
+                eqx = eq_prev_mask16(qa, qb);
+                uint32_t eqy = 0u, eqz = 0u;
+                if (y > 0) { const uint4* q = reinterpret_cast<const uint4*>(vox + (r - 1) * 16); eqy = eq_mask16(qa, qb, q[0], q[1]); }
+                if (z > 0) { const uint4* q = reinterpret_cast<const uint4*>(vox + (r - 16) * 16); eqz = eq_mask16(qa, qb, q[0], q[1]); }
 #pragma unroll
-            for (int d = 0; d < 4; ++d) s_F[d * kRows + r] = static_cast<uint16_t>(A[d]);
-            s_eqx[r] = static_cast<uint16_t>(eqx);
-            // RIGHT / LEFT run along y: rows -> columns (lane l of a half warp: row y = l  ->  column x = l, same z)
-            const uint32_t tf = transpose16x16_pair(A[4] | (A[5] << 16), lane);
-            const uint32_t te = transpose16x16_pair(eqy | (eqz << 16), lane);
-            fT[0] = tf & 0xFFFFu; fT[1] = tf >> 16;
-            eqrunT = te & 0xFFFFu;
-            const uint32_t eqstackT = te >> 16;
-            s_FT[tid] = static_cast<uint16_t>(fT[0]);
-            s_FT[kRows + tid] = static_cast<uint16_t>(fT[1]);
-            s_eqrunT[tid] = static_cast<uint16_t>(eqrunT);
-            __syncthreads();
-            // ---- 3. continued runs -> anchors
-            uint32_t Cm[4] = {0u, 0u, 0u, 0u};
-            if (z > 0) {
-                const uint32_t eqa = s_eqx[r - 16];
-                Cm[0] = continued_runs(s_F[0 * kRows + r - 16], eqa, A[0], eqx, eqz);
-                Cm[1] = continued_runs(s_F[1 * kRows + r - 16], eqa, A[1], eqx, eqz);
-            }
-            if (y > 0) {
-                const uint32_t eqa = s_eqx[r - 1];
-                Cm[2] = continued_runs(s_F[2 * kRows + r - 1], eqa, A[2], eqx, eqy);
-                Cm[3] = continued_runs(s_F[3 * kRows + r - 1], eqa, A[3], eqx, eqy);
-            }
-            uint32_t CT[2] = {0u, 0u};
-            if (z > 0) {
-                const uint32_t eqa = s_eqrunT[tid - 16];
-                CT[0] = continued_runs(s_FT[tid - 16], eqa, fT[0], eqrunT, eqstackT);
-                CT[1] = continued_runs(s_FT[kRows + tid - 16], eqa, fT[1], eqrunT, eqstackT);
-            }
+                for (int d = 0; d < 4; ++d) s_F[d * kRows + r] = static_cast<uint16_t>(A[d]);
+                s_eqx[r] = static_cast<uint16_t>(eqx);
+                // RIGHT / LEFT run along y: rows -> columns (lane l of a half warp: row y = l  ->  column x = l, same z)
+                const uint32_t tf = transpose16x16_pair(A[4] | (A[5] << 16), lane);
+                const uint32_t te = transpose16x16_pair(eqy | (eqz << 16), lane);
+                fT[0] = tf & 0xFFFFu; fT[1] = tf >> 16;
+                eqrunT = te & 0xFFFFu;
+                const uint32_t eqstackT = te >> 16;
+                s_FT[tid] = static_cast<uint16_t>(fT[0]);
+                s_FT[kRows + tid] = static_cast<uint16_t>(fT[1]);
+                s_eqrunT[tid] = static_cast<uint16_t>(eqrunT);
+                __syncthreads();
+                // ---- 3. continued runs -> anchors
+                uint32_t Cm[4] = {0u, 0u, 0u, 0u};
+                if (z > 0) {
+                    const uint32_t eqa = s_eqx[r - 16];
+                    Cm[0] = continued_runs(s_F[0 * kRows + r - 16], eqa, A[0], eqx, eqz);
+                    Cm[1] = continued_runs(s_F[1 * kRows + r - 16], eqa, A[1], eqx, eqz);
+                }
+                if (y > 0) {
+                    const uint32_t eqa = s_eqx[r - 1];
+                    Cm[2] = continued_runs(s_F[2 * kRows + r - 1], eqa, A[2], eqx, eqy);
+                    Cm[3] = continued_runs(s_F[3 * kRows + r - 1], eqa, A[3], eqx, eqy);
+                }
+                uint32_t CT[2] = {0u, 0u};
+                if (z > 0) {
+                    const uint32_t eqa = s_eqrunT[tid - 16];
+                    CT[0] = continued_runs(s_FT[tid - 16], eqa, fT[0], eqrunT, eqstackT);
+                    CT[1] = continued_runs(s_FT[kRows + tid - 16], eqa, fT[1], eqrunT, eqstackT);
+                }
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                s_C[d * kRows + r] = static_cast<uint16_t>(Cm[d]);
-                A[d] = run_starts(A[d], eqx) & ~Cm[d];
-            }
-            s_CT[tid] = static_cast<uint16_t>(CT[0]);
-            s_CT[kRows + tid] = static_cast<uint16_t>(CT[1]);
-            AT[0] = run_starts(fT[0], eqrunT) & ~CT[0];
-            AT[1] = run_starts(fT[1], eqrunT) & ~CT[1];
-            const uint32_t ta = transpose16x16_pair(AT[0] | (AT[1] << 16), lane);  // columns -> rows
-            A[4] = ta & 0xFFFFu;
-            A[5] = ta >> 16;
+                for (int d = 0; d < 4; ++d) {
+                    s_C[d * kRows + r] = static_cast<uint16_t>(Cm[d]);
+                    A[d] = run_starts(A[d], eqx) & ~Cm[d];
+                }
+                s_CT[tid] = static_cast<uint16_t>(CT[0]);
+                s_CT[kRows + tid] = static_cast<uint16_t>(CT[1]);
+                AT[0] = run_starts(fT[0], eqrunT) & ~CT[0];
+                AT[1] = run_starts(fT[1], eqrunT) & ~CT[1];
+                const uint32_t ta = transpose16x16_pair(AT[0] | (AT[1] << 16), lane);  // columns -> rows
+                A[4] = ta & 0xFFFFu;
+                A[5] = ta >> 16;
 #pragma unroll
-            for (int d = 0; d < 6; ++d) s_A[d * kRows + r] = static_cast<uint16_t>(A[d]);
-        }
+                for (int d = 0; d < 6; ++d) s_A[d * kRows + r] = static_cast<uint16_t>(A[d]);
+            }
 
-        // ---- 4. count, scan
-        const uint32_t cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]) + __popc(A[4]) + __popc(A[5]);
-        uint32_t incl = cnt;
+            // ---- 4. count, scan
+            cnt = __popc(A[0]) + __popc(A[1]) + __popc(A[2]) + __popc(A[3]) + __popc(A[4]) + __popc(A[5]);
+            uint32_t incl = cnt;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        uint32_t wpre = 0, Q = 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            uint32_t wpre = 0;
+            Q = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-            const uint32_t v = s_warp[w];
-            wpre += w < warp ? v : 0u;
-            Q += v;
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t v = s_warp[w];
+                wpre += w < warp ? v : 0u;
+                Q += v;
+            }
+            first = wpre + incl - cnt;
+            if (GREEDY) {
+                s_first[r] = static_cast<uint16_t>(first);
+                __syncthreads();  // s_first is read by the column threads below
+            }
         }
-        const uint32_t first = wpre + incl - cnt;
-        if (GREEDY) s_first[r] = static_cast<uint16_t>(first);
-        if (tid == 0) {  // claim the chunk's arena slot
-            const uint64_t bytes = quad_slot_bytes(Q, INDEXED);
-            const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
-            *s_base = base;
-            if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
-            p.entries[cur] = MeshEntry{p.arena_offset + base, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
-        }
+        // claim the chunk's arena slot; the result is first touched after this thread's records are written
+        const uint64_t slot_bytes = quad_slot_bytes(Q, INDEXED);
+        uint64_t claimed = 0;
+        if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(slot_bytes));
         const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
         const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
         const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
 
-        if (GREEDY) __syncthreads();  // s_first is read by the column threads below
-
         // ---- 5./6. records of a window of quads, then their expansion
-        for (uint32_t q0 = 0; q0 == 0 || q0 < Q; q0 += kQuadRecCap) {
+        for (uint32_t q0 = 0; q0 == 0 || q0 < Q; q0 += kRecCap) {
             if (q0 > 0) __syncthreads();  // the previous window's records are consumed
-            if (cnt) {
-                uint32_t ord = first - q0;  // wraps below the window; the unsigned compare rejects those
-                const uint32_t rbase = static_cast<uint32_t>(r) << 4;
-#pragma unroll 1
-                for (int x = 0; x < 16; ++x) {
-                    const uint32_t six = ((A[0] >> x) & 1u) | (((A[1] >> x) & 1u) << 1) | (((A[2] >> x) & 1u) << 2) |
-                                         (((A[3] >> x) & 1u) << 3) | (((A[4] >> x) & 1u) << 4) | (((A[5] >> x) & 1u) << 5);
-                    if (!six) continue;
+            if (!GREEDY) {
+                if (cnt && Q <= kRecCap) {  // everything fits one window: straight-line predicated appends
+                    uint32_t* rp = s_rec + first;
+                    const uint32_t rbase = static_cast<uint32_t>(r) << 4;
 #pragma unroll
-                    for (uint32_t d = 0; d < 6; ++d) {
-                        if (!((six >> d) & 1u)) continue;
-                        if (ord < kQuadRecCap && (!GREEDY || d < 4u)) {
-                            uint32_t rec = (rbase + x) | (d << 12);
-                            if (GREEDY) {
+                    for (int x = 0; x < 16; ++x) {
+                        const uint32_t bit = 1u << x, v = rbase | x;
+#pragma unroll
+                        for (uint32_t d = 0; d < 6; ++d)
+                            if (A[d] & bit) *rp++ = v | (d << 12);
+                    }
+                } else if (cnt) {
+                    uint32_t ord = first - q0;  // wraps below the window; the unsigned compare rejects those
+                    const uint32_t rbase = static_cast<uint32_t>(r) << 4;
+#pragma unroll 1
+                    for (int x = 0; x < 16; ++x) {
+#pragma unroll
+                        for (uint32_t d = 0; d < 6; ++d)
+                            if ((A[d] >> x) & 1u) { if (ord < kRecCap) s_rec[ord] = (rbase + x) | (d << 12); ++ord; }
+                    }
+                }
+            } else if (!solid_uniform) {
+                if (cnt) {
+                    // anchors are sparse: visit only the voxels that carry one
+                    uint32_t ord = first - q0;
+                    const uint32_t rbase = static_cast<uint32_t>(r) << 4;
+                    uint32_t any = A[0] | A[1] | A[2] | A[3] | A[4] | A[5];
+                    while (any) {
+                        const int x = __ffs(any) - 1;
+                        any &= any - 1;
+#pragma unroll
+                        for (uint32_t d = 0; d < 6; ++d) {
+                            if (!((A[d] >> x) & 1u)) continue;
+                            if (d < 4u && ord < kRecCap) {  // RIGHT / LEFT records are written by the column threads
                                 // run length from the row's end mask; height = rows along the stack axis that continue it
                                 const uint32_t fmask = d == 0 ? fm.top : d == 1 ? fm.bot : d == 2 ? fm.rear : fm.front;
                                 const uint32_t w1 = __ffs(run_ends(fmask, eqx) >> x) - 1;
@@ -311,15 +373,12 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
                                 const int left = d < 2u ? 15 - z : 15 - y;
                                 int h1 = 0;
                                 while (h1 < left && ((s_C[d * kRows + r + (h1 + 1) * stride] >> x) & 1u)) ++h1;
-                                rec |= (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
+                                s_rec[ord] = (rbase + x) | (d << 12) | (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
                             }
-                            s_rec[ord] = rec;
+                            ++ord;
                         }
-                        ++ord;
                     }
                 }
-            }
-            if (GREEDY) {
                 // RIGHT / LEFT anchors are known to the column threads: column (tx, z), anchor bit = y
 #pragma unroll
                 for (int dd = 0; dd < 2; ++dd) {
@@ -337,7 +396,7 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
                             ord += __popc(a & below) + ((d < 4 + dd) ? ((a >> tx) & 1u) : 0u);
                         }
                         ord -= q0;
-                        if (ord < kQuadRecCap) {
+                        if (ord < kRecCap) {
                             const uint32_t w1 = __ffs(run_ends(fT[dd], eqrunT) >> y0) - 1;
                             int h1 = 0;
                             while (h1 < 15 - z && ((s_CT[dd * kRows + tid + (h1 + 1) * 16] >> y0) & 1u)) ++h1;
@@ -347,17 +406,22 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
                     }
                 }
             }
+            if (tid == 0 && q0 == 0) {
+                *s_base = claimed;
+                if (claimed + slot_bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                p.entries[cur] = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
+            }
             __syncthreads();  // records and s_base visible
             const uint64_t base = *s_base;
-            const bool fits = base + quad_slot_bytes(Q, INDEXED) <= p.arena_room;
+            const bool fits = base + slot_bytes <= p.arena_room;
             uint8_t* const gout = p.arena + base;
             uint8_t* const gidx = gout + ((static_cast<uint64_t>(Q) * kQuadVertexBytesIdx + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1));
-            const uint32_t q1 = min(Q, q0 + kQuadRecCap);
-            for (uint32_t f0 = q0; f0 < q1; f0 += kTileFaces) {
+            const uint32_t q1 = min(Q, q0 + kRecCap);
+            for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {
                 if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
                 __syncthreads();
                 const uint32_t f = f0 + tid;
-                if (f < Q) {
+                if (tid < kTile && f < Q) {
                     const QuadGeom g = quad_geom(s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
                     float cx[4], cy[4], cz[4], cu[4], cv[4];
 #pragma unroll
@@ -376,7 +440,7 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
                         o[2] = make_float4(cu[1], cv[1], cx[2], cy[2]);
                         o[3] = make_float4(cz[2], cu[2], cv[2], cx[3]);
                         o[4] = make_float4(cy[3], cz[3], cu[3], cv[3]);
-                        uint2* io = reinterpret_cast<uint2*>(s_stage + 256 * 20 + tid * 6);  // 24 bytes: 3 conflict-free STS.64
+                        uint2* io = reinterpret_cast<uint2*>(s_istage + tid * 6);  // 24 bytes: 3 conflict-free STS.64
                         const uint32_t v0 = f * 4u;
                         io[0] = make_uint2(v0, v0 + 1u);
                         io[1] = make_uint2(v0 + 2u, v0 + 2u);
@@ -389,17 +453,17 @@ __global__ void __launch_bounds__(256, 3) mesh_chunks_quads_kernel(const MeshPar
                         o[9] = make_float2(cu[2], cv[2]);   o[10] = make_float2(cx[3], cy[3]);  o[11] = make_float2(cz[3], cu[3]);
                         o[12] = make_float2(cv[3], cx[0]);  o[13] = make_float2(cy[0], cz[0]);  o[14] = make_float2(cu[0], cv[0]);
                     }
-                } else if (f == Q && (Q & 1u)) {  // odd count: pad the last 16-byte unit with zeros (inside the slot's alignment gap)
-                    if (INDEXED) *reinterpret_cast<uint2*>(s_stage + 256 * 20 + tid * 6) = make_uint2(0u, 0u);
+                } else if (tid < kTile && f == Q && (Q & 1u)) {  // odd count: pad the last 16-byte unit with zeros (inside the slot's alignment gap)
+                    if (INDEXED) *reinterpret_cast<uint2*>(s_istage + tid * 6) = make_uint2(0u, 0u);
                     else *reinterpret_cast<float2*>(s_stage + tid * kFaceWords) = make_float2(0.0f, 0.0f);
                 }
                 fence_proxy_async_smem();
                 __syncthreads();
                 if (tid == 0 && fits) {
-                    const uint32_t nq = min(static_cast<uint32_t>(kTileFaces), Q - f0);
+                    const uint32_t nq = min(static_cast<uint32_t>(kTile), Q - f0);
                     if (INDEXED) {
                         bulk_store(gout + static_cast<size_t>(f0) * kQuadVertexBytesIdx, s_stage, nq * kQuadVertexBytesIdx);
-                        bulk_store(gidx + static_cast<size_t>(f0) * kQuadIndexBytes, s_stage + 256 * 20, (nq * kQuadIndexBytes + 15u) & ~15u);
+                        bulk_store(gidx + static_cast<size_t>(f0) * kQuadIndexBytes, s_istage, (nq * kQuadIndexBytes + 15u) & ~15u);
                     } else {
                         bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, s_stage, (nq * kFaceBytes + 15u) & ~15u);
                     }
