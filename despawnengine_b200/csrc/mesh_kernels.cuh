@@ -561,8 +561,8 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
 #ifdef DSP_PHASE_TIMERS
     c.tlast = clock64();
 #endif
-    // (Measured alternatives that were NOT faster on B200: consuming the ticket atomic only after the record phase, and
-    // running tickets two chunks ahead of the tiles; see profiles/README.md.)
+    // (Measured alternatives that were NOT faster on B200: consuming the ticket atomic only after the record phase,
+    // running tickets two chunks ahead of the tiles, a static first ticket per CTA; see profiles/README.md.)
     while (cur < p.n) {
         const int buf = it & 1;
         if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed

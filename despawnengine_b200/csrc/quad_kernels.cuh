@@ -28,7 +28,7 @@ constexpr int kQuadVertexBytesIdx = 80;   // 4 vertices
 constexpr int kQuadIndexBytes = 24;       // 6 x u32
 
 // Shared-memory plan.  Greedy output is small (typically 10x fewer quads than faces), so the merge kernel trades
-// staging space for residency: 128-quad tiles and a 2,048-record window make room for 4 CTAs per SM, which is what
+// staging space for residency and tile prefetch depth: 128-quad tiles and a 2,048-record window make room for 4 CTAs per SM, which is what
 // hides the per-chunk latencies (tile, barriers, the slot atomic) once there is little emission to hide them behind.
 // The unit-quad indexed kernel keeps the 256-quad tile / 4,096-record window of the parity kernel (3 CTAs per SM).
 template <bool GREEDY>
@@ -36,9 +36,10 @@ struct QuadSmem {
     static constexpr int kCtasPerSm = GREEDY ? 4 : 3;
     static constexpr int kTileQuads = GREEDY ? 128 : 256;
     static constexpr uint32_t kRecCap = GREEDY ? 2048 : 4096;         // records per window (u32 each)
+    static constexpr int kVoxBufs = 2;                                // voxel tile ring: kVoxBufs - 1 tiles in flight per CTA (3 measured slower)
     static constexpr int kT = GREEDY ? kRows * 2 : 0;                 // bytes of one [256] u16 table (none without merging)
-    static constexpr int kVox = 0;                                    // 2 x 8192
-    static constexpr int kStage = 2 * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
+    static constexpr int kVox = 0;                                    // kVoxBufs x 8192
+    static constexpr int kStage = kVoxBufs * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
     static constexpr int kRec = kStage + kTileQuads * kFaceBytes;     // kRecCap x u32
     static constexpr int kRowMask = kRec + kRecCap * 4;               // 256 x u16
     static constexpr int kF = kRowMask + kRows * 2;                   // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
@@ -50,10 +51,10 @@ struct QuadSmem {
     static constexpr int kA = kCT + 2 * kT;                           // [6][256] u16 anchor masks per row
     static constexpr int kFirst = kA + 6 * kT;                        // [256] u16 ordinal of the row's first quad
     static constexpr int kWarpTot = kFirst + kT;                      // 8 x u32 (+ pad)
-    static constexpr int kBar = kWarpTot + 64;                        // 2 x u64
-    static constexpr int kBase = kBar + 16;                           // u64
-    static constexpr int kNext = kBase + 8;                           // 2 x u32
-    static constexpr int kBytes = kNext + 8;
+    static constexpr int kBar = kWarpTot + 64;                        // kVoxBufs (<= 4) x u64
+    static constexpr int kBase = kBar + 32;                           // u64
+    static constexpr int kNext = kBase + 8;                           // kVoxBufs (<= 4) x u32
+    static constexpr int kBytes = kNext + 16;
 };
 static_assert(QuadSmem<true>::kBytes <= 57344 && QuadSmem<false>::kBytes <= 76800, "4 / 3 CTAs per SM");
 
@@ -128,7 +129,8 @@ __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox,
     const uint32_t idx = rec & 0xFFFu, d = (rec >> 12) & 7u, w1 = (rec >> 15) & 15u, h1 = (rec >> 19) & 15u;
     const uint32_t id = vox[idx];
     QuadGeom g;
-    g.uv = __ldg(&uvmap[id < n_blocks ? id : n_blocks]);
+    const uint32_t row = id < n_blocks ? id : n_blocks;  // last row = the reference's fallback (chunk_mesh.rs:53-56)
+    g.uv = __ldg(&uvmap[row]);
     const uint32_t ax = idx & 15u, ay = (idx >> 4) & 15u, az = idx >> 8;
     // far cell per axis: TOP/BOTTOM run x, stack z; REAR/FRONT run x, stack y; RIGHT/LEFT run y, stack z
     const uint32_t fx = ax + (d < 4u ? w1 : 0u);
@@ -175,32 +177,35 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
     };
 
-    // Tickets run one chunk ahead of the tiles: the atomic that fetches the ticket after next is issued at the top of an
-    // iteration and its result is first touched at the top of the following one, so its round trip to L2 is never waited
-    // for (with little emission per chunk it would otherwise sit on the critical path of every chunk).
-    uint32_t pending = 0;  // thread 0: the ticket after s_next[(it + 1) & 1]
+    // Tickets.  The first chunk of a CTA is its block index (no atomic: hundreds of CTAs hitting one counter in the same
+    // microsecond serialise in L2); later tickets are gridDim.x + atomicAdd(counter).  The atomic for the ticket after
+    // next is issued at the top of an iteration and its result is first touched at the top of the following one, so its
+    // round trip is not waited for.  (Fetching two iterations ahead measured slower: 43 -> 50 us on the bench region.)
+    constexpr int NB = L::kVoxBufs;
+    static_assert(NB == 2, "the prologue below assigns one buffer");
+    uint32_t pending = 0;  // thread 0: the ticket after the one whose tile is in flight
     if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) mbar_init(&s_bar[b], 1);
         fence_mbar_init();
-        const uint32_t t0 = atomicAdd(p.ticket, 2u);
-        s_next[0] = t0;
-        pending = t0 + 1u;
-        if (t0 < p.n) issue_load(t0, 0);
+        s_next[0] = blockIdx.x;
+        if (blockIdx.x < p.n) issue_load(blockIdx.x, 0);
+        pending = gridDim.x + atomicAdd(p.ticket, 1u);
     }
     __syncthreads();
     uint32_t cur = s_next[0];
     uint32_t it = 0;
+    int buf = 0, par = 0;  // ring position of `cur` and the phase parity of its barrier
     while (cur < p.n) {
-        const int buf = it & 1;
         if (tid == 0) {
             const uint32_t t = pending;
-            s_next[(it + 1) & 1] = t;
-            if (t < p.n) issue_load(t, buf ^ 1);  // lands while this chunk is processed
-            pending = atomicAdd(p.ticket, 1u);
+            const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
+            s_next[nb] = t;
+            if (t < p.n) issue_load(t, nb);
+            pending = gridDim.x + atomicAdd(p.ticket, 1u);
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
-        mbar_wait(&s_bar[buf], (it >> 1) & 1);
+        mbar_wait(&s_bar[buf], par);
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
 
         // ---- 1. row occupancy; is the whole chunk one block id?
@@ -223,7 +228,8 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             // all air: the reference's palette.len() == 1 early-out (chunk_mesh.rs:18-20)
             if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
             ++it;
-            cur = s_next[it & 1];
+            if (++buf == NB) { buf = 0; par ^= 1; }
+            cur = s_next[buf];
             continue;
         }
         // one solid block id throughout, chunk-local cull: exactly one 16x16 quad per side
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         uint32_t A[6] = {0u, 0u, 0u, 0u, 0u, 0u};
         uint32_t fT[2] = {0u, 0u}, AT[2] = {0u, 0u}, eqx = 0u, eqrunT = 0u;
         FaceMasks fm{};
-        uint32_t cnt = 0, first = 0, Q;
+        uint32_t cnt = 0, first = 0, wpre = 0, Q;
         if (solid_uniform) {
             Q = 6u;
             if (tid < 6) {
@@ -306,8 +312,8 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 if (lane >= o) incl += v;
             }
             if (lane == 31) s_warp[warp] = incl;
+            if (GREEDY) s_first[r] = static_cast<uint16_t>(incl - cnt);  // warp-local; a column thread's anchors lie in rows of its own warp
             __syncthreads();
-            uint32_t wpre = 0;
             Q = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -316,10 +322,6 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 Q += v;
             }
             first = wpre + incl - cnt;
-            if (GREEDY) {
-                s_first[r] = static_cast<uint16_t>(first);
-                __syncthreads();  // s_first is read by the column threads below
-            }
         }
         // claim the chunk's arena slot; the result is first touched after this thread's records are written
         const uint64_t slot_bytes = quad_slot_bytes(Q, INDEXED);
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                         const int row = y0 + 16 * z;
                         // ordinal: first quad of the anchor's row + anchors of that row that precede (tx, direction)
                         const uint32_t below = (1u << tx) - 1u;
-                        uint32_t ord = s_first[row];
+                        uint32_t ord = wpre + s_first[row];
 #pragma unroll
                         for (int d = 0; d < 6; ++d) {
                             const uint32_t a = s_A[d * kRows + row];
@@ -406,6 +408,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                     }
                 }
             }
+            if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
             if (tid == 0 && q0 == 0) {
                 *s_base = claimed;
                 if (claimed + slot_bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
@@ -418,8 +421,10 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             uint8_t* const gidx = gout + ((static_cast<uint64_t>(Q) * kQuadVertexBytesIdx + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1));
             const uint32_t q1 = min(Q, q0 + kRecCap);
             for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {
-                if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
-                __syncthreads();
+                if (f0 > q0) {  // (for the window's first tile the records barrier above did this)
+                    if (tid == 0) bulk_wait_read<0>();
+                    __syncthreads();
+                }
                 const uint32_t f = f0 + tid;
                 if (tid < kTile && f < Q) {
                     const QuadGeom g = quad_geom(s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
@@ -471,9 +476,12 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
             }
         }
-        __syncthreads();  // all reads of vox(buf), tables, s_rec, s_next done before they are overwritten
+        // No barrier here: everything the next iteration overwrites (row masks, tables, records, the staging tile, the
+        // other voxel buffer) was last read before a barrier that every thread has already passed, and each of those
+        // writes sits behind at least one barrier of the next iteration.
         ++it;
-        cur = s_next[it & 1];
+        if (++buf == NB) { buf = 0; par ^= 1; }
+        cur = s_next[buf];
     }
     if (lane == 0) bulk_wait<0>();
 }
