@@ -27,6 +27,12 @@ OPPOSITE_FACE = (1, 0, 3, 2, 5, 4)
 MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("index_count", np.uint32)])
 EDIT_DTYPE = np.dtype([("wx", np.int32), ("wy", np.int32), ("wz", np.int32), ("block", np.uint32)])
 VERTEX_DTYPE = np.dtype([("position", np.float32, 3), ("tex_coords", np.float32, 2)])  # vertex.rs:5-12
+SCENE_CONFIG_DTYPE = np.dtype([("horizontal_render_distance", np.uint32), ("vertical_render_distance", np.uint32), ("gen_kind", np.int32),
+                               ("seed", np.uint32), ("mesh_mode", np.uint32), ("reserved", np.uint32)])
+SCENE_STATS_DTYPE = np.dtype([("current_chunk", np.int32, 3), ("changed", np.uint32), ("n_visible", np.uint64), ("n_loaded_now", np.uint64),
+                              ("n_unloaded_now", np.uint64), ("n_loaded_total", np.uint64), ("n_meshes", np.uint64), ("vertex_total", np.uint64),
+                              ("index_total", np.uint64), ("arena_bytes_used", np.uint64)])
+assert SCENE_CONFIG_DTYPE.itemsize == 24 and SCENE_STATS_DTYPE.itemsize == 80
 assert MESH_ENTRY_DTYPE.itemsize == 16 and EDIT_DTYPE.itemsize == 16 and VERTEX_DTYPE.itemsize == 20
 
 # Every symbol include/despawn_b200.h declares: name -> (restype, argtypes)
@@ -56,6 +62,10 @@ SYMBOLS = {
     "dsp_pack_border_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_set_halo_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_clear_halo_slabs": (_int, [_vp]),
+    "dsp_visible_chunks": (_int, [_P(C.c_float), _u32, _u32, _u64, _P(_i32), _P(_u64)]),
+    "dsp_scene_update": (_int, [_vp, _P(C.c_float), _vp, _vp]),
+    "dsp_scene_draw_list": (_int, [_vp, _u64, _P(_i32), _vp, _P(_u64)]),
+    "dsp_scene_reset": (_int, [_vp]),
     "dsp_download_arena": (_int, [_vp, _u64, _u64, _vp]),
     "dsp_download_chunk": (_int, [_vp, _u32, _P(C.c_uint16), _P(_i32)]),
     "dsp_arena_device_ptr": (_vp, [_vp]),
@@ -88,6 +98,21 @@ def lib() -> C.CDLL:
             raise RuntimeError("ABI version mismatch between capi.py and libdespawn_b200.so")
         _lib = L
     return _lib
+
+
+def visible_chunks(camera_pos, horizontal: int, vertical: int) -> np.ndarray:
+    """get_all_chunk_pos_in_render (scene_game.rs:170-223) through the C ABI; host only, needs no GPU."""
+    cam = np.ascontiguousarray(camera_pos, dtype=np.float32).reshape(3)
+    n = C.c_uint64(0)
+    rc = lib().dsp_visible_chunks(cam.ctypes.data_as(C.POINTER(C.c_float)), horizontal, vertical, 0, None, C.byref(n))
+    if rc != OK:
+        raise RuntimeError(f"dsp_visible_chunks: status {rc}")
+    out = np.empty((int(n.value), 3), dtype=np.int32)
+    rc = lib().dsp_visible_chunks(cam.ctypes.data_as(C.POINTER(C.c_float)), horizontal, vertical, out.shape[0],
+                                  out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n))
+    if rc != OK:
+        raise RuntimeError(f"dsp_visible_chunks: status {rc}")
+    return out
 
 
 class DspError(RuntimeError):
@@ -255,6 +280,27 @@ class Context:
         nd = C.c_uint64(0)
         self._check(lib().dsp_apply_edits(self._h, e.shape[0], e.ctypes.data_as(C.c_void_p), _ptr(dirty, C.c_uint32), dirty.shape[0], C.byref(nd)))
         return dirty[: int(nd.value)].copy()
+
+    # -- scene (GameScene::update, scene_game.rs:39-82) ---------------------------------------------------
+    def scene_update(self, camera_pos, horizontal: int, vertical: int, gen_kind: int = GEN_REFERENCE, seed: int = 0, mesh_mode: int = MESH_PARITY):
+        cam = np.ascontiguousarray(camera_pos, dtype=np.float32).reshape(3)
+        cfg = np.zeros(1, dtype=SCENE_CONFIG_DTYPE)
+        cfg["horizontal_render_distance"], cfg["vertical_render_distance"] = horizontal, vertical
+        cfg["gen_kind"], cfg["seed"], cfg["mesh_mode"] = gen_kind, seed & 0xFFFFFFFF, mesh_mode
+        stats = np.zeros(1, dtype=SCENE_STATS_DTYPE)
+        self._check(lib().dsp_scene_update(self._h, _ptr(cam, C.c_float), cfg.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p)))
+        return stats[0]
+
+    def scene_draw_list(self):
+        n = C.c_uint64(0)
+        self._check(lib().dsp_scene_draw_list(self._h, 0, None, None, C.byref(n)))
+        pos = np.empty((int(n.value), 3), dtype=np.int32)
+        entries = np.empty(int(n.value), dtype=MESH_ENTRY_DTYPE)
+        self._check(lib().dsp_scene_draw_list(self._h, pos.shape[0], _ptr(pos, C.c_int32), entries.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return pos, entries
+
+    def scene_reset(self):
+        self._check(lib().dsp_scene_reset(self._h))
 
     # -- data access -------------------------------------------------------------------------------------
     def download_arena(self, offset: int, nbytes: int) -> np.ndarray:

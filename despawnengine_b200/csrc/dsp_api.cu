@@ -12,6 +12,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 #include "mesh_kernels.cuh"
@@ -98,7 +99,19 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
+    uint64_t arena_limit = 0;  // when non-zero, a mesh call may only write below this arena offset (scene allocator)
     std::string err;
+
+    // ---- scene state (dsp_scene_update): World.loaded_chunks + GameScene.chunk_meshes + last_chunk_pos
+    struct SceneChunk { uint32_t slot; uint32_t batch; dsp_mesh_entry entry; };
+    struct SceneBatch { uint64_t offset, bytes; uint32_t live; };
+    std::unordered_map<PosKey, SceneChunk, PosHash> scene_loaded;
+    std::vector<SceneBatch> scene_batches;
+    std::vector<uint32_t> scene_free_batch_ids;
+    std::map<uint64_t, uint64_t> scene_free;  // free arena intervals: offset -> bytes
+    bool scene_init = false, scene_has_last = false;
+    int32_t scene_last[3] = {0, 0, 0};
+    uint64_t scene_meshes = 0, scene_vertices = 0, scene_indices = 0;
 };
 
 namespace {
@@ -328,7 +341,7 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.n = static_cast<uint32_t>(n);
     p.arena = ctx->d_arena + arena_offset;
     p.arena_offset = arena_offset;
-    p.arena_room = ctx->arena_bytes - arena_offset;
+    p.arena_room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
     p.entries = ctx->d_entries + entry0;
     p.ticket = ctx->d_tickets + sub;
     p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
@@ -965,3 +978,5 @@ int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_m
 }
 
 }  // extern "C"
+
+#include "dsp_scene.inl"

@@ -190,6 +190,38 @@ int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int f
 int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, const void* src_device);
 int dsp_clear_halo_slabs(dsp_ctx* ctx);
 
+/* ---- scene: GameScene::update's visible set -> load -> mesh -> unload cycle (engine/scenes/scene_game.rs:39-82) -------- */
+typedef struct dsp_scene_config {
+    uint32_t horizontal_render_distance; /* "Horizonal Render Distance" of settings.json5 (engine/core/user_settings.rs:55-75) */
+    uint32_t vertical_render_distance;
+    int32_t gen_kind;                    /* dsp_gen_kind used by World::get_chunk; DSP_GEN_REFERENCE is the reference's rule */
+    uint32_t seed;
+    uint32_t mesh_mode;                  /* DSP_MESH_* (not ORDERED) */
+    uint32_t reserved;
+} dsp_scene_config;
+typedef struct dsp_scene_stats {
+    int32_t current_chunk[3]; /* (camera as i32).div_euclid(16), scene_game.rs:41-46 */
+    uint32_t changed;         /* 0: the camera is still in last_chunk_pos and nothing was done (scene_game.rs:48) */
+    uint64_t n_visible;       /* get_all_chunk_pos_in_render(...).len() */
+    uint64_t n_loaded_now, n_unloaded_now;
+    uint64_t n_loaded_total;  /* world.loaded_chunks.len() */
+    uint64_t n_meshes;        /* amount_of_chunk_meshes(): chunk_meshes.values().flatten().count() */
+    uint64_t vertex_total, index_total;
+    uint64_t arena_bytes_used;
+} dsp_scene_stats;
+/* get_all_chunk_pos_in_render (scene_game.rs:170-223) for a camera position, in the reference's order (x, then y, then z
+ * ascending).  Host only, no context.  out_pos (cap x 3, may be NULL to query the count). */
+int dsp_visible_chunks(const float camera_pos[3], uint32_t horizontal, uint32_t vertical, uint64_t cap, int32_t* out_pos, uint64_t* out_n);
+/* GameScene::update for one camera position: if the camera's chunk changed, every visible chunk that is not loaded is
+ * generated and meshed -- one terrain launch and one mesh launch for the whole set -- into a free interval of the arena,
+ * and every loaded chunk that left the visible set is unloaded (its voxel slot and, once its whole batch is gone, its
+ * arena interval are recycled).  Blocking, like the reference's update.  DSP_ERR_ARENA_FULL / DSP_ERR_STORE_FULL leave
+ * the scene as it was.  Do not mix with arena offsets chosen by hand on the same context. */
+int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_config* cfg, dsp_scene_stats* out_stats);
+/* GameScene::draw's iteration (scene_game.rs:101-125): position and arena window of every non-empty mesh. */
+int dsp_scene_draw_list(dsp_ctx* ctx, uint64_t cap, int32_t* out_pos /* cap x 3 */, dsp_mesh_entry* out_entries, uint64_t* out_n);
+int dsp_scene_reset(dsp_ctx* ctx); /* unloads everything the scene loaded */
+
 /* ---- data access ------------------------------------------------------------------------------------ */
 int dsp_download_arena(dsp_ctx* ctx, uint64_t offset_bytes, uint64_t bytes, void* host_dst);
 int dsp_download_chunk(dsp_ctx* ctx, uint32_t slot, uint16_t* host_dst /* 4096 */, int32_t* out_pos /* 3, may be NULL */);
