@@ -59,6 +59,7 @@ SYMBOLS = {
     "dsp_sync": (_int, [_vp]),
     "dsp_mesh_result": (_int, [_vp, _vp, _P(_u64)]),
     "dsp_apply_edits": (_int, [_vp, _u64, _vp, _P(_u32), _u64, _P(_u64)]),
+    "dsp_apply_edits_and_remesh": (_int, [_vp, _u64, _vp, _u32, _u64, _P(_u32), _u64, _P(_u64), _vp, _P(_u64)]),
     "dsp_pack_border_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_set_halo_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_clear_halo_slabs": (_int, [_vp]),
@@ -206,6 +207,10 @@ class Context:
         return int(s.value) if rc == OK else None
 
     @property
+    def max_chunks(self) -> int:
+        return int(lib().dsp_max_chunks(self._h))
+
+    @property
     def resident_chunks(self) -> int:
         return int(lib().dsp_resident_chunks(self._h))
 
@@ -280,6 +285,18 @@ class Context:
         nd = C.c_uint64(0)
         self._check(lib().dsp_apply_edits(self._h, e.shape[0], e.ctypes.data_as(C.c_void_p), _ptr(dirty, C.c_uint32), dirty.shape[0], C.byref(nd)))
         return dirty[: int(nd.value)].copy()
+
+    def apply_edits_and_remesh(self, edits, mode: int = MESH_PARITY, arena_offset: int = 0):
+        """Returns (dirty slots ascending, their mesh entries, total bytes)."""
+        e = np.ascontiguousarray(edits, dtype=EDIT_DTYPE).reshape(-1)
+        cap = min(e.shape[0], self.max_chunks) if e.shape[0] else 0
+        dirty = np.empty(max(cap, 1), dtype=np.uint32)
+        entries = np.zeros(max(cap, 1), dtype=MESH_ENTRY_DTYPE)
+        nd, total = C.c_uint64(0), C.c_uint64(0)
+        self._check(lib().dsp_apply_edits_and_remesh(self._h, e.shape[0], e.ctypes.data_as(C.c_void_p), mode, arena_offset, _ptr(dirty, C.c_uint32),
+                                                     dirty.shape[0], C.byref(nd), entries.ctypes.data_as(C.c_void_p), C.byref(total)))
+        k = int(nd.value)
+        return dirty[:k].copy(), entries[:k].copy(), int(total.value)
 
     # -- scene (GameScene::update, scene_game.rs:39-82) ---------------------------------------------------
     def scene_update(self, camera_pos, horizontal: int, vertical: int, gen_kind: int = GEN_REFERENCE, seed: int = 0, mesh_mode: int = MESH_PARITY):

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <map>
@@ -96,6 +97,7 @@ struct dsp_ctx {
     std::vector<uint8_t> resident;
     uint64_t next_unused = 0, n_resident = 0;
     bool nbr_dirty = true;
+    bool region_holes = false;  // a slot inside a box region has been unloaded (device-side edit addressing needs full boxes)
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
@@ -213,16 +215,24 @@ int upload_positions_and_slots(dsp_ctx* ctx, uint64_t n, const int32_t* pos, con
     uint8_t* h;
     int rc = stage_host(ctx, n * (sizeof(int4) + sizeof(uint32_t)), &h);
     if (rc != DSP_OK) return rc;
-    if (pos) {
-        int4* p4 = reinterpret_cast<int4*>(h);
-        for (uint64_t i = 0; i < n; ++i) p4[i] = make_int4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0);
-        if ((rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_pos), sizeof(int4), slots, n, h)) != DSP_OK) return rc;
-    }
     if (!consecutive) {
         uint32_t* hl = reinterpret_cast<uint32_t*>(h + n * sizeof(int4));
         std::memcpy(hl, slots, n * sizeof(uint32_t));
         DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_slots, hl, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         *d_list = ctx->d_slots;
+    }
+    if (pos) {
+        int4* p4 = reinterpret_cast<int4*>(h);
+        for (uint64_t i = 0; i < n; ++i) p4[i] = make_int4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0);
+        if (consecutive) {
+            DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos + *first, h, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+        } else {  // recycled slots are scattered: one copy + one scatter launch, not one copy per run of slots
+            if ((rc = ensure_scratch(ctx, n * sizeof(int4))) != DSP_OK) return rc;
+            DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, h, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+            dsp::scatter_pos_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_slots, reinterpret_cast<const int4*>(ctx->d_scratch),
+                                                                                                  static_cast<uint32_t>(n));
+            DSP_CUDA(ctx, cudaGetLastError());
+        }
     }
     return stage_release(ctx);
 }
@@ -451,6 +461,55 @@ int build_neighbour_table(dsp_ctx* ctx) {
         DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     ctx->nbr_dirty = false;
+    return DSP_OK;
+}
+
+// Device-side edit pipeline (terrain_kernels.cuh "device-side edit pipeline"): usable when every resident chunk lives in
+// a full box region, so that world -> slot is arithmetic.  On success the ascending dirty-slot list is in ctx->d_slots and
+// its length in *n_dirty.  *handled == false: the caller must take the host path.
+int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool* handled, uint32_t* n_dirty) {
+    *handled = false;
+    *n_dirty = 0;
+    if (!ctx->map.empty() || ctx->regions.empty() || ctx->regions.size() > dsp::kMaxEditRegions || ctx->region_holes || n >= (1u << 20)) return DSP_OK;
+    uint32_t table_size = 1024;
+    while (table_size < 4 * n) table_size <<= 1;
+    const uint32_t n_words = static_cast<uint32_t>((ctx->next_unused + 31) / 32);
+    const size_t off_table = (n * sizeof(int4) + 255) & ~size_t(255);
+    const size_t off_bitmap = off_table + static_cast<size_t>(table_size) * 8;
+    const size_t off_count = off_bitmap + static_cast<size_t>(n_words) * 4;
+    int rc = ensure_scratch(ctx, off_count + 256);
+    if (rc != DSP_OK) return rc;
+    uint8_t* h;
+    if ((rc = stage_host(ctx, n * sizeof(dsp_edit), &h)) != DSP_OK) return rc;
+    std::memcpy(h, edits, n * sizeof(dsp_edit));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, h, n * sizeof(dsp_edit), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = stage_release(ctx)) != DSP_OK) return rc;
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_scratch + off_table, 0, off_count + 4 - off_table, ctx->stream));
+    dsp::EditParams p{};
+    p.edits = reinterpret_cast<const int4*>(ctx->d_scratch);
+    p.n = static_cast<uint32_t>(n);
+    p.n_regions = static_cast<int>(ctx->regions.size());
+    for (int r = 0; r < p.n_regions; ++r) {
+        const Region& g = ctx->regions[r];
+        p.regions[r] = dsp::EditRegion{g.origin[0], g.origin[1], g.origin[2], g.dims[0], g.dims[1], g.dims[2], g.first_slot};
+    }
+    p.table = reinterpret_cast<unsigned long long*>(ctx->d_scratch + off_table);
+    p.table_mask = table_size - 1;
+    p.voxels = ctx->d_voxels;
+    p.dirty_bitmap = reinterpret_cast<uint32_t*>(ctx->d_scratch + off_bitmap);
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    dsp::edit_file_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    DSP_CUDA(ctx, cudaGetLastError());
+    dsp::edit_apply_kernel<<<grid, 256, 0, ctx->stream>>>(p);
+    DSP_CUDA(ctx, cudaGetLastError());
+    uint32_t* d_count = reinterpret_cast<uint32_t*>(ctx->d_scratch + off_count);
+    dsp::bitmap_to_list_kernel<<<1, 1024, 0, ctx->stream>>>(p.dirty_bitmap, n_words, ctx->d_slots, d_count);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 64, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_dirty = *reinterpret_cast<uint32_t*>(ctx->h_pinned + 64);
+    *handled = true;
     return DSP_OK;
 }
 
@@ -696,7 +755,7 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
         bool in_region = false;
         for (const Region& r : ctx->regions) {
             const uint64_t cnt = static_cast<uint64_t>(r.dims[0]) * r.dims[1] * r.dims[2];
-            if (s >= r.first_slot && s < r.first_slot + cnt) { in_region = true; break; }
+            if (s >= r.first_slot && s < r.first_slot + cnt) { in_region = true; ctx->region_holes = true; break; }
         }
         if (!in_region) {
             int4 p;
@@ -830,7 +889,23 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
     if (n == 0) return DSP_OK;
     if (!edits) return fail(ctx, DSP_ERR_BAD_ARG, "edits is NULL");
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
-    // world.rs:69-74 to_chunk_coord: chunk = div_euclid(w, 16), local = rem_euclid(w, 16)
+    for (uint64_t i = 0; i < n; ++i)
+        if (edits[i].block > 0xFFFFu) return fail(ctx, DSP_ERR_BAD_ARG, "edit %llu: block id %u does not fit u16", (unsigned long long)i, edits[i].block);
+    {
+        bool handled = false;
+        uint32_t nd = 0;
+        int rc = apply_edits_device(ctx, n, edits, &handled, &nd);
+        if (rc != DSP_OK) return rc;
+        if (handled) {
+            if (out_n_dirty) *out_n_dirty = nd;
+            if (out_dirty_slots) {
+                if (nd > cap_dirty) return fail(ctx, DSP_ERR_BAD_ARG, "dirty list needs %u entries, capacity %llu", nd, (unsigned long long)cap_dirty);
+                if (nd) DSP_CUDA(ctx, cudaMemcpy(out_dirty_slots, ctx->d_slots, nd * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+            }
+            return DSP_OK;
+        }
+    }
+    // host path (chunks addressed through the position map): world.rs:69-74 to_chunk_coord: chunk = div_euclid(w, 16), local = rem_euclid(w, 16)
     std::unordered_map<uint64_t, uint32_t> last;  // (slot << 12 | voxel index) -> position in `packed`
     std::vector<uint2> packed;
     packed.reserve(n);
@@ -870,6 +945,39 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
         std::memcpy(out_dirty_slots, dirty.data(), dirty.size() * sizeof(uint32_t));
     }
     return DSP_OK;
+}
+
+int dsp_apply_edits_and_remesh(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t mode, uint64_t arena_offset, uint32_t* out_dirty_slots,
+                               uint64_t cap_dirty, uint64_t* out_n_dirty, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (out_n_dirty) *out_n_dirty = 0;
+    if (out_total_bytes) *out_total_bytes = 0;
+    if (n == 0) return DSP_OK;
+    if (!edits) return fail(ctx, DSP_ERR_BAD_ARG, "edits is NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint64_t i = 0; i < n; ++i)
+        if (edits[i].block > 0xFFFFu) return fail(ctx, DSP_ERR_BAD_ARG, "edit %llu: block id %u does not fit u16", (unsigned long long)i, edits[i].block);
+    bool handled = false;
+    uint32_t nd = 0;
+    int rc = apply_edits_device(ctx, n, edits, &handled, &nd);
+    if (rc != DSP_OK) return rc;
+    if (!handled) {  // host addressing, then the ordinary mesh call
+        std::vector<uint32_t> dirty(std::min<uint64_t>(n, ctx->max_chunks));
+        uint64_t nd64 = 0;
+        if ((rc = dsp_apply_edits(ctx, n, edits, dirty.data(), dirty.size(), &nd64)) != DSP_OK) return rc;
+        if (out_n_dirty) *out_n_dirty = nd64;
+        if (out_dirty_slots) {
+            if (nd64 > cap_dirty) return fail(ctx, DSP_ERR_BAD_ARG, "dirty list needs %llu entries, capacity %llu", (unsigned long long)nd64, (unsigned long long)cap_dirty);
+            std::memcpy(out_dirty_slots, dirty.data(), nd64 * sizeof(uint32_t));
+        }
+        return dsp_mesh_chunks(ctx, nd64, dirty.data(), mode, arena_offset, out_entries, out_total_bytes);
+    }
+    if (out_n_dirty) *out_n_dirty = nd;
+    if (out_dirty_slots && nd > cap_dirty) return fail(ctx, DSP_ERR_BAD_ARG, "dirty list needs %u entries, capacity %llu", nd, (unsigned long long)cap_dirty);
+    // the dirty list never leaves the device between the edit kernels and the mesh kernel
+    if ((rc = enqueue_mesh(ctx, nd, ctx->d_slots, 0, mode, arena_offset)) != DSP_OK) return rc;
+    if (out_dirty_slots && nd) DSP_CUDA(ctx, cudaMemcpyAsync(out_dirty_slots, ctx->d_slots, nd * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    return finish_mesh(ctx, out_entries, out_total_bytes);
 }
 
 int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, void* dst_device) {

@@ -105,6 +105,8 @@ int dsp_scene_reset(dsp_ctx* ctx) {
         ctx->resident[s] = 0;
         ctx->n_resident--;
     }
+    // hand slots out again lowest first (free_slots is popped from the back): consecutive slots are one copy / no list
+    std::sort(ctx->free_slots.begin(), ctx->free_slots.end(), std::greater<uint32_t>());
     if (!ctx->scene_loaded.empty()) ctx->nbr_dirty = true;
     ctx->scene_loaded.clear();
     ctx->scene_batches.clear();

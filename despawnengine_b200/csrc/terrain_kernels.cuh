@@ -215,6 +215,10 @@ __global__ void region_neighbours_kernel(uint32_t* nbr, uint32_t first_slot, uin
         o[5] = a + 1 < dims.x ? s + 1 : 0xFFFFFFFFu;
     }
 }
+__global__ void scatter_pos_kernel(int4* chunk_pos, const uint32_t* slots, const int4* src, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) chunk_pos[slots[i]] = src[i];
+}
 __global__ void scatter_u32_kernel(uint32_t* dst, const uint2* idx_val, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[idx_val[i].x] = idx_val[i].y;
@@ -251,6 +255,106 @@ __global__ void edit_scatter_kernel(uint16_t* voxels, const uint2* edits, uint32
     if (i >= n) return;
     const uint2 e = edits[i];
     voxels[static_cast<size_t>(e.x) * kChunkVoxels + (e.y & 0xFFFu)] = static_cast<uint16_t>(e.y >> 16);
+}
+
+// ---- device-side edit pipeline for worlds made of box regions (dsp_apply_edits / dsp_apply_edits_and_remesh) ------------
+// World::get_block_world addressing (world.rs:50-74): chunk = div_euclid(w, 16), local = rem_euclid(w, 16); Chunk::set_block
+// (chunk.rs:49-68) on the voxel.  The edits of one call apply IN ORDER, so when several hit the same voxel the last
+// one must win: pass 1 files every edit under its voxel key in an open-addressed table keeping the highest edit index
+// (one atomicMax per edit), pass 2 lets only that edit write, and marks the chunk in a bitmap; pass 3 turns the
+// bitmap into the ascending list of dirty slots that the mesh kernel then consumes straight from device memory.
+struct EditRegion {
+    int32_t ox, oy, oz;
+    uint32_t dx, dy, dz;
+    uint32_t first_slot;
+};
+constexpr int kMaxEditRegions = 8;
+struct EditParams {
+    const int4* edits;        // wx, wy, wz, block
+    uint32_t n;
+    EditRegion regions[kMaxEditRegions];
+    int n_regions;
+    unsigned long long* table;  // (key + 1) << 20 | edit index; zeroed before the call
+    uint32_t table_mask;
+    uint16_t* voxels;
+    uint32_t* dirty_bitmap;   // one bit per slot; zeroed before the call
+};
+
+__device__ __forceinline__ bool edit_key(const EditParams& p, const int4 e, uint64_t* key) {
+    const int32_t cx = e.x >> 4, cy = e.y >> 4, cz = e.z >> 4;
+    for (int r = 0; r < p.n_regions; ++r) {
+        const EditRegion& g = p.regions[r];
+        const int64_t a = static_cast<int64_t>(cx) - g.ox, b = static_cast<int64_t>(cy) - g.oy, c = static_cast<int64_t>(cz) - g.oz;
+        if (a < 0 || b < 0 || c < 0 || a >= g.dx || b >= g.dy || c >= g.dz) continue;
+        const uint64_t slot = g.first_slot + static_cast<uint64_t>(a) + g.dx * (static_cast<uint64_t>(b) + static_cast<uint64_t>(g.dy) * c);
+        *key = (slot << 12) | static_cast<uint32_t>((e.x & 15) + 16 * (e.y & 15) + 256 * (e.z & 15));
+        return true;
+    }
+    return false;  // not resident: ignored, like an edit outside the loaded world
+}
+__device__ __forceinline__ uint32_t edit_hash(uint64_t key) {
+    key *= 0x9E3779B97F4A7C15ull;
+    return static_cast<uint32_t>(key >> 32);
+}
+
+__global__ void edit_file_kernel(const EditParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    uint64_t key;
+    if (!edit_key(p, p.edits[i], &key)) return;
+    const unsigned long long tag = (key + 1ull) << 20, mine = tag | i;
+    for (uint32_t h = edit_hash(key) & p.table_mask;; h = (h + 1) & p.table_mask) {
+        unsigned long long cur = p.table[h];
+        if (cur == 0ull) {
+            cur = atomicCAS(&p.table[h], 0ull, mine);
+            if (cur == 0ull) return;
+        }
+        if ((cur >> 20) == (tag >> 20)) { atomicMax(&p.table[h], mine); return; }
+    }
+}
+
+__global__ void edit_apply_kernel(const EditParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    const int4 e = p.edits[i];
+    uint64_t key;
+    if (!edit_key(p, e, &key)) return;
+    const unsigned long long tag = (key + 1ull) << 20;
+    for (uint32_t h = edit_hash(key) & p.table_mask;; h = (h + 1) & p.table_mask) {
+        const unsigned long long cur = p.table[h];
+        if ((cur >> 20) != (tag >> 20)) continue;  // filed by pass 1, so the probe always ends
+        if ((cur & 0xFFFFFull) == i) {
+            p.voxels[key] = static_cast<uint16_t>(e.w);  // key == slot * 4096 + voxel index
+            const uint32_t slot = static_cast<uint32_t>(key >> 12);
+            atomicOr(&p.dirty_bitmap[slot >> 5], 1u << (slot & 31u));
+        }
+        return;
+    }
+}
+
+// One CTA of 1,024 threads: ascending list of the set bits of bitmap[0 .. n_words).
+__global__ void __launch_bounds__(1024) bitmap_to_list_kernel(const uint32_t* bitmap, uint32_t n_words, uint32_t* out_list, uint32_t* out_count) {
+    __shared__ uint32_t s_warp[32];
+    const uint32_t t = threadIdx.x, per = (n_words + 1023u) / 1024u;
+    const uint32_t w0 = min(n_words, t * per), w1 = min(n_words, w0 + per);
+    uint32_t cnt = 0;
+    for (uint32_t w = w0; w < w1; ++w) cnt += __popc(bitmap[w]);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if ((t & 31u) >= static_cast<uint32_t>(o)) incl += v;
+    }
+    if ((t & 31u) == 31u) s_warp[t >> 5] = incl;
+    __syncthreads();
+    uint32_t pre = 0, total = 0;
+    for (uint32_t w = 0; w < 32; ++w) { const uint32_t v = s_warp[w]; pre += w < (t >> 5) ? v : 0u; total += v; }
+    uint32_t o = pre + incl - cnt;
+    for (uint32_t w = w0; w < w1; ++w) {
+        uint32_t bits = bitmap[w];
+        while (bits) { out_list[o++] = w * 32u + (__ffs(bits) - 1); bits &= bits - 1; }
+    }
+    if (t == 0) *out_count = total;
 }
 
 // Border layer of each listed chunk at `face` (0 top y=15, 1 bottom y=0, 2 rear z=0, 3 front z=15, 4 right x=0, 5 left

@@ -68,6 +68,7 @@ struct Chunk {
 struct ChunkMesh {
     uint64_t offset_bytes = 0;
     uint32_t vertex_count = 0;
+    uint32_t index_count = 0;  // > 0 with DSP_MESH_INDEXED: u32 indices at offset_bytes + align128(20 * vertex_count)
     uint32_t len() const { return vertex_count; }  // mesh.len() as used by draw(), scene_game.rs:118-122
 };
 
@@ -164,7 +165,7 @@ inline std::vector<std::optional<ChunkMesh>> build_chunk_meshes(World& world, co
     world.arena_top += total;
     std::vector<std::optional<ChunkMesh>> out;
     for (const dsp_mesh_entry& e : entries)
-        out.push_back(e.vertex_count ? std::optional<ChunkMesh>(ChunkMesh{e.offset_bytes, e.vertex_count}) : std::nullopt);
+        out.push_back(e.vertex_count ? std::optional<ChunkMesh>(ChunkMesh{e.offset_bytes, e.vertex_count, e.index_count}) : std::nullopt);
     return out;
 }
 // chunk_mesh.rs:13-17 -- nullopt where the reference returns None
@@ -183,5 +184,37 @@ inline std::vector<ChunkPos> visible_chunks(const ChunkPos& cam, int32_t hori_di
             }
     return out;
 }
+
+// GameScene (engine/scenes/scene_game.rs:27-32, 39-82, 101-125) over dsp_scene_update: `update` is the whole per-frame
+// cycle (early-out while the camera stays in its chunk, visible set, batched load + mesh, unload), `draw_list` the
+// chunk_meshes.values().flatten() walk of draw().
+class GameScene {
+public:
+    GameScene(World& world, uint32_t horizontal_render_distance, uint32_t vertical_render_distance, int gen_kind = DSP_GEN_REFERENCE,
+              uint32_t seed = 0, uint32_t mesh_mode = DSP_MESH_PARITY)
+        : world_(world), cfg_{horizontal_render_distance, vertical_render_distance, gen_kind, seed, mesh_mode, 0u} {}
+    dsp_scene_stats update(const std::array<float, 3>& camera_pos, const BlockUvs& block_uvs) {
+        world_.set_block_uvs(block_uvs);
+        dsp_scene_stats st{};
+        world_.check(dsp_scene_update(world_.ctx(), camera_pos.data(), &cfg_, &st));
+        return st;
+    }
+    std::vector<std::pair<ChunkPos, ChunkMesh>> draw_list() {
+        uint64_t n = 0;
+        world_.check(dsp_scene_draw_list(world_.ctx(), 0, nullptr, nullptr, &n));
+        std::vector<int32_t> pos(3 * n);
+        std::vector<dsp_mesh_entry> entries(n);
+        world_.check(dsp_scene_draw_list(world_.ctx(), n, pos.data(), entries.data(), &n));
+        std::vector<std::pair<ChunkPos, ChunkMesh>> out;
+        for (uint64_t i = 0; i < n; ++i)
+            out.push_back({ChunkPos{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, ChunkMesh{entries[i].offset_bytes, entries[i].vertex_count, entries[i].index_count}});
+        return out;
+    }
+    size_t amount_of_chunk_meshes() { return draw_list().size(); }  // scene_game.rs:272-274
+
+private:
+    World& world_;
+    dsp_scene_config cfg_;
+};
 
 }  // namespace despawn

@@ -172,6 +172,15 @@ int dsp_mesh_result(dsp_ctx* ctx, dsp_mesh_entry* out_entries /* n of the last m
 int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty,
                     uint64_t* out_n_dirty);
 
+/* dsp_apply_edits followed by the whole-chunk remesh of the dirty chunks (the reference's only granularity:
+ * build_chunk_mesh, chunk_mesh.rs:13-129) in one call.  When every resident chunk belongs to a dsp_generate_region box,
+ * world -> (slot, voxel) addressing, last-edit-wins de-duplication, the voxel writes and the ascending dirty list all run
+ * on the device and the mesh kernel takes the list from device memory; otherwise addressing runs on the host.
+ * out_entries[i] is the mesh of out_dirty_slots[i].  Blocking. */
+int dsp_apply_edits_and_remesh(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t mode, uint64_t arena_offset,
+                               uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty, dsp_mesh_entry* out_entries,
+                               uint64_t* out_total_bytes);
+
 /* ---- region seams (multi-GPU halo mode) ----------------------------------------------------- */
 /* Faces are numbered in the reference's emission order (chunk_mesh.rs:46-51, 65-106). */
 #define DSP_FACE_TOP 0    /* +Y, layer y = 15 */

@@ -24,6 +24,14 @@ int main(int argc, char** argv) {
         world.put_chunk(c);
         const auto m = build_chunk_mesh(world, {40, 0, 0}, block_uvs);
         std::printf("%u\n", m ? m->len() : 0u);
+        {   // the same first frame through GameScene::update (one terrain launch + one mesh launch), then one chunk to the +x
+            World w2(4096, 512ull << 20);
+            GameScene scene(w2, 10, 4);
+            const dsp_scene_stats a = scene.update({2.5f, 22.5f, -2.5f}, block_uvs);
+            const dsp_scene_stats b = scene.update({18.5f, 22.5f, -2.5f}, block_uvs);
+            std::printf("%llu %llu %llu %llu %llu %zu\n", (unsigned long long)a.n_loaded_total, (unsigned long long)a.n_meshes, (unsigned long long)a.vertex_total,
+                        (unsigned long long)b.n_loaded_now, (unsigned long long)b.n_unloaded_now, scene.amount_of_chunk_meshes());
+        }
         if (argc > 1) {
             const auto origin = build_chunk_mesh(world, {0, 0, 0}, block_uvs);
             const auto v = world.download(*origin);

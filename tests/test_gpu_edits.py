@@ -1,0 +1,104 @@
+"""Config 4 semantics (incremental remesh): block edits in world coordinates (world.rs:50-74 addressing, Chunk::set_block
+chunk.rs:49-68), edits of one call apply in order (the last edit of a voxel wins), the dirty chunks are re-meshed whole
+(build_chunk_mesh is the reference's only granularity).  Both addressing paths -- on the device for box-region worlds, on
+the host for chunks held in the position map -- must give the same voxels, dirty list and byte-exact meshes."""
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from despawnengine_b200 import capi
+from oracle import loader as orc
+
+pytestmark = pytest.mark.gpu
+SEED = 0xD5E50001
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    entry.build()
+
+
+def make_edits(rng, k, lo, hi, dup_frac=0.3):
+    e = np.zeros(k, dtype=capi.EDIT_DTYPE)
+    for a, name in enumerate(("wx", "wy", "wz")):
+        e[name] = rng.integers(lo[a], hi[a], k)
+    e["block"] = np.where(rng.random(k) < 0.5, 0, rng.integers(1, 4, k))
+    nd = int(k * dup_frac)  # many repeated voxels with different blocks: order matters
+    src = rng.integers(0, k, nd)
+    dst = rng.integers(0, k, nd)
+    for name in ("wx", "wy", "wz"):
+        e[name][dst] = e[name][src]
+    return e
+
+
+def replay(edits, chunks):
+    """chunks: {chunk pos: ids (modified in place)}.  Returns the set of touched chunk positions."""
+    touched = set()
+    for e in edits:
+        c = (int(e["wx"]) >> 4, int(e["wy"]) >> 4, int(e["wz"]) >> 4)  # div_euclid(16)
+        if c in chunks:
+            chunks[c][(int(e["wx"]) & 15) + 16 * (int(e["wy"]) & 15) + 256 * (int(e["wz"]) & 15)] = e["block"]  # rem_euclid(16)
+            touched.add(c)
+    return touched
+
+
+@pytest.mark.parametrize("layout", ["regions", "map", "mixed"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_edits_apply_in_order_and_dirty_chunks_remesh_byte_exact(uv_default, layout, fused):
+    rng = np.random.default_rng(11)
+    with capi.Context(0, 1024, 256 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        slot_of = {}
+        boxes = [((-2, 5, -3), (3, 3, 4)), ((4, 6, 1), (2, 2, 2))]
+        if layout in ("regions", "mixed"):
+            for origin, dims in boxes:
+                first = ctx.generate_region(origin, dims, capi.GEN_NOISE, SEED)
+                for c in range(dims[2]):
+                    for b in range(dims[1]):
+                        for a in range(dims[0]):
+                            slot_of[(origin[0] + a, origin[1] + b, origin[2] + c)] = first + a + dims[0] * (b + dims[1] * c)
+        if layout in ("map", "mixed"):
+            extra = [(-3, 6, 0), (-3, 7, 0), (10, 6, 10)] if layout == "mixed" else [(origin[0] + a, origin[1] + b, origin[2] + c) for origin, dims in boxes
+                                                                                      for c in range(dims[2]) for b in range(dims[1]) for a in range(dims[0])]
+            for p, s in zip(extra, ctx.generate_chunks(extra, capi.GEN_NOISE, SEED)):
+                slot_of[p] = int(s)
+        chunks = {p: orc.generate(orc.GEN_NOISE, SEED, p) for p in slot_of}
+        pos_of = {s: p for p, s in slot_of.items()}
+        for frame in range(3):
+            edits = make_edits(rng, 4000, (-4 * 16, 4 * 16, -4 * 16), (12 * 16, 9 * 16, 12 * 16))
+            if fused:
+                dirty, entries, total = ctx.apply_edits_and_remesh(edits)
+            else:
+                dirty = ctx.apply_edits(edits)
+                entries, total = ctx.mesh_chunks(dirty)
+            touched = replay(edits, chunks)
+            assert list(map(int, dirty)) == sorted(slot_of[p] for p in touched)
+            assert total == int(sum(((int(e["vertex_count"]) * 20 + 127) & ~127) for e in entries))
+            for s, e in zip(dirty, entries):
+                p = pos_of[int(s)]
+                assert np.array_equal(ctx.download_chunk(int(s))[0], chunks[p]), p
+                assert ctx.download_vertices(e).tobytes() == orc.mesh_chunk(p, chunks[p], uv_default).tobytes(), p
+
+
+def test_many_edits_to_one_voxel_and_no_resident_target(uv_default):
+    with capi.Context(0, 64, 16 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        first = ctx.generate_region((0, -1, 0), (1, 1, 1), capi.GEN_REFERENCE, 0)  # one full chunk
+        e = np.zeros(5000, dtype=capi.EDIT_DTYPE)
+        e["wx"], e["wy"], e["wz"] = 3, -5, 9
+        e["block"] = np.arange(5000) % 3
+        e["block"][-1] = 0  # the last one destroys the block
+        dirty, entries, _ = ctx.apply_edits_and_remesh(e)
+        ids = orc.generate(orc.GEN_REFERENCE, 0, (0, -1, 0))
+        ids[3 + 16 * 11 + 256 * 9] = 0
+        assert list(dirty) == [first] and np.array_equal(ctx.download_chunk(first)[0], ids)
+        assert ctx.download_vertices(entries[0]).tobytes() == orc.mesh_chunk((0, -1, 0), ids, uv_default).tobytes()
+        far = np.zeros(10, dtype=capi.EDIT_DTYPE)
+        far["wx"] = 1000
+        dirty, entries, total = ctx.apply_edits_and_remesh(far)
+        assert len(dirty) == 0 and total == 0
+        bad = np.zeros(1, dtype=capi.EDIT_DTYPE)
+        bad["block"] = 70000
+        with pytest.raises(capi.DspError) as ei:
+            ctx.apply_edits(bad)
+        assert ei.value.status == capi.ERR_BAD_ARG

@@ -40,5 +40,7 @@ def test_cpp_host_mirror_first_frame(tmp_path):
     lines = r.stdout.strip().splitlines()
     assert lines[0].split() == ["2853", "1268", "10712064"]
     assert lines[1] == "72"  # two isolated voxels: 12 faces
+    # GameScene::update: same first frame; one chunk to +x swaps 21 columns x 9 layers in and out, mesh count unchanged
+    assert lines[2].split() == ["2853", "1268", "10712064", "189", "189", "1268"]
     golden = np.fromfile(os.path.join(ROOT, "tests", "golden", "flat_chunk_origin.bin"), dtype=np.uint8)
     assert np.fromfile(dump, dtype=np.uint8).tobytes() == golden.tobytes()
