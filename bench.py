@@ -25,6 +25,16 @@ import time
 
 import numpy as np
 
+# The contract is ONE JSON line on stdout.  Libraries below us write there too (NCCL prints "NCCL version ..." to fd 1 when
+# a communicator is created), so fd 1 is pointed at stderr for the whole run and the line goes to the saved descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -145,7 +155,7 @@ def reference_arm(args, rank):
                          "sample": f"all {N_CHUNKS} chunks of the workload per step, {steps_done} steps"},
         "e2e": {"value": value, "unit": "chunks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -376,7 +386,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if distributed:
         dist.destroy_process_group()
