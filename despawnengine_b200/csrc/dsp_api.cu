@@ -654,7 +654,7 @@ int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_ki
     const uint32_t* d_list; uint32_t first;
     int rc = upload_positions_and_slots(ctx, n, pos, slots.data(), &d_list, &first);
     if (rc != DSP_OK) return rc;
-    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed};
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr};
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
     dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
@@ -692,14 +692,14 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches += 1;
     } else {
-        dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
-            ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), n);
-        DSP_CUDA(ctx, cudaGetLastError());
-        dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed};
+        if (n > 0xFFFFFFFFull) return fail(ctx, DSP_ERR_BAD_ARG, "region too large");
+        // positions are arithmetic in a box: the fill kernel derives them from the chunk's index and records them itself
+        dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed,
+                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos};
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
         dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
         DSP_CUDA(ctx, cudaGetLastError());
-        ctx->launches += 2;
+        ctx->launches += 1;
     }
     *out_first_slot = first;
     return DSP_OK;

@@ -248,7 +248,9 @@ struct MeshCta {
 
     // ---- count phase: row occupancy -> six face masks -> per-row count -> block scan.  2 CTA barriers.
     //      With `publish`, thread 0 posts the chunk's byte size for the look-back of later chunks.
-    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish) const {
+    // `skip_empty`: when the chunk is all air (the reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20) only the
+    // first barrier is executed and total = cnt = 0 is returned with *empty = true; the caller then does nothing else.
+    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish, bool* empty = nullptr) const {
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
         uint32_t m;
         {
@@ -258,7 +260,12 @@ struct MeshCta {
             m = (nonzero_mask8(qa) << (8 * h)) | (nonzero_mask8(qb) << (8 * (h ^ 1)));
         }
         s_rowmask[r] = static_cast<uint16_t>(m);
-        __syncthreads();
+        if (empty != nullptr) {
+            *empty = __syncthreads_or(m != 0u) == 0;
+            if (*empty) return RowFaces{};
+        } else {
+            __syncthreads();
+        }
         RowFaces f;
         {
             const FaceMasks fm = row_face_masks<HALO>(p, HALO ? slot_of(chunk) : 0u, s_rowmask, r, y, z, m);
@@ -573,8 +580,22 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         c.tick(7);
         mbar_wait(&c.s_bar[buf], (it >> 1) & 1);
         c.tick(2);
+#ifndef DSP_NO_EMPTY_SKIP
+        bool empty;
+        const RowFaces fc = c.count_phase(cur, buf, false, &empty);
+        c.tick(3);
+        if (empty) {
+            // Nothing to emit and no slot to claim.  No further barrier is needed: every read of vox(buf) precedes the
+            // barrier inside count_phase, and s_next[(it + 1) & 1] was written by thread 0 before it.
+            if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+            ++it;
+            cur = c.s_next[it & 1];
+            continue;
+        }
+#else
         const RowFaces fc = c.count_phase(cur, buf, false);
         c.tick(3);
+#endif
         c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
             if (tid == 0) {  // claim the chunk's arena slot
                 const uint64_t bytes = slot_bytes_of(fc.total);

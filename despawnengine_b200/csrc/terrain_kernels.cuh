@@ -21,6 +21,11 @@ struct TerrainParams {
     uint32_t n;
     int kind;
     uint32_t seed;
+    // box form (dsp_generate_region): when dims.x != 0 chunk i of the box is at origin + (i % dx, (i / dx) % dy, i / (dx dy)),
+    // no position is loaded and chunk_pos_out[slot] is written instead
+    int3 origin;
+    uint3 dims;
+    int4* chunk_pos_out;
 };
 
 // smoothstep-weighted bilinear value noise on a lattice whose values were hashed once per chunk
@@ -39,22 +44,26 @@ __device__ __forceinline__ uint32_t octave_from_lattice(const uint32_t* lat, int
     return (a * (256U - sz) + b * sz) >> 16;
 }
 
+// Store shape: a chunk is 512 half-rows of 8 voxels (16 bytes).  Thread t writes half-rows t and t + 256, so every
+// warp-wide store instruction covers 512 CONTIGUOUS bytes (four full 128-byte lines).  (The first version gave each
+// thread one whole row = two 16-byte stores 32 bytes apart; each instruction then touched only half of every 32-byte
+// sector and the kernel stalled at 3.8-4.0 TB/s of a ~6.8 TB/s write path, profiles/README.md.)
 __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p) {
     __shared__ uint32_t s_lat[3][9];
     __shared__ int32_t s_h[256];  // [z][x] column heights
     const int tid = threadIdx.x;
     for (uint32_t i = blockIdx.x; i < p.n; i += gridDim.x) {
         const uint32_t slot = p.slot_list ? p.slot_list[i] : p.first_slot + i;
-        const int4 cp = p.chunk_pos[slot];
-        const int y = tid & 15, z = tid >> 4;
-        const int32_t wy = cp.y * 16 + y, wz = cp.z * 16 + z, wx0 = cp.x * 16;
-        uint32_t w[8];  // 16 voxels, two per word, x ascending
-        if (p.kind == 0) {
-            // world.rs:35-42: Y > 0 empty, Y == 0 bottom half dirt (y < 8), Y < 0 full.
-            const uint32_t id = cp.y > 0 ? 0u : (cp.y == 0 ? (y < 8 ? 1u : 0u) : 1u);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = id | (id << 16);
-        } else if (p.kind == 1) {
+        int4 cp;
+        if (p.dims.x != 0u) {
+            const uint32_t a = i % p.dims.x, t = i / p.dims.x;
+            cp = make_int4(p.origin.x + static_cast<int32_t>(a), p.origin.y + static_cast<int32_t>(t % p.dims.y), p.origin.z + static_cast<int32_t>(t / p.dims.y), 0);
+            if (tid == 0) p.chunk_pos_out[slot] = cp;
+        } else {
+            cp = p.chunk_pos[slot];
+        }
+        const int32_t wx0 = cp.x * 16;
+        if (p.kind == 1) {
             if (tid < 27) {  // lattice values for the three octaves, hashed once per chunk
                 const int o = tid / 9, q = tid % 9, s = 5 - o;
                 s_lat[o][q] = hash2(p.seed + static_cast<uint32_t>(o), (wx0 >> s) + q % 3, ((cp.z * 16) >> s) + q / 3) & 0xFFU;
@@ -72,39 +81,59 @@ __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p
                 s_h[tid] = 16 + static_cast<int32_t>(n >> 3);
             }
             __syncthreads();
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int32_t h0 = s_h[z * 16 + 2 * k], h1 = s_h[z * 16 + 2 * k + 1];
-                const uint32_t a = wy < h0 - 1 ? 1u : (wy == h0 - 1 ? 2u : 0u);
-                const uint32_t b = wy < h1 - 1 ? 1u : (wy == h1 - 1 ? 2u : 0u);
-                w[k] = a | (b << 16);
-            }
-            __syncthreads();  // s_h / s_lat reused by the next chunk of this CTA
-        } else if (p.kind == 2) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const uint32_t r0 = hash3(p.seed, wx0 + 2 * k, wy, wz), r1 = hash3(p.seed, wx0 + 2 * k + 1, wy, wz);
-                const uint32_t a = (r0 & 1U) ? 1U + ((r0 >> 1) & 1U) : 0U;
-                const uint32_t b = (r1 & 1U) ? 1U + ((r1 >> 1) & 1U) : 0U;
-                w[k] = a | (b << 16);
-            }
-        } else {
-            // checkerboard: (wx+wy+wz) even -> 1.  wx0 is a multiple of 16, so parity is local.
-            const uint32_t even_first = ((wy + wz) & 1) == 0 ? 1u : 0u;  // voxel at even x
-            const uint32_t word = even_first | ((even_first ^ 1u) << 16);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w[k] = word;
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        if (p.kind == 2) {
+            // hash3(seed, wx, wy, wz) = mix32(hash2(seed, wx, wy) + wz * K): the inner hash2 (three of the four mix32 rounds)
+            // is shared by the 16 voxels of a z-column, so it is computed once per (x, y) and kept in shared memory
+            s_h[tid] = static_cast<int32_t>(hash2(p.seed, wx0 + (tid & 15), cp.y * 16 + (tid >> 4)));
+            __syncthreads();
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels);
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+            const int hr = tid + 256 * part;          // half-row: voxels [8 hr, 8 hr + 8)
+            const int row = hr >> 1, x0 = (hr & 1) * 8, y = row & 15, z = row >> 4;
+            const int32_t wy = cp.y * 16 + y, wz = cp.z * 16 + z;
+            uint32_t w[4];  // 8 voxels, two per word, x ascending
+            if (p.kind == 0) {
+                // world.rs:35-42: Y > 0 empty, Y == 0 bottom half dirt (y < 8), Y < 0 full.
+                const uint32_t id = cp.y > 0 ? 0u : (cp.y == 0 ? (y < 8 ? 1u : 0u) : 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = id | (id << 16);
+            } else if (p.kind == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int32_t h0 = s_h[z * 16 + x0 + 2 * k], h1 = s_h[z * 16 + x0 + 2 * k + 1];
+                    const uint32_t a = wy < h0 - 1 ? 1u : (wy == h0 - 1 ? 2u : 0u);
+                    const uint32_t b = wy < h1 - 1 ? 1u : (wy == h1 - 1 ? 2u : 0u);
+                    w[k] = a | (b << 16);
+                }
+            } else if (p.kind == 2) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t zk = static_cast<uint32_t>(wz) * 0x27D4EB2FU;
+                    const uint32_t r0 = mix32(static_cast<uint32_t>(s_h[y * 16 + x0 + 2 * k]) + zk), r1 = mix32(static_cast<uint32_t>(s_h[y * 16 + x0 + 2 * k + 1]) + zk);
+                    const uint32_t a = (r0 & 1U) ? 1U + ((r0 >> 1) & 1U) : 0U;
+                    const uint32_t b = (r1 & 1U) ? 1U + ((r1 >> 1) & 1U) : 0U;
+                    w[k] = a | (b << 16);
+                }
+            } else {
+                // checkerboard: (wx+wy+wz) even -> 1.  wx0 and x0 are even, so parity is local.
+                const uint32_t even_first = ((wy + wz) & 1) == 0 ? 1u : 0u;  // voxel at even x
+                const uint32_t word = even_first | ((even_first ^ 1u) << 16);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] = word;
+            }
+            dst[hr] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (p.kind == 1 || p.kind == 2) __syncthreads();  // s_h / s_lat reused by the next chunk of this CTA
     }
 }
 
 // NOISE terrain for a whole box of chunks (dsp_generate_region).  The heightmap depends on (x, z) only, so one CTA
 // takes a chunk column (a, c) and a run of `ny` vertically stacked chunks: the 27 lattice hashes and the 256 column
 // heights are computed ONCE and reused for every chunk of the run; per chunk only the row compare/pack and the two
-// 128-bit stores per thread remain, and rows entirely below / above the surface of their z-slice skip the per-voxel
+// 128-bit stores per thread remain (coalesced as in terrain_fill_kernel), and rows entirely below / above the surface of their z-slice skip the per-voxel
 // compare.  (The per-chunk kernel above spends 2,500 warp-instructions per chunk on the heights and is issue-bound at
 // 2.2 TB/s; this one is bound by the 8,192 bytes it writes per chunk.)  Same integer arithmetic as the oracle.
 struct RegionFillParams {
@@ -155,32 +184,35 @@ __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const Re
             if (x == 0) { s_zmin[zc] = lo; s_zmax[zc] = hi; }
         }
         __syncthreads();
-        const int y = tid & 15, z = tid >> 4;
-        const int32_t zlo = s_zmin[z], zhi = s_zmax[z];
         const uint32_t b0 = piece * p.ny, b1 = min(p.dims.y, b0 + p.ny);
         for (uint32_t b = b0; b < b1; ++b) {
             const int32_t cy = p.origin.y + static_cast<int32_t>(b);
-            const int32_t wy = cy * 16 + y;
             const uint32_t slot = p.first_slot + a + p.dims.x * (b + p.dims.y * c);
-            uint32_t w[8];
-            if (wy < zlo - 1) {            // whole row below every surface voxel of the slice: body block
+            uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[k] = 0x00010001u;
-            } else if (wy > zhi - 1) {     // whole row above the surface: air
+            for (int part = 0; part < 2; ++part) {
+                const int hr = tid + 256 * part;  // half-row: 512 contiguous bytes per warp-wide store (see terrain_fill_kernel)
+                const int row = hr >> 1, x0 = (hr & 1) * 8, y = row & 15, z = row >> 4;
+                const int32_t wy = cy * 16 + y;
+                const int32_t zlo = s_zmin[z], zhi = s_zmax[z];
+                uint32_t w[4];
+                if (wy < zlo - 1) {            // whole row below every surface voxel of the slice: body block
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w[k] = 0u;
-            } else {
+                    for (int k = 0; k < 4; ++k) w[k] = 0x00010001u;
+                } else if (wy > zhi - 1) {     // whole row above the surface: air
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int32_t h0 = s_h[z * 16 + 2 * k], h1 = s_h[z * 16 + 2 * k + 1];
-                    const uint32_t v0 = wy < h0 - 1 ? 1u : (wy == h0 - 1 ? 2u : 0u);
-                    const uint32_t v1 = wy < h1 - 1 ? 1u : (wy == h1 - 1 ? 2u : 0u);
-                    w[k] = v0 | (v1 << 16);
+                    for (int k = 0; k < 4; ++k) w[k] = 0u;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int32_t h0 = s_h[z * 16 + x0 + 2 * k], h1 = s_h[z * 16 + x0 + 2 * k + 1];
+                        const uint32_t v0 = wy < h0 - 1 ? 1u : (wy == h0 - 1 ? 2u : 0u);
+                        const uint32_t v1 = wy < h1 - 1 ? 1u : (wy == h1 - 1 ? 2u : 0u);
+                        w[k] = v0 | (v1 << 16);
+                    }
                 }
+                dst[hr] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            uint4* dst = reinterpret_cast<uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
-            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
             if (tid == 0) p.chunk_pos[slot] = make_int4(cx, cy, cz, 0);
         }
         __syncthreads();  // s_h / s_lat are rewritten for the next column
