@@ -289,7 +289,7 @@ class Context:
     def apply_edits_and_remesh(self, edits, mode: int = MESH_PARITY, arena_offset: int = 0):
         """Returns (dirty slots ascending, their mesh entries, total bytes)."""
         e = np.ascontiguousarray(edits, dtype=EDIT_DTYPE).reshape(-1)
-        cap = min(e.shape[0], self.max_chunks) if e.shape[0] else 0
+        cap = min(4 * e.shape[0], self.max_chunks) if e.shape[0] else 0  # halo mode also dirties border neighbours
         dirty = np.empty(max(cap, 1), dtype=np.uint32)
         entries = np.zeros(max(cap, 1), dtype=MESH_ENTRY_DTYPE)
         nd, total = C.c_uint64(0), C.c_uint64(0)

@@ -467,7 +467,7 @@ int build_neighbour_table(dsp_ctx* ctx) {
 // Device-side edit pipeline (terrain_kernels.cuh "device-side edit pipeline"): usable when every resident chunk lives in
 // a full box region, so that world -> slot is arithmetic.  On success the ascending dirty-slot list is in ctx->d_slots and
 // its length in *n_dirty.  *handled == false: the caller must take the host path.
-int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool* handled, uint32_t* n_dirty) {
+int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool halo, bool* handled, uint32_t* n_dirty) {
     *handled = false;
     *n_dirty = 0;
     if (!ctx->map.empty() || ctx->regions.empty() || ctx->regions.size() > dsp::kMaxEditRegions || ctx->region_holes || n >= (1u << 20)) return DSP_OK;
@@ -497,6 +497,11 @@ int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool* ha
     p.table_mask = table_size - 1;
     p.voxels = ctx->d_voxels;
     p.dirty_bitmap = reinterpret_cast<uint32_t*>(ctx->d_scratch + off_bitmap);
+    p.nbr = nullptr;
+    if (halo) {
+        if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc;
+        p.nbr = ctx->d_nbr;
+    }
     const unsigned grid = static_cast<unsigned>((n + 255) / 256);
     dsp::edit_file_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
@@ -894,7 +899,7 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
     {
         bool handled = false;
         uint32_t nd = 0;
-        int rc = apply_edits_device(ctx, n, edits, &handled, &nd);
+        int rc = apply_edits_device(ctx, n, edits, false, &handled, &nd);
         if (rc != DSP_OK) return rc;
         if (handled) {
             if (out_n_dirty) *out_n_dirty = nd;
@@ -959,12 +964,34 @@ int dsp_apply_edits_and_remesh(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, 
         if (edits[i].block > 0xFFFFu) return fail(ctx, DSP_ERR_BAD_ARG, "edit %llu: block id %u does not fit u16", (unsigned long long)i, edits[i].block);
     bool handled = false;
     uint32_t nd = 0;
-    int rc = apply_edits_device(ctx, n, edits, &handled, &nd);
+    const bool halo = (mode & DSP_MESH_HALO) != 0;
+    int rc = apply_edits_device(ctx, n, edits, halo, &handled, &nd);
     if (rc != DSP_OK) return rc;
     if (!handled) {  // host addressing, then the ordinary mesh call
         std::vector<uint32_t> dirty(std::min<uint64_t>(n, ctx->max_chunks));
         uint64_t nd64 = 0;
         if ((rc = dsp_apply_edits(ctx, n, edits, dirty.data(), dirty.size(), &nd64)) != DSP_OK) return rc;
+        if (halo) {  // an edit on a chunk border also changes what the resident neighbour across that border may cull
+            std::vector<uint32_t> more(dirty.begin(), dirty.begin() + nd64);
+            for (uint64_t i = 0; i < n; ++i) {
+                const dsp_edit& e = edits[i];
+                const int32_t c[3] = {e.wx >> 4, e.wy >> 4, e.wz >> 4};
+                uint32_t self;
+                if (!find_slot(ctx, c, &self)) continue;
+                const int l[3] = {e.wx & 15, e.wy & 15, e.wz & 15};
+                for (int a = 0; a < 3; ++a) {
+                    if (l[a] != 0 && l[a] != 15) continue;
+                    int32_t q[3] = {c[0], c[1], c[2]};
+                    q[a] += l[a] == 0 ? -1 : 1;
+                    uint32_t s;
+                    if (find_slot(ctx, q, &s)) more.push_back(s);
+                }
+            }
+            std::sort(more.begin(), more.end());
+            more.erase(std::unique(more.begin(), more.end()), more.end());
+            dirty = more;
+            nd64 = dirty.size();
+        }
         if (out_n_dirty) *out_n_dirty = nd64;
         if (out_dirty_slots) {
             if (nd64 > cap_dirty) return fail(ctx, DSP_ERR_BAD_ARG, "dirty list needs %llu entries, capacity %llu", (unsigned long long)nd64, (unsigned long long)cap_dirty);

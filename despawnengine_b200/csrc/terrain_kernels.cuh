@@ -310,6 +310,7 @@ struct EditParams {
     uint32_t table_mask;
     uint16_t* voxels;
     uint32_t* dirty_bitmap;   // one bit per slot; zeroed before the call
+    const uint32_t* nbr;      // halo mode: [slot][6] neighbour table; an edit on a chunk border also dirties the resident neighbour
 };
 
 __device__ __forceinline__ bool edit_key(const EditParams& p, const int4 e, uint64_t* key) {
@@ -359,6 +360,16 @@ __global__ void edit_apply_kernel(const EditParams p) {
             p.voxels[key] = static_cast<uint16_t>(e.w);  // key == slot * 4096 + voxel index
             const uint32_t slot = static_cast<uint32_t>(key >> 12);
             atomicOr(&p.dirty_bitmap[slot >> 5], 1u << (slot & 31u));
+            if (p.nbr != nullptr) {  // cross-chunk culling: the neighbour's border faces depend on this voxel
+                const int lx = e.x & 15, ly = e.y & 15, lz = e.z & 15;
+                const int faces[3] = {ly == 15 ? 0 : (ly == 0 ? 1 : -1), lz == 0 ? 2 : (lz == 15 ? 3 : -1), lx == 0 ? 4 : (lx == 15 ? 5 : -1)};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    if (faces[a] < 0) continue;
+                    const uint32_t s = p.nbr[static_cast<size_t>(slot) * 6 + faces[a]];
+                    if (s != 0xFFFFFFFFu && !(s & 0x80000000u)) atomicOr(&p.dirty_bitmap[s >> 5], 1u << (s & 31u));
+                }
+            }
         }
         return;
     }

@@ -176,6 +176,8 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
  * build_chunk_mesh, chunk_mesh.rs:13-129) in one call.  When every resident chunk belongs to a dsp_generate_region box,
  * world -> (slot, voxel) addressing, last-edit-wins de-duplication, the voxel writes and the ascending dirty list all run
  * on the device and the mesh kernel takes the list from device memory; otherwise addressing runs on the host.
+ * With DSP_MESH_HALO an edit on a chunk's border layer also dirties the resident neighbour across that border (its border
+ * faces are culled against the edited voxel); neighbours on other devices are the caller's to re-exchange (dsp_pack_border_slabs).
  * out_entries[i] is the mesh of out_dirty_slots[i].  Blocking. */
 int dsp_apply_edits_and_remesh(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t mode, uint64_t arena_offset,
                                uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty, dsp_mesh_entry* out_entries,

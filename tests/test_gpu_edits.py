@@ -102,3 +102,62 @@ def test_many_edits_to_one_voxel_and_no_resident_target(uv_default):
         with pytest.raises(capi.DspError) as ei:
             ctx.apply_edits(bad)
         assert ei.value.status == capi.ERR_BAD_ARG
+
+
+@pytest.mark.parametrize("layout", ["regions", "map"])
+def test_halo_mode_edits_also_remesh_the_neighbour_across_an_edited_border(uv_default, layout):
+    """SURVEY.md section 8e, incremental case: with cross-chunk culling an edit on a border voxel changes the neighbour's mesh."""
+    rng = np.random.default_rng(5)
+    origin, dims = (0, 0, 0), (3, 3, 3)
+    positions = [(origin[0] + a, origin[1] + b, origin[2] + c) for c in range(3) for b in range(3) for a in range(3)]
+    with capi.Context(0, 256, 256 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        if layout == "regions":
+            first = ctx.generate_region(origin, dims, capi.GEN_RANDOM, 21)
+            slot_of = {p: first + i for i, p in enumerate(positions)}
+        else:
+            slot_of = {p: int(s) for p, s in zip(positions, ctx.generate_chunks(positions, capi.GEN_RANDOM, 21))}
+        chunks = {p: orc.generate(orc.GEN_RANDOM, 21, p) for p in positions}
+        pos_of = {s: p for p, s in slot_of.items()}
+        dirs = [(0, 1, 0), (0, -1, 0), (0, 0, -1), (0, 0, 1), (-1, 0, 0), (1, 0, 0)]
+
+        def halo_mesh(p):
+            slabs = np.zeros((6, 256), dtype=np.uint16)
+            present = np.zeros(6, dtype=np.uint8)
+            for f, d in enumerate(dirs):
+                q = (p[0] + d[0], p[1] + d[1], p[2] + d[2])
+                if q in chunks:
+                    v = chunks[q].reshape(16, 16, 16)
+                    present[f] = 1
+                    slabs[f] = [v[:, 0, :], v[:, 15, :], v[15, :, :], v[0, :, :], v[:, :, 15], v[:, :, 0]][f].reshape(256)
+            return orc.mesh_chunk_halo(p, chunks[p], slabs, present, uv_default)
+
+        for frame in range(3):
+            k = 300
+            e = np.zeros(k, dtype=capi.EDIT_DTYPE)
+            for name in ("wx", "wy", "wz"):
+                coarse = rng.integers(0, 3, k) * 16
+                fine = np.where(rng.random(k) < 0.6, rng.choice([0, 15], k), rng.integers(0, 16, k))  # mostly border layers
+                e[name] = coarse + fine
+            e["block"] = rng.integers(0, 3, k)
+            dirty, entries, total = ctx.apply_edits_and_remesh(e, capi.MESH_HALO)
+            want = set()
+            for ed in e:
+                w = (int(ed["wx"]), int(ed["wy"]), int(ed["wz"]))
+                c = tuple(v >> 4 for v in w)
+                chunks[c][(w[0] & 15) + 16 * (w[1] & 15) + 256 * (w[2] & 15)] = ed["block"]
+                want.add(c)
+                for a in range(3):
+                    if (w[a] & 15) in (0, 15):
+                        q = list(c); q[a] += -1 if (w[a] & 15) == 0 else 1
+                        if tuple(q) in chunks:
+                            want.add(tuple(q))
+            assert list(map(int, dirty)) == sorted(slot_of[p] for p in want)
+            for s, en in zip(dirty, entries):
+                p = pos_of[int(s)]
+                assert ctx.download_vertices(en).tobytes() == halo_mesh(p).tobytes(), (frame, p)
+            # and the whole world is consistent: nothing outside the dirty set needed a remesh
+            all_slots = np.array([slot_of[p] for p in positions], dtype=np.uint32)
+            entries_all, _ = ctx.mesh_chunks(all_slots, capi.MESH_HALO, arena_offset=(total + 127) & ~127)
+            for p, en in zip(positions, entries_all):
+                assert ctx.download_vertices(en).tobytes() == halo_mesh(p).tobytes(), ("full", frame, p)
