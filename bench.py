@@ -338,6 +338,42 @@ def main():
     rb_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     rb_value = world * N_CHUNKS * rb_steps / (rb_ms * 1e-3)
 
+    # ---- the reference's own call pattern, end to end: chunk POSITIONS in (World::load_chunk generates, scene_game.rs:56-64),
+    #      terrain fill + mesh on the device, entry table out.  Reported beside `e2e`, which carries host voxels.
+    gp_steps = max(3, min(20, e2e_steps))
+    slots_region = np.arange(first, first + N_CHUNKS, dtype=np.uint32)
+
+    def positions_step():
+        ctx.generate_chunks(pos, capi.GEN_NOISE, SEED)      # 48 KiB of positions H2D, voxels never exist on the host
+        ctx.mesh_chunks(slots_region, mode)                  # blocking: entry table D2H
+
+    for _ in range(2):
+        positions_step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(gp_steps):
+        positions_step()
+    torch.cuda.synchronize()
+    gp_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    gp_value = world * N_CHUNKS * gp_steps / (gp_ms * 1e-3)
+
+    # ---- extension modes on the same region (kernel time from the library's own events; L2 not flushed here) ----------
+    modes_out = {}
+    for mname, m in (("indexed", capi.MESH_INDEXED), ("greedy", capi.MESH_GREEDY), ("greedy_indexed", capi.MESH_GREEDY | capi.MESH_INDEXED)):
+        e_m, tot_m = ctx.mesh_range(first, N_CHUNKS, m)
+        quads = int(e_m["vertex_count"].astype(np.int64).sum()) // (4 if m & capi.MESH_INDEXED else 6)
+        ctx.sync()
+        k0, t0ms, _ = ctx.mesh_kernel_stats()
+        for _ in range(10):
+            ctx.mesh_range_async(first, N_CHUNKS, m)
+        ctx.sync()
+        k1, t1ms, _ = ctx.mesh_kernel_stats()
+        kms = (t1ms - t0ms) / max(1, k1 - k0)
+        ab = N_CHUNKS * (8192 + 32) + (104 if m & capi.MESH_INDEXED else 120) * quads
+        modes_out[mname] = {"quads": quads, "arena_bytes": int(tot_m), "kernel_ms": kms, "chunks_per_s_per_gpu": N_CHUNKS / (kms * 1e-3),
+                            "algorithmic_GBps": ab / (kms * 1e-3) / 1e9}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -382,6 +418,10 @@ def main():
                             "(the reference's result is a device buffer too, chunk_mesh.rs:111-124)"},
             "e2e_vertex_readback": {"value": rb_value, "unit": "chunks/s", "d2h_bytes_per_step": int(total_bytes) + d2h, "steps": rb_steps,
                                     "what": "same, plus the whole vertex stream copied to pinned host memory"},
+            "e2e_from_positions": {"value": gp_value, "unit": "chunks/s", "h2d_bytes_per_step": N_CHUNKS * 16, "d2h_bytes_per_step": d2h, "steps": gp_steps,
+                                   "what": "dsp_generate_chunks(host positions) + dsp_mesh_chunks -> entry table on the host: the reference's load loop "
+                                           "(World::load_chunk generates the chunk, scene_game.rs:56-64), voxels never cross PCIe"},
+            "modes_per_gpu": modes_out,
             "clocks": sampler.summary(note),
         }
         if cpu is not None:
