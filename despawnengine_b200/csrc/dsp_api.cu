@@ -94,6 +94,7 @@ struct dsp_ctx {
     std::unordered_map<PosKey, uint32_t, PosHash> map;
     std::vector<Region> regions;
     std::vector<uint32_t> free_slots;
+    std::vector<PosKey> slot_pos;  // position of every slot handed out through the map (not region slots)
     std::vector<uint8_t> resident;
     uint64_t next_unused = 0, n_resident = 0;
     bool nbr_dirty = true;
@@ -184,6 +185,8 @@ int acquire_slot(dsp_ctx* ctx, const int32_t p[3], uint32_t* out) {
     else return fail(ctx, DSP_ERR_STORE_FULL, "voxel store full: %llu chunks resident of %llu",
                      (unsigned long long)ctx->n_resident, (unsigned long long)ctx->max_chunks);
     ctx->map.emplace(PosKey{p[0], p[1], p[2]}, s);
+    if (ctx->slot_pos.size() <= s) ctx->slot_pos.resize(static_cast<size_t>(s) + 1);
+    ctx->slot_pos[s] = PosKey{p[0], p[1], p[2]};
     ctx->resident[s] = 1;
     ctx->n_resident++;
     ctx->nbr_dirty = true;
@@ -751,9 +754,8 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
     if (n && !slots) return fail(ctx, DSP_ERR_BAD_ARG, "slots is NULL");
     int rc = validate_slots(ctx, n, slots);
     if (rc != DSP_OK) return rc;
-    // positions of map-resident chunks are needed to erase them: read them back from the device
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
-    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nothing in flight may still use the slots that are recycled
     for (uint64_t i = 0; i < n; ++i) {
         const uint32_t s = slots[i];
         if (!ctx->resident[s]) continue;  // duplicate in the list
@@ -763,9 +765,7 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
             if (s >= r.first_slot && s < r.first_slot + cnt) { in_region = true; ctx->region_holes = true; break; }
         }
         if (!in_region) {
-            int4 p;
-            DSP_CUDA(ctx, cudaMemcpy(&p, ctx->d_pos + s, sizeof p, cudaMemcpyDeviceToHost));
-            ctx->map.erase(PosKey{p.x, p.y, p.z});
+            ctx->map.erase(ctx->slot_pos[s]);
             ctx->free_slots.push_back(s);  // region slots are not recycled (their addresses are arithmetic)
         }
         ctx->resident[s] = 0;

@@ -165,3 +165,32 @@ def test_config2_full_region_greedy_indexed_checksum(ctx, uv_default):
         assert area * 6 == int(e_par[k]["vertex_count"])
     assert got.hexdigest() == want.hexdigest()
     assert quads_total * 4 == int(entries["vertex_count"].astype(np.int64).sum())
+
+
+def test_host_chunk_pipeline_in_quad_mode(ctx, uv_default):
+    """dsp_mesh_host_chunks (H2D sub-batches overlapped with meshing) with DSP_MESH_GREEDY | DSP_MESH_INDEXED: the sub-batches
+    share one arena cursor, so slots stay gap-free and disjoint across them."""
+    dims = (12, 10, 10)  # 1,200 chunks -> 3 sub-batches
+    pos = np.array([(a, 3 + b, c) for c in range(dims[2]) for b in range(dims[1]) for a in range(dims[0])], dtype=np.int32)
+    ids = orc.generate_batch(orc.GEN_NOISE, SEED_NOISE, pos)
+    slots, entries, total = ctx.mesh_host_chunks(pos, ids, capi.MESH_GREEDY | capi.MESH_INDEXED)
+    check_layout(entries, total)
+    for k in range(0, len(pos), 7):
+        v, i, _ = orc.mesh_chunk_ext(pos[k], ids[k], uv_default, greedy=True, indexed=True)
+        assert ctx.download_vertices(entries[k]).tobytes() == v.tobytes() and np.array_equal(ctx.download_indices(entries[k]), i), pos[k]
+
+
+def test_arena_offsets_beyond_4_gib(uv_default):
+    """Config 3a size: 4,096 checkerboard chunks = 6.04 GB of vertices; offsets are 64-bit end to end."""
+    with capi.Context(0, 4096, 6 << 30) as c:
+        c.set_uv_table(uv_default)
+        first = c.generate_region((0, 0, 0), (16, 16, 16), capi.GEN_CHECKER, 0)
+        entries, total = c.mesh_range(first, 4096, capi.MESH_PARITY)
+        assert total == 4096 * 12288 * 120 and int(entries["offset_bytes"].max()) > (5 << 30)
+        hi = int(np.argmax(entries["offset_bytes"]))
+        for k in (0, hi, 2049):
+            p = (k % 16, (k // 16) % 16, k // 256)
+            want = orc.mesh_chunk(p, orc.generate(orc.GEN_CHECKER, 0, p), uv_default)
+            assert c.download_vertices(entries[k]).tobytes() == want.tobytes(), p
+        offs = np.sort(entries["offset_bytes"].astype(np.int64))
+        assert np.array_equal(np.diff(offs), np.full(4095, 12288 * 120))
