@@ -77,6 +77,7 @@ SYMBOLS = {
     "dsp_max_chunks": (_u64, [_vp]),
     "dsp_kernel_launches": (_u64, [_vp]),
     "dsp_debug_phase_cycles": (_int, [_vp, _P(_u64)]),
+    "dsp_set_kernel_timing": (_int, [_vp, _int]),
     "dsp_mesh_kernel_stats": (_int, [_vp, _P(_u64), _P(C.c_double), _P(C.c_float)]),
 }
 
@@ -291,7 +292,7 @@ class Context:
         e = np.ascontiguousarray(edits, dtype=EDIT_DTYPE).reshape(-1)
         cap = min(4 * e.shape[0], self.max_chunks) if e.shape[0] else 0  # halo mode also dirties border neighbours
         dirty = np.empty(max(cap, 1), dtype=np.uint32)
-        entries = np.zeros(max(cap, 1), dtype=MESH_ENTRY_DTYPE)
+        entries = np.empty(max(cap, 1), dtype=MESH_ENTRY_DTYPE)
         nd, total = C.c_uint64(0), C.c_uint64(0)
         self._check(lib().dsp_apply_edits_and_remesh(self._h, e.shape[0], e.ctypes.data_as(C.c_void_p), mode, arena_offset, _ptr(dirty, C.c_uint32),
                                                      dirty.shape[0], C.byref(nd), entries.ctypes.data_as(C.c_void_p), C.byref(total)))
@@ -366,6 +367,9 @@ class Context:
         out = np.zeros(16, dtype=np.uint64)
         self._check(lib().dsp_debug_phase_cycles(self._h, _ptr(out, C.c_uint64)))
         return out
+
+    def set_kernel_timing(self, on: bool):
+        self._check(lib().dsp_set_kernel_timing(self._h, 1 if on else 0))
 
     def mesh_kernel_stats(self):
         """(launch count, summed device ms, newest launch ms) of the mesh kernel alone."""

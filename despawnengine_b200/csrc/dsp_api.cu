@@ -102,6 +102,9 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
+    bool kernel_timing = true;  // record an event pair around every mesh launch (dsp_mesh_kernel_stats)
+    bool ctl_clean = false;    // the control block is all zero (left so by a self-resetting launch): no memset needed
+    bool result_in_tail = false;  // the last mesh call's {status, total} are in the result words, not in the control block
     uint64_t arena_limit = 0;  // when non-zero, a mesh call may only write below this arena offset (scene allocator)
     std::string err;
 
@@ -268,6 +271,12 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
     dsp::MeshParams pp = p;
     pp.phase_cycles = ctx->d_phase;
     pp.prefetch_ahead = ctx->mesh_prefetch_mult * grid;
+    if (!ctx->kernel_timing) {
+        kern<<<grid, 256, smem, ctx->stream>>>(pp);
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        return DSP_OK;
+    }
     const int e = ctx->ev_next;
     int rc = drain_kernel_event(ctx, e);  // the pair from kEvRing launches ago: long finished
     if (rc != DSP_OK) return rc;
@@ -307,6 +316,12 @@ int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
         if (occ < 1) return fail(ctx, DSP_ERR_INTERNAL, "quad mesh kernel does not fit on an SM (smem %d)", smem);
     }
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, static_cast<uint64_t>(ctx->num_sms) * occ));
+    if (!ctx->kernel_timing) {
+        kern<<<grid, 256, smem, ctx->stream>>>(p);
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        return DSP_OK;
+    }
     const int e = ctx->ev_next;
     int rc = drain_kernel_event(ctx, e);
     if (rc != DSP_OK) return rc;
@@ -340,7 +355,7 @@ int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offs
 }
 
 // One mesh launch over `n` chunks whose entries start at entry index `entry0`; `sub` picks the ticket counter.
-int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub) {
+int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub, bool self_reset = false) {
     const bool halo = (mode & DSP_MESH_HALO) != 0;
     dsp::MeshParams p{};
     p.voxels = ctx->d_voxels;
@@ -356,8 +371,12 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.arena_offset = arena_offset;
     p.arena_room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
     p.entries = ctx->d_entries + entry0;
-    p.ticket = ctx->d_tickets + sub;
+    p.ticket = sub == 0 ? reinterpret_cast<uint32_t*>(ctx->d_ctl) : ctx->d_tickets + sub;  // control block: [ticket][status][done][-][total 8 B][-]
     p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
+    if (self_reset) {
+        p.done = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 2;
+        p.result = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32 + 8 * ctx->max_chunks);
+    }
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
     p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
     if (mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return halo ? launch_quads<true>(ctx, p, mode) : launch_quads<false>(ctx, p, mode);
@@ -369,11 +388,21 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     int rc = check_mesh_args(ctx, n, mode, arena_offset);
     if (rc != DSP_OK) return rc;
     ctx->last_mesh_n = n;
-    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + ((mode & DSP_MESH_ORDERED) ? 8 * n : 0), ctx->stream));
-    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t), ctx->stream));
+    // Control block.  The atomic-claim kernels reset it themselves at their end (control_block_epilogue), so in steady state a
+    // mesh call is one kernel launch and nothing else; a memset is only needed for the first call, after a multi-launch or
+    // look-back call, and for the look-back words of DSP_MESH_ORDERED.
+    const bool ordered = (mode & DSP_MESH_ORDERED) != 0;
+    if (ordered || !ctx->ctl_clean || n == 0) {
+        DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + (ordered ? 8 * n : 0), ctx->stream));
+        ctx->ctl_clean = !ordered;
+    }
+    ctx->result_in_tail = false;
     if (n == 0) return DSP_OK;
     if (mode & DSP_MESH_HALO) { if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc; }
-    return launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0);
+    ctx->ctl_clean = false;  // until the launch below is known to have been enqueued
+    rc = launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0, !ordered);
+    if (rc == DSP_OK && !ordered) { ctx->ctl_clean = true; ctx->result_in_tail = true; }
+    return rc;
 }
 
 int validate_slots(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
@@ -526,10 +555,19 @@ int finish_mesh(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total) 
     if (out_total) *out_total = 0;
     if (n && out_entries)
         DSP_CUDA(ctx, cudaMemcpyAsync(out_entries, ctx->d_entries, n * sizeof(dsp_mesh_entry), cudaMemcpyDeviceToHost, ctx->stream));
-    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_ctl, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const uint32_t status = reinterpret_cast<uint32_t*>(ctx->h_pinned)[1];
-    const uint64_t total = *reinterpret_cast<uint64_t*>(ctx->h_pinned + 16);
+    uint32_t status;
+    uint64_t total;
+    if (ctx->result_in_tail) {  // written by the last CTA of a self-resetting launch
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_ctl + 32 + 8 * ctx->max_chunks, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        status = static_cast<uint32_t>(reinterpret_cast<uint64_t*>(ctx->h_pinned)[0]);
+        total = reinterpret_cast<uint64_t*>(ctx->h_pinned)[1];
+    } else {
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_ctl, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        status = reinterpret_cast<uint32_t*>(ctx->h_pinned)[1];
+        total = *reinterpret_cast<uint64_t*>(ctx->h_pinned + 16);
+    }
     if (out_total) *out_total = total;
     if (status & dsp::kStatusSpin) return fail(ctx, DSP_ERR_INTERNAL, "mesh kernel look-back timed out");
     if (status & dsp::kStatusOverflow)
@@ -850,6 +888,8 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
     const int subs = static_cast<int>((n + sub_n - 1) / sub_n);
     DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32, ctx->stream));
     DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, dsp_ctx::kMaxSub * sizeof(uint32_t), ctx->stream));
+    ctx->ctl_clean = false;  // the sub-batch launches share the cursor and leave the block as it is
+    ctx->result_in_tail = false;
     if (n == 0) return finish_mesh(ctx, out_entries, out_total_bytes);
     uint8_t* h;
     if ((rc = stage_host(ctx, n * (sizeof(int4) + sizeof(uint32_t)), &h)) != DSP_OK) return rc;
@@ -1097,6 +1137,12 @@ int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16) {
     DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     DSP_CUDA(ctx, cudaMemcpy(out16, ctx->d_phase, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     DSP_CUDA(ctx, cudaMemset(ctx->d_phase, 0, 16 * sizeof(uint64_t)));
+    return DSP_OK;
+}
+
+int dsp_set_kernel_timing(dsp_ctx* ctx, int on) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    ctx->kernel_timing = on != 0;
     return DSP_OK;
 }
 

@@ -55,7 +55,26 @@ struct MeshParams {
     uint64_t* total_bytes;      // out
     unsigned long long* phase_cycles;  // [16] debug: per-phase SM cycles of thread 0 summed over CTAs (DSP_PHASE_TIMERS builds)
     uint32_t prefetch_ahead;    // L2-prefetch the tile of ticket + prefetch_ahead when a tile load is issued (0 = off)
+    // Self-resetting control block (single-launch calls): every CTA counts itself out on `done`; the last one copies
+    // {status, total} to `result` and zeroes ticket / status / total / done, so the NEXT launch needs no memset in front
+    // of it -- a step is exactly one kernel launch.  nullptr: the caller resets the block itself (multi-launch calls).
+    uint32_t* done;
+    uint64_t* result;           // [0] = status, [1] = total bytes
 };
+
+// Last instructions of a persistent mesh kernel (thread 0 of every CTA, after its stores were issued).
+__device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
+    if (p.done == nullptr) return;
+    __threadfence();  // this CTA's atomics on total / status are performed before it counts itself out
+    if (atomicAdd(p.done, 1u) != gridDim.x - 1u) return;
+    __threadfence();
+    p.result[0] = atomicOr(p.status, 0u);
+    p.result[1] = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), 0ull);
+    *p.ticket = 0u;
+    *p.status = 0u;
+    *p.total_bytes = 0ull;
+    *p.done = 0u;
+}
 
 constexpr uint32_t kNbrNone = 0xFFFFFFFFu;
 constexpr uint32_t kNbrExternal = 0x80000000u;  // neighbour lives on another device: low bits index halo_slabs
@@ -611,6 +630,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         cur = c.s_next[it & 1];
     }
     if (c.lane == 0) bulk_wait<0>();
+    if (tid == 0) control_block_epilogue(p);
 #ifdef DSP_PHASE_TIMERS
     c.tick(9);
     if (tid == 0 && p.phase_cycles) for (int k = 0; k < 16; ++k) atomicAdd(&p.phase_cycles[k], static_cast<unsigned long long>(c.ph[k]));

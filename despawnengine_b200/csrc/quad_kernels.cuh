@@ -31,12 +31,15 @@ constexpr int kQuadIndexBytes = 24;       // 6 x u32
 // staging space for residency and tile prefetch depth: 128-quad tiles and a 2,048-record window make room for 4 CTAs per SM, which is what
 // hides the per-chunk latencies (tile, barriers, the slot atomic) once there is little emission to hide them behind.
 // The unit-quad indexed kernel keeps the 256-quad tile / 4,096-record window of the parity kernel (3 CTAs per SM).
+#ifndef DSP_QUAD_NB
+#define DSP_QUAD_NB 2
+#endif
 template <bool GREEDY>
 struct QuadSmem {
     static constexpr int kCtasPerSm = GREEDY ? 4 : 3;
     static constexpr int kTileQuads = GREEDY ? 128 : 256;
-    static constexpr uint32_t kRecCap = GREEDY ? 2048 : 4096;         // records per window (u32 each)
-    static constexpr int kVoxBufs = 2;                                // voxel tile ring: kVoxBufs - 1 tiles in flight per CTA (3 measured slower)
+    static constexpr uint32_t kRecCap = GREEDY ? (DSP_QUAD_NB > 2 ? 1024 : 2048) : 4096;         // records per window (u32 each)
+    static constexpr int kVoxBufs = GREEDY ? DSP_QUAD_NB : 2;                                // voxel tile ring: kVoxBufs - 1 tiles in flight per CTA (3 measured slower)
     static constexpr int kT = GREEDY ? kRows * 2 : 0;                 // bytes of one [256] u16 table (none without merging)
     static constexpr int kVox = 0;                                    // kVoxBufs x 8192
     static constexpr int kStage = kVoxBufs * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
@@ -182,15 +185,25 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     // next is issued at the top of an iteration and its result is first touched at the top of the following one, so its
     // round trip is not waited for.  (Fetching two iterations ahead measured slower: 43 -> 50 us on the bench region.)
     constexpr int NB = L::kVoxBufs;
-    static_assert(NB == 2, "the prologue below assigns one buffer");
-    uint32_t pending = 0;  // thread 0: the ticket after the one whose tile is in flight
+    uint32_t pending = 0;  // thread 0: the ticket after those whose tiles are in flight
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) mbar_init(&s_bar[b], 1);
         fence_mbar_init();
+#ifdef DSP_QUAD_STATIC
+#pragma unroll
+        for (int b = 0; b < NB - 1; ++b) {
+            const uint32_t t = blockIdx.x + b * gridDim.x;
+            s_next[b] = t;
+            if (t < p.n) issue_load(t, b);
+        }
+        pending = blockIdx.x + (NB - 1) * gridDim.x;
+#else
+        static_assert(NB == 2 || true, "");
         s_next[0] = blockIdx.x;
         if (blockIdx.x < p.n) issue_load(blockIdx.x, 0);
         pending = gridDim.x + atomicAdd(p.ticket, 1u);
+#endif
     }
     __syncthreads();
     uint32_t cur = s_next[0];
@@ -202,7 +215,11 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
             s_next[nb] = t;
             if (t < p.n) issue_load(t, nb);
+#ifdef DSP_QUAD_STATIC
+            pending += gridDim.x;
+#else
             pending = gridDim.x + atomicAdd(p.ticket, 1u);
+#endif
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         mbar_wait(&s_bar[buf], par);
@@ -484,6 +501,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         cur = s_next[buf];
     }
     if (lane == 0) bulk_wait<0>();
+    if (tid == 0) control_block_epilogue(p);
 }
 
 }  // namespace dsp

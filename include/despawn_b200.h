@@ -251,6 +251,9 @@ uint64_t dsp_kernel_launches(const dsp_ctx* ctx);
  * launch on the context's stream: number of launches, their summed duration, and the newest one.
  * Waits for outstanding launches. */
 int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_ms, float* out_last_ms);
+/* The event pair around every mesh launch costs about 2 us of stream time per call; a caller that does not read
+ * dsp_mesh_kernel_stats can switch it off (on by default). */
+int dsp_set_kernel_timing(dsp_ctx* ctx, int on);
 
 /* Debug aid: per-phase SM-cycle counters of the mesh kernel, summed over CTAs, read and cleared.  All zero
  * unless the library was built with -DDSP_PHASE_TIMERS (not the shipped build). */
