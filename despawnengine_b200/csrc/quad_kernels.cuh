@@ -31,15 +31,12 @@ constexpr int kQuadIndexBytes = 24;       // 6 x u32
 // staging space for residency and tile prefetch depth: 128-quad tiles and a 2,048-record window make room for 4 CTAs per SM, which is what
 // hides the per-chunk latencies (tile, barriers, the slot atomic) once there is little emission to hide them behind.
 // The unit-quad indexed kernel keeps the 256-quad tile / 4,096-record window of the parity kernel (3 CTAs per SM).
-#ifndef DSP_QUAD_NB
-#define DSP_QUAD_NB 2
-#endif
 template <bool GREEDY>
 struct QuadSmem {
     static constexpr int kCtasPerSm = GREEDY ? 4 : 3;
     static constexpr int kTileQuads = GREEDY ? 128 : 256;
-    static constexpr uint32_t kRecCap = GREEDY ? (DSP_QUAD_NB > 2 ? 1024 : 2048) : 4096;         // records per window (u32 each)
-    static constexpr int kVoxBufs = GREEDY ? DSP_QUAD_NB : 2;                                // voxel tile ring: kVoxBufs - 1 tiles in flight per CTA (3 measured slower)
+    static constexpr uint32_t kRecCap = GREEDY ? 2048 : 4096;         // records per window (u32 each)
+    static constexpr int kVoxBufs = 2;                                // voxel tile ring: kVoxBufs - 1 tiles in flight per CTA (3 measured slower)
     static constexpr int kT = GREEDY ? kRows * 2 : 0;                 // bytes of one [256] u16 table (none without merging)
     static constexpr int kVox = 0;                                    // kVoxBufs x 8192
     static constexpr int kStage = kVoxBufs * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
@@ -183,31 +180,22 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     // Tickets.  The first chunk of a CTA is its block index (no atomic: hundreds of CTAs hitting one counter in the same
     // microsecond serialise in L2); later tickets are gridDim.x + atomicAdd(counter).  The atomic for the ticket after
     // next is issued at the top of an iteration and its result is first touched at the top of the following one, so its
-    // round trip is not waited for.  (Fetching two iterations ahead measured slower: 43 -> 50 us on the bench region.)
+    // round trip is not waited for.  Measured alternatives, all slower or equal on B200 (profiles/README.md): fetching two
+    // iterations ahead, a 3-deep tile ring (with static striding to take the atomics out of the picture: no gain, so tile
+    // latency is not what bounds short chunks), static striding itself (no atomics, but 15 % slower on uneven regions).
     constexpr int NB = L::kVoxBufs;
-    uint32_t pending = 0;  // thread 0: the ticket after those whose tiles are in flight
+    static_assert(NB == 2, "the prologue assigns one buffer");
+    uint32_t pending = 0;  // thread 0: the ticket after the one whose tile is in flight
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) mbar_init(&s_bar[b], 1);
         fence_mbar_init();
-#ifdef DSP_QUAD_STATIC
-#pragma unroll
-        for (int b = 0; b < NB - 1; ++b) {
-            const uint32_t t = blockIdx.x + b * gridDim.x;
-            s_next[b] = t;
-            if (t < p.n) issue_load(t, b);
-        }
-        pending = blockIdx.x + (NB - 1) * gridDim.x;
-#else
-        static_assert(NB == 2 || true, "");
         s_next[0] = blockIdx.x;
         if (blockIdx.x < p.n) issue_load(blockIdx.x, 0);
         pending = gridDim.x + atomicAdd(p.ticket, 1u);
-#endif
     }
     __syncthreads();
     uint32_t cur = s_next[0];
-    uint32_t it = 0;
     int buf = 0, par = 0;  // ring position of `cur` and the phase parity of its barrier
     while (cur < p.n) {
         if (tid == 0) {
@@ -215,11 +203,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
             s_next[nb] = t;
             if (t < p.n) issue_load(t, nb);
-#ifdef DSP_QUAD_STATIC
-            pending += gridDim.x;
-#else
             pending = gridDim.x + atomicAdd(p.ticket, 1u);
-#endif
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         mbar_wait(&s_bar[buf], par);
@@ -244,7 +228,6 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         if (uniform && id0 == 0u) {
             // all air: the reference's palette.len() == 1 early-out (chunk_mesh.rs:18-20)
             if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
-            ++it;
             if (++buf == NB) { buf = 0; par ^= 1; }
             cur = s_next[buf];
             continue;
@@ -496,7 +479,6 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         // No barrier here: everything the next iteration overwrites (row masks, tables, records, the staging tile, the
         // other voxel buffer) was last read before a barrier that every thread has already passed, and each of those
         // writes sits behind at least one barrier of the next iteration.
-        ++it;
         if (++buf == NB) { buf = 0; par ^= 1; }
         cur = s_next[buf];
     }

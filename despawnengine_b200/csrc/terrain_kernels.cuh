@@ -247,6 +247,14 @@ __global__ void region_neighbours_kernel(uint32_t* nbr, uint32_t first_slot, uin
         o[5] = a + 1 < dims.x ? s + 1 : 0xFFFFFFFFu;
     }
 }
+// positions and slot list of a sub-batch, read directly from pinned host memory (no copy engine involved)
+__global__ void stage_positions_kernel(int4* chunk_pos, uint32_t* slot_list_out, const int4* host_pos, const uint32_t* host_slots, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = host_slots[i];
+    chunk_pos[s] = host_pos[i];
+    slot_list_out[i] = s;
+}
 __global__ void scatter_pos_kernel(int4* chunk_pos, const uint32_t* slots, const int4* src, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) chunk_pos[slots[i]] = src[i];
