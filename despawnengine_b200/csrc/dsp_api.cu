@@ -887,9 +887,19 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
     const auto tr0 = std::chrono::steady_clock::now();
     auto tr = [&](const char* what) { if (trace) fprintf(stderr, "[trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count()); };
     // sub-batches: copy k+1 crosses PCIe while sub-batch k is meshed
-    uint64_t sub_n = 512;
-    while ((n + sub_n - 1) / sub_n > static_cast<uint64_t>(dsp_ctx::kMaxSub)) sub_n *= 2;
-    const int subs = static_cast<int>((n + sub_n - 1) / sub_n);
+    // Sub-batch plan.  Every copy costs a few microseconds of gap on the DMA engine, so the body is cut into pieces of about
+    // 1,024 chunks (8 MiB); the LAST piece is small (256 chunks) because its kernel and the entry read-back are the only work
+    // that cannot hide behind a copy.
+    std::vector<uint64_t> sub_begin;
+    {
+        const uint64_t tail = n > 512 ? 256 : 0, body = n - tail;
+        uint64_t pieces = std::max<uint64_t>(1, (body + 1023) / 1024);
+        pieces = std::min<uint64_t>(pieces, dsp_ctx::kMaxSub - 1);
+        for (uint64_t k = 0; k < pieces; ++k) sub_begin.push_back(body * k / pieces);
+        if (tail) sub_begin.push_back(body);
+        sub_begin.push_back(n);
+    }
+    const int subs = static_cast<int>(sub_begin.size()) - 1;
     DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32, ctx->stream));
     DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, dsp_ctx::kMaxSub * sizeof(uint32_t), ctx->stream));
     ctx->ctl_clean = false;  // the sub-batch launches share the cursor and leave the block as it is
@@ -905,7 +915,8 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
     DSP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
     cudaStream_t main_stream = ctx->stream;
     for (int j = 0; j < subs; ++j) {
-        const uint64_t i0 = j * sub_n, m = std::min<uint64_t>(sub_n, n - i0);
+        const uint64_t i0 = sub_begin[j], m = sub_begin[j + 1] - i0;
+        if (m == 0) continue;
         bool consecutive = true;
         for (uint64_t i = 0; i < m; ++i) {
             if ((rc = acquire_slot(ctx, pos + 3 * (i0 + i), &h_slots[i0 + i])) != DSP_OK) return rc;
