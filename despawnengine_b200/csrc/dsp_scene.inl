@@ -123,6 +123,8 @@ int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_co
     if (!camera_pos || !cfg) return fail(ctx, DSP_ERR_BAD_ARG, "NULL argument");
     if (cfg->gen_kind < 0 || cfg->gen_kind > 3) return fail(ctx, DSP_ERR_BAD_ARG, "unknown gen_kind %d", cfg->gen_kind);
     if (cfg->mesh_mode & DSP_MESH_ORDERED) return fail(ctx, DSP_ERR_BAD_ARG, "DSP_MESH_ORDERED has no meaning for a scene (slots come and go)");
+    if (!ctx->regions.empty())
+        return fail(ctx, DSP_ERR_BAD_ARG, "a scene manages its own chunk slots: use a context without dsp_generate_region boxes");
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->scene_init) {
         ctx->scene_free.clear();
@@ -148,6 +150,8 @@ int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_co
         if (ctx->n_resident + n_new > ctx->max_chunks)
             return fail(ctx, DSP_ERR_STORE_FULL, "scene needs %llu more chunk slots, %llu free", (unsigned long long)n_new,
                         (unsigned long long)(ctx->max_chunks - ctx->n_resident));
+        ctx->map.reserve(ctx->map.size() + n_new);  // one rehash at most, instead of several while thousands of chunks arrive
+        ctx->scene_loaded.reserve(ctx->scene_loaded.size() + n_new);
         std::vector<uint32_t> slots(n_new);
         int rc = dsp_generate_chunks(ctx, n_new, todo.data(), cfg->gen_kind, cfg->seed, slots.data());  // World::load_chunk -> get_chunk
         if (rc != DSP_OK) return rc;

@@ -112,10 +112,12 @@ __device__ __forceinline__ uint32_t continued_runs(uint32_t fa, uint32_t eqa, ui
     return out;
 }
 
-__device__ __forceinline__ uint64_t quad_slot_bytes(uint32_t quads, bool indexed) {
-    const uint64_t a = kSlotAlign - 1;
-    if (!indexed) return (static_cast<uint64_t>(quads) * kFaceBytes + a) & ~a;
-    return ((static_cast<uint64_t>(quads) * kQuadVertexBytesIdx + a) & ~a) + ((static_cast<uint64_t>(quads) * kQuadIndexBytes + a) & ~a);
+// (Q <= 12,288, so every size below fits 32 bits)
+__device__ __forceinline__ uint32_t quad_vertex_region_bytes(uint32_t quads, bool indexed) {
+    return (quads * static_cast<uint32_t>(indexed ? kQuadVertexBytesIdx : kFaceBytes) + (kSlotAlign - 1)) & ~static_cast<uint32_t>(kSlotAlign - 1);
+}
+__device__ __forceinline__ uint32_t quad_slot_bytes(uint32_t quads, bool indexed) {
+    return quad_vertex_region_bytes(quads, indexed) + (indexed ? ((quads * kQuadIndexBytes + (kSlotAlign - 1)) & ~static_cast<uint32_t>(kSlotAlign - 1)) : 0u);
 }
 
 // Corners of one quad record: positions lo/hi per axis and the block's mapped uv row.
@@ -324,12 +326,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             first = wpre + incl - cnt;
         }
         // claim the chunk's arena slot; the result is first touched after this thread's records are written
-        const uint64_t slot_bytes = quad_slot_bytes(Q, INDEXED);
+        // (everything about the slot -- size, claim, overflow check, destination pointers -- is thread 0's business alone)
         uint64_t claimed = 0;
-        if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(slot_bytes));
-        const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
-        const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
-        const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
+        if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(quad_slot_bytes(Q, INDEXED)));
 
         // ---- 5./6. records of a window of quads, then their expansion
         for (uint32_t q0 = 0; q0 == 0 || q0 < Q; q0 += kRecCap) {
@@ -410,15 +409,11 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             }
             if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
             if (tid == 0 && q0 == 0) {
-                *s_base = claimed;
-                if (claimed + slot_bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                *s_base = claimed;  // read back by thread 0 only (it alone issues the bulk stores)
+                if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
                 p.entries[cur] = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
             }
-            __syncthreads();  // records and s_base visible
-            const uint64_t base = *s_base;
-            const bool fits = base + slot_bytes <= p.arena_room;
-            uint8_t* const gout = p.arena + base;
-            uint8_t* const gidx = gout + ((static_cast<uint64_t>(Q) * kQuadVertexBytesIdx + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1));
+            __syncthreads();  // records visible
             const uint32_t q1 = min(Q, q0 + kRecCap);
             for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {
                 if (f0 > q0) {  // (for the window's first tile the records barrier above did this)
@@ -427,6 +422,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
                 const uint32_t f = f0 + tid;
                 if (tid < kTile && f < Q) {
+                    const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
+                    const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
+                    const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
                     const QuadGeom g = quad_geom(s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
                     float cx[4], cy[4], cz[4], cu[4], cv[4];
 #pragma unroll
@@ -464,7 +462,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
                 fence_proxy_async_smem();
                 __syncthreads();
-                if (tid == 0 && fits) {
+                if (tid == 0 && *s_base + quad_slot_bytes(Q, INDEXED) <= p.arena_room) {
+                    uint8_t* const gout = p.arena + *s_base;
+                    uint8_t* const gidx = gout + quad_vertex_region_bytes(Q, true);
                     const uint32_t nq = min(static_cast<uint32_t>(kTile), Q - f0);
                     if (INDEXED) {
                         bulk_store(gout + static_cast<size_t>(f0) * kQuadVertexBytesIdx, s_stage, nq * kQuadVertexBytesIdx);

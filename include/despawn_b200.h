@@ -227,7 +227,8 @@ int dsp_visible_chunks(const float camera_pos[3], uint32_t horizontal, uint32_t 
  * generated and meshed -- one terrain launch and one mesh launch for the whole set -- into a free interval of the arena,
  * and every loaded chunk that left the visible set is unloaded (its voxel slot and, once its whole batch is gone, its
  * arena interval are recycled).  Blocking, like the reference's update.  DSP_ERR_ARENA_FULL / DSP_ERR_STORE_FULL leave
- * the scene as it was.  Do not mix with arena offsets chosen by hand on the same context. */
+ * the scene as it was.  The scene owns the chunks it loads and the arena: use it on a context without dsp_generate_region
+ * boxes (DSP_ERR_BAD_ARG otherwise), and do not unload its chunks or choose arena offsets by hand on the same context. */
 int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_config* cfg, dsp_scene_stats* out_stats);
 /* GameScene::draw's iteration (scene_game.rs:101-125): position and arena window of every non-empty mesh. */
 int dsp_scene_draw_list(dsp_ctx* ctx, uint64_t cap, int32_t* out_pos /* cap x 3 */, dsp_mesh_entry* out_entries, uint64_t* out_n);

@@ -128,3 +128,13 @@ def test_arena_too_small_rolls_the_update_back(uv_default):
         assert ei.value.status == capi.ERR_ARENA_FULL and ctx.resident_chunks == 0
         st = ctx.scene_update(START_CAMERA, 1, 0)  # a smaller view fits: the scene is usable after the failure
         assert st["n_loaded_total"] == len(sco.visible_chunks(START_CAMERA, 1, 0))
+
+
+@pytest.mark.gpu
+def test_scene_refuses_a_context_with_box_regions(uv_default):
+    with capi.Context(0, 256, 16 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        ctx.generate_region((0, 0, 0), (2, 2, 2), capi.GEN_REFERENCE, 0)
+        with pytest.raises(capi.DspError) as ei:
+            ctx.scene_update(START_CAMERA, 1, 1)
+        assert ei.value.status == capi.ERR_BAD_ARG
