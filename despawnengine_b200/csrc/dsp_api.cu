@@ -66,7 +66,10 @@ struct dsp_ctx {
     uint32_t* d_nbr = nullptr;  // [max_chunks][6], allocated on first halo mesh
     uint16_t* d_halo = nullptr; // [halo_cap][256] border slabs of neighbours that live on other devices
     uint64_t halo_cap = 0, halo_n = 0;
-    std::unordered_map<uint64_t, uint32_t> halo_of;  // slot * 8 + face -> slab index
+    // received border slabs, one batch per dsp_set_halo_slabs call: slab first_index + i stands in for the neighbour of
+    // slots[i] across `face` wherever no resident neighbour exists (applied to the neighbour table on the device)
+    struct HaloBatch { int face; uint32_t first_index; uint32_t* d_slots_copy; uint32_t n; std::vector<uint32_t> slots; };
+    std::vector<HaloBatch> halo_batches;
     uint8_t* d_arena = nullptr;
     dsp::MeshEntry* d_entries = nullptr;
     uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
@@ -343,6 +346,7 @@ int launch_quads(dsp_ctx* ctx, const dsp::MeshParams& p, uint32_t mode) {
 }
 
 int build_neighbour_table(dsp_ctx* ctx);
+int apply_halo_batches(dsp_ctx* ctx);
 
 int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offset) {
     if (mode & ~(DSP_MESH_HALO | DSP_MESH_ORDERED | DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
@@ -419,6 +423,18 @@ int validate_range(dsp_ctx* ctx, uint32_t first, uint64_t n) {
     return DSP_OK;
 }
 
+// Received border slabs -> neighbour table, on the device: entry (slot, face) that is still "none" after the resident
+// neighbours were resolved points at the slab.  Newest batch first, so a (slot, face) registered again uses the newer slab.
+int apply_halo_batches(dsp_ctx* ctx) {
+    for (auto it = ctx->halo_batches.rbegin(); it != ctx->halo_batches.rend(); ++it) {
+        if (it->n == 0) continue;
+        dsp::apply_halo_batch_kernel<<<(it->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nbr, it->d_slots_copy, it->face, it->first_index, it->n);
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    return DSP_OK;
+}
+
 // Neighbour slots for halo culling: order top(+Y), bottom(-Y), rear(-Z), front(+Z), right(-X), left(+X)
 // (the reference's face order, chunk_mesh.rs:46-51).  Resolved on the host from the chunk map.
 int build_neighbour_table(dsp_ctx* ctx) {
@@ -435,33 +451,7 @@ int build_neighbour_table(dsp_ctx* ctx) {
                 ctx->d_nbr, r.first_slot, make_uint3(r.dims[0], r.dims[1], r.dims[2]), n);
             DSP_CUDA(ctx, cudaGetLastError());
             ctx->launches++;
-            if (!ctx->halo_of.empty()) {
-                std::vector<uint2> ov;
-                ov.reserve(ctx->halo_of.size());
-                for (const auto& kv : ctx->halo_of)
-                    ov.push_back(make_uint2(static_cast<uint32_t>((kv.first >> 3) * 6 + (kv.first & 7)), dsp::kNbrExternal | kv.second));
-                // a halo slab only stands in for a neighbour that is NOT resident: inside the box the resident one wins
-                std::vector<uint2> keep;
-                keep.reserve(ov.size());
-                for (const uint2& e : ov) {
-                    const uint64_t slot = e.x / 6, i = slot - r.first_slot;
-                    const uint32_t f = e.x % 6, a = static_cast<uint32_t>(i % r.dims[0]), b = static_cast<uint32_t>((i / r.dims[0]) % r.dims[1]),
-                                   c = static_cast<uint32_t>(i / (static_cast<uint64_t>(r.dims[0]) * r.dims[1]));
-                    const bool on_boundary = (f == 0 && b + 1 == r.dims[1]) || (f == 1 && b == 0) || (f == 2 && c == 0) || (f == 3 && c + 1 == r.dims[2]) ||
-                                             (f == 4 && a == 0) || (f == 5 && a + 1 == r.dims[0]);
-                    if (on_boundary) keep.push_back(e);
-                }
-                if (!keep.empty()) {
-                    int rc = ensure_scratch(ctx, keep.size() * sizeof(uint2));
-                    if (rc != DSP_OK) return rc;
-                    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, keep.data(), keep.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
-                    dsp::scatter_u32_kernel<<<static_cast<unsigned>((keep.size() + 255) / 256), 256, 0, ctx->stream>>>(
-                        ctx->d_nbr, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(keep.size()));
-                    DSP_CUDA(ctx, cudaGetLastError());
-                    ctx->launches++;
-                    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `keep` is pageable
-                }
-            }
+            { int rc = apply_halo_batches(ctx); if (rc != DSP_OK) return rc; }
             ctx->nbr_dirty = false;
             return DSP_OK;
         }
@@ -472,11 +462,7 @@ int build_neighbour_table(dsp_ctx* ctx) {
         for (int f = 0; f < 6; ++f) {
             const int32_t q[3] = {p[0] + dirs[f][0], p[1] + dirs[f][1], p[2] + dirs[f][2]};
             uint32_t s;
-            if (find_slot(ctx, q, &s)) { nbr[static_cast<size_t>(slot) * 6 + f] = s; continue; }
-            if (!ctx->halo_of.empty()) {  // no resident neighbour: maybe its border layer was received from another device
-                auto it = ctx->halo_of.find(static_cast<uint64_t>(slot) * 8 + f);
-                if (it != ctx->halo_of.end()) nbr[static_cast<size_t>(slot) * 6 + f] = dsp::kNbrExternal | it->second;
-            }
+            if (find_slot(ctx, q, &s)) nbr[static_cast<size_t>(slot) * 6 + f] = s;
         }
     };
     for (const auto& kv : ctx->map) { const int32_t p[3] = {kv.first.x, kv.first.y, kv.first.z}; fill(kv.second, p); }
@@ -493,6 +479,7 @@ int build_neighbour_table(dsp_ctx* ctx) {
         DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_nbr, nbr.data(), nbr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    { int rc = apply_halo_batches(ctx); if (rc != DSP_OK) return rc; }  // where no resident neighbour exists, a received slab may stand in
     ctx->nbr_dirty = false;
     return DSP_OK;
 }
@@ -651,6 +638,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     if (!ctx) return DSP_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (auto& hb : ctx->halo_batches) cudaFree(hb.d_slots_copy);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_halo); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
@@ -809,7 +797,11 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
         }
         ctx->resident[s] = 0;
         ctx->n_resident--;
-        for (int f = 0; f < 6 && !ctx->halo_of.empty(); ++f) ctx->halo_of.erase(static_cast<uint64_t>(s) * 8 + f);
+        for (auto& hb : ctx->halo_batches) {  // its received slabs go with it (rare path: linear scan, then the device copy is refreshed)
+            bool hit = false;
+            for (uint32_t& v : hb.slots) if (v == s) { v = DSP_NO_SLOT; hit = true; }
+            if (hit) DSP_CUDA(ctx, cudaMemcpy(hb.d_slots_copy, hb.slots.data(), hb.n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
     }
     ctx->nbr_dirty = true;
     return DSP_OK;
@@ -1108,7 +1100,16 @@ int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face
         ctx->halo_cap = cap;
     }
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo + ctx->halo_n * 256, src_device, n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
-    for (uint64_t i = 0; i < n; ++i) ctx->halo_of[static_cast<uint64_t>(slots[i]) * 8 + face] = static_cast<uint32_t>(ctx->halo_n + i);
+    dsp_ctx::HaloBatch hb{face, static_cast<uint32_t>(ctx->halo_n), nullptr, static_cast<uint32_t>(n), std::vector<uint32_t>(slots, slots + n)};
+    DSP_CUDA(ctx, cudaMalloc(&hb.d_slots_copy, n * sizeof(uint32_t)));
+    {
+        uint8_t* h;
+        if ((rc = stage_host(ctx, n * sizeof(uint32_t), &h)) != DSP_OK) { cudaFree(hb.d_slots_copy); return rc; }
+        std::memcpy(h, slots, n * sizeof(uint32_t));
+        DSP_CUDA(ctx, cudaMemcpyAsync(hb.d_slots_copy, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        if ((rc = stage_release(ctx)) != DSP_OK) return rc;
+    }
+    ctx->halo_batches.push_back(std::move(hb));
     ctx->halo_n += n;
     ctx->nbr_dirty = true;
     return DSP_OK;
@@ -1116,7 +1117,9 @@ int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face
 
 int dsp_clear_halo_slabs(dsp_ctx* ctx) {
     if (!ctx) return DSP_ERR_BAD_ARG;
-    ctx->halo_of.clear();
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& hb : ctx->halo_batches) cudaFree(hb.d_slots_copy);
+    ctx->halo_batches.clear();
     ctx->halo_n = 0;
     ctx->nbr_dirty = true;
     return DSP_OK;

@@ -259,6 +259,15 @@ __global__ void scatter_pos_kernel(int4* chunk_pos, const uint32_t* slots, const
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) chunk_pos[slots[i]] = src[i];
 }
+// neighbour table entry (slots[i], face) := external slab first_index + i, unless a resident neighbour is already there
+__global__ void apply_halo_batch_kernel(uint32_t* nbr, const uint32_t* slots, int face, uint32_t first_index, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slots[i];
+    if (s == 0xFFFFFFFFu) return;  // unloaded since
+    uint32_t* e = nbr + static_cast<size_t>(s) * 6 + face;
+    if (*e == 0xFFFFFFFFu) *e = 0x80000000u | (first_index + i);
+}
 __global__ void scatter_u32_kernel(uint32_t* dst, const uint2* idx_val, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[idx_val[i].x] = idx_val[i].y;

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--dims", type=int, nargs=3, default=[512, 32, 512], help="world size in chunks: x y z (y is up)")
     ap.add_argument("--batch", type=int, default=32768, help="chunks per mesh launch (arena is reused between launches)")
     ap.add_argument("--arena-gib", type=float, default=8.0)
+    ap.add_argument("--quad-modes", action="store_true", help="also run the greedy + indexed modes (chunk-local and halo culling)")
     ap.add_argument("--verify", action="store_true", help="check a sample of seam chunks against the oracle (small worlds)")
     args = ap.parse_args()
 
@@ -72,9 +73,13 @@ def main():
     gen_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
 
     out = []
-    for mode_name, mode in (("parity", capi.MESH_PARITY), ("halo", capi.MESH_HALO)):
+    modes = [("parity", capi.MESH_PARITY), ("halo", capi.MESH_HALO)]
+    if args.quad_modes:
+        modes += [("greedy_indexed", capi.MESH_GREEDY | capi.MESH_INDEXED), ("halo_greedy_indexed", capi.MESH_HALO | capi.MESH_GREEDY | capi.MESH_INDEXED)]
+    for mode_name, mode in modes:
         xchg_s, xchg_bytes = 0.0, 0
-        if mode == capi.MESH_HALO:
+        if mode & capi.MESH_HALO:
+            ctx.clear_halo_slabs()
             if world > 1:  # first exchange pays NCCL's lazy point-to-point setup; time the second
                 exchange_region_halos(dev, sp, rank, dist)
                 ctx.clear_halo_slabs()
