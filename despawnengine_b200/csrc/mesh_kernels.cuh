@@ -603,9 +603,10 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         bool empty;
         const RowFaces fc = c.count_phase(cur, buf, false, &empty);
         c.tick(3);
-        if (empty) {
-            // Nothing to emit and no slot to claim.  No further barrier is needed: every read of vox(buf) precedes the
-            // barrier inside count_phase, and s_next[(it + 1) & 1] was written by thread 0 before it.
+        if (empty || fc.total == 0u) {
+            // Nothing to emit and no slot to claim (all air; or, with cross-chunk culling, a chunk buried among solid
+            // neighbours).  No further barrier is needed: every read of vox(buf), the row masks and the warp totals precedes a
+            // barrier inside count_phase that all threads have passed, and s_next[(it + 1) & 1] was written before it.
             if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
             ++it;
             cur = c.s_next[it & 1];

@@ -326,6 +326,12 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             first = wpre + incl - cnt;
         }
         // claim the chunk's arena slot; the result is first touched after this thread's records are written
+        if (Q == 0u) {  // e.g. a chunk buried among solid neighbours under cross-chunk culling: no slot, no records, no emission
+            if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+            if (++buf == NB) { buf = 0; par ^= 1; }
+            cur = s_next[buf];
+            continue;
+        }
         // (everything about the slot -- size, claim, overflow check, destination pointers -- is thread 0's business alone)
         uint64_t claimed = 0;
         if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(quad_slot_bytes(Q, INDEXED)));

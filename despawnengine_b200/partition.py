@@ -117,6 +117,31 @@ class SlabPartition:
             out.append(SeamTransfer(rank + 1, FACE_LEFT, reg.face_positions(FACE_LEFT)))
         return out
 
+    def route_edits(self, edits: np.ndarray, halo: bool = False):
+        """SURVEY.md section 8e, incremental case: every edit goes to the rank that owns its chunk (by chunk X); edits outside
+        the world are dropped.  Returns (per_rank, seam_touched): per_rank[r] = the edits of rank r in their original order
+        (so "the last edit of a voxel wins" holds per rank), seam_touched[r] = True when, with cross-chunk culling (`halo`),
+        rank r must repack its border slabs for a neighbour because one of its edits lies on a seam-facing border layer.
+        `edits` is a structured array with fields wx, wy, wz (world voxel coordinates) and block (capi.EDIT_DTYPE)."""
+        e = np.asarray(edits)
+        cx = (e["wx"].astype(np.int64) >> 4) - self.world.origin[0]          # div_euclid(16), world.rs:69-74
+        cy = (e["wy"].astype(np.int64) >> 4) - self.world.origin[1]
+        cz = (e["wz"].astype(np.int64) >> 4) - self.world.origin[2]
+        inside = (cx >= 0) & (cx < self.world.dims[0]) & (cy >= 0) & (cy < self.world.dims[1]) & (cz >= 0) & (cz < self.world.dims[2])
+        starts = np.array([c[0] for c in self._cuts], dtype=np.int64)
+        owner = np.searchsorted(starts, cx, side="right") - 1
+        per_rank, seam_touched = [], []
+        for r, (start, cnt) in enumerate(self._cuts):
+            sel = inside & (owner == r)
+            per_rank.append(e[sel])
+            touched = False
+            if halo and sel.any():
+                lx = e["wx"][sel].astype(np.int64) & 15
+                c = cx[sel]
+                touched = bool(((r > 0) & (c == start) & (lx == 0)).any() or ((r < self.world_size - 1) & (c == start + cnt - 1) & (lx == 15)).any())
+            seam_touched.append(touched)
+        return per_rank, seam_touched
+
     def seam_bytes(self, rank: int) -> int:
         """Bytes this rank sends (== receives) per exchange."""
         return sum(len(t.positions) * SLAB_ELEMS * 2 for t in self.seam_transfers(rank))

@@ -98,3 +98,33 @@ def test_halo_exchange_over_gloo(tmp_path, world_size):
     orc.lib()  # build the oracle before forking
     mp.spawn(_rank_main, args=(world_size, _free_port(), str(tmp_path)), nprocs=world_size, join=True)
     assert sorted(os.listdir(tmp_path)) == [f"ok{r}" for r in range(world_size)]
+
+
+def test_edits_are_routed_to_the_owning_rank_in_order():
+    """SURVEY.md section 8e, incremental case: edits go to the rank owning the chunk (by chunk X), keep their order, and
+    an edit on a seam-facing border layer flags the slab the neighbour holds as stale (halo mode)."""
+    from despawnengine_b200 import capi
+    sp = part.SlabPartition(WORLD, 3)  # X cuts of 5 chunks starting at -2: [-2,-1], [0,1], [2]
+    rng = np.random.default_rng(3)
+    e = np.zeros(2000, dtype=capi.EDIT_DTYPE)
+    e["wx"] = rng.integers(-3 * 16, 4 * 16, 2000)   # some outside the world on both sides
+    e["wy"] = rng.integers(-8, 3 * 16 + 8, 2000)
+    e["wz"] = rng.integers(16 - 8, 4 * 16 + 8, 2000)
+    e["block"] = rng.integers(0, 3, 2000)
+    per_rank, seam = sp.route_edits(e, halo=True)
+    want = [[], [], []]
+    for ed in e:
+        c = (int(ed["wx"]) >> 4, int(ed["wy"]) >> 4, int(ed["wz"]) >> 4)
+        try:
+            WORLD.index_of(c)
+        except KeyError:
+            continue
+        want[sp.owner_of(c)].append(tuple(ed.tolist()))
+    for r in range(3):
+        assert [tuple(x.tolist()) for x in per_rank[r]] == want[r]
+    assert sum(len(p) for p in per_rank) < 2000 and all(len(p) > 0 for p in per_rank)
+    # seam flags: rank 0's +X seam layer is world x = -1 (voxel wx in [-16, -1], local x == 15 -> wx == -1)
+    assert seam[0] == bool(((e["wx"] == -1) & np.isin(np.arange(2000), np.nonzero([t in set(want[0]) for t in map(lambda x: tuple(x.tolist()), e)])[0])).any())
+    only_interior = e[(e["wx"] & 15 != 0) & (e["wx"] & 15 != 15)]
+    assert sp.route_edits(only_interior, halo=True)[1] == [False, False, False]
+    assert sp.route_edits(e, halo=False)[1] == [False, False, False]
