@@ -194,3 +194,35 @@ def test_arena_offsets_beyond_4_gib(uv_default):
             assert c.download_vertices(entries[k]).tobytes() == want.tobytes(), p
         offs = np.sort(entries["offset_bytes"].astype(np.int64))
         assert np.array_equal(np.diff(offs), np.full(4095, 12288 * 120))
+
+
+def _chunk_with_face_count(n_faces, mixed_ids):
+    """A chunk with exactly n_faces visible faces (= quads when mixed_ids: the two voxels of a pair differ, so nothing merges).
+    Lines along x at (y, z): even lines (y + z even) offer slots x0 in {0,3,6,9,12} for a pair (10 faces) or a single voxel
+    (6 faces); odd lines offer single-voxel slots at x in {2,5,8,11,14}, which are only diagonal to the even lines' cells."""
+    even = [(x0, y, z) for z in range(16) for y in range(16) if (y + z) % 2 == 0 for x0 in (0, 3, 6, 9, 12)]
+    odd = [(x, y, z) for z in range(16) for y in range(16) if (y + z) % 2 == 1 for x in (2, 5, 8, 11, 14)]
+    b = next(b for b in range(min(len(even), n_faces // 10), -1, -1) if (n_faces - 10 * b) % 6 == 0 and (n_faces - 10 * b) // 6 <= len(even) - b + len(odd))
+    a = (n_faces - 10 * b) // 6
+    ids = np.zeros(4096, dtype=np.uint16)
+    for k, (x0, y, z) in enumerate(even[:b]):
+        ids[x0 + 16 * y + 256 * z] = 1
+        ids[x0 + 1 + 16 * y + 256 * z] = 2 if mixed_ids else 1
+    for (x, y, z) in (even[b:] + odd)[:a]:
+        ids[x + 16 * y + 256 * z] = 1
+    return ids
+
+
+@pytest.mark.parametrize("mode,greedy,indexed,cap", [(capi.MESH_INDEXED, False, True, 4096), (capi.MESH_GREEDY, True, False, 2048),
+                                                      (capi.MESH_GREEDY | capi.MESH_INDEXED, True, True, 2048)])
+def test_quad_counts_around_the_record_window(ctx, uv_default, mode, greedy, indexed, cap):
+    """Chunks whose quad count is exactly the kernel's record window, one less, one more (window +- 2, counts are even), twice
+    the window, and a tile boundary: the windowed record / emission loops must not drop or duplicate a quad."""
+    counts = [cap - 2, cap, cap + 2, 2 * cap, 2 * cap + 2, 128, 126, 130, 256, 258]
+    blocks = [_chunk_with_face_count(c, mixed_ids=True) for c in counts]
+    positions = [(k, -k, 2 * k) for k in range(len(counts))]
+    slots = ctx.load_chunks(positions, np.stack(blocks))
+    entries, total = ctx.mesh_chunks(slots, mode)
+    check_layout(entries, total)
+    assert [int(e["vertex_count"]) // (4 if indexed else 6) for e in entries] == counts
+    compare(ctx, positions, blocks, entries, uv_default, greedy, indexed)
