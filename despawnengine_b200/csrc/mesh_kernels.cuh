@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         mbar_init(&c.s_bar[0], 1);
         mbar_init(&c.s_bar[1], 1);
         fence_mbar_init();
-        const uint32_t t0 = atomicAdd(p.ticket, 1u);
+        const uint32_t t0 = blockIdx.x;  // first chunk = block index: the tile load starts without waiting for an atomic
         c.s_next[0] = t0;
         if (t0 < p.n) c.issue_load(t0, 0);
     }
@@ -588,11 +588,11 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
     c.tlast = clock64();
 #endif
     // (Measured alternatives that were NOT faster on B200: consuming the ticket atomic only after the record phase,
-    // running tickets two chunks ahead of the tiles, a static first ticket per CTA; see profiles/README.md.)
+    // running tickets two chunks ahead of the tiles; see profiles/README.md.  A static first ticket is worth ~0.3 us.)
     while (cur < p.n) {
         const int buf = it & 1;
         if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
-            const uint32_t t = atomicAdd(p.ticket, 1u);
+            const uint32_t t = gridDim.x + atomicAdd(p.ticket, 1u);
             c.s_next[(it + 1) & 1] = t;
             if (t < p.n) c.issue_load(t, buf ^ 1);  // buf^1 was released by the barrier that ended the previous iteration
         }
@@ -630,8 +630,8 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         ++it;
         cur = c.s_next[it & 1];
     }
+    if (tid == 0) control_block_epilogue(p);  // control words only: its atomic's round trip overlaps the drain of the last stores
     if (c.lane == 0) bulk_wait<0>();
-    if (tid == 0) control_block_epilogue(p);
 #ifdef DSP_PHASE_TIMERS
     c.tick(9);
     if (tid == 0 && p.phase_cycles) for (int k = 0; k < 16; ++k) atomicAdd(&p.phase_cycles[k], static_cast<unsigned long long>(c.ph[k]));

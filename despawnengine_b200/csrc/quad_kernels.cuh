@@ -488,8 +488,8 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         if (++buf == NB) { buf = 0; par ^= 1; }
         cur = s_next[buf];
     }
+    if (tid == 0) control_block_epilogue(p);  // control words only: overlaps the drain of the last stores
     if (lane == 0) bulk_wait<0>();
-    if (tid == 0) control_block_epilogue(p);
 }
 
 }  // namespace dsp
