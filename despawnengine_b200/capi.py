@@ -60,6 +60,7 @@ SYMBOLS = {
     "dsp_mesh_result": (_int, [_vp, _vp, _P(_u64)]),
     "dsp_apply_edits": (_int, [_vp, _u64, _vp, _P(_u32), _u64, _P(_u64)]),
     "dsp_apply_edits_and_remesh": (_int, [_vp, _u64, _vp, _u32, _u64, _P(_u32), _u64, _P(_u64), _vp, _P(_u64)]),
+    "dsp_get_block_world": (_int, [_vp, _i32, _i32, _i32, _P(C.c_uint16)]),
     "dsp_pack_border_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_set_halo_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_clear_halo_slabs": (_int, [_vp]),
@@ -286,6 +287,15 @@ class Context:
         nd = C.c_uint64(0)
         self._check(lib().dsp_apply_edits(self._h, e.shape[0], e.ctypes.data_as(C.c_void_p), _ptr(dirty, C.c_uint32), dirty.shape[0], C.byref(nd)))
         return dirty[: int(nd.value)].copy()
+
+    def get_block_world(self, wx: int, wy: int, wz: int):
+        """Global block id at world voxel coordinates, or None when the chunk is not resident (world.rs:50-65)."""
+        out = C.c_uint16(0)
+        rc = lib().dsp_get_block_world(self._h, wx, wy, wz, C.byref(out))
+        if rc == ERR_NOT_RESIDENT:
+            return None
+        self._check(rc)
+        return int(out.value)
 
     def apply_edits_and_remesh(self, edits, mode: int = MESH_PARITY, arena_offset: int = 0):
         """Returns (dirty slots ascending, their mesh entries, total bytes)."""

@@ -1060,6 +1060,19 @@ int dsp_apply_edits_and_remesh(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, 
     return finish_mesh(ctx, out_entries, out_total_bytes);
 }
 
+int dsp_get_block_world(dsp_ctx* ctx, int32_t wx, int32_t wy, int32_t wz, uint16_t* out_block) {
+    if (!ctx || !out_block) return DSP_ERR_BAD_ARG;
+    const int32_t c[3] = {wx >> 4, wy >> 4, wz >> 4};  // div_euclid(16)
+    uint32_t slot;
+    if (!find_slot(ctx, c, &slot)) return fail(ctx, DSP_ERR_NOT_RESIDENT, "chunk (%d, %d, %d) is not resident", c[0], c[1], c[2]);
+    const uint32_t idx = static_cast<uint32_t>(wx & 15) + 16u * static_cast<uint32_t>(wy & 15) + 256u * static_cast<uint32_t>(wz & 15);  // rem_euclid(16), chunk.rs:44-46
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 128, ctx->d_voxels + static_cast<size_t>(slot) * dsp::kChunkVoxels + idx, sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out_block = *reinterpret_cast<uint16_t*>(ctx->h_pinned + 128);
+    return DSP_OK;
+}
+
 int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, void* dst_device) {
     if (!ctx) return DSP_ERR_BAD_ARG;
     if (face < 0 || face > 5) return fail(ctx, DSP_ERR_BAD_ARG, "face %d out of range", face);

@@ -162,6 +162,11 @@ class World:
         self.chunks[tuple(chunk.position)] = slot
         return slot
 
+    def get_block_world(self, wx: int, wy: int, wz: int) -> Optional[str]:
+        """world.rs:50-65: the block id string at world voxel coordinates; None when the chunk is not in `chunks`."""
+        gid = self.ctx.get_block_world(int(wx), int(wy), int(wz))
+        return None if gid is None else self.registry.name_of(gid)
+
     def load_chunk(self, chunk_pos) -> None:  # world.rs:80-84
         p = tuple(int(c) for c in chunk_pos)
         self.loaded_chunks[p] = self.get_chunk(p)

@@ -183,6 +183,11 @@ int dsp_apply_edits_and_remesh(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, 
                                uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty, dsp_mesh_entry* out_entries,
                                uint64_t* out_total_bytes);
 
+/* World::get_block_world (world.rs:50-65) / Chunk::get_block (chunk.rs:71-82) on the device store: the global block id at world
+ * voxel coordinates (chunk = div_euclid(w, 16), local = rem_euclid(w, 16), world.rs:69-74).  DSP_ERR_NOT_RESIDENT where the
+ * reference returns None because the chunk is not in `chunks`.  Blocking (one 2-byte read-back). */
+int dsp_get_block_world(dsp_ctx* ctx, int32_t wx, int32_t wy, int32_t wz, uint16_t* out_block);
+
 /* ---- region seams (multi-GPU halo mode) ----------------------------------------------------- */
 /* Faces are numbered in the reference's emission order (chunk_mesh.rs:46-51, 65-106). */
 #define DSP_FACE_TOP 0    /* +Y, layer y = 15 */

@@ -161,3 +161,16 @@ def test_halo_mode_edits_also_remesh_the_neighbour_across_an_edited_border(uv_de
             entries_all, _ = ctx.mesh_chunks(all_slots, capi.MESH_HALO, arena_offset=(total + 127) & ~127)
             for p, en in zip(positions, entries_all):
                 assert ctx.download_vertices(en).tobytes() == halo_mesh(p).tobytes(), ("full", frame, p)
+
+
+def test_get_block_world_reads_what_edits_wrote(uv_default):
+    """World::get_block_world (world.rs:50-65) on the device store, negative coordinates included."""
+    with capi.Context(0, 64, 16 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        ctx.generate_chunks([(-1, 0, -1), (0, 0, 0)], capi.GEN_REFERENCE)
+        assert ctx.get_block_world(-1, 7, -16) == 1 and ctx.get_block_world(-1, 8, -16) == 0   # flat chunk: y < 8 dirt
+        assert ctx.get_block_world(16, 0, 0) is None                                           # chunk (1,0,0) is not resident
+        e = np.zeros(2, dtype=capi.EDIT_DTYPE)
+        e["wx"], e["wy"], e["wz"], e["block"] = [-16, 15], [15, 0], [-1, 15], [2, 0]
+        ctx.apply_edits(e)
+        assert ctx.get_block_world(-16, 15, -1) == 2 and ctx.get_block_world(15, 0, 15) == 0
