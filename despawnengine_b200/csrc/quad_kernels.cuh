@@ -253,6 +253,15 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             // ---- 2. face masks (chunk_mesh.rs:46-51); anchors = faces unless merging
             fm = row_face_masks<HALO>(p, HALO ? slot_of(cur) : 0u, s_rowmask, r, y, z, m);
             A[0] = fm.top; A[1] = fm.bot; A[2] = fm.rear; A[3] = fm.front; A[4] = fm.right; A[5] = fm.left;
+            if (HALO && GREEDY) {
+                // cross-chunk culling buries most solid chunks completely: find that out before the merge machinery runs
+                if (__syncthreads_or((A[0] | A[1] | A[2] | A[3] | A[4] | A[5]) != 0u) == 0) {
+                    if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+                    if (++buf == NB) { buf = 0; par ^= 1; }
+                    cur = s_next[buf];
+                    continue;
+                }
+            }
             if (GREEDY) {
                 eqx = eq_prev_mask16(qa, qb);
                 uint32_t eqy = 0u, eqz = 0u;

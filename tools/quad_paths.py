@@ -27,7 +27,7 @@ for name, kind, seed, origin in cases:
         else:
             first = ctx.generate_region(origin, (16, 16, 16), kind, seed)
         out = {"case": name}
-        for mname, mode in (("parity", 0), ("indexed", 8), ("greedy", 4), ("greedy_indexed", 12)):
+        for mname, mode in (("parity", 0), ("indexed", 8), ("greedy", 4), ("greedy_indexed", 12), ("halo", 1), ("halo_greedy_indexed", 13)):
             e, total = ctx.mesh_range(first, 4096, mode)
             out[mname + "_us"] = round(kernel_ms(ctx, lambda: ctx.mesh_range_async(first, 4096, mode), 20) * 1e3, 2)
             out[mname + "_MB"] = round(total / 1e6, 1)
