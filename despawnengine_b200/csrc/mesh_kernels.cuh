@@ -9,20 +9,20 @@
 //                                                     byte-identical, not merely set-equal
 //   :109-128 one device buffer per chunk            -> one 128-byte aligned slot of a shared arena
 //
-// One persistent CTA (256 threads) takes chunks from an atomic ticket counter.  Per chunk:
+// One persistent CTA (256 threads) takes chunks from a ticket counter (first chunk = block index).  Per chunk:
 //   1. the 8 KiB voxel tile arrives in shared memory by a 1-D bulk (TMA) copy that was issued
 //      while the previous chunk was being processed (2-deep mbarrier pipeline);
 //   2. thread r builds the occupancy mask of x-row r, derives the six face masks and its face
 //      count; a warp-shuffle + 8-way scan gives every row its first face ordinal and the CTA the
-//      chunk's face total F;
-//   3. thread 0 publishes align128(120*F) right after the count; the count phase of chunk k+1 runs BEFORE the
-//      emission of chunk k, so every ticket's size is published early and nobody's look-back waits on a CTA
-//      that is busy writing vertices.  Warp 0 then resolves the chunk's arena offset with a decoupled
-//      look-back over the earlier tickets (single pass: voxels are read from HBM exactly once);
-//      all rows write 16-bit face records (voxel index, direction) in stream order;
-//   4. faces are expanded one thread per face; each warp stages its 32 faces (3,840 B = 30 full lines) in a
-//      private shared-memory slot and sends it with ONE bulk shared->global copy (cp.async.bulk), so only
-//      full-line writes reach L2/HBM and the emission loop has no CTA-wide barrier.
+//      chunk's face total F (all-air chunks, and chunks with no visible face, leave here);
+//   3. the chunk's arena slot of align128(120*F) bytes:
+//        mesh_chunks_bump_kernel (default)  one 64-bit atomicAdd on a cursor -- slots gap-free, in completion order;
+//        mesh_chunks_kernel (DSP_MESH_ORDERED)  decoupled look-back over the earlier tickets, the count phase of chunk
+//        k+1 running before the emission of chunk k so that sizes are published early -- slots in call order;
+//      meanwhile all rows write 16-bit face records (voxel index, direction) in stream order;
+//   4. faces are expanded one thread per face into a 30,720-byte staging tile (256 faces) that leaves with ONE bulk
+//      shared->global copy (cp.async.bulk), so only full-line writes reach L2/HBM (MeshCfg variants: per-warp tiles);
+//   5. the last CTA to finish publishes {status, total} and zeroes the control block for the next launch.
 // Algorithmic HBM bytes per chunk: 8,192 (voxels) + 120*F (vertices) + 16 (position) + 16 (entry).
 #pragma once
 #include "dsp_common.cuh"
