@@ -71,27 +71,17 @@ __device__ __forceinline__ uint32_t transpose16x16_pair(uint32_t v, int lane) {
     return v;
 }
 
-// bit x = ids equal at position x of two rows of 16 u16 (held as 8 words each)
+// bit x = ids equal at position x of two rows of 16 u16 (held as 8 words each): "differs" is nonzero_mask8 of the XOR
 __device__ __forceinline__ uint32_t eq_mask16(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
-    const uint32_t d[8] = {a0.x ^ b0.x, a0.y ^ b0.y, a0.z ^ b0.z, a0.w ^ b0.w, a1.x ^ b1.x, a1.y ^ b1.y, a1.z ^ b1.z, a1.w ^ b1.w};
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        m |= (d[k] & 0xFFFFu) ? 0u : (1u << (2 * k));
-        m |= (d[k] >> 16) ? 0u : (2u << (2 * k));
-    }
-    return m;
+    const uint32_t ne = nonzero_mask8(make_uint4(a0.x ^ b0.x, a0.y ^ b0.y, a0.z ^ b0.z, a0.w ^ b0.w)) |
+                        (nonzero_mask8(make_uint4(a1.x ^ b1.x, a1.y ^ b1.y, a1.z ^ b1.z, a1.w ^ b1.w)) << 8);
+    return ~ne & 0xFFFFu;
 }
-// bit x (x >= 1) = id[x] == id[x-1] within one row
+// bit x (x >= 1) = id[x] == id[x-1] within one row: the row against itself shifted by one voxel (funnel shifts)
 __device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 a0, const uint4 a1) {
-    const uint32_t w[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    uint32_t m = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        m |= ((w[k] & 0xFFFFu) == (w[k] >> 16)) ? (2u << (2 * k)) : 0u;
-        if (k > 0) m |= ((w[k] & 0xFFFFu) == (w[k - 1] >> 16)) ? (1u << (2 * k)) : 0u;
-    }
-    return m;
+    const uint4 p0 = make_uint4(a0.x << 16, __funnelshift_l(a0.x, a0.y, 16), __funnelshift_l(a0.y, a0.z, 16), __funnelshift_l(a0.z, a0.w, 16));
+    const uint4 p1 = make_uint4(__funnelshift_l(a0.w, a1.x, 16), __funnelshift_l(a1.x, a1.y, 16), __funnelshift_l(a1.y, a1.z, 16), __funnelshift_l(a1.z, a1.w, 16));
+    return eq_mask16(a0, a1, p0, p1) & 0xFFFEu;
 }
 
 __device__ __forceinline__ uint32_t run_starts(uint32_t f, uint32_t eq) { return f & ~((f << 1) & eq); }
