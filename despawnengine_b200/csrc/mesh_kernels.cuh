@@ -462,8 +462,13 @@ struct MeshCta {
     __device__ __forceinline__ void tick(int) {}
 #endif
 
+    // `claimed` (atomic-claim kernel, tile emission): thread 0's slot offset, the result of an atomicAdd issued BEFORE this
+    // call and first touched AFTER the record barrier -- only thread 0 issues bulk stores, so nobody else needs the value, and
+    // the atomic's round trip hides behind the record phase instead of holding the whole CTA at the barrier (7.8 % of the
+    // stall samples sat on that atomic when its result was stored to shared memory before the barrier).
     template <class Between>
-    __device__ __forceinline__ void records_and_emit(uint32_t chunk, const RowFaces& fc, const uint16_t* vox, Between between) {
+    __device__ __forceinline__ void records_and_emit(uint32_t chunk, const RowFaces& fc, const uint16_t* vox, Between between,
+                                                     const uint64_t* claimed = nullptr) {
         const uint32_t F = fc.total;
         tick(0);
         // issued first so that its global-memory latency hides behind the record phase (it used to sit right after the
@@ -475,7 +480,16 @@ struct MeshCta {
         tick(4);
         __syncthreads();  // s_rec, s_base visible
         tick(5);
-        const uint64_t base = *s_base;
+        uint64_t base = 0;
+        if (claimed != nullptr) {
+            if (tid == 0) {
+                base = *claimed;
+                if (base + slot_bytes_of(F) > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                p.entries[chunk] = MeshEntry{p.arena_offset + base, F * 6u, 0u};
+            }
+        } else {
+            base = *s_base;
+        }
         const bool fits = base + slot_bytes_of(F) <= p.arena_room;
         uint8_t* gout = p.arena + base;
         const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
@@ -617,15 +631,22 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         const RowFaces fc = c.count_phase(cur, buf, false);
         c.tick(3);
 #endif
-        c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
-            if (tid == 0) {  // claim the chunk's arena slot
-                const uint64_t bytes = slot_bytes_of(fc.total);
-                const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
-                *c.s_base = base;
-                if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                p.entries[cur] = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
-            }
-        });
+        if (!Cfg::WARP_EMIT) {
+            // claim the chunk's arena slot now; the result is not touched until the records are written (see records_and_emit)
+            uint64_t claimed = 0;
+            if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(slot_bytes_of(fc.total)));
+            c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, []() {}, &claimed);
+        } else {
+            c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
+                if (tid == 0) {  // every warp issues its own stores: the offset goes through shared memory
+                    const uint64_t bytes = slot_bytes_of(fc.total);
+                    const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
+                    *c.s_base = base;
+                    if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                    p.entries[cur] = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
+                }
+            });
+        }
         __syncthreads();  // all reads of vox(buf), s_rec, s_next done before they are overwritten
         c.tick(8);
         ++it;

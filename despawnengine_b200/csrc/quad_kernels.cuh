@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     uint16_t* const s_first = reinterpret_cast<uint16_t*>(smem + L::kFirst);
     uint32_t* const s_warp = reinterpret_cast<uint32_t*>(smem + L::kWarpTot);
     uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
-    uint64_t* const s_base = reinterpret_cast<uint64_t*>(smem + L::kBase);
     uint32_t* const s_next = reinterpret_cast<uint32_t*>(smem + L::kNext);
     float* const s_istage = s_stage + kTile * 20;  // indexed layout: the tile's indices follow its vertices
 
@@ -413,12 +412,11 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
             }
             if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
-            if (tid == 0 && q0 == 0) {
-                *s_base = claimed;  // read back by thread 0 only (it alone issues the bulk stores)
+            __syncthreads();  // records visible
+            if (tid == 0 && q0 == 0) {  // first touch of the claim's result: after the barrier, so the CTA never waits on that atomic
                 if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
                 p.entries[cur] = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
             }
-            __syncthreads();  // records visible
             const uint32_t q1 = min(Q, q0 + kRecCap);
             for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {
                 if (f0 > q0) {  // (for the window's first tile the records barrier above did this)
@@ -467,8 +465,8 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
                 fence_proxy_async_smem();
                 __syncthreads();
-                if (tid == 0 && *s_base + quad_slot_bytes(Q, INDEXED) <= p.arena_room) {
-                    uint8_t* const gout = p.arena + *s_base;
+                if (tid == 0 && claimed + quad_slot_bytes(Q, INDEXED) <= p.arena_room) {
+                    uint8_t* const gout = p.arena + claimed;
                     uint8_t* const gidx = gout + quad_vertex_region_bytes(Q, true);
                     const uint32_t nq = min(static_cast<uint32_t>(kTile), Q - f0);
                     if (INDEXED) {

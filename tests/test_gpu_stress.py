@@ -2,6 +2,7 @@
 orders and batch sizes, in every mode, and every result must hash to what the oracle produced once.  A missing barrier in
 the persistent kernels (tile reuse, record windows, staging tiles, ticket hand-over) shows up as an intermittent mismatch."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -38,7 +39,7 @@ def test_repeated_shuffled_batches_are_stable_in_every_mode(uv_default):
     with capi.Context(0, 4096, 1 << 30) as ctx:
         ctx.set_uv_table(uv_default)
         slots = ctx.load_chunks([p for p, _ in chunks], np.stack([ids for _, ids in chunks]))
-        for rep in range(12):
+        for rep in range(int(os.environ.get("DSP_STRESS_REPS", "12"))):
             for m in modes:
                 # many copies of the list in random order: enough chunks that every resident CTA takes several tickets
                 order = rng.permutation(np.tile(np.arange(len(chunks)), int(rng.integers(8, 40))))
