@@ -53,3 +53,45 @@ def test_repeated_shuffled_batches_are_stable_in_every_mode(uv_default):
                     oi = o + ((nv * 20 + 127) & ~127)
                     got = hashlib.sha256(blob[o:o + nv * 20].tobytes() + blob[oi:oi + ni * 4].tobytes()).digest()
                     assert got == digest, (rep, m, int(j), chunks[int(j)][0])
+
+
+def test_repeated_shuffled_batches_are_stable_with_cross_chunk_culling(uv_default):
+    rng = np.random.default_rng(7)
+    dirs = [(0, 1, 0), (0, -1, 0), (0, 0, -1), (0, 0, 1), (-1, 0, 0), (1, 0, 0)]
+    with capi.Context(0, 4096, 1 << 30) as ctx:
+        ctx.set_uv_table(uv_default)
+        worlds = []
+        for origin, dims, kind, seed in (((0, 6, 0), (3, 3, 3), capi.GEN_NOISE, 0xD5E50001), ((20, 0, 0), (3, 2, 2), capi.GEN_RANDOM, 9),
+                                         ((40, -2, 0), (2, 3, 2), capi.GEN_REFERENCE, 0)):
+            first = ctx.generate_region(origin, dims, kind, seed)
+            for c in range(dims[2]):
+                for b in range(dims[1]):
+                    for a in range(dims[0]):
+                        p = (origin[0] + a, origin[1] + b, origin[2] + c)
+                        worlds.append((p, first + a + dims[0] * (b + dims[1] * c), orc.generate(kind, seed, p)))
+        ids_of = {p: ids for p, _, ids in worlds}
+        slots = np.array([s for _, s, _ in worlds], dtype=np.uint32)
+        want = {}
+        for m in (capi.MESH_HALO, capi.MESH_HALO | capi.MESH_GREEDY | capi.MESH_INDEXED):
+            for i, (p, _, ids) in enumerate(worlds):
+                slabs, present = np.zeros((6, 256), dtype=np.uint16), np.zeros(6, dtype=np.uint8)
+                for f, d in enumerate(dirs):
+                    q = (p[0] + d[0], p[1] + d[1], p[2] + d[2])
+                    if q in ids_of:
+                        v = ids_of[q].reshape(16, 16, 16)
+                        present[f] = 1
+                        slabs[f] = [v[:, 0, :], v[:, 15, :], v[15, :, :], v[0, :, :], v[:, :, 15], v[:, :, 0]][f].reshape(256)
+                g = bool(m & capi.MESH_GREEDY)
+                v, ix, _ = orc.mesh_chunk_ext(p, ids, uv_default, greedy=g, indexed=g, nbr_slabs=slabs, nbr_present=present)
+                want[(m, i)] = (v.shape[0], ix.shape[0], hashlib.sha256(v.tobytes() + ix.tobytes()).digest())
+        for rep in range(int(os.environ.get("DSP_STRESS_REPS", "12"))):
+            for m in (capi.MESH_HALO, capi.MESH_HALO | capi.MESH_GREEDY | capi.MESH_INDEXED):
+                order = rng.permutation(np.tile(np.arange(len(worlds)), int(rng.integers(8, 30))))
+                entries, total = ctx.mesh_chunks(slots[order], m)
+                blob = ctx.download_arena(0, total)
+                for j, e in zip(order, entries):
+                    nv, ni, digest = want[(m, int(j))]
+                    assert (int(e["vertex_count"]), int(e["index_count"])) == (nv, ni), (rep, m, j)
+                    o = int(e["offset_bytes"])
+                    oi = o + ((nv * 20 + 127) & ~127)
+                    assert hashlib.sha256(blob[o:o + nv * 20].tobytes() + blob[oi:oi + ni * 4].tobytes()).digest() == digest, (rep, m, worlds[int(j)][0])
