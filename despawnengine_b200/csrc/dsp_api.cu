@@ -74,6 +74,9 @@ struct dsp_ctx {
     dsp::MeshEntry* d_entries = nullptr;
     uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
     uint32_t* d_slots = nullptr;
+    uint8_t* d_summary = nullptr;     // per slot: dsp::kSummary* (all air / uniformly solid / unknown)
+    uint32_t* d_work_slots = nullptr; // device-built work list of halo-mode mesh calls (allocated on first use)
+    uint32_t* d_work_entry = nullptr;
     float4* d_uv_rows = nullptr;
     float4* d_uvmap = nullptr;
     uint32_t n_blocks = 0, uv_cap = 0;
@@ -236,10 +239,11 @@ int upload_positions_and_slots(dsp_ctx* ctx, uint64_t n, const int32_t* pos, con
         for (uint64_t i = 0; i < n; ++i) p4[i] = make_int4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 0);
         if (consecutive) {
             DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos + *first, h, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
+            DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_summary + *first, dsp::kSummaryUnknown, n, ctx->stream));  // the slots are being (re)defined
         } else {  // recycled slots are scattered: one copy + one scatter launch, not one copy per run of slots
             if ((rc = ensure_scratch(ctx, n * sizeof(int4))) != DSP_OK) return rc;
             DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, h, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-            dsp::scatter_pos_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_slots, reinterpret_cast<const int4*>(ctx->d_scratch),
+            dsp::scatter_pos_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_summary, ctx->d_slots, reinterpret_cast<const int4*>(ctx->d_scratch),
                                                                                                   static_cast<uint32_t>(n));
             DSP_CUDA(ctx, cudaGetLastError());
         }
@@ -360,7 +364,8 @@ int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offs
 }
 
 // One mesh launch over `n` chunks whose entries start at entry index `entry0`; `sub` picks the ticket counter.
-int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub, bool self_reset = false) {
+int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub, bool self_reset = false,
+                bool work_list = false) {
     const bool halo = (mode & DSP_MESH_HALO) != 0;
     dsp::MeshParams p{};
     p.voxels = ctx->d_voxels;
@@ -378,6 +383,11 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.entries = ctx->d_entries + entry0;
     p.ticket = sub == 0 ? reinterpret_cast<uint32_t*>(ctx->d_ctl) : ctx->d_tickets + sub;  // control block: [ticket][status][done][-][total 8 B][-]
     p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
+    if (work_list) {  // classify_chunks_kernel left the chunks that need meshing in d_work_slots, their count in the control block
+        p.slot_list = ctx->d_work_slots;
+        p.entry_map = ctx->d_work_entry;
+        p.n_dev = reinterpret_cast<const uint32_t*>(ctx->d_ctl) + 3;
+    }
     if (self_reset) {
         p.done = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 2;
         p.result = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32 + 8 * ctx->max_chunks);
@@ -405,7 +415,22 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     if (n == 0) return DSP_OK;
     if (mode & DSP_MESH_HALO) { if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc; }
     ctx->ctl_clean = false;  // until the launch below is known to have been enqueued
-    rc = launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0, !ordered);
+    bool work_list = false;
+    if ((mode & DSP_MESH_HALO) && !ordered) {
+        // Cross-chunk culling leaves most chunks of a large world without a single face (all air, or solid among solid
+        // neighbours): a pre-pass over the chunk summaries writes their empty entries and hands the mesh kernel only the rest.
+        if (!ctx->d_work_slots) {
+            DSP_CUDA(ctx, cudaMalloc(&ctx->d_work_slots, ctx->max_chunks * sizeof(uint32_t)));
+            DSP_CUDA(ctx, cudaMalloc(&ctx->d_work_entry, ctx->max_chunks * sizeof(uint32_t)));
+        }
+        dsp::classify_chunks_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
+            ctx->d_summary, ctx->d_nbr, d_list, first_slot, static_cast<uint32_t>(n), arena_offset, ctx->d_entries, ctx->d_work_slots, ctx->d_work_entry,
+            reinterpret_cast<uint32_t*>(ctx->d_ctl) + 3);
+        DSP_CUDA(ctx, cudaGetLastError());
+        ctx->launches++;
+        work_list = true;
+    }
+    rc = launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0, !ordered, work_list);
     if (rc == DSP_OK && !ordered) { ctx->ctl_clean = true; ctx->result_in_tail = true; }
     return rc;
 }
@@ -518,6 +543,7 @@ int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool hal
     p.voxels = ctx->d_voxels;
     p.dirty_bitmap = reinterpret_cast<uint32_t*>(ctx->d_scratch + off_bitmap);
     p.nbr = nullptr;
+    p.summary = ctx->d_summary;
     if (halo) {
         if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc;
         p.nbr = ctx->d_nbr;
@@ -618,6 +644,8 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     if ((e = cudaMalloc(&ctx->d_entries, max_chunks * sizeof(dsp::MeshEntry))) != cudaSuccess) return bail("cudaMalloc(entries)", e);
     if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks + 64)) != cudaSuccess) return bail("cudaMalloc(control)", e);
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
+    if ((e = cudaMalloc(&ctx->d_summary, max_chunks)) != cudaSuccess) return bail("cudaMalloc(chunk summaries)", e);
+    if ((e = cudaMemset(ctx->d_summary, 0, max_chunks)) != cudaSuccess) return bail("cudaMemset(chunk summaries)", e);
     if ((e = cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
     cudaMemset(ctx->d_phase, 0, 16 * sizeof(unsigned long long));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -644,6 +672,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     cudaFree(ctx->d_tickets);
+    cudaFree(ctx->d_summary); cudaFree(ctx->d_work_slots); cudaFree(ctx->d_work_entry);
     cudaFree(ctx->d_phase); cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -689,7 +718,7 @@ int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_ki
     const uint32_t* d_list; uint32_t first;
     int rc = upload_positions_and_slots(ctx, n, pos, slots.data(), &d_list, &first);
     if (rc != DSP_OK) return rc;
-    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr};
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary};
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
     dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
@@ -716,7 +745,7 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
     ctx->nbr_dirty = true;
     if (gen_kind == DSP_GEN_NOISE) {
         // heightmap computed once per chunk column and reused up the stack (terrain_fill_region_noise_kernel)
-        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed};
+        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed, ctx->d_summary};
         // enough CTAs to fill the machine a few times over, but as tall a run per CTA as that allows
         const uint64_t columns = static_cast<uint64_t>(dims[0]) * dims[2], want = static_cast<uint64_t>(ctx->num_sms) * 16;
         uint32_t pieces = static_cast<uint32_t>(std::min<uint64_t>(dims[1], std::max<uint64_t>(1, (want + columns - 1) / columns)));
@@ -730,7 +759,7 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
         if (n > 0xFFFFFFFFull) return fail(ctx, DSP_ERR_BAD_ARG, "region too large");
         // positions are arithmetic in a box: the fill kernel derives them from the chunk's index and records them itself
         dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed,
-                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos};
+                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos, ctx->d_summary};
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
         dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
         DSP_CUDA(ctx, cudaGetLastError());
@@ -920,7 +949,7 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
         // DMA engine until all tile copies are through (0.73 -> 0.93 ms).  So positions and the slot list do not use a copy
         // engine at all: a small kernel on the main stream reads them straight from the pinned staging block (UVA).
         dsp::stage_positions_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_pos, ctx->d_slots + i0, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
+            ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
         DSP_CUDA(ctx, cudaGetLastError());
         const uint32_t* d_list = consecutive ? nullptr : ctx->d_slots + i0;
         ctx->stream = ctx->copy_stream;  // upload_by_runs enqueues on ctx->stream
@@ -992,7 +1021,7 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
         if (rc != DSP_OK) return rc;
         DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, packed.data(), packed.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
         dsp::edit_scatter_kernel<<<static_cast<unsigned>((packed.size() + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_voxels, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(packed.size()));
+            ctx->d_voxels, ctx->d_summary, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(packed.size()));
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }

@@ -60,7 +60,15 @@ struct MeshParams {
     // of it -- a step is exactly one kernel launch.  nullptr: the caller resets the block itself (multi-launch calls).
     uint32_t* done;
     uint64_t* result;           // [0] = status, [1] = total bytes
+    // Work list produced on the device by classify_chunks_kernel (halo mode: all-air and buried chunks never reach the mesh
+    // kernel): when n_dev != nullptr the number of chunks is read from it and entry_map[i] is the entry index of chunk i.
+    const uint32_t* n_dev;
+    const uint32_t* entry_map;
 };
+
+__device__ __forceinline__ MeshEntry* entry_of(const MeshParams& p, uint32_t chunk) {
+    return p.entries + (p.entry_map ? __ldg(p.entry_map + chunk) : chunk);
+}
 
 // Last instructions of a persistent mesh kernel (thread 0 of every CTA, after its stores were issued).
 __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
@@ -70,7 +78,8 @@ __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
     __threadfence();
     p.result[0] = atomicOr(p.status, 0u);
     p.result[1] = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), 0ull);
-    *p.ticket = 0u;
+    p.ticket[0] = 0u;
+    p.ticket[3] = 0u;  // the work-list count of classify_chunks_kernel lives in the same 16-byte word group
     *p.status = 0u;
     *p.total_bytes = 0ull;
     *p.done = 0u;
@@ -485,7 +494,7 @@ struct MeshCta {
             if (tid == 0) {
                 base = *claimed;
                 if (base + slot_bytes_of(F) > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                p.entries[chunk] = MeshEntry{p.arena_offset + base, F * 6u, 0u};
+                *entry_of(p, chunk) = MeshEntry{p.arena_offset + base, F * 6u, 0u};
             }
         } else {
             base = *s_base;
@@ -584,7 +593,9 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const
 // ORDER of the slots in the arena follows completion order instead of call order (DSP_MESH_ORDERED selects the
 // look-back organisation when a reproducible layout matters).
 template <class Cfg, bool HALO>
-__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p) {
+__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p_in) {
+    MeshParams p = p_in;
+    if (p.n_dev != nullptr) p.n = *p.n_dev;  // device-built work list (written by an earlier kernel of the same stream)
     extern __shared__ __align__(128) uint8_t smem[];
     MeshCta<Cfg, HALO> c(p, smem);
     const int tid = c.tid;
@@ -622,7 +633,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
             // Nothing to emit and no slot to claim (all air; or, with cross-chunk culling, a chunk buried among solid
             // neighbours).  No further barrier is needed: every read of vox(buf), the row masks and the warp totals precedes a
             // barrier inside count_phase that all threads have passed, and s_next[(it + 1) & 1] was written before it.
-            if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+            if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
             ++it;
             cur = c.s_next[it & 1];
             continue;
@@ -643,7 +654,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
                     const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
                     *c.s_base = base;
                     if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                    p.entries[cur] = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
+                    *entry_of(p, cur) = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
                 }
             });
         }

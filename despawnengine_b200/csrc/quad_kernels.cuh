@@ -137,7 +137,9 @@ __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox,
 }
 
 template <bool HALO, bool GREEDY, bool INDEXED>
-__global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p) {
+__global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p_in) {
+    MeshParams p = p_in;
+    if (p.n_dev != nullptr) p.n = *p.n_dev;  // device-built work list (see classify_chunks_kernel)
     using L = QuadSmem<GREEDY>;
     constexpr uint32_t kRecCap = L::kRecCap;
     constexpr int kTile = L::kTileQuads;
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         const bool uniform = __syncthreads_and(differs == 0u) != 0;  // also publishes s_rowmask
         if (uniform && id0 == 0u) {
             // all air: the reference's palette.len() == 1 early-out (chunk_mesh.rs:18-20)
-            if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+            if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
             if (++buf == NB) { buf = 0; par ^= 1; }
             cur = s_next[buf];
             continue;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             if (HALO && GREEDY) {
                 // cross-chunk culling buries most solid chunks completely: find that out before the merge machinery runs
                 if (__syncthreads_or((A[0] | A[1] | A[2] | A[3] | A[4] | A[5]) != 0u) == 0) {
-                    if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+                    if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
                     if (++buf == NB) { buf = 0; par ^= 1; }
                     cur = s_next[buf];
                     continue;
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         }
         // claim the chunk's arena slot; the result is first touched after this thread's records are written
         if (Q == 0u) {  // e.g. a chunk buried among solid neighbours under cross-chunk culling: no slot, no records, no emission
-            if (tid == 0) p.entries[cur] = MeshEntry{p.arena_offset, 0u, 0u};
+            if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
             if (++buf == NB) { buf = 0; par ^= 1; }
             cur = s_next[buf];
             continue;
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             __syncthreads();  // records visible
             if (tid == 0 && q0 == 0) {  // first touch of the claim's result: after the barrier, so the CTA never waits on that atomic
                 if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                p.entries[cur] = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
+                *entry_of(p, cur) = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
             }
             const uint32_t q1 = min(Q, q0 + kRecCap);
             for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {

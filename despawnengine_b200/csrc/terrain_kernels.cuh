@@ -10,6 +10,7 @@
 // z = r >> 4) and stores its 32 bytes with two 128-bit stores, so a warp writes 1 KiB contiguous.
 #pragma once
 #include "dsp_common.cuh"
+#include "mesh_kernels.cuh"  // MeshEntry
 
 namespace dsp {
 
@@ -26,7 +27,16 @@ struct TerrainParams {
     int3 origin;
     uint3 dims;
     int4* chunk_pos_out;
+    uint8_t* summary;  // per slot: kSummaryUnknown / kSummaryAir / kSummarySolid, written where the generator knows (may be nullptr)
 };
+
+// Chunk summaries let the halo-mode mesh call drop all-air chunks and chunks buried among solid neighbours before the mesh
+// kernel ever sees them (classify_chunks_kernel).  Anything that writes voxels keeps them honest: generators set them,
+// edits and host uploads reset them to "unknown".
+// Bits: air = every voxel is air; solid = no voxel is air; layer f = the one-voxel border layer at face f (order top,
+// bottom, rear, front, right, left) has no air.  0 = nothing known.  A solid chunk is buried, i.e. has no visible face,
+// when across every face a RESIDENT neighbour's facing layer is solid.
+constexpr uint8_t kSummaryUnknown = 0, kSummaryAir = 1, kSummarySolid = 2, kSummaryLayer0 = 4, kSummaryAllSolid = 2 | (63 << 2);
 
 // smoothstep-weighted bilinear value noise on a lattice whose values were hashed once per chunk
 // into `lat` (3x3 per octave, [dz][dx]); identical arithmetic to oracle/mesher_oracle.cpp.
@@ -51,6 +61,7 @@ __device__ __forceinline__ uint32_t octave_from_lattice(const uint32_t* lat, int
 __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p) {
     __shared__ uint32_t s_lat[3][9];
     __shared__ int32_t s_h[256];  // [z][x] column heights
+    __shared__ uint32_t s_red[8];
     const int tid = threadIdx.x;
     for (uint32_t i = blockIdx.x; i < p.n; i += gridDim.x) {
         const uint32_t slot = p.slot_list ? p.slot_list[i] : p.first_slot + i;
@@ -126,7 +137,24 @@ __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p
             }
             dst[hr] = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        if (p.kind == 1 || p.kind == 2) __syncthreads();  // s_h / s_lat reused by the next chunk of this CTA
+        uint32_t summary = kSummaryUnknown;
+        if (p.kind == 0) {  // flat chunk (Y == 0): y < 8 is dirt, so only its bottom layer is free of air
+            summary = cp.y > 0 ? kSummaryAir : (cp.y < 0 ? kSummaryAllSolid : (kSummaryLayer0 << 1));
+        } else if (p.kind == 1) {
+            // thread t holds the height h of column t = (x, z): voxel (x, y, z) is solid iff wy <= h - 1.  Each condition below
+            // must hold for every column (for a side layer: every column of that side), i.e. an AND over the CTA.
+            const int32_t h = s_h[tid], top = cp.y * 16 + 15, bot = cp.y * 16;
+            const int cx_ = tid & 15, cz_ = tid >> 4;
+            uint32_t bits = (bot > h - 1 ? kSummaryAir : 0u) | (top <= h - 1 ? kSummarySolid | kSummaryLayer0 : 0u) | (bot <= h - 1 ? kSummaryLayer0 << 1 : 0u);
+            bits |= (cz_ != 0 || top <= h - 1 ? kSummaryLayer0 << 2 : 0u) | (cz_ != 15 || top <= h - 1 ? kSummaryLayer0 << 3 : 0u);
+            bits |= (cx_ != 0 || top <= h - 1 ? kSummaryLayer0 << 4 : 0u) | (cx_ != 15 || top <= h - 1 ? kSummaryLayer0 << 5 : 0u);
+            bits = __reduce_and_sync(0xFFFFFFFFu, bits);
+            if ((tid & 31) == 0) s_red[tid >> 5] = bits;
+            __syncthreads();
+            summary = s_red[0] & s_red[1] & s_red[2] & s_red[3] & s_red[4] & s_red[5] & s_red[6] & s_red[7];
+        }
+        if (tid == 0 && p.summary != nullptr) p.summary[slot] = static_cast<uint8_t>(summary);
+        if (p.kind == 1 || p.kind == 2) __syncthreads();  // s_h / s_lat / s_red reused by the next chunk of this CTA
     }
 }
 
@@ -144,6 +172,7 @@ struct RegionFillParams {
     uint3 dims;
     uint32_t ny;         // chunks of a column handled by one CTA
     uint32_t seed;
+    uint8_t* summary;    // see TerrainParams
 };
 
 __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const RegionFillParams p) {
@@ -213,7 +242,23 @@ __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const Re
                 }
                 dst[hr] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            if (tid == 0) p.chunk_pos[slot] = make_int4(cx, cy, cz, 0);
+            if (tid == 0) {
+                p.chunk_pos[slot] = make_int4(cx, cy, cz, 0);
+                if (p.summary != nullptr) {
+                    // column-wide extremes of the heightmap: whole chunk, and the four side layers (x = 0 / 15, z = 0 / 15)
+                    int32_t lo = s_zmin[0], hi = s_zmax[0], lo_x0 = s_h[0], lo_x15 = s_h[15];
+#pragma unroll
+                    for (int k = 1; k < 16; ++k) {
+                        lo = min(lo, s_zmin[k]); hi = max(hi, s_zmax[k]);
+                        lo_x0 = min(lo_x0, s_h[k * 16]); lo_x15 = min(lo_x15, s_h[k * 16 + 15]);
+                    }
+                    const int32_t top = cy * 16 + 15, bot = cy * 16, lo_z0 = s_zmin[0], lo_z15 = s_zmin[15];
+                    uint32_t bits = (bot > hi - 1 ? kSummaryAir : 0u) | (top <= lo - 1 ? kSummarySolid | kSummaryLayer0 : 0u) | (bot <= lo - 1 ? kSummaryLayer0 << 1 : 0u);
+                    bits |= (top <= lo_z0 - 1 ? kSummaryLayer0 << 2 : 0u) | (top <= lo_z15 - 1 ? kSummaryLayer0 << 3 : 0u);
+                    bits |= (top <= lo_x0 - 1 ? kSummaryLayer0 << 4 : 0u) | (top <= lo_x15 - 1 ? kSummaryLayer0 << 5 : 0u);
+                    p.summary[slot] = static_cast<uint8_t>(bits);
+                }
+            }
         }
         __syncthreads();  // s_h / s_lat are rewritten for the next column
     }
@@ -248,16 +293,56 @@ __global__ void region_neighbours_kernel(uint32_t* nbr, uint32_t first_slot, uin
     }
 }
 // positions and slot list of a sub-batch, read directly from pinned host memory (no copy engine involved)
-__global__ void stage_positions_kernel(int4* chunk_pos, uint32_t* slot_list_out, const int4* host_pos, const uint32_t* host_slots, uint32_t n) {
+__global__ void stage_positions_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, const int4* host_pos, const uint32_t* host_slots, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t s = host_slots[i];
     chunk_pos[s] = host_pos[i];
     slot_list_out[i] = s;
+    summary[s] = kSummaryUnknown;  // host voxels are about to land in this slot
 }
-__global__ void scatter_pos_kernel(int4* chunk_pos, const uint32_t* slots, const int4* src, uint32_t n) {
+__global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, const uint32_t* slots, const int4* src, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) chunk_pos[slots[i]] = src[i];
+    if (i >= n) return;
+    chunk_pos[slots[i]] = src[i];
+    summary[slots[i]] = kSummaryUnknown;  // the slot is being (re)defined; a generator that follows sets it again
+}
+
+// Halo-mode pre-pass: chunk i of the call needs no meshing when it is all air, or free of air with six RESIDENT neighbours
+// whose facing border layers are free of air (every face culled); its entry is written here.  Everything else is appended to the work list that the
+// mesh kernel then consumes straight from device memory (count in *n_work; order within the list does not matter, the arena
+// slots are claimed in completion order anyway).  One warp-aggregated atomic per warp.
+__global__ void classify_chunks_kernel(const uint8_t* summary, const uint32_t* nbr, const uint32_t* slot_list, uint32_t first_slot, uint32_t n,
+                                       uint64_t arena_offset, MeshEntry* entries, uint32_t* work_slots, uint32_t* work_entry, uint32_t* n_work) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool work = false;
+    uint32_t slot = 0;
+    if (i < n) {
+        slot = slot_list ? slot_list[i] : first_slot + i;
+        const uint8_t s = summary[slot];
+        bool skip = (s & kSummaryAir) != 0;
+        if (s & kSummarySolid) {
+            skip = true;
+#pragma unroll
+            for (int f = 0; f < 6; ++f) {  // the neighbour across face f shows us its layer at the opposite face f ^ 1
+                const uint32_t q = nbr[static_cast<size_t>(slot) * 6 + f];
+                skip = skip && q != 0xFFFFFFFFu && !(q & 0x80000000u) && (summary[q] & (kSummaryLayer0 << (f ^ 1))) != 0;
+            }
+        }
+        if (skip) entries[i] = MeshEntry{arena_offset, 0u, 0u};
+        work = !skip;
+    }
+    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, work);
+    if (ballot == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(n_work, static_cast<uint32_t>(__popc(ballot)));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (work) {
+        const uint32_t k = base + __popc(ballot & ((1u << lane) - 1u));
+        work_slots[k] = slot;
+        work_entry[k] = i;
+    }
 }
 // neighbour table entry (slots[i], face) := external slab first_index + i, unless a resident neighbour is already there
 __global__ void apply_halo_batch_kernel(uint32_t* nbr, const uint32_t* slots, int face, uint32_t first_index, uint32_t n) {
@@ -299,11 +384,12 @@ __global__ void __launch_bounds__(256) palette_remap_kernel(uint16_t* voxels, co
 // Chunk::set_block on resident chunks (chunk.rs:49-68).  The host has already resolved world
 // coordinates to (slot, voxel index) and kept only the last edit per voxel, so the scatter is
 // race-free.  packed = slot (u32), idx | block << 16 (u32).
-__global__ void edit_scatter_kernel(uint16_t* voxels, const uint2* edits, uint32_t n) {
+__global__ void edit_scatter_kernel(uint16_t* voxels, uint8_t* summary, const uint2* edits, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2 e = edits[i];
     voxels[static_cast<size_t>(e.x) * kChunkVoxels + (e.y & 0xFFFu)] = static_cast<uint16_t>(e.y >> 16);
+    summary[e.x] = kSummaryUnknown;
 }
 
 // ---- device-side edit pipeline for worlds made of box regions (dsp_apply_edits / dsp_apply_edits_and_remesh) ------------
@@ -328,6 +414,7 @@ struct EditParams {
     uint16_t* voxels;
     uint32_t* dirty_bitmap;   // one bit per slot; zeroed before the call
     const uint32_t* nbr;      // halo mode: [slot][6] neighbour table; an edit on a chunk border also dirties the resident neighbour
+    uint8_t* summary;         // edited chunks become kSummaryUnknown
 };
 
 __device__ __forceinline__ bool edit_key(const EditParams& p, const int4 e, uint64_t* key) {
@@ -377,6 +464,7 @@ __global__ void edit_apply_kernel(const EditParams p) {
             p.voxels[key] = static_cast<uint16_t>(e.w);  // key == slot * 4096 + voxel index
             const uint32_t slot = static_cast<uint32_t>(key >> 12);
             atomicOr(&p.dirty_bitmap[slot >> 5], 1u << (slot & 31u));
+            p.summary[slot] = kSummaryUnknown;
             if (p.nbr != nullptr) {  // cross-chunk culling: the neighbour's border faces depend on this voxel
                 const int lx = e.x & 15, ly = e.y & 15, lz = e.z & 15;
                 const int faces[3] = {ly == 15 ? 0 : (ly == 0 ? 1 : -1), lz == 0 ? 2 : (lz == 15 ? 3 : -1), lx == 0 ? 4 : (lx == 15 ? 5 : -1)};

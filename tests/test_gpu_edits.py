@@ -174,3 +174,54 @@ def test_get_block_world_reads_what_edits_wrote(uv_default):
         e["wx"], e["wy"], e["wz"], e["block"] = [-16, 15], [15, 0], [-1, 15], [2, 0]
         ctx.apply_edits(e)
         assert ctx.get_block_world(-16, 15, -1) == 2 and ctx.get_block_world(15, 0, 15) == 0
+
+
+def test_buried_chunks_are_skipped_by_summary_until_an_edit_touches_them(uv_default):
+    """Halo mode drops all-air chunks and chunks buried among uniformly solid neighbours before the mesh kernel (chunk
+    summaries written by the generators).  An edit must reset the summary: carving a cavity INSIDE a buried chunk gives it
+    faces again, and opening a hole in its border gives faces to the neighbour too."""
+    origin, dims = (0, -4, 0), (3, 6, 3)  # reference terrain: y < 0 solid, y == 0 flat, y > 0 air
+    positions = [(origin[0] + a, origin[1] + b, origin[2] + c) for c in range(dims[2]) for b in range(dims[1]) for a in range(dims[0])]
+    dirs = [(0, 1, 0), (0, -1, 0), (0, 0, -1), (0, 0, 1), (-1, 0, 0), (1, 0, 0)]
+    with capi.Context(0, 256, 256 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        first = ctx.generate_region(origin, dims, capi.GEN_REFERENCE, 0)
+        chunks = {p: orc.generate(orc.GEN_REFERENCE, 0, p) for p in positions}
+        slot_of = {p: first + i for i, p in enumerate(positions)}
+
+        def halo_mesh(p):
+            slabs, present = np.zeros((6, 256), dtype=np.uint16), np.zeros(6, dtype=np.uint8)
+            for f, d in enumerate(dirs):
+                q = (p[0] + d[0], p[1] + d[1], p[2] + d[2])
+                if q in chunks:
+                    v = chunks[q].reshape(16, 16, 16)
+                    present[f] = 1
+                    slabs[f] = [v[:, 0, :], v[:, 15, :], v[15, :, :], v[0, :, :], v[:, :, 15], v[:, :, 0]][f].reshape(256)
+            return orc.mesh_chunk_halo(p, chunks[p], slabs, present, uv_default)
+
+        def check_world(mode, greedy):
+            entries, total = ctx.mesh_range(first, len(positions), mode)
+            for p, e in zip(positions, entries):
+                if greedy:
+                    continue
+                assert ctx.download_vertices(e).tobytes() == halo_mesh(p).tobytes(), p
+            return entries
+
+        e0 = check_world(capi.MESH_HALO, False)
+        buried = (1, -2, 1)
+        assert int(e0[positions.index(buried)]["vertex_count"]) == 0 and int(e0[positions.index((1, 1, 1))]["vertex_count"]) == 0
+        # a cavity in the middle of the buried chunk, and a hole through its +x border layer
+        ed = np.zeros(2, dtype=capi.EDIT_DTYPE)
+        ed["wx"], ed["wy"], ed["wz"], ed["block"] = [16 + 8, 16 + 15], [-32 + 8, -32 + 3], [16 + 8, 16 + 4], [0, 0]
+        dirty, entries, _ = ctx.apply_edits_and_remesh(ed, capi.MESH_HALO)
+        for w in ((24, -24, 24), (31, -29, 20)):
+            chunks[buried][(w[0] & 15) + 16 * (w[1] & 15) + 256 * (w[2] & 15)] = 0
+        assert sorted(map(int, dirty)) == sorted([slot_of[buried], slot_of[(2, -2, 1)]])
+        for s, e in zip(dirty, entries):
+            p = positions[int(s) - first]
+            assert int(e["vertex_count"]) > 0 and ctx.download_vertices(e).tobytes() == halo_mesh(p).tobytes(), p
+        e1 = check_world(capi.MESH_HALO, False)
+        assert int(e1[positions.index(buried)]["vertex_count"]) == 6 * (6 + 5) and int(e1[positions.index((2, -2, 1))]["vertex_count"]) == 6 * (256 + 1)  # world-edge +x faces + the one behind the hole
+        # quad mode goes through the same pre-pass
+        eg, _ = ctx.mesh_range(first, len(positions), capi.MESH_HALO | capi.MESH_GREEDY | capi.MESH_INDEXED)
+        assert int(eg[positions.index((0, -2, 0))]["vertex_count"]) > 0 and int(eg[positions.index((1, -3, 1))]["vertex_count"]) == 0

@@ -28,6 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dims", type=int, nargs=3, default=[512, 32, 512], help="world size in chunks: x y z (y is up)")
     ap.add_argument("--batch", type=int, default=32768, help="chunks per mesh launch (arena is reused between launches)")
+    ap.add_argument("--small-output-batch", type=int, default=262144, help="chunks per launch in the halo / greedy modes (their output is 10-20x smaller)")
     ap.add_argument("--arena-gib", type=float, default=8.0)
     ap.add_argument("--quad-modes", action="store_true", help="also run the greedy + indexed modes (chunk-local and halo culling)")
     ap.add_argument("--verify", action="store_true", help="check a sample of seam chunks against the oracle (small worlds)")
@@ -90,14 +91,15 @@ def main():
             ctx.sync()
             barrier()
             xchg_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+        batch = args.batch if mode == capi.MESH_PARITY else args.small_output_batch
         # warm-up batch (also builds the neighbour table in halo mode)
         ctx.mesh_range(dev.first_slot, min(n, args.batch), mode)
         faces = 0
         vbytes = 0
         barrier()
         t0 = time.perf_counter()
-        for b0 in range(0, n, args.batch):
-            m = min(args.batch, n - b0)
+        for b0 in range(0, n, batch):
+            m = min(batch, n - b0)
             ctx.mesh_range_async(dev.first_slot + b0, m, mode)
             _, total = ctx.mesh_result(m, entries_ptr=0)  # syncs; raises on arena overflow
             vbytes += total
@@ -106,7 +108,7 @@ def main():
         kn, kms, _ = ctx.mesh_kernel_stats()
         vbytes_all = reduce(float(vbytes), dist.ReduceOp.SUM if world > 1 else None)
         line = {"workload": f"configs[4]: {args.dims[0]}x{args.dims[2]}x{args.dims[1]}-chunk world (x,z,y-up), X-slab partition", "mode": mode_name,
-                "n_gpus": world, "chunks": W.n_chunks, "chunks_per_gpu": n, "batch": args.batch,
+                "n_gpus": world, "chunks": W.n_chunks, "chunks_per_gpu": n, "batch": batch,
                 "terrain_fill_s": gen_s, "terrain_fill_GBps_per_gpu": n * 8192 / gen_s / 1e9,
                 "halo_exchange_s": xchg_s, "halo_bytes_sent_rank0": xchg_bytes,
                 "mesh_wall_s": mesh_s, "chunks_per_s": W.n_chunks / mesh_s, "voxels_per_s": W.n_chunks * 4096 / mesh_s,
