@@ -68,7 +68,8 @@ struct dsp_ctx {
     uint64_t halo_cap = 0, halo_n = 0;
     // received border slabs, one batch per dsp_set_halo_slabs call: slab first_index + i stands in for the neighbour of
     // slots[i] across `face` wherever no resident neighbour exists (applied to the neighbour table on the device)
-    struct HaloBatch { int face; uint32_t first_index; uint32_t* d_slots_copy; uint32_t n; std::vector<uint32_t> slots; };
+    struct HaloBatch { int face; uint32_t first_index; uint32_t n; std::vector<uint32_t> slots; };  // device copy of slots: d_halo_slots + first_index
+    uint32_t* d_halo_slots = nullptr;  // [halo_cap], parallel to d_halo
     std::vector<HaloBatch> halo_batches;
     uint8_t* d_arena = nullptr;
     dsp::MeshEntry* d_entries = nullptr;
@@ -453,7 +454,7 @@ int validate_range(dsp_ctx* ctx, uint32_t first, uint64_t n) {
 int apply_halo_batches(dsp_ctx* ctx) {
     for (auto it = ctx->halo_batches.rbegin(); it != ctx->halo_batches.rend(); ++it) {
         if (it->n == 0) continue;
-        dsp::apply_halo_batch_kernel<<<(it->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nbr, it->d_slots_copy, it->face, it->first_index, it->n);
+        dsp::apply_halo_batch_kernel<<<(it->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nbr, ctx->d_halo_slots + it->first_index, it->face, it->first_index, it->n);
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }
@@ -666,7 +667,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     if (!ctx) return DSP_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (auto& hb : ctx->halo_batches) cudaFree(hb.d_slots_copy);
+    cudaFree(ctx->d_halo_slots);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_halo); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
@@ -829,7 +830,7 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
         for (auto& hb : ctx->halo_batches) {  // its received slabs go with it (rare path: linear scan, then the device copy is refreshed)
             bool hit = false;
             for (uint32_t& v : hb.slots) if (v == s) { v = DSP_NO_SLOT; hit = true; }
-            if (hit) DSP_CUDA(ctx, cudaMemcpy(hb.d_slots_copy, hb.slots.data(), hb.n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            if (hit) DSP_CUDA(ctx, cudaMemcpy(ctx->d_halo_slots + hb.first_index, hb.slots.data(), hb.n * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
     }
     ctx->nbr_dirty = true;
@@ -1130,25 +1131,31 @@ int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = validate_slots(ctx, n, slots);
     if (rc != DSP_OK) return rc;
-    // slabs of one call are stored contiguously; a (slot, face) set again simply points at the newer slab
+    // slabs of one call are stored contiguously (and their slots in a parallel array); a (slot, face) set again uses the newer slab
     if (ctx->halo_n + n > ctx->halo_cap) {
         const uint64_t cap = std::max<uint64_t>(ctx->halo_n + n, std::max<uint64_t>(1024, ctx->halo_cap * 2));
         uint16_t* grown = nullptr;
+        uint32_t* grown_slots = nullptr;
         DSP_CUDA(ctx, cudaMalloc(&grown, cap * 512));
-        if (ctx->halo_n) DSP_CUDA(ctx, cudaMemcpyAsync(grown, ctx->d_halo, ctx->halo_n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+        DSP_CUDA(ctx, cudaMalloc(&grown_slots, cap * sizeof(uint32_t)));
+        if (ctx->halo_n) {
+            DSP_CUDA(ctx, cudaMemcpyAsync(grown, ctx->d_halo, ctx->halo_n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+            DSP_CUDA(ctx, cudaMemcpyAsync(grown_slots, ctx->d_halo_slots, ctx->halo_n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         cudaFree(ctx->d_halo);
+        cudaFree(ctx->d_halo_slots);
         ctx->d_halo = grown;
+        ctx->d_halo_slots = grown_slots;
         ctx->halo_cap = cap;
     }
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo + ctx->halo_n * 256, src_device, n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
-    dsp_ctx::HaloBatch hb{face, static_cast<uint32_t>(ctx->halo_n), nullptr, static_cast<uint32_t>(n), std::vector<uint32_t>(slots, slots + n)};
-    DSP_CUDA(ctx, cudaMalloc(&hb.d_slots_copy, n * sizeof(uint32_t)));
+    dsp_ctx::HaloBatch hb{face, static_cast<uint32_t>(ctx->halo_n), static_cast<uint32_t>(n), std::vector<uint32_t>(slots, slots + n)};
     {
         uint8_t* h;
-        if ((rc = stage_host(ctx, n * sizeof(uint32_t), &h)) != DSP_OK) { cudaFree(hb.d_slots_copy); return rc; }
+        if ((rc = stage_host(ctx, n * sizeof(uint32_t), &h)) != DSP_OK) return rc;
         std::memcpy(h, slots, n * sizeof(uint32_t));
-        DSP_CUDA(ctx, cudaMemcpyAsync(hb.d_slots_copy, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo_slots + ctx->halo_n, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         if ((rc = stage_release(ctx)) != DSP_OK) return rc;
     }
     ctx->halo_batches.push_back(std::move(hb));
@@ -1159,9 +1166,7 @@ int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face
 
 int dsp_clear_halo_slabs(dsp_ctx* ctx) {
     if (!ctx) return DSP_ERR_BAD_ARG;
-    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (auto& hb : ctx->halo_batches) cudaFree(hb.d_slots_copy);
-    ctx->halo_batches.clear();
+    ctx->halo_batches.clear();  // the slab and slot arrays are kept for the next exchange
     ctx->halo_n = 0;
     ctx->nbr_dirty = true;
     return DSP_OK;

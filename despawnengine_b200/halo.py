@@ -17,6 +17,7 @@ class RegionOnDevice:
     def __init__(self, ctx: capi.Context, region: Region, gen_kind: int, seed: int):
         self.ctx, self.region = ctx, region
         self.first_slot = ctx.generate_region(region.origin, region.dims, gen_kind, seed)
+        self.seam_slots = {}  # (face, n) -> slots of this region's boundary chunks at that face (X-slab partition: one seam per face)
 
     def slots_of(self, positions: np.ndarray) -> np.ndarray:
         p = np.asarray(positions, dtype=np.int64).reshape(-1, 3) - np.array(self.region.origin, dtype=np.int64)
@@ -33,13 +34,19 @@ def exchange_region_halos(dev: RegionOnDevice, partition: SlabPartition, rank: i
     ctx = dev.ctx
     device = torch.device("cuda", ctx.device)
 
+    def slots(positions, face):  # a seam's slot list does not change between exchanges
+        key = (face, len(positions))
+        if key not in dev.seam_slots:
+            dev.seam_slots[key] = dev.slots_of(positions)
+        return dev.seam_slots[key]
+
     def pack(positions, face):
         t = torch.empty((len(positions), 512), dtype=torch.uint8, device=device)  # NCCL has no 16-bit integer type: ship bytes
-        ctx.pack_border_slabs(dev.slots_of(positions), face, t.data_ptr())
+        ctx.pack_border_slabs(slots(positions, face), face, t.data_ptr())
         return t
 
     def unpack(positions, face, t):
-        ctx.set_halo_slabs(dev.slots_of(positions), face, t.data_ptr())
+        ctx.set_halo_slabs(slots(positions, face), face, t.data_ptr())
         ctx.sync()  # the copy out of `t` is enqueued on the context's stream; `t` may be freed after this returns
 
     def sync():

@@ -97,6 +97,7 @@ class SlabPartition:
             raise ValueError(f"cannot cut {world.dims[0]} chunks of X extent into {world_size} slabs")
         self.world, self.world_size = world, world_size
         self._cuts = split_extent(world.dims[0], world_size)
+        self._transfers = {}  # rank -> seam transfers (the position lists are thousands of entries: built once)
 
     def region(self, rank: int) -> Region:
         start, cnt = self._cuts[rank]
@@ -110,6 +111,13 @@ class SlabPartition:
         raise KeyError(tuple(pos))
 
     def seam_transfers(self, rank: int) -> List[SeamTransfer]:
+        cached = self._transfers.get(rank)
+        if cached is not None:
+            return cached
+        out = self._transfers[rank] = self._seam_transfers(rank)
+        return out
+
+    def _seam_transfers(self, rank: int) -> List[SeamTransfer]:
         reg, out = self.region(rank), []
         if rank > 0:
             out.append(SeamTransfer(rank - 1, FACE_RIGHT, reg.face_positions(FACE_RIGHT)))
@@ -156,9 +164,14 @@ def exchange_halos(transfers: Sequence[SeamTransfer], pack: Callable[[np.ndarray
     cannot deadlock on ordering.  Returns the bytes sent."""
     if not transfers:
         return 0
+    import os
+    import time
+    trace = os.environ.get("DSP_TRACE") is not None
+    t0 = time.perf_counter()
     send_bufs = [pack(t.positions, t.send_face) for t in transfers]
     if sync is not None:
         sync()  # packing ran on the context's stream; the collective runs on torch's
+    t1 = time.perf_counter()
     recv_bufs = [alloc_like(b) for b in send_bufs]
     ops = []
     for t, sb, rb in zip(transfers, send_bufs, recv_bufs):
@@ -168,6 +181,10 @@ def exchange_halos(transfers: Sequence[SeamTransfer], pack: Callable[[np.ndarray
         req.wait()
     if sync is not None:
         sync()
+    t2 = time.perf_counter()
     for t, rb in zip(transfers, recv_bufs):
         unpack(t.positions, t.send_face, rb)
+    if trace:
+        import sys
+        print(f"[trace] halo exchange: pack {1e3 * (t1 - t0):.2f} ms, send/recv {1e3 * (t2 - t1):.2f} ms, register {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr)
     return sum(int(b.numel()) * int(b.element_size()) for b in send_bufs)
