@@ -417,7 +417,9 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     if (mode & DSP_MESH_HALO) { if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc; }
     ctx->ctl_clean = false;  // until the launch below is known to have been enqueued
     bool work_list = false;
-    if ((mode & DSP_MESH_HALO) && !ordered) {
+    const bool halo_prepass = (mode & DSP_MESH_HALO) != 0;
+    const bool air_prepass = !halo_prepass && (mode & DSP_MESH_GREEDY) && n >= 16384;  // large merged-quad calls: drop the all-air chunks
+    if ((halo_prepass || air_prepass) && !ordered) {
         // Cross-chunk culling leaves most chunks of a large world without a single face (all air, or solid among solid
         // neighbours): a pre-pass over the chunk summaries writes their empty entries and hands the mesh kernel only the rest.
         if (!ctx->d_work_slots) {
@@ -425,7 +427,7 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
             DSP_CUDA(ctx, cudaMalloc(&ctx->d_work_entry, ctx->max_chunks * sizeof(uint32_t)));
         }
         dsp::classify_chunks_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_summary, ctx->d_nbr, d_list, first_slot, static_cast<uint32_t>(n), arena_offset, ctx->d_entries, ctx->d_work_slots, ctx->d_work_entry,
+            ctx->d_summary, halo_prepass ? ctx->d_nbr : nullptr, d_list, first_slot, static_cast<uint32_t>(n), arena_offset, ctx->d_entries, ctx->d_work_slots, ctx->d_work_entry,
             reinterpret_cast<uint32_t*>(ctx->d_ctl) + 3);
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;

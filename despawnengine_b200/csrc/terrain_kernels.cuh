@@ -321,7 +321,7 @@ __global__ void classify_chunks_kernel(const uint8_t* summary, const uint32_t* n
         slot = slot_list ? slot_list[i] : first_slot + i;
         const uint8_t s = summary[slot];
         bool skip = (s & kSummaryAir) != 0;
-        if (s & kSummarySolid) {
+        if ((s & kSummarySolid) && nbr != nullptr) {  // (nbr == nullptr: chunk-local culling, only all-air chunks can be dropped)
             skip = true;
 #pragma unroll
             for (int f = 0; f < 6; ++f) {  // the neighbour across face f shows us its layer at the opposite face f ^ 1
