@@ -138,3 +138,37 @@ def test_scene_refuses_a_context_with_box_regions(uv_default):
         with pytest.raises(capi.DspError) as ei:
             ctx.scene_update(START_CAMERA, 1, 1)
         assert ei.value.status == capi.ERR_BAD_ARG
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed,cam", [(capi.GEN_NOISE, 0xD5E50001, (8.0, 120.0, 8.0)), (capi.GEN_REFERENCE, 0, START_CAMERA)])
+def test_first_frame_with_cross_chunk_culling(uv_default, kind, seed, cam):
+    """DSP_MESH_HALO through the scene: chunks addressed by the position map, summaries written by the list-form generators,
+    all-air and buried chunks dropped by the pre-pass -- every chunk of the frame must equal the extended oracle with the
+    frame's other chunks as neighbours."""
+    h, v = 3, 2
+    dirs = [(0, 1, 0), (0, -1, 0), (0, 0, -1), (0, 0, 1), (-1, 0, 0), (1, 0, 0)]
+    with capi.Context(0, 1024, 128 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        st = ctx.scene_update(cam, h, v, kind, seed, capi.MESH_HALO)
+        vis = sco.visible_chunks(cam, h, v)
+        assert int(st["n_loaded_total"]) == len(vis)
+        ids = {p: orc.generate(kind, seed, p) for p in vis}
+        pos, entries = ctx.scene_draw_list()
+        got = {tuple(p): e for p, e in zip(pos.tolist(), entries)}
+        n_meshes = 0
+        for p in vis:
+            slabs, present = np.zeros((6, 256), dtype=np.uint16), np.zeros(6, dtype=np.uint8)
+            for f, d in enumerate(dirs):
+                q = (p[0] + d[0], p[1] + d[1], p[2] + d[2])
+                if q in ids:
+                    vv = ids[q].reshape(16, 16, 16)
+                    present[f] = 1
+                    slabs[f] = [vv[:, 0, :], vv[:, 15, :], vv[15, :, :], vv[0, :, :], vv[:, :, 15], vv[:, :, 0]][f].reshape(256)
+            want = orc.mesh_chunk_halo(p, ids[p], slabs, present, uv_default)
+            if want.shape[0] == 0:
+                assert p not in got, p
+            else:
+                n_meshes += 1
+                assert ctx.download_vertices(got[p]).tobytes() == want.tobytes(), p
+        assert n_meshes == len(got) == int(st["n_meshes"]) and 0 < n_meshes < len(vis)
