@@ -232,7 +232,10 @@ int dsp_visible_chunks(const float camera_pos[3], uint32_t horizontal, uint32_t 
  * generated and meshed -- one terrain launch and one mesh launch for the whole set -- into a free interval of the arena,
  * and every loaded chunk that left the visible set is unloaded (its voxel slot and, once its whole batch is gone, its
  * arena interval are recycled).  Blocking, like the reference's update.  DSP_ERR_ARENA_FULL / DSP_ERR_STORE_FULL leave
- * the scene as it was.  The scene owns the chunks it loads and the arena: use it on a context without dsp_generate_region
+ * the scene as it was.  With DSP_MESH_HALO only the newly loaded chunks are meshed (against every chunk resident at that
+ * moment); chunks meshed earlier keep their meshes, which at worst contain border faces that a later neighbour now hides, or
+ * lack faces that only an unloaded neighbour's solid voxels used to cover -- neither is visible from inside the loaded set.
+ * The scene owns the chunks it loads and the arena: use it on a context without dsp_generate_region
  * boxes (DSP_ERR_BAD_ARG otherwise), and do not unload its chunks or choose arena offsets by hand on the same context. */
 int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_config* cfg, dsp_scene_stats* out_stats);
 /* GameScene::draw's iteration (scene_game.rs:101-125): position and arena window of every non-empty mesh. */
