@@ -57,6 +57,7 @@ struct dsp_ctx {
     uint64_t max_chunks = 0, arena_bytes = 0;
     int num_sms = 0;
     int mesh_variant = 0;
+    bool mesh_variant_forced = false;  // DSP_MESH_VARIANT was given
     unsigned mesh_prefetch_mult = 2;  // L2 prefetch distance in units of the grid size (0 = off)
     int mesh_ctas_per_sm[4][4] = {};  // [variant][halo], filled on first launch
     int quad_ctas_per_sm[8] = {};     // [halo + 2 greedy + 4 indexed]
@@ -305,7 +306,10 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
 constexpr int kMeshVariants = 4;
 template <bool HALO, bool ORDERED>
 int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
-    switch (ctx->mesh_variant) {
+    // Cross-chunk culling leaves little to emit per chunk and adds dependent neighbour reads: what it needs is more CTAs in
+    // flight, so its default is the 4-CTAs/SM shape (config-5 world: 28.4 -> 24.1 ms); DSP_MESH_VARIANT still overrides.
+    const int variant = (HALO && !ctx->mesh_variant_forced) ? 2 : ctx->mesh_variant;
+    switch (variant) {
         case 1: return launch_mesh_t<dsp::MeshCfg<3, 1, true>, HALO, ORDERED>(ctx, p, 1);
         case 2: return launch_mesh_t<dsp::MeshCfg<4, 1, false>, HALO, ORDERED>(ctx, p, 2);
         case 3: return launch_mesh_t<dsp::MeshCfg<4, 1, true>, HALO, ORDERED>(ctx, p, 3);
@@ -633,7 +637,7 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     ctx->arena_bytes = arena_bytes;
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
-    if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) ctx->mesh_variant = v; }
+    if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
     auto bail = [&](const char* what, cudaError_t err) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(err);
         dsp_destroy(ctx);
