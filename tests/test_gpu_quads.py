@@ -226,3 +226,16 @@ def test_quad_counts_around_the_record_window(ctx, uv_default, mode, greedy, ind
     check_layout(entries, total)
     assert [int(e["vertex_count"]) // (4 if indexed else 6) for e in entries] == counts
     compare(ctx, positions, blocks, entries, uv_default, greedy, indexed)
+
+
+@pytest.mark.parametrize("mode,greedy,indexed", MODES)
+def test_structured_patterns(ctx, uv_default, mode, greedy, indexed):
+    """Runs that change block id, shifted runs, cavities, plates in every orientation (tests/patterns.py)."""
+    from patterns import structured_chunks
+    pats = structured_chunks()
+    positions = [(k - 5, 3 - k, 2 * k) for k in range(len(pats))]
+    blocks = list(pats.values())
+    slots = ctx.load_chunks(positions, np.stack(blocks))
+    entries, total = ctx.mesh_chunks(slots, mode)
+    check_layout(entries, total)
+    compare(ctx, positions, blocks, entries, uv_default, greedy, indexed)

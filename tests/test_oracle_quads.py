@@ -86,3 +86,16 @@ def test_halo_masks_feed_the_merge(uv_default):
     present = np.array([1, 0, 1, 0, 1, 0], dtype=np.uint8)  # solid neighbours above, behind (-z) and at -x
     _, _, q = orc.mesh_chunk_ext(pos, ids, uv_default, greedy=True, nbr_slabs=slabs, nbr_present=present)
     assert sorted(int((r >> 12) & 7) for r in q) == [1, 3, 5]
+
+
+def test_structured_patterns_agree_between_formulations(uv_default):
+    from patterns import structured_chunks
+    for name, ids in structured_chunks().items():
+        stream, _, quads = orc.mesh_chunk_ext((3, -1, 2), ids, uv_default, greedy=True)
+        assert np.array_equal(quads, npo.greedy_records(ids)), name
+        assert np.array_equal(npo.expand_records_to_unit_faces(quads), npo.face_masks(ids).reshape(6, 4096)), name
+        unit = orc.mesh_chunk((3, -1, 2), ids, uv_default)
+        assert quads.shape[0] <= unit.shape[0] // 6, name
+    # a merge must never cross a block-id boundary: two ids side by side give two quads per long side
+    _, _, q = orc.mesh_chunk_ext((0, 0, 0), structured_chunks()["two_halves"], uv_default, greedy=True)
+    assert q.shape[0] == 2 + 4 * 2
