@@ -11,8 +11,10 @@
 // No decision depends on an earlier one, so all 256 rows of a chunk decide at once:
 //   1. thread r (x-row r = y + 16 z) holds the six 16-bit face masks of its row and three id-equality masks
 //      (towards x-1, y-1, z-1);
-//   2. for RIGHT/LEFT the run axis is y: the 16 rows of a z-slice sit in 16 lanes of one warp, so the row masks are
-//      turned into column masks (bit = y) by a 4-step butterfly of warp shuffles, two 16-bit matrices per register;
+//   2. for RIGHT/LEFT the run axis is y: the 16 rows of a z-slice sit in 16 lanes of one warp, so a row learns about its
+//      neighbours along y by warp shuffle -- run starts / ends are bit-parallel over the 16 x positions, both directions
+//      packed in one register; whether a whole run (lanes y0..y1) agrees with the row one z below is a 4-step
+//      segmented OR-scan of shuffles delivered to the run's first lane;
 //   3. a run is a (start bit, end bit) pair of the row mask; comparing a row with its predecessor along v gives the
 //      mask of CONTINUED runs, anchors = starts & ~continued; height = how many following rows continue the run;
 //   4. anchors are counted, scanned (warp shuffle + 8-way), the slot is claimed with one atomic, records
@@ -44,32 +46,16 @@ struct QuadSmem {
     static constexpr int kRowMask = kRec + kRecCap * 4;               // 256 x u16
     static constexpr int kF = kRowMask + kRows * 2;                   // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
     static constexpr int kEqx = kF + 4 * kT;                          // [256] u16
-    static constexpr int kFT = kEqx + kT;                             // [2][256] u16: RIGHT, LEFT masks per column (bit = y)
-    static constexpr int kEqRunT = kFT + 2 * kT;                      // [256] u16: id equality towards y-1, per column
-    static constexpr int kC = kEqRunT + kT;                           // [4][256] u16 continued-run masks per row
-    static constexpr int kCT = kC + 4 * kT;                           // [2][256] u16 continued-run masks per column
-    static constexpr int kA = kCT + 2 * kT;                           // [6][256] u16 anchor masks per row
-    static constexpr int kFirst = kA + 6 * kT;                        // [256] u16 ordinal of the row's first quad
-    static constexpr int kWarpTot = kFirst + kT;                      // 8 x u32 (+ pad)
+    static constexpr int kSE45 = kEqx + kT;                           // [2][256] u32: run starts / ends along y of RIGHT (low half) and LEFT (high half)
+    static constexpr int kC = kSE45 + 4 * kT;                         // [4][256] u16 continued-run masks per row (TOP, BOTTOM, REAR, FRONT)
+    static constexpr int kC45 = kC + 4 * kT;                          // [256] u32 continued-run masks of RIGHT | LEFT << 16
+    static constexpr int kWarpTot = kC45 + 2 * kT;                      // 8 x u32 (+ pad)
     static constexpr int kBar = kWarpTot + 64;                        // kVoxBufs (<= 4) x u64
     static constexpr int kBase = kBar + 32;                           // u64
     static constexpr int kNext = kBase + 8;                           // kVoxBufs (<= 4) x u32
     static constexpr int kBytes = kNext + 16;
 };
 static_assert(QuadSmem<true>::kBytes <= 57344 && QuadSmem<false>::kBytes <= 76800, "4 / 3 CTAs per SM");
-
-// 16x16 bit-matrix transpose across the 16 lanes of a half warp, two matrices at once (low / high half of v):
-// lane i holds row i; afterwards lane i holds column i.  Four shuffle steps.
-__device__ __forceinline__ uint32_t transpose16x16_pair(uint32_t v, int lane) {
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        const int j = 8 >> s;
-        const uint32_t mk = s == 0 ? 0x00FF00FFu : s == 1 ? 0x0F0F0F0Fu : s == 2 ? 0x33333333u : 0x55555555u;
-        const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, v, j);
-        v = (lane & j) ? (((other >> j) & mk) | (v & ~mk)) : ((v & mk) | ((other & mk) << j));
-    }
-    return v;
-}
 
 // bit x = ids equal at position x of two rows of 16 u16 (held as 8 words each): "differs" is nonzero_mask8 of the XOR
 __device__ __forceinline__ uint32_t eq_mask16(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
@@ -150,20 +136,16 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     uint16_t* const s_rowmask = reinterpret_cast<uint16_t*>(smem + L::kRowMask);
     uint16_t* const s_F = reinterpret_cast<uint16_t*>(smem + L::kF);
     uint16_t* const s_eqx = reinterpret_cast<uint16_t*>(smem + L::kEqx);
-    uint16_t* const s_FT = reinterpret_cast<uint16_t*>(smem + L::kFT);
-    uint16_t* const s_eqrunT = reinterpret_cast<uint16_t*>(smem + L::kEqRunT);
+    uint32_t* const s_SE45 = reinterpret_cast<uint32_t*>(smem + L::kSE45);
     uint16_t* const s_C = reinterpret_cast<uint16_t*>(smem + L::kC);
-    uint16_t* const s_CT = reinterpret_cast<uint16_t*>(smem + L::kCT);
-    uint16_t* const s_A = reinterpret_cast<uint16_t*>(smem + L::kA);
-    uint16_t* const s_first = reinterpret_cast<uint16_t*>(smem + L::kFirst);
+    uint32_t* const s_C45 = reinterpret_cast<uint32_t*>(smem + L::kC45);
     uint32_t* const s_warp = reinterpret_cast<uint32_t*>(smem + L::kWarpTot);
     uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
     uint32_t* const s_next = reinterpret_cast<uint32_t*>(smem + L::kNext);
     float* const s_istage = s_stage + kTile * 20;  // indexed layout: the tile's indices follow its vertices
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int r = tid, y = r & 15, z = r >> 4;   // as a row thread: x-row (y, z), masks over x
-    const int tx = tid & 15;                      // as a column thread: column (tx, z), masks over y
+    const int r = tid, y = r & 15, z = r >> 4;   // thread r owns x-row (y, z): masks over x
     auto slot_of = [&](uint32_t chunk) -> uint32_t { return p.slot_list ? __ldg(p.slot_list + chunk) : p.first_slot + chunk; };
     auto issue_load = [&](uint32_t chunk, int buf) {
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
@@ -229,7 +211,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         const bool solid_uniform = GREEDY && !HALO && uniform;
 
         uint32_t A[6] = {0u, 0u, 0u, 0u, 0u, 0u};
-        uint32_t fT[2] = {0u, 0u}, AT[2] = {0u, 0u}, eqx = 0u, eqrunT = 0u;
+        uint32_t eqx = 0u, E45 = 0u;
         FaceMasks fm{};
         uint32_t cnt = 0, first = 0, wpre = 0, Q;
         if (solid_uniform) {
@@ -261,15 +243,18 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
 #pragma unroll
                 for (int d = 0; d < 4; ++d) s_F[d * kRows + r] = static_cast<uint16_t>(A[d]);
                 s_eqx[r] = static_cast<uint16_t>(eqx);
-                // RIGHT / LEFT run along y: rows -> columns (lane l of a half warp: row y = l  ->  column x = l, same z)
-                const uint32_t tf = transpose16x16_pair(A[4] | (A[5] << 16), lane);
-                const uint32_t te = transpose16x16_pair(eqy | (eqz << 16), lane);
-                fT[0] = tf & 0xFFFFu; fT[1] = tf >> 16;
-                eqrunT = te & 0xFFFFu;
-                const uint32_t eqstackT = te >> 16;
-                s_FT[tid] = static_cast<uint16_t>(fT[0]);
-                s_FT[kRows + tid] = static_cast<uint16_t>(fT[1]);
-                s_eqrunT[tid] = static_cast<uint16_t>(eqrunT);
+                // RIGHT / LEFT run along y: the row's neighbours along y are the adjacent lanes of its half warp.  Both directions
+                // ride in one register (RIGHT low half, LEFT high half); everything is bit-parallel over the 16 x positions.
+                const uint32_t f45 = A[4] | (A[5] << 16), eqy2 = eqy | (eqy << 16), eqz2 = eqz | (eqz << 16);
+                uint32_t f_prev = __shfl_up_sync(0xFFFFFFFFu, f45, 1), f_next = __shfl_down_sync(0xFFFFFFFFu, f45, 1);
+                uint32_t eqy_next = __shfl_down_sync(0xFFFFFFFFu, eqy2, 1);
+                if (y == 0) f_prev = 0u;
+                if (y == 15) { f_next = 0u; eqy_next = 0u; }
+                const uint32_t S45 = f45 & ~(f_prev & eqy2);       // a run starts here: no visible equal-id face one step down in y
+                E45 = f45 & ~(f_next & eqy_next);                   // ... ends here
+                const uint32_t joins_next = f45 & f_next & eqy_next;  // lane y + 1 belongs to the same run as lane y
+                s_SE45[r] = S45;
+                s_SE45[kRows + r] = E45;
                 __syncthreads();
                 // ---- 3. continued runs -> anchors
                 uint32_t Cm[4] = {0u, 0u, 0u, 0u};
@@ -283,26 +268,30 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                     Cm[2] = continued_runs(s_F[2 * kRows + r - 1], eqa, A[2], eqx, eqy);
                     Cm[3] = continued_runs(s_F[3 * kRows + r - 1], eqa, A[3], eqx, eqy);
                 }
-                uint32_t CT[2] = {0u, 0u};
-                if (z > 0) {
-                    const uint32_t eqa = s_eqrunT[tid - 16];
-                    CT[0] = continued_runs(s_FT[tid - 16], eqa, fT[0], eqrunT, eqstackT);
-                    CT[1] = continued_runs(s_FT[kRows + tid - 16], eqa, fT[1], eqrunT, eqstackT);
+                // RIGHT / LEFT: a run (lanes y0..y1 of this z-slice) continues the row one z below when that row has a run with
+                // the same start, the same id and the same end.  "Same end" = the end masks of the two rows agree on every lane
+                // of the run: OR the disagreement over the run and deliver it to the run's first lane -- a segmented suffix
+                // OR-scan in four shuffle steps (lane y absorbs lane y + k only while no run boundary lies between them).
+                uint32_t C45 = 0u;
+                {
+                    uint32_t acc = z > 0 ? (E45 ^ s_SE45[kRows + r - 16]) : 0u, open = joins_next;
+#pragma unroll
+                    for (int k = 1; k < 16; k <<= 1) {
+                        const uint32_t acc_k = __shfl_down_sync(0xFFFFFFFFu, acc, k), open_k = __shfl_down_sync(0xFFFFFFFFu, open, k);
+                        const bool in_slice = y + k <= 15;
+                        acc |= in_slice ? (acc_k & open) : 0u;
+                        open &= in_slice ? open_k : 0u;
+                    }
+                    if (z > 0) C45 = S45 & s_SE45[r - 16] & eqz2 & ~acc;
                 }
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     s_C[d * kRows + r] = static_cast<uint16_t>(Cm[d]);
                     A[d] = run_starts(A[d], eqx) & ~Cm[d];
                 }
-                s_CT[tid] = static_cast<uint16_t>(CT[0]);
-                s_CT[kRows + tid] = static_cast<uint16_t>(CT[1]);
-                AT[0] = run_starts(fT[0], eqrunT) & ~CT[0];
-                AT[1] = run_starts(fT[1], eqrunT) & ~CT[1];
-                const uint32_t ta = transpose16x16_pair(AT[0] | (AT[1] << 16), lane);  // columns -> rows
-                A[4] = ta & 0xFFFFu;
-                A[5] = ta >> 16;
-#pragma unroll
-                for (int d = 0; d < 6; ++d) s_A[d * kRows + r] = static_cast<uint16_t>(A[d]);
+                s_C45[r] = C45;
+                A[4] = (S45 & ~C45) & 0xFFFFu;
+                A[5] = (S45 & ~C45) >> 16;
             }
 
             // ---- 4. count, scan
@@ -314,7 +303,6 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 if (lane >= o) incl += v;
             }
             if (lane == 31) s_warp[warp] = incl;
-            if (GREEDY) s_first[r] = static_cast<uint16_t>(incl - cnt);  // warp-local; a column thread's anchors lie in rows of its own warp
             __syncthreads();
             Q = 0;
 #pragma unroll
@@ -372,43 +360,27 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
 #pragma unroll
                         for (uint32_t d = 0; d < 6; ++d) {
                             if (!((A[d] >> x) & 1u)) continue;
-                            if (d < 4u && ord < kRecCap) {  // RIGHT / LEFT records are written by the column threads
-                                // run length from the row's end mask; height = rows along the stack axis that continue it
-                                const uint32_t fmask = d == 0 ? fm.top : d == 1 ? fm.bot : d == 2 ? fm.rear : fm.front;
-                                const uint32_t w1 = __ffs(run_ends(fmask, eqx) >> x) - 1;
-                                const int stride = d < 2u ? 16 : 1;
-                                const int left = d < 2u ? 15 - z : 15 - y;
+                            if (ord < kRecCap) {
+                                uint32_t w1;
                                 int h1 = 0;
-                                while (h1 < left && ((s_C[d * kRows + r + (h1 + 1) * stride] >> x) & 1u)) ++h1;
+                                if (d < 4u) {
+                                    // run length from the row's end mask; height = rows along the stack axis that continue it
+                                    const uint32_t fmask = d == 0 ? fm.top : d == 1 ? fm.bot : d == 2 ? fm.rear : fm.front;
+                                    w1 = __ffs(run_ends(fmask, eqx) >> x) - 1;
+                                    const int stride = d < 2u ? 16 : 1;
+                                    const int left = d < 2u ? 15 - z : 15 - y;
+                                    while (h1 < left && ((s_C[d * kRows + r + (h1 + 1) * stride] >> x) & 1u)) ++h1;
+                                } else {
+                                    // RIGHT / LEFT: the run climbs the rows of this z-slice until one carries its end bit; it is
+                                    // stacked along z while the rows 16 further on continue it
+                                    const int bit = x + 16 * static_cast<int>(d - 4u);
+                                    w1 = 0u;
+                                    if (!((E45 >> bit) & 1u)) { do { ++w1; } while (!((s_SE45[kRows + r + w1] >> bit) & 1u)); }
+                                    while (h1 < 15 - z && ((s_C45[r + (h1 + 1) * 16] >> bit) & 1u)) ++h1;
+                                }
                                 s_rec[ord] = (rbase + x) | (d << 12) | (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
                             }
                             ++ord;
-                        }
-                    }
-                }
-                // RIGHT / LEFT anchors are known to the column threads: column (tx, z), anchor bit = y
-#pragma unroll
-                for (int dd = 0; dd < 2; ++dd) {
-                    uint32_t am = AT[dd];
-                    while (am) {
-                        const int y0 = __ffs(am) - 1;
-                        am &= am - 1;
-                        const int row = y0 + 16 * z;
-                        // ordinal: first quad of the anchor's row + anchors of that row that precede (tx, direction)
-                        const uint32_t below = (1u << tx) - 1u;
-                        uint32_t ord = wpre + s_first[row];
-#pragma unroll
-                        for (int d = 0; d < 6; ++d) {
-                            const uint32_t a = s_A[d * kRows + row];
-                            ord += __popc(a & below) + ((d < 4 + dd) ? ((a >> tx) & 1u) : 0u);
-                        }
-                        ord -= q0;
-                        if (ord < kRecCap) {
-                            const uint32_t w1 = __ffs(run_ends(fT[dd], eqrunT) >> y0) - 1;
-                            int h1 = 0;
-                            while (h1 < 15 - z && ((s_CT[dd * kRows + tid + (h1 + 1) * 16] >> y0) & 1u)) ++h1;
-                            s_rec[ord] = static_cast<uint32_t>(tx + 16 * y0 + 256 * z) | (static_cast<uint32_t>(4 + dd) << 12) | (w1 << 15) |
-                                         (static_cast<uint32_t>(h1) << 19);
                         }
                     }
                 }
