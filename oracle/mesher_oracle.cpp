@@ -6,11 +6,15 @@
 // `--impl reference` legs may load it.  The product library (libdespawn_b200.so) never
 // links, loads or calls anything in oracle/.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-//  and its Rust sources cannot be compiled in this image (no
-// rustc/cargo).  The pins used instead are the known answers derived from the reference
-// source (tests/test_oracle_known_answers.py) and an independent numpy restatement
-// (oracle/numpy_oracle.py) that must agree with this file byte for byte.
+// PARITY PIN: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md
+// section 4 / 8c) and its Rust sources cannot be compiled in this image (no rustc/cargo), so there is
+// no oracle/_ref.  The pin is the reference's SOURCE TEXT: oracle/reference_source.py parses cube.rs,
+// chunk_mesh.rs, chunk.rs, world.rs and math.rs under /root/reference at test time and meshes chunks
+// from the parsed tables / conditions / order (sharing nothing with this file);
+// tests/test_oracle_vs_reference_source.py holds this oracle to it byte for byte, and the committed
+// fixtures tests/golden/refsrc_* + flat_chunk_origin.bin are generated from that parser
+// (tests/golden/make_golden_from_reference.py).  Further pins: the hand-derived known answers
+// (tests/test_oracle_known_answers.py) and an independent numpy restatement (oracle/numpy_oracle.py).
 //
 // Reference anchors (paths relative to /root/reference):
 //   src/content/world/chunks/chunk.rs:7-12,15-68,86-120   Chunk storage, palette, generators

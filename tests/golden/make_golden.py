@@ -1,9 +1,10 @@
-"""Writes tests/golden/oracle_digests.json and tests/golden/flat_chunk_origin.bin.
+"""Writes tests/golden/oracle_digests.json: a freeze of the BUILDER-DEFINED terrain generators (noise, random,
+checker: the reference has none of them) and of the oracle's meshes of those chunks, so that a later edit to the
+oracle or to the terrain spec cannot silently drift.
 
-The reference is Rust and cannot be built or imported here (no rustc), so these goldens are
-produced by the C++ restatement in oracle/ AFTER it has passed the hand-derived known answers in
-tests/test_oracle_known_answers.py and agreed with the numpy restatement.  They freeze that state so
-a later edit to the oracle (or to the terrain spec) cannot silently drift.
+These are NOT the reference pins.  The fixtures that say what the reference does -- refsrc_cases.npz,
+refsrc_digests.json, flat_chunk_origin.bin -- are written by make_golden_from_reference.py from the reference's
+parsed Rust sources, with no oracle involved.
 
 Run from the repo root:  python tests/golden/make_golden.py
 """
@@ -36,7 +37,4 @@ for kind, seed, pos in CASES:
                          "ids_sha256": hashlib.sha256(ids.tobytes()).hexdigest(),
                          "mesh_sha256": hashlib.sha256(v.tobytes()).hexdigest()})
 json.dump(out, open(os.path.join(here, "oracle_digests.json"), "w"), indent=1)
-# one full small fixture: the reference's default chunk (config 1), 122,880 bytes
-ids = orc.generate(orc.GEN_REFERENCE, 0, (0, 0, 0))
-orc.mesh_chunk((0, 0, 0), ids, UV).tofile(os.path.join(here, "flat_chunk_origin.bin"))
 print("wrote", len(out["cases"]), "cases")
