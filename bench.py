@@ -228,8 +228,9 @@ def main():
     ctx = capi.Context(local_rank, N_CHUNKS * COPIES, COPIES * SLICE)
     ctx.set_uv_table(UV)
     origin = (DIMS[0] * rank, 0, 0)
-    firsts = [ctx.generate_region(origin, DIMS, capi.GEN_NOISE, SEED) for _ in range(COPIES)]
-    first = firsts[0]
+    first = ctx.generate_region(origin, DIMS, capi.GEN_NOISE, SEED)
+    # identical voxels at other places of the world (a position holds one chunk): same faces, same bytes per step
+    firsts = [first] + [ctx.clone_region(first, (origin[0], 4096 * k, 0)) for k in range(1, COPIES)]
     mode = capi.MESH_ORDERED if args.ordered else capi.MESH_PARITY
     entries, total_bytes = ctx.mesh_range(first, N_CHUNKS, mode)
     assert total_bytes <= SLICE
@@ -353,7 +354,7 @@ def main():
     slots_region = np.arange(first, first + N_CHUNKS, dtype=np.uint32)
 
     def positions_step():
-        ctx.generate_chunks(pos, capi.GEN_NOISE, SEED)      # 48 KiB of positions H2D, voxels never exist on the host
+        ctx.regenerate_chunks(pos, capi.GEN_NOISE, SEED)    # 48 KiB of positions H2D, voxels never exist on the host (the generator runs every step)
         ctx.mesh_chunks(slots_region, mode)                  # blocking: entry table D2H
 
     for _ in range(2):

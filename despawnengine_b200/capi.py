@@ -46,7 +46,10 @@ SYMBOLS = {
     "dsp_abi_version": (_int, []),
     "dsp_set_uv_table": (_int, [_vp, _u32, _P(C.c_float)]),
     "dsp_generate_chunks": (_int, [_vp, _u64, _P(_i32), _int, _u32, _P(_u32)]),
+    "dsp_regenerate_chunks": (_int, [_vp, _u64, _P(_i32), _int, _u32, _P(_u32)]),
     "dsp_generate_region": (_int, [_vp, _P(_i32), _P(_u32), _int, _u32, _P(_u32)]),
+    "dsp_clone_region": (_int, [_vp, _u32, _P(_i32), _P(_u32)]),
+    "dsp_invalidate_chunks": (_int, [_vp, _u64, _P(_u32)]),
     "dsp_load_chunks": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _P(C.c_uint16), _P(_u32), _P(_u32)]),
     "dsp_unload_chunks": (_int, [_vp, _u64, _P(_u32)]),
     "dsp_find_chunk": (_int, [_vp, _P(_i32), _P(_u32)]),
@@ -171,6 +174,23 @@ class Context:
         slots = np.empty(pos.shape[0], dtype=np.uint32)
         self._check(lib().dsp_generate_chunks(self._h, pos.shape[0], _ptr(pos, C.c_int32), kind, seed & 0xFFFFFFFF, _ptr(slots, C.c_uint32)))
         return slots
+
+    def regenerate_chunks(self, pos, kind: int = GEN_REFERENCE, seed: int = 0) -> np.ndarray:
+        """dsp_generate_chunks that also runs the generator over resident positions (edits are discarded)."""
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        slots = np.empty(pos.shape[0], dtype=np.uint32)
+        self._check(lib().dsp_regenerate_chunks(self._h, pos.shape[0], _ptr(pos, C.c_int32), kind, seed & 0xFFFFFFFF, _ptr(slots, C.c_uint32)))
+        return slots
+
+    def clone_region(self, src_first_slot: int, new_origin) -> int:
+        o = np.ascontiguousarray(new_origin, dtype=np.int32).reshape(3)
+        first = C.c_uint32(0)
+        self._check(lib().dsp_clone_region(self._h, src_first_slot, _ptr(o, C.c_int32), C.byref(first)))
+        return int(first.value)
+
+    def invalidate_chunks(self, slots):
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        self._check(lib().dsp_invalidate_chunks(self._h, s.shape[0], _ptr(s, C.c_uint32)))
 
     def generate_region(self, origin, dims, kind: int = GEN_NOISE, seed: int = 0) -> int:
         o = np.ascontiguousarray(origin, dtype=np.int32).reshape(3)

@@ -106,6 +106,8 @@ struct dsp_ctx {
     std::vector<PosKey> slot_pos;  // position of every slot handed out through the map (not region slots)
     std::vector<uint8_t> resident;
     uint64_t next_unused = 0, n_resident = 0;
+    std::vector<uint32_t> slot_stamp;  // per-call duplicate detection (stamp_slot)
+    uint32_t stamp = 0;
     bool nbr_dirty = true;
     bool region_holes = false;  // a slot inside a box region has been unloaded (device-side edit addressing needs full boxes)
 
@@ -188,9 +190,38 @@ bool find_slot(const dsp_ctx* ctx, const int32_t p[3], uint32_t* out) {
     return false;
 }
 
-// World::get_chunk's "insert if absent" (world.rs:29-31, 44-46) on slots.
-int acquire_slot(dsp_ctx* ctx, const int32_t p[3], uint32_t* out) {
+// Does the box hold a position that is resident already (in another box region or in the position map)?
+bool region_overlaps(const dsp_ctx* ctx, const int32_t origin[3], const uint32_t dims[3]) {
+    for (const Region& r : ctx->regions) {
+        bool apart = false;
+        for (int a = 0; a < 3; ++a) {
+            const int64_t lo0 = origin[a], hi0 = lo0 + dims[a], lo1 = r.origin[a], hi1 = lo1 + r.dims[a];
+            if (hi0 <= lo1 || hi1 <= lo0) apart = true;
+        }
+        if (!apart) return true;  // (slots unloaded from inside a box keep their address, so the whole box stays reserved)
+    }
+    const uint64_t n = static_cast<uint64_t>(dims[0]) * dims[1] * dims[2];
+    auto inside = [&](const PosKey& k) {
+        const int64_t a = static_cast<int64_t>(k.x) - origin[0], b = static_cast<int64_t>(k.y) - origin[1], c = static_cast<int64_t>(k.z) - origin[2];
+        return a >= 0 && b >= 0 && c >= 0 && a < dims[0] && b < dims[1] && c < dims[2];
+    };
+    if (ctx->map.size() <= n) {
+        for (const auto& kv : ctx->map) if (inside(kv.first)) return true;
+    } else {
+        for (uint32_t c = 0; c < dims[2]; ++c)
+            for (uint32_t b = 0; b < dims[1]; ++b)
+                for (uint32_t a = 0; a < dims[0]; ++a)
+                    if (ctx->map.count(PosKey{origin[0] + static_cast<int32_t>(a), origin[1] + static_cast<int32_t>(b), origin[2] + static_cast<int32_t>(c)})) return true;
+    }
+    return false;
+}
+
+// World::get_chunk's "insert if absent" (world.rs:29-31, 44-46) on slots.  *fresh (may be NULL) tells whether the slot
+// was created by this call (the chunk still has to be generated / uploaded) or was resident already.
+int acquire_slot(dsp_ctx* ctx, const int32_t p[3], uint32_t* out, bool* fresh = nullptr) {
+    if (fresh) *fresh = false;
     if (find_slot(ctx, p, out)) return DSP_OK;
+    if (fresh) *fresh = true;
     uint32_t s;
     if (!ctx->free_slots.empty()) { s = ctx->free_slots.back(); ctx->free_slots.pop_back(); }
     else if (ctx->next_unused < ctx->max_chunks) { s = static_cast<uint32_t>(ctx->next_unused++); }
@@ -204,6 +235,30 @@ int acquire_slot(dsp_ctx* ctx, const int32_t p[3], uint32_t* out) {
     ctx->nbr_dirty = true;
     *out = s;
     return DSP_OK;
+}
+
+// Undo of acquire_slot for the slots a failing call created (nothing of theirs is in flight: the caller synchronises).
+void release_fresh_slots(dsp_ctx* ctx, const std::vector<uint32_t>& fresh) {
+    for (uint32_t s : fresh) {
+        if (s >= ctx->resident.size() || !ctx->resident[s]) continue;
+        ctx->map.erase(ctx->slot_pos[s]);
+        ctx->free_slots.push_back(s);
+        ctx->resident[s] = 0;
+        ctx->n_resident--;
+    }
+    if (!fresh.empty()) ctx->nbr_dirty = true;
+}
+
+// Per-call duplicate detection: a slot may appear once in the batch of an upload call (two copies into one slot race,
+// and the palette remap would run twice over it).  Returns false when `slot` was already stamped by this call.
+bool stamp_slot(dsp_ctx* ctx, uint32_t slot) {
+    if (ctx->slot_stamp.size() <= slot) ctx->slot_stamp.resize(std::max<size_t>(static_cast<size_t>(slot) + 1, ctx->slot_stamp.size() * 2), 0u);
+    if (ctx->slot_stamp[slot] == ctx->stamp) return false;
+    ctx->slot_stamp[slot] = ctx->stamp;
+    return true;
+}
+void new_stamp(dsp_ctx* ctx) {
+    if (++ctx->stamp == 0u) { std::fill(ctx->slot_stamp.begin(), ctx->slot_stamp.end(), 0u); ctx->stamp = 1u; }
 }
 
 // Copies n elements of elem_bytes each from host `src` to dst_base[slot[i]], one cudaMemcpyAsync per
@@ -713,25 +768,49 @@ int dsp_set_uv_table(dsp_ctx* ctx, uint32_t n_blocks, const float* uv_rows) {
     return DSP_OK;
 }
 
-int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots) {
+// World::get_chunk (world.rs:28-47): a position that is already in `chunks` is returned as it is -- edits made to it since
+// it was generated survive a second load_chunk; only absent positions are generated.  `regenerate` forces the generator
+// over resident positions as well (dsp_regenerate_chunks: no counterpart in the reference).
+static int generate_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots, bool regenerate) {
     if (!ctx) return DSP_ERR_BAD_ARG;
     if (gen_kind < 0 || gen_kind > 3) return fail(ctx, DSP_ERR_BAD_ARG, "unknown gen_kind %d", gen_kind);
     if (n == 0) return DSP_OK;
     if (!pos) return fail(ctx, DSP_ERR_BAD_ARG, "pos is NULL");
     if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "n exceeds max_chunks");
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<uint32_t> slots(n);
-    for (uint64_t i = 0; i < n; ++i) { int rc = acquire_slot(ctx, pos + 3 * i, &slots[i]); if (rc != DSP_OK) return rc; }
+    std::vector<uint32_t> slots(n), fresh_slots;
+    std::vector<int32_t> todo_pos;
+    std::vector<uint32_t> todo_slots;
+    new_stamp(ctx);
+    for (uint64_t i = 0; i < n; ++i) {
+        bool fresh = false;
+        int rc = acquire_slot(ctx, pos + 3 * i, &slots[i], &fresh);
+        if (rc != DSP_OK) { release_fresh_slots(ctx, fresh_slots); return rc; }  // the call did not happen
+        if (fresh) fresh_slots.push_back(slots[i]);
+        if ((fresh || regenerate) && stamp_slot(ctx, slots[i])) {  // (a position listed twice is generated once)
+            todo_pos.insert(todo_pos.end(), pos + 3 * i, pos + 3 * i + 3);
+            todo_slots.push_back(slots[i]);
+        }
+    }
+    if (out_slots) std::memcpy(out_slots, slots.data(), n * sizeof(uint32_t));
+    const uint64_t m = todo_slots.size();
+    if (m == 0) return DSP_OK;
     const uint32_t* d_list; uint32_t first;
-    int rc = upload_positions_and_slots(ctx, n, pos, slots.data(), &d_list, &first);
-    if (rc != DSP_OK) return rc;
-    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(n), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary};
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
+    int rc = upload_positions_and_slots(ctx, m, todo_pos.data(), todo_slots.data(), &d_list, &first);
+    if (rc != DSP_OK) { cudaStreamSynchronize(ctx->stream); release_fresh_slots(ctx, fresh_slots); return rc; }
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(m), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary};
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(m, static_cast<uint64_t>(ctx->num_sms) * 64));
     dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
-    if (out_slots) std::memcpy(out_slots, slots.data(), n * sizeof(uint32_t));
     return DSP_OK;
+}
+
+int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots) {
+    return generate_chunks_impl(ctx, n, pos, gen_kind, seed, out_slots, false);
+}
+int dsp_regenerate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots) {
+    return generate_chunks_impl(ctx, n, pos, gen_kind, seed, out_slots, true);
 }
 
 int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t dims[3], int gen_kind, uint32_t seed, uint32_t* out_first_slot) {
@@ -742,6 +821,9 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
     if (n == 0) return fail(ctx, DSP_ERR_BAD_ARG, "empty region");
     if (ctx->next_unused + n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "region of %llu chunks does not fit (%llu unused slots)",
                                                             (unsigned long long)n, (unsigned long long)(ctx->max_chunks - ctx->next_unused));
+    if (region_overlaps(ctx, origin, dims))
+        return fail(ctx, DSP_ERR_BAD_ARG, "region (%d, %d, %d) + %u x %u x %u overlaps chunks that are already resident (a position has one chunk: "
+                    "use dsp_clone_region for identical copies elsewhere)", origin[0], origin[1], origin[2], dims[0], dims[1], dims[2]);
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t first = static_cast<uint32_t>(ctx->next_unused);
     ctx->next_unused += n;
@@ -776,6 +858,55 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
     return DSP_OK;
 }
 
+int dsp_clone_region(dsp_ctx* ctx, uint32_t src_first_slot, const int32_t new_origin[3], uint32_t* out_first_slot) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (!new_origin || !out_first_slot) return fail(ctx, DSP_ERR_BAD_ARG, "NULL argument");
+    const Region* src = nullptr;
+    for (const Region& r : ctx->regions) if (r.first_slot == src_first_slot) src = &r;
+    if (!src) return fail(ctx, DSP_ERR_BAD_ARG, "slot %u is not the first slot of a dsp_generate_region box", src_first_slot);
+    const Region from = *src;
+    const uint64_t n = static_cast<uint64_t>(from.dims[0]) * from.dims[1] * from.dims[2];
+    for (uint64_t i = 0; i < n; ++i)
+        if (!ctx->resident[from.first_slot + i]) return fail(ctx, DSP_ERR_NOT_RESIDENT, "source region has unloaded chunks");
+    if (ctx->next_unused + n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "clone of %llu chunks does not fit", (unsigned long long)n);
+    if (region_overlaps(ctx, new_origin, from.dims)) return fail(ctx, DSP_ERR_BAD_ARG, "the clone would overlap resident chunks");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t first = static_cast<uint32_t>(ctx->next_unused);
+    ctx->next_unused += n;
+    ctx->regions.push_back(Region{{new_origin[0], new_origin[1], new_origin[2]}, {from.dims[0], from.dims[1], from.dims[2]}, first});
+    std::fill(ctx->resident.begin() + first, ctx->resident.begin() + first + n, 1);
+    ctx->n_resident += n;
+    ctx->nbr_dirty = true;
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels + static_cast<size_t>(first) * dsp::kChunkVoxels, ctx->d_voxels + static_cast<size_t>(from.first_slot) * dsp::kChunkVoxels,
+                                  n * dsp::kChunkBytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_summary + first, ctx->d_summary + from.first_slot, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
+        ctx->d_pos, first, make_int3(new_origin[0], new_origin[1], new_origin[2]), make_uint3(from.dims[0], from.dims[1], from.dims[2]), n);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    *out_first_slot = first;
+    return DSP_OK;
+}
+
+int dsp_invalidate_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (n == 0) return DSP_OK;
+    if (!slots) return fail(ctx, DSP_ERR_BAD_ARG, "slots is NULL");
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = validate_slots(ctx, n, slots);
+    if (rc != DSP_OK) return rc;
+    uint8_t* h;
+    if ((rc = stage_host(ctx, n * sizeof(uint32_t), &h)) != DSP_OK) return rc;
+    std::memcpy(h, slots, n * sizeof(uint32_t));
+    if ((rc = ensure_scratch(ctx, n * sizeof(uint32_t))) != DSP_OK) return rc;
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = stage_release(ctx)) != DSP_OK) return rc;
+    dsp::invalidate_summaries_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_summary, reinterpret_cast<const uint32_t*>(ctx->d_scratch), static_cast<uint32_t>(n));
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    return DSP_OK;
+}
+
 int dsp_load_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint16_t* palette_ids,
                     const uint32_t* palette_offsets, uint32_t* out_slots) {
     if (!ctx) return DSP_ERR_BAD_ARG;
@@ -784,11 +915,19 @@ int dsp_load_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t
     if ((palette_ids == nullptr) != (palette_offsets == nullptr)) return fail(ctx, DSP_ERR_BAD_ARG, "palette_ids and palette_offsets go together");
     if (n > ctx->max_chunks) return fail(ctx, DSP_ERR_STORE_FULL, "n exceeds max_chunks");
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
-    std::vector<uint32_t> slots(n);
-    for (uint64_t i = 0; i < n; ++i) { int rc = acquire_slot(ctx, pos + 3 * i, &slots[i]); if (rc != DSP_OK) return rc; }
+    std::vector<uint32_t> slots(n), fresh_slots;
+    new_stamp(ctx);
+    for (uint64_t i = 0; i < n; ++i) {
+        bool fresh = false;
+        int rc = acquire_slot(ctx, pos + 3 * i, &slots[i], &fresh);
+        if (rc == DSP_OK && !stamp_slot(ctx, slots[i]))
+            rc = fail(ctx, DSP_ERR_BAD_ARG, "position (%d, %d, %d) appears twice in the batch (entry %llu): one chunk per position", pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], (unsigned long long)i);
+        if (rc != DSP_OK) { release_fresh_slots(ctx, fresh_slots); return rc; }
+        if (fresh) fresh_slots.push_back(slots[i]);
+    }
     const uint32_t* d_unused; uint32_t first_unused;
     int rc = upload_positions_and_slots(ctx, n, pos, slots.data(), &d_unused, &first_unused);
-    if (rc != DSP_OK) return rc;
+    if (rc != DSP_OK) { cudaStreamSynchronize(ctx->stream); release_fresh_slots(ctx, fresh_slots); return rc; }
     if ((rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, slots.data(), n,
                              reinterpret_cast<const uint8_t*>(blocks))) != DSP_OK) return rc;
     if (palette_ids) {
@@ -942,12 +1081,31 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
     DSP_CUDA(ctx, cudaEventRecord(ctx->ev_done, ctx->stream));
     DSP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0));
     cudaStream_t main_stream = ctx->stream;
+    std::vector<uint32_t> fresh_slots;
+    new_stamp(ctx);
+    // A failure part-way leaves no trace: earlier sub-batches are drained, the slots this call created are given back and the
+    // staging block is released (the reference's load loop has no partial state either: it panics, chunk_mesh.rs:124).
+    auto bail = [&](int code) {
+        const std::string msg = ctx->err;
+        ctx->stream = main_stream;
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        release_fresh_slots(ctx, fresh_slots);
+        stage_release(ctx);
+        ctx->err = msg;
+        return code;
+    };
     for (int j = 0; j < subs; ++j) {
         const uint64_t i0 = sub_begin[j], m = sub_begin[j + 1] - i0;
         if (m == 0) continue;
         bool consecutive = true;
         for (uint64_t i = 0; i < m; ++i) {
-            if ((rc = acquire_slot(ctx, pos + 3 * (i0 + i), &h_slots[i0 + i])) != DSP_OK) return rc;
+            bool fresh = false;
+            if ((rc = acquire_slot(ctx, pos + 3 * (i0 + i), &h_slots[i0 + i], &fresh)) != DSP_OK) return bail(rc);
+            if (fresh) fresh_slots.push_back(h_slots[i0 + i]);
+            if (!stamp_slot(ctx, h_slots[i0 + i]))  // the copy of a later sub-batch would overwrite a slot an earlier one is still meshing
+                return bail(fail(ctx, DSP_ERR_BAD_ARG, "position (%d, %d, %d) appears twice in the batch (entry %llu): one chunk per position",
+                                 pos[3 * (i0 + i)], pos[3 * (i0 + i) + 1], pos[3 * (i0 + i) + 2], (unsigned long long)(i0 + i)));
             h_pos[i0 + i] = make_int4(pos[3 * (i0 + i)], pos[3 * (i0 + i) + 1], pos[3 * (i0 + i) + 2], 0);
             if (i && h_slots[i0 + i] != h_slots[i0 + i - 1] + 1) consecutive = false;
         }
@@ -957,16 +1115,16 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
         // engine at all: a small kernel on the main stream reads them straight from the pinned staging block (UVA).
         dsp::stage_positions_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
             ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
-        DSP_CUDA(ctx, cudaGetLastError());
+        if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "stage_positions_kernel launch failed"));
         const uint32_t* d_list = consecutive ? nullptr : ctx->d_slots + i0;
         ctx->stream = ctx->copy_stream;  // upload_by_runs enqueues on ctx->stream
         rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, h_slots + i0, m,
                             reinterpret_cast<const uint8_t*>(blocks + (i0 * dsp::kChunkVoxels)));
         ctx->stream = main_stream;
-        if (rc != DSP_OK) return rc;
-        DSP_CUDA(ctx, cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream));
-        DSP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0));
-        if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j)) != DSP_OK) return rc;
+        if (rc != DSP_OK) return bail(rc);
+        if (cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
+            return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the copy pipeline"));
+        if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j)) != DSP_OK) return bail(rc);
         tr("sub-batch enqueued");
     }
     if (out_slots) std::memcpy(out_slots, h_slots, n * sizeof(uint32_t));
@@ -1137,7 +1295,15 @@ int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = validate_slots(ctx, n, slots);
     if (rc != DSP_OK) return rc;
-    // slabs of one call are stored contiguously (and their slots in a parallel array); a (slot, face) set again uses the newer slab
+    // A seam is exchanged again after every edit that touches it: the same (face, slot list) then REPLACES its earlier slabs in
+    // place, so that repeated exchanges neither grow the slab store nor add launches to the neighbour-table rebuild.
+    for (auto& hb : ctx->halo_batches) {
+        if (hb.face != face || hb.n != n || std::memcmp(hb.slots.data(), slots, n * sizeof(uint32_t)) != 0) continue;
+        DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_halo + static_cast<size_t>(hb.first_index) * 256, src_device, n * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+        return DSP_OK;  // same slabs indices: the neighbour table stays valid
+    }
+    // slabs of one call are stored contiguously (and their slots in a parallel array); a (slot, face) set again with a different
+    // list uses the newer slab
     if (ctx->halo_n + n > ctx->halo_cap) {
         const uint64_t cap = std::max<uint64_t>(ctx->halo_n + n, std::max<uint64_t>(1024, ctx->halo_cap * 2));
         uint16_t* grown = nullptr;

@@ -125,6 +125,9 @@ int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_co
     if (cfg->mesh_mode & DSP_MESH_ORDERED) return fail(ctx, DSP_ERR_BAD_ARG, "DSP_MESH_ORDERED has no meaning for a scene (slots come and go)");
     if (!ctx->regions.empty())
         return fail(ctx, DSP_ERR_BAD_ARG, "a scene manages its own chunk slots: use a context without dsp_generate_region boxes");
+    if (ctx->map.size() != ctx->scene_loaded.size())
+        return fail(ctx, DSP_ERR_BAD_ARG, "a scene owns every chunk of its context: %llu chunks here were loaded by hand (dsp_generate_chunks / dsp_load_chunks); "
+                    "unload them or use a separate context", (unsigned long long)(ctx->map.size() - ctx->scene_loaded.size()));
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!ctx->scene_init) {
         ctx->scene_free.clear();
@@ -184,13 +187,12 @@ int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_co
                     }
                 }
                 done = true;
-            } else if (rc != DSP_ERR_ARENA_FULL) {
-                return rc;
             }
         }
         if (!done) {
-            // give the voxel slots back: the update did not happen
-            DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            // give the voxel slots back: the update did not happen (whatever the reason -- every error path rolls back)
+            const std::string why = ctx->err;
+            cudaStreamSynchronize(ctx->stream);
             for (uint64_t i = 0; i < n_new; ++i) {
                 ctx->map.erase(PosKey{todo[3 * i], todo[3 * i + 1], todo[3 * i + 2]});
                 ctx->free_slots.push_back(slots[i]);
@@ -198,6 +200,7 @@ int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_co
                 ctx->n_resident--;
             }
             ctx->nbr_dirty = true;
+            if (rc != DSP_OK && rc != DSP_ERR_ARENA_FULL) { ctx->err = why; return rc; }
             return fail(ctx, DSP_ERR_ARENA_FULL, "no free arena interval of %llu bytes for the meshes of %llu newly visible chunks",
                         (unsigned long long)total, (unsigned long long)n_new);
         }

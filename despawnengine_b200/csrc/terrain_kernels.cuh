@@ -308,6 +308,12 @@ __global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, const uint
     summary[slots[i]] = kSummaryUnknown;  // the slot is being (re)defined; a generator that follows sets it again
 }
 
+// dsp_invalidate_chunks: the caller wrote voxels behind the library's back (dsp_voxel_device_ptr); forget what is known
+__global__ void invalidate_summaries_kernel(uint8_t* summary, const uint32_t* slots, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) summary[slots[i]] = kSummaryUnknown;
+}
+
 // Halo-mode pre-pass: chunk i of the call needs no meshing when it is all air, or free of air with six RESIDENT neighbours
 // whose facing border layers are free of air (every face culled); its entry is written here.  Everything else is appended to the work list that the
 // mesh kernel then consumes straight from device memory (count in *n_work; order within the list does not matter, the arena

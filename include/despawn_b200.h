@@ -113,25 +113,40 @@ int dsp_set_uv_table(dsp_ctx* ctx, uint32_t n_blocks, const float* uv_rows /* n_
 
 /* ---- chunk residency (World) ----------------------------------------------------------------------- */
 /* World::get_chunk + load_chunk with on-device generation (world.rs:28-47, 80-84; chunk.rs:86-120).
- * pos: n x 3 chunk coordinates.  Positions already resident are regenerated in place.
- * out_slots (n, may be NULL) receives the slot of each chunk. */
+ * pos: n x 3 chunk coordinates.  As in the reference (world.rs:29-31: `if let Some(chunk_data) = self.chunks.get(&pos)
+ * { return Ok(chunk_data.clone()) }`) a position that is already resident is returned AS IT IS -- its slot, its voxels,
+ * edits included -- and only absent positions are generated; a position listed twice is one chunk.
+ * out_slots (n, may be NULL) receives the slot of each chunk.  On DSP_ERR_STORE_FULL nothing was loaded. */
 int dsp_generate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots);
+/* Same, but resident positions are generated again in place, discarding edits (no counterpart in the reference, whose
+ * `chunks` map never forgets; used by benches that want the generator inside the timed region). */
+int dsp_regenerate_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, int gen_kind, uint32_t seed, uint32_t* out_slots);
 
 /* Bulk form: a dims[0] x dims[1] x dims[2] box of chunks with minimum corner `origin`, generated into
- * consecutive slots; chunk (i,j,k) of the box gets slot *out_first_slot + i + dims[0]*(j + dims[1]*k). */
+ * consecutive slots; chunk (i,j,k) of the box gets slot *out_first_slot + i + dims[0]*(j + dims[1]*k).
+ * A position holds one chunk: a box that overlaps another box or any resident position is DSP_ERR_BAD_ARG. */
 int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t dims[3], int gen_kind, uint32_t seed,
                         uint32_t* out_first_slot);
+/* A second box with the voxels of an existing one (device-to-device copy) at another origin -- "paste this structure
+ * there".  src_first_slot is the first slot of a fully resident dsp_generate_region / dsp_clone_region box. */
+int dsp_clone_region(dsp_ctx* ctx, uint32_t src_first_slot, const int32_t new_origin[3], uint32_t* out_first_slot);
 
 /* World::load_chunk for host-resident Chunk data (the reference's Chunk.blocks, chunk.rs:17).
  * blocks: n x 4096 u16 in host memory.  If palette_ids != NULL the values are per-chunk palette
  * indices and chunk i's palette is palette_ids[palette_offsets[i] .. palette_offsets[i+1]) (global id
- * per palette index, entry 0 = air = 0); the remap runs on the device.  If NULL, values are global ids. */
+ * per palette index, entry 0 = air = 0); the remap runs on the device.  If NULL, values are global ids.
+ * A resident position's voxels are replaced.  A position may appear once per call (DSP_ERR_BAD_ARG otherwise; nothing is
+ * loaded then). */
 int dsp_load_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint16_t* palette_ids,
                     const uint32_t* palette_offsets, uint32_t* out_slots);
 
 /* World::unload_chunk (world.rs:85-87): frees the slots. */
 int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots);
 int dsp_find_chunk(const dsp_ctx* ctx, const int32_t pos[3], uint32_t* out_slot); /* DSP_ERR_NOT_RESIDENT if absent */
+/* Tells the library that the caller changed the voxels of these slots through dsp_voxel_device_ptr (interop writers):
+ * the per-chunk summaries that let DSP_MESH_HALO / large DSP_MESH_GREEDY calls skip all-air and buried chunks are
+ * reset to "unknown".  Every writer inside the library does this itself. */
+int dsp_invalidate_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots);
 uint64_t dsp_resident_chunks(const dsp_ctx* ctx);
 
 /* ---- meshing (build_chunk_mesh) ---------------------------------------------------------------------- */
@@ -152,7 +167,9 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
  * by the mesh of the same chunks, pipelined in sub-batches so that the host->device copy of sub-batch k+1 overlaps
  * the meshing of sub-batch k (pass pinned host memory for `blocks` to get a truly asynchronous copy).  This is the
  * end-to-end entry point for a caller that, like the reference, holds Chunk.blocks in host memory
- * (chunks/chunk.rs:17, scene_game.rs:56-64).  out_slots (n, may be NULL) receives the slot of each chunk.  Blocking. */
+ * (chunks/chunk.rs:17, scene_game.rs:56-64).  out_slots (n, may be NULL) receives the slot of each chunk.  Blocking.
+ * A position may appear once per call.  On any error the call leaves no trace: work already enqueued is drained and
+ * every slot it created is released. */
 int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
                          uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes);
 
@@ -172,6 +189,11 @@ int dsp_mesh_result(dsp_ctx* ctx, dsp_mesh_entry* out_entries /* n of the last m
 int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty,
                     uint64_t* out_n_dirty);
 
+/* Where the edits are resolved.  DEVICE pipeline (world -> (slot, voxel) addressing, last-edit-wins and the dirty list
+ * all in kernels; 10,000 edits + remesh in ~0.4 ms) when ALL of these hold: every resident chunk belongs to a
+ * dsp_generate_region / dsp_clone_region box, there are at most 8 boxes, no slot of a box has been unloaded, and the call
+ * carries fewer than 2^20 edits.  Otherwise HOST addressing (one hash-map probe per edit, ~4x slower at 10,000 edits);
+ * the results are identical. */
 /* dsp_apply_edits followed by the whole-chunk remesh of the dirty chunks (the reference's only granularity:
  * build_chunk_mesh, chunk_mesh.rs:13-129) in one call.  When every resident chunk belongs to a dsp_generate_region box,
  * world -> (slot, voxel) addressing, last-edit-wins de-duplication, the voxel writes and the ascending dirty list all run
@@ -202,9 +224,12 @@ int dsp_get_block_world(dsp_ctx* ctx, int32_t wx, int32_t wy, int32_t wz, uint16
 int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, void* dst_device);
 /* Registers, for each listed resident chunk, the border layer of its NON-resident neighbour across `face` (as packed
  * by the owning device with the opposite face).  DSP_MESH_HALO then culls against it exactly as against a resident
- * neighbour.  src_device: n x 512 bytes of device memory, copied. */
+ * neighbour.  src_device: n x 512 bytes of device memory, copied.
+ * Lifetime: registered slabs stay until dsp_clear_halo_slabs or until their chunk is unloaded.  Registering the SAME
+ * (face, slot list) again -- the re-exchange after an edit on the seam -- replaces the slabs in place; a different list
+ * adds a batch (newest wins where they overlap), so call dsp_clear_halo_slabs when the seam's chunk set changes. */
 int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, const void* src_device);
-int dsp_clear_halo_slabs(dsp_ctx* ctx);
+int dsp_clear_halo_slabs(dsp_ctx* ctx); /* forgets every registered slab (the buffers are kept for the next exchange) */
 
 /* ---- scene: GameScene::update's visible set -> load -> mesh -> unload cycle (engine/scenes/scene_game.rs:39-82) -------- */
 typedef struct dsp_scene_config {
@@ -235,8 +260,9 @@ int dsp_visible_chunks(const float camera_pos[3], uint32_t horizontal, uint32_t 
  * the scene as it was.  With DSP_MESH_HALO only the newly loaded chunks are meshed (against every chunk resident at that
  * moment); chunks meshed earlier keep their meshes, which at worst contain border faces that a later neighbour now hides, or
  * lack faces that only an unloaded neighbour's solid voxels used to cover -- neither is visible from inside the loaded set.
- * The scene owns the chunks it loads and the arena: use it on a context without dsp_generate_region
- * boxes (DSP_ERR_BAD_ARG otherwise), and do not unload its chunks or choose arena offsets by hand on the same context. */
+ * The scene owns every chunk of its context and the arena: a context with dsp_generate_region boxes or with chunks
+ * loaded by hand is refused (DSP_ERR_BAD_ARG); do not choose arena offsets by hand on the same context.  Every error
+ * leaves the scene as it was. */
 int dsp_scene_update(dsp_ctx* ctx, const float camera_pos[3], const dsp_scene_config* cfg, dsp_scene_stats* out_stats);
 /* GameScene::draw's iteration (scene_game.rs:101-125): position and arena window of every non-empty mesh. */
 int dsp_scene_draw_list(dsp_ctx* ctx, uint64_t cap, int32_t* out_pos /* cap x 3 */, dsp_mesh_entry* out_entries, uint64_t* out_n);
@@ -249,7 +275,7 @@ int dsp_download_chunk(dsp_ctx* ctx, uint32_t slot, uint16_t* host_dst /* 4096 *
  * exchange, torch tensors over the same memory).  Valid until dsp_destroy. */
 void* dsp_arena_device_ptr(dsp_ctx* ctx);
 uint64_t dsp_arena_bytes(const dsp_ctx* ctx);
-void* dsp_voxel_device_ptr(dsp_ctx* ctx);   /* max_chunks x 4096 u16 */
+void* dsp_voxel_device_ptr(dsp_ctx* ctx);   /* max_chunks x 4096 u16; after writing through it call dsp_invalidate_chunks */
 void* dsp_entries_device_ptr(dsp_ctx* ctx); /* dsp_mesh_entry[n] of the last mesh call */
 void* dsp_stream(dsp_ctx* ctx);             /* cudaStream_t all work of this context is enqueued on */
 uint64_t dsp_max_chunks(const dsp_ctx* ctx);
