@@ -52,18 +52,19 @@ def cases(ref):
     for p, hi in [(0.5, 3), (0.1, 3), (0.9, 3), (0.5, 10)]:
         ids = rng.integers(1, hi, size=4096) * (rng.random(4096) < p)
         add(f"bernoulli_p{p}_ids<{hi}", rng.integers(-50, 50, size=3), ids)
-    add("checkerboard", (0, 0, 0), ((x + y + z) % 2 == 0).astype(np.uint16))
+    add("checkerboard", (3, 3, 3), ((x + y + z) % 2 == 0).astype(np.uint16))
     add("checkerboard_inverse", (1, 1, 1), ((x + y + z) % 2 == 1).astype(np.uint16) * 2)
     for k, idx in enumerate([0, 4095, 8 + 16 * 8 + 256 * 8, 15, 15 * 16, 15 * 256]):
         ids = np.zeros(4096, dtype=np.uint16)
         ids[idx] = 1 + k % 2
-        add(f"single_voxel_{idx}", (k, -k, 2 * k), ids)
+        add(f"single_voxel_{idx}", (k + 1, -k, 2 * k), ids)
     for name, ids in structured_chunks().items():
         add("pattern_" + name, rng.integers(-9, 9, size=3), ids)
     for k in range(4):  # heightfield terrain with a surface block: solid below h(x,z), id 2 on top
         h = (6 + 5 * np.sin((x + 16 * k) * 0.37) + 4 * np.cos(z * 0.23 + k)).astype(np.int64)
         ids = np.where(y < h - 1, 1, np.where(y == h - 1, 2, 0))
-        add(f"heightfield_{k}", (k, 0, -k), ids)
+        add(f"heightfield_{k}", (k + 30, 0, -k), ids)
+    assert len({c[1] for c in out}) == len(out), "positions must be unique: the fixtures are loaded as one batch (one chunk per position)"
     return out
 
 
