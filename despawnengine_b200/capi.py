@@ -24,6 +24,7 @@ NO_SLOT = 0xFFFFFFFF
 FACE_TOP, FACE_BOTTOM, FACE_REAR, FACE_FRONT, FACE_RIGHT, FACE_LEFT = range(6)
 OPPOSITE_FACE = (1, 0, 3, 2, 5, 4)
 
+SEAM_HANDLE_BYTES = 128
 MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("index_count", np.uint32)])
 EDIT_DTYPE = np.dtype([("wx", np.int32), ("wy", np.int32), ("wz", np.int32), ("block", np.uint32)])
 VERTEX_DTYPE = np.dtype([("position", np.float32, 3), ("tex_coords", np.float32, 2)])  # vertex.rs:5-12
@@ -67,6 +68,10 @@ SYMBOLS = {
     "dsp_pack_border_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_set_halo_slabs": (_int, [_vp, _u64, _P(_u32), _int, _vp]),
     "dsp_clear_halo_slabs": (_int, [_vp]),
+    "dsp_seam_create": (_int, [_vp, _int, _u64, _P(_u32), _P(_u32), _vp]),
+    "dsp_seam_connect": (_int, [_vp, _u32, _vp]),
+    "dsp_seam_exchange_async": (_int, [_vp]),
+    "dsp_seam_epoch": (_u32, [_vp]),
     "dsp_visible_chunks": (_int, [_P(C.c_float), _u32, _u32, _u64, _P(_i32), _P(_u64)]),
     "dsp_scene_update": (_int, [_vp, _P(C.c_float), _vp, _vp]),
     "dsp_scene_draw_list": (_int, [_vp, _u64, _P(_i32), _vp, _P(_u64)]),
@@ -299,6 +304,26 @@ class Context:
 
     def clear_halo_slabs(self):
         self._check(lib().dsp_clear_halo_slabs(self._h))
+
+    def seam_create(self, face: int, slots):
+        """Returns (seam id, 128-byte handle to give to the neighbouring context / rank)."""
+        s = np.ascontiguousarray(slots, dtype=np.uint32).reshape(-1)
+        seam = C.c_uint32(0)
+        handle = C.create_string_buffer(SEAM_HANDLE_BYTES)
+        self._check(lib().dsp_seam_create(self._h, face, s.shape[0], _ptr(s, C.c_uint32), C.byref(seam), C.cast(handle, C.c_void_p)))
+        return int(seam.value), handle.raw
+
+    def seam_connect(self, seam: int, peer_handle: bytes):
+        assert len(peer_handle) == SEAM_HANDLE_BYTES
+        buf = C.create_string_buffer(peer_handle, SEAM_HANDLE_BYTES)
+        self._check(lib().dsp_seam_connect(self._h, seam, C.cast(buf, C.c_void_p)))
+
+    def seam_exchange_async(self):
+        self._check(lib().dsp_seam_exchange_async(self._h))
+
+    @property
+    def seam_epoch(self) -> int:
+        return int(lib().dsp_seam_epoch(self._h))
 
     # -- edits -----------------------------------------------------------------------------------------
     def apply_edits(self, edits) -> np.ndarray:

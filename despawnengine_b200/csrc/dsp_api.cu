@@ -14,8 +14,10 @@
 #include <functional>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <map>
 #include <vector>
+#include <unistd.h>
 
 #include "mesh_kernels.cuh"
 #include "quad_kernels.cuh"
@@ -72,6 +74,17 @@ struct dsp_ctx {
     struct HaloBatch { int face; uint32_t first_index; uint32_t n; std::vector<uint32_t> slots; };  // device copy of slots: d_halo_slots + first_index
     uint32_t* d_halo_slots = nullptr;  // [halo_cap], parallel to d_halo
     std::vector<HaloBatch> halo_batches;
+    // region seams (dsp_seam.inl): inboxes in this GPU's memory that neighbour GPUs write into
+    struct Seam {
+        int face = 0; uint32_t n = 0;
+        std::vector<uint32_t> slots; uint32_t* d_slots = nullptr;   // this context's boundary chunks at the seam
+        uint8_t* inbox = nullptr; size_t inbox_bytes = 0;           // ours: {flag, ack, data[2][n][256]}
+        uint8_t* peer = nullptr; bool peer_ipc = false, connected = false;  // the neighbour's inbox, mapped
+        uint32_t* d_done = nullptr;
+    };
+    std::vector<Seam> seams;
+    std::unordered_set<uint32_t> seam_slots;  // every slot listed by a seam (they may not be unloaded)
+    uint32_t seam_epoch = 0;
     uint8_t* d_arena = nullptr;
     dsp::MeshEntry* d_entries = nullptr;
     uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
@@ -411,6 +424,9 @@ int launch_quads(dsp_ctx* ctx, const dsp::MeshParams& p, uint32_t mode) {
 
 int build_neighbour_table(dsp_ctx* ctx);
 int apply_halo_batches(dsp_ctx* ctx);
+int apply_seam_batches(dsp_ctx* ctx);
+void fill_seam_params(const dsp_ctx* ctx, dsp::MeshParams& p);
+void destroy_seams(dsp_ctx* ctx);
 
 int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offset) {
     if (mode & ~(DSP_MESH_HALO | DSP_MESH_ORDERED | DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return fail(ctx, DSP_ERR_BAD_ARG, "unknown mesh mode bits 0x%x", mode);
@@ -433,6 +449,7 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.slot_list = d_list;
     p.nbr_slots = ctx->d_nbr;
     p.halo_slabs = ctx->d_halo;
+    fill_seam_params(ctx, p);
     p.uvmap = ctx->d_uvmap;
     p.n_blocks = ctx->n_blocks;
     p.first_slot = first_slot;
@@ -513,9 +530,10 @@ int validate_range(dsp_ctx* ctx, uint32_t first, uint64_t n) {
 // Received border slabs -> neighbour table, on the device: entry (slot, face) that is still "none" after the resident
 // neighbours were resolved points at the slab.  Newest batch first, so a (slot, face) registered again uses the newer slab.
 int apply_halo_batches(dsp_ctx* ctx) {
+    { int rc = apply_seam_batches(ctx); if (rc != DSP_OK) return rc; }  // a connected seam takes precedence over hand-registered slabs
     for (auto it = ctx->halo_batches.rbegin(); it != ctx->halo_batches.rend(); ++it) {
         if (it->n == 0) continue;
-        dsp::apply_halo_batch_kernel<<<(it->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nbr, ctx->d_halo_slots + it->first_index, it->face, it->first_index, it->n);
+        dsp::apply_halo_batch_kernel<<<(it->n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nbr, ctx->d_halo_slots + it->first_index, it->face, 0u, it->first_index, it->n);
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }
@@ -646,6 +664,9 @@ int finish_mesh(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total) 
     }
     if (out_total) *out_total = total;
     if (status & dsp::kStatusSpin) return fail(ctx, DSP_ERR_INTERNAL, "mesh kernel look-back timed out");
+    if (status & dsp::kStatusSeam)
+        return fail(ctx, DSP_ERR_INTERNAL, "a region seam timed out: the neighbour's border layers (or its ack) for epoch %u never arrived -- every side of a seam "
+                    "must call dsp_seam_exchange_async once per epoch, before its halo-mode mesh call", ctx->seam_epoch);
     if (status & dsp::kStatusOverflow)
         return fail(ctx, DSP_ERR_ARENA_FULL, "vertex arena too small: need %llu bytes from the given offset", (unsigned long long)total);
     return DSP_OK;
@@ -728,6 +749,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     if (!ctx) return DSP_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    destroy_seams(ctx);
     cudaFree(ctx->d_halo_slots);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_halo); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
@@ -956,6 +978,9 @@ int dsp_unload_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
     if (n && !slots) return fail(ctx, DSP_ERR_BAD_ARG, "slots is NULL");
     int rc = validate_slots(ctx, n, slots);
     if (rc != DSP_OK) return rc;
+    if (!ctx->seam_slots.empty())
+        for (uint64_t i = 0; i < n; ++i)
+            if (ctx->seam_slots.count(slots[i])) return fail(ctx, DSP_ERR_BAD_ARG, "slot %u belongs to a region seam: seam chunks stay resident for the life of the context", slots[i]);
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nothing in flight may still use the slots that are recycled
     for (uint64_t i = 0; i < n; ++i) {
@@ -1404,3 +1429,4 @@ int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_m
 }  // extern "C"
 
 #include "dsp_scene.inl"
+#include "dsp_seam.inl"

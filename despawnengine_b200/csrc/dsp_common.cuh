@@ -82,6 +82,27 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// system-scope acquire / release on 32-bit flags: region-seam hand-shake between GPUs (the writer sits across NVLink)
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// L2-coherent 128-bit load (no L1, no read-only path): data another GPU wrote into this GPU's memory during the kernel
+__device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u16(const uint16_t* p) {
+    uint16_t v;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(v) : "l"(p) : "memory");
+    return v;
+}
+
 // ---- builder-defined terrain spec (DESIGN.md "Terrain spec"); integer-only ---------------------------
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {
     h ^= h >> 16; h *= 0x7feb352dU; h ^= h >> 15; h *= 0x846ca68bU; h ^= h >> 16;

@@ -64,10 +64,58 @@ struct MeshParams {
     // kernel): when n_dev != nullptr the number of chunks is read from it and entry_map[i] is the entry index of chunk i.
     const uint32_t* n_dev;
     const uint32_t* entry_map;
+    // Work list layout: chunks that need nothing from another GPU fill it from the FRONT (count n_dev[0]), chunks with a
+    // neighbour across a region seam from the BACK (count n_dev[3], list index n_cap - 1 - k).  Tickets run over the front
+    // part first, so by the time a CTA reaches a seam chunk the neighbour GPU's border layers have usually arrived --
+    // the exchange hides behind the interior of the region, inside ONE launch (seam_wait below).
+    uint32_t n_front, n_cap;    // filled in by the kernel from n_dev
+    // Region seams (dsp_seam_*): ext_base[0] = halo_slabs; ext_base[1 + s] = the inbox buffer of seam s that holds the current
+    // epoch's border layers, written by the neighbour GPU over NVLink; seam_flag[s] = the inbox word the neighbour sets to the
+    // epoch once its layers are complete.
+    const uint16_t* ext_base[8];
+    const uint32_t* seam_flag[7];
+    uint32_t n_seams, seam_epoch;
 };
 
+constexpr uint32_t kNbrNone = 0xFFFFFFFFu;
+constexpr uint32_t kNbrExternal = 0x80000000u;  // neighbour lives on another device: bits 28-30 = source (0: dsp_set_halo_slabs,
+constexpr uint32_t kNbrSrcShift = 28u;          // 1 + s: seam s), bits 0-27 = slab index within that source
+constexpr uint32_t kNbrIndexMask = 0x0FFFFFFFu;
+constexpr uint32_t kStatusOverflow = 1u;
+constexpr uint32_t kStatusSpin = 2u;
+constexpr uint32_t kStatusSeam = 4u;  // a neighbour GPU's border layers did not arrive (dsp_seam_exchange_async missing on the peer?)
+
+// position in the work list of ticket `chunk` (identity without a device-built list)
+__device__ __forceinline__ uint32_t work_index(const MeshParams& p, uint32_t chunk) {
+    return (p.n_dev == nullptr || chunk < p.n_front) ? chunk : p.n_cap - 1u - (chunk - p.n_front);
+}
+// called at kernel start on the kernel's own copy of the parameters
+__device__ __forceinline__ void adopt_work_list(MeshParams& p) {
+    if (p.n_dev == nullptr) { p.n_front = 0u; return; }
+    p.n_cap = p.n;
+    p.n_front = p.n_dev[0];
+    p.n = p.n_front + p.n_dev[3];
+}
+// A chunk of the seam part of the list may only be culled once every neighbour GPU has delivered this epoch's layers.
+// Every thread spins for itself (acquire loads on a word in LOCAL memory that the peer sets with a system-scope release
+// after its data); the spin is bounded so that a missing peer becomes an error code, not a hung GPU.
+template <bool HALO>
+__device__ __forceinline__ void seam_wait(const MeshParams& p, uint32_t chunk) {
+    if (!HALO || p.n_seams == 0u || chunk < p.n_front) return;
+#pragma unroll
+    for (uint32_t s = 0; s < 7u; ++s) {  // (fully unrolled: a dynamic index would push the parameter block into local memory)
+        if (s >= p.n_seams) break;
+        uint32_t spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys_u32(p.seam_flag[s]) - p.seam_epoch) < 0) {
+            __nanosleep(200);
+            if (++spins > (1u << 22)) { atomicOr(p.status, kStatusSeam); break; }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t work_index(const MeshParams& p, uint32_t chunk);
 __device__ __forceinline__ MeshEntry* entry_of(const MeshParams& p, uint32_t chunk) {
-    return p.entries + (p.entry_map ? __ldg(p.entry_map + chunk) : chunk);
+    return p.entries + (p.entry_map ? __ldg(p.entry_map + work_index(p, chunk)) : chunk);
 }
 
 // Last instructions of a persistent mesh kernel (thread 0 of every CTA, after its stores were issued).
@@ -79,16 +127,12 @@ __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
     p.result[0] = atomicOr(p.status, 0u);
     p.result[1] = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), 0ull);
     p.ticket[0] = 0u;
-    p.ticket[3] = 0u;  // the work-list count of classify_chunks_kernel lives in the same 16-byte word group
+    p.ticket[3] = 0u;  // the work-list counts of classify_chunks_kernel live in the same block
+    p.ticket[6] = 0u;
     *p.status = 0u;
     *p.total_bytes = 0ull;
     *p.done = 0u;
 }
-
-constexpr uint32_t kNbrNone = 0xFFFFFFFFu;
-constexpr uint32_t kNbrExternal = 0x80000000u;  // neighbour lives on another device: low bits index halo_slabs
-constexpr uint32_t kStatusOverflow = 1u;
-constexpr uint32_t kStatusSpin = 2u;
 
 constexpr int kTileFaces = 256;
 constexpr int kTileBytes = kTileFaces * kFaceBytes;  // 30,720
@@ -193,15 +237,24 @@ __device__ __forceinline__ FaceMasks row_face_masks(const MeshParams& p, uint32_
 #pragma unroll
         for (int f = 0; f < 6; ++f) code[f] = __ldg(nb + f);  // (arithmetic neighbour slots for box worlds measured no faster)
         // occupancy of 16 consecutive voxels: row `nr` of a resident neighbour chunk, or row `sr` of a received slab
+        // (external layers are read through L2 only: a seam's inbox is written by the neighbour GPU while this kernel runs)
+        auto ext_slab = [&](uint32_t code) -> const uint16_t* {
+            const uint32_t src = (code >> kNbrSrcShift) & 7u;
+            const uint16_t* base = p.ext_base[0];
+#pragma unroll
+            for (uint32_t k = 1; k < 8u; ++k) base = src == k ? p.ext_base[k] : base;  // selects, not a dynamic index (see seam_wait)
+            return base + static_cast<size_t>(code & kNbrIndexMask) * 256;
+        };
         auto row_mask_of = [&](uint32_t code, int nr, int sr) -> uint32_t {
-            const uint16_t* base = (code & kNbrExternal) ? p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sr * 16
-                                                         : p.voxels + static_cast<size_t>(code) * kChunkVoxels + nr * 16;
-            const uint4* q = reinterpret_cast<const uint4*>(base);
+            if (code & kNbrExternal) {
+                const uint4* q = reinterpret_cast<const uint4*>(ext_slab(code) + sr * 16);
+                return nonzero_mask8(ld_cg_u4(q)) | (nonzero_mask8(ld_cg_u4(q + 1)) << 8);
+            }
+            const uint4* q = reinterpret_cast<const uint4*>(p.voxels + static_cast<size_t>(code) * kChunkVoxels + nr * 16);
             return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
         };
         auto voxel_of = [&](uint32_t code, int vidx, int sidx) -> uint32_t {
-            return (code & kNbrExternal) ? __ldg(p.halo_slabs + static_cast<size_t>(code & ~kNbrExternal) * 256 + sidx)
-                                         : __ldg(p.voxels + static_cast<size_t>(code) * kChunkVoxels + vidx);
+            return (code & kNbrExternal) ? ld_cg_u16(ext_slab(code) + sidx) : __ldg(p.voxels + static_cast<size_t>(code) * kChunkVoxels + vidx);
         };
         // slab layouts: +-Y faces [z][x], +-Z faces [y][x], +-X faces [z][y] (== row index r)
         if (y == 15) { const uint32_t s = code[0]; if (s != kNbrNone) up = row_mask_of(s, 0 + 16 * z, z); }
@@ -262,7 +315,7 @@ struct MeshCta {
         r = tid; y = r & 15; z = r >> 4;
     }
 
-    __device__ __forceinline__ uint32_t slot_of(uint32_t chunk) const { return p.slot_list ? __ldg(p.slot_list + chunk) : p.first_slot + chunk; }
+    __device__ __forceinline__ uint32_t slot_of(uint32_t chunk) const { return p.slot_list ? __ldg(p.slot_list + work_index(p, chunk)) : p.first_slot + chunk; }
 
     // thread 0 only: 8 KiB voxel tile of `chunk` -> voxel buffer `buf`, completion on s_bar[buf]
     __device__ __forceinline__ void issue_load(uint32_t chunk, int buf) const {
@@ -526,7 +579,9 @@ struct MeshCta {
 // ticket's size is published within (tile latency + count) of the ticket being taken.  The price of the reproducible
 // layout is the look-back itself: ~1.3 us per chunk on the critical path of the CTA (profiles/README.md).
 template <class Cfg, bool HALO>
-__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const MeshParams p) {
+__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const MeshParams p_in) {
+    MeshParams p = p_in;
+    adopt_work_list(p);
     extern __shared__ __align__(128) uint8_t smem[];
     MeshCta<Cfg, HALO> c(p, smem);
     const int tid = c.tid;
@@ -545,6 +600,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const
     __syncthreads();
     uint32_t cur = c.s_next[0];
     if (cur >= p.n) return;
+    seam_wait<HALO>(p, cur);  // no work list in this organisation (n_front == 0): every CTA waits for the seams first
     mbar_wait(&c.s_bar[0], 0);
     RowFaces fc = c.count_phase(cur, 0, true);
     uint32_t it = 0;
@@ -595,7 +651,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const
 template <class Cfg, bool HALO>
 __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p_in) {
     MeshParams p = p_in;
-    if (p.n_dev != nullptr) p.n = *p.n_dev;  // device-built work list (written by an earlier kernel of the same stream)
+    adopt_work_list(p);  // device-built work list (written by an earlier kernel of the same stream)
     extern __shared__ __align__(128) uint8_t smem[];
     MeshCta<Cfg, HALO> c(p, smem);
     const int tid = c.tid;
@@ -623,6 +679,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
             if (t < p.n) c.issue_load(t, buf ^ 1);  // buf^1 was released by the barrier that ended the previous iteration
         }
         c.tick(7);
+        seam_wait<HALO>(p, cur);
         mbar_wait(&c.s_bar[buf], (it >> 1) & 1);
         c.tick(2);
 #ifndef DSP_NO_EMPTY_SKIP

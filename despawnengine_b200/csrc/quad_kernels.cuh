@@ -125,7 +125,7 @@ __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox,
 template <bool HALO, bool GREEDY, bool INDEXED>
 __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p_in) {
     MeshParams p = p_in;
-    if (p.n_dev != nullptr) p.n = *p.n_dev;  // device-built work list (see classify_chunks_kernel)
+    adopt_work_list(p);  // device-built work list (see classify_chunks_kernel)
     using L = QuadSmem<GREEDY>;
     constexpr uint32_t kRecCap = L::kRecCap;
     constexpr int kTile = L::kTileQuads;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = tid, y = r & 15, z = r >> 4;   // thread r owns x-row (y, z): masks over x
-    auto slot_of = [&](uint32_t chunk) -> uint32_t { return p.slot_list ? __ldg(p.slot_list + chunk) : p.first_slot + chunk; };
+    auto slot_of = [&](uint32_t chunk) -> uint32_t { return p.slot_list ? __ldg(p.slot_list + work_index(p, chunk)) : p.first_slot + chunk; };
     auto issue_load = [&](uint32_t chunk, int buf) {
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
         bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             pending = gridDim.x + atomicAdd(p.ticket, 1u);
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
+        seam_wait<HALO>(p, cur);
         mbar_wait(&s_bar[buf], par);
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
 

@@ -321,43 +321,125 @@ __global__ void invalidate_summaries_kernel(uint8_t* summary, const uint32_t* sl
 __global__ void classify_chunks_kernel(const uint8_t* summary, const uint32_t* nbr, const uint32_t* slot_list, uint32_t first_slot, uint32_t n,
                                        uint64_t arena_offset, MeshEntry* entries, uint32_t* work_slots, uint32_t* work_entry, uint32_t* n_work) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool work = false;
+    bool work = false, seam = false;
     uint32_t slot = 0;
     if (i < n) {
         slot = slot_list ? slot_list[i] : first_slot + i;
         const uint8_t s = summary[slot];
         bool skip = (s & kSummaryAir) != 0;
-        if ((s & kSummarySolid) && nbr != nullptr) {  // (nbr == nullptr: chunk-local culling, only all-air chunks can be dropped)
-            skip = true;
+        if (nbr != nullptr) {  // (nbr == nullptr: chunk-local culling, only all-air chunks can be dropped)
+            bool buried = (s & kSummarySolid) != 0;
 #pragma unroll
             for (int f = 0; f < 6; ++f) {  // the neighbour across face f shows us its layer at the opposite face f ^ 1
                 const uint32_t q = nbr[static_cast<size_t>(slot) * 6 + f];
-                skip = skip && q != 0xFFFFFFFFu && !(q & 0x80000000u) && (summary[q] & (kSummaryLayer0 << (f ^ 1))) != 0;
+                const bool external = q != 0xFFFFFFFFu && (q & 0x80000000u) != 0u;
+                seam = seam || (external && ((q >> kNbrSrcShift) & 7u) != 0u);  // a dsp_seam_* inbox: filled by another GPU, maybe not yet
+                buried = buried && q != 0xFFFFFFFFu && !external && (summary[q] & (kSummaryLayer0 << (f ^ 1))) != 0;
             }
+            skip = skip || buried;
         }
         if (skip) entries[i] = MeshEntry{arena_offset, 0u, 0u};
         work = !skip;
+        seam = seam && work;
     }
-    const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, work);
-    if (ballot == 0u) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(n_work, static_cast<uint32_t>(__popc(ballot)));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (work) {
-        const uint32_t k = base + __popc(ballot & ((1u << lane) - 1u));
-        work_slots[k] = slot;
-        work_entry[k] = i;
+    // two warp-aggregated appends: local chunks grow the list from the front (count n_work[0]), seam chunks from the back
+    // (count n_work[3], position n - 1 - k): the mesh kernel's tickets reach the seam chunks last
+    const int lane = threadIdx.x & 31;
+    const uint32_t b_front = __ballot_sync(0xFFFFFFFFu, work && !seam), b_back = __ballot_sync(0xFFFFFFFFu, seam);
+    if (b_front) {
+        const int leader = __ffs(b_front) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(n_work, static_cast<uint32_t>(__popc(b_front)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (work && !seam) {
+            const uint32_t k = base + __popc(b_front & ((1u << lane) - 1u));
+            work_slots[k] = slot;
+            work_entry[k] = i;
+        }
+    }
+    if (b_back) {
+        const int leader = __ffs(b_back) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(n_work + 3, static_cast<uint32_t>(__popc(b_back)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (seam) {
+            const uint32_t k = n - 1u - (base + __popc(b_back & ((1u << lane) - 1u)));
+            work_slots[k] = slot;
+            work_entry[k] = i;
+        }
     }
 }
-// neighbour table entry (slots[i], face) := external slab first_index + i, unless a resident neighbour is already there
-__global__ void apply_halo_batch_kernel(uint32_t* nbr, const uint32_t* slots, int face, uint32_t first_index, uint32_t n) {
+// neighbour table entry (slots[i], face) := external slab first_index + i of source `src` (0: dsp_set_halo_slabs store,
+// 1 + s: inbox of seam s), unless a resident neighbour is already there
+__global__ void apply_halo_batch_kernel(uint32_t* nbr, const uint32_t* slots, int face, uint32_t src, uint32_t first_index, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t s = slots[i];
     if (s == 0xFFFFFFFFu) return;  // unloaded since
     uint32_t* e = nbr + static_cast<size_t>(s) * 6 + face;
-    if (*e == 0xFFFFFFFFu) *e = 0x80000000u | (first_index + i);
+    if (*e == 0xFFFFFFFFu) *e = kNbrExternal | (src << kNbrSrcShift) | (first_index + i);
+}
+
+// ---- region seams between GPUs (dsp_seam_*) ------------------------------------------------------------------------
+// Inbox of one seam, allocated by the RECEIVING context and mapped into the sender (same process: peer access; another
+// process: CUDA IPC).  The sender writes everything in it: its border layers for epoch e into data[e & 1], then `flag` = e
+// (system-scope release); `ack` = the last epoch of OUR layers the peer has finished reading.
+struct SeamInbox {
+    uint32_t flag;       // newest complete epoch in data[]
+    uint32_t pad0[31];
+    uint32_t ack;        // the peer is done with the layers we sent it for every epoch <= ack
+    uint32_t pad1[31];
+    // uint16_t data[2][n][256] follows at byte 256
+};
+constexpr size_t kSeamInboxHeader = 256;
+
+// One launch per seam and exchange.  (1) tell the peer which of its epochs we are done with: everything on this stream
+// before this launch -- in particular every mesh launch that read the peer's layers of epoch e - 1 -- has completed, so
+// ack = e - 1; (2) wait until the peer has released the buffer we are about to overwrite (it last held our epoch e - 2);
+// (3) write this epoch's layers straight into the peer's inbox over NVLink (plain coalesced stores through the peer
+// mapping: 512 B per chunk face); (4) the last CTA publishes flag = e behind a system-scope fence.
+struct SeamPushParams {
+    const uint16_t* voxels;
+    const uint32_t* slots;    // this context's boundary chunks at the seam, canonical order
+    uint32_t n;
+    int face;
+    uint32_t epoch;
+    SeamInbox* peer;          // the neighbour's inbox (peer-mapped)
+    const SeamInbox* mine;    // our inbox: the peer writes `ack` here
+    uint32_t* done;           // CTA counter (local), zeroed by the last CTA
+    uint32_t* status;         // context status word: kStatusSeam on time-out
+};
+__global__ void __launch_bounds__(256) seam_push_kernel(const SeamPushParams p) {
+    const int t = threadIdx.x, a = t >> 4, b = t & 15;
+    if (blockIdx.x == 0 && t == 0) st_release_sys_u32(&p.peer->ack, p.epoch - 1u);
+    if (p.epoch >= 3u) {
+        uint32_t spins = 0;
+        while (static_cast<int32_t>(ld_acquire_sys_u32(&p.mine->ack) - (p.epoch - 2u)) < 0) {
+            __nanosleep(200);
+            if (++spins > (1u << 22)) { if (t == 0) atomicOr(p.status, kStatusSeam); break; }
+        }
+    }
+    int idx;
+    switch (p.face) {  // as pack_border_slabs_kernel: +-Y [z][x], +-Z [y][x], +-X [z][y]
+        case 0: idx = b + 16 * 15 + 256 * a; break;
+        case 1: idx = b + 256 * a; break;
+        case 2: idx = b + 16 * a; break;
+        case 3: idx = b + 16 * a + 256 * 15; break;
+        case 4: idx = 16 * b + 256 * a; break;
+        default: idx = 15 + 16 * b + 256 * a; break;
+    }
+    uint16_t* out = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(p.peer) + kSeamInboxHeader) + static_cast<size_t>(p.epoch & 1u) * p.n * 256;
+    for (uint32_t i = blockIdx.x; i < p.n; i += gridDim.x)
+        out[static_cast<size_t>(i) * 256 + t] = p.voxels[static_cast<size_t>(p.slots[i]) * kChunkVoxels + idx];
+    __threadfence_system();  // this thread's stores are performed at the peer before the CTA counts itself out
+    __syncthreads();
+    if (t == 0) {
+        if (atomicAdd(p.done, 1u) == gridDim.x - 1u) {
+            __threadfence_system();
+            st_release_sys_u32(&p.peer->flag, p.epoch);
+            *p.done = 0u;
+        }
+    }
 }
 __global__ void scatter_u32_kernel(uint32_t* dst, const uint2* idx_val, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -8,7 +8,7 @@ from typing import Dict, Tuple
 import numpy as np
 
 from . import capi
-from .partition import Region, SlabPartition, exchange_halos
+from .partition import Region, SlabPartition, connect_seams, exchange_halos
 
 
 class RegionOnDevice:
@@ -54,3 +54,21 @@ def exchange_region_halos(dev: RegionOnDevice, partition: SlabPartition, rank: i
         torch.cuda.synchronize(device)
 
     return exchange_halos(partition.seam_transfers(rank), pack, torch.empty_like, unpack, dist=dist, sync=sync)
+
+
+def connect_region_seams(dev: RegionOnDevice, partition: SlabPartition, rank: int, dist=None):
+    """In-library seams (dsp_seam_*, the product path): creates this rank's inboxes, swaps the 128-byte handles with the
+    neighbouring ranks once (all_gather_object; `dist` None = single process, nothing to connect) and maps the peers' inboxes.
+    From then on `dev.ctx.seam_exchange_async()` followed by a DSP_MESH_HALO call is all an epoch takes: the border layers
+    travel by peer stores over NVLink and the wait for them sits inside the mesh kernel, behind the interior chunks."""
+    transfers = partition.seam_transfers(rank)
+    if not transfers:
+        return []
+
+    def all_gather(obj):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, obj)
+        return out
+
+    return connect_seams(transfers, rank, lambda face, positions: dev.ctx.seam_create(face, dev.slots_of(positions)),
+                         dev.ctx.seam_connect, all_gather)

@@ -188,3 +188,27 @@ def exchange_halos(transfers: Sequence[SeamTransfer], pack: Callable[[np.ndarray
         import sys
         print(f"[trace] halo exchange: pack {1e3 * (t1 - t0):.2f} ms, send/recv {1e3 * (t2 - t1):.2f} ms, register {1e3 * (time.perf_counter() - t2):.2f} ms", file=sys.stderr)
     return sum(int(b.numel()) * int(b.element_size()) for b in send_bufs)
+
+
+def connect_seams(transfers: Sequence[SeamTransfer], rank: int, create: Callable[[int, np.ndarray], Tuple[int, bytes]],
+                  connect: Callable[[int, bytes], None], all_gather: Callable[[dict], List[dict]]) -> List[int]:
+    """Sets up the in-library seams (dsp_seam_*) of `rank`: one seam per transfer, created with `create(face, positions)
+    -> (seam id, handle)`; every rank publishes {(rank, face): handle} through `all_gather` (torch.distributed
+    all_gather_object on GPUs and in the gloo tests; any host channel will do -- it runs once, at set-up) and connects
+    each of its seams to the handle its peer published for the OPPOSITE face.  Returns the seam ids in transfer order.
+    After this, an exchange is `dsp_seam_exchange_async` on every rank: device-to-device stores over NVLink, no host
+    in the data path."""
+    mine, seams = {}, []
+    for t in transfers:
+        seam, handle = create(t.send_face, t.positions)
+        mine[(rank, t.send_face)] = handle
+        seams.append(seam)
+    published = {}
+    for d in all_gather(mine):
+        published.update(d)
+    for t, seam in zip(transfers, seams):
+        key = (t.peer, OPPOSITE_FACE[t.send_face])
+        if key not in published:
+            raise KeyError(f"rank {t.peer} published no seam handle for face {OPPOSITE_FACE[t.send_face]} (wanted by rank {rank})")
+        connect(seam, published[key])
+    return seams

@@ -231,6 +231,29 @@ int dsp_pack_border_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int f
 int dsp_set_halo_slabs(dsp_ctx* ctx, uint64_t n, const uint32_t* slots, int face, const void* src_device);
 int dsp_clear_halo_slabs(dsp_ctx* ctx); /* forgets every registered slab (the buffers are kept for the next exchange) */
 
+/* Seams inside the library: peer memory instead of pack -> copy -> register.  Each side of a seam creates an INBOX in its own
+ * HBM and hands the other side a handle to it; an exchange is one small kernel per seam that writes this GPU's border
+ * layers straight into the neighbour's inbox over NVLink (peer access within a process, CUDA IPC between processes) and
+ * flags the epoch; the DSP_MESH_HALO call that follows meshes the interior of the region first and lets a CTA that reaches
+ * a seam chunk wait on the (local) inbox flag -- the transfer hides behind the interior inside ONE mesh launch, with no
+ * host synchronisation anywhere.  Nothing like this exists in the reference (single process, chunk-local cull,
+ * chunk_mesh.rs:46-51); semantics are those of DSP_MESH_HALO: results equal a single context holding the whole world.
+ *
+ *   rank r: dsp_seam_create(face, slots)  ->  seam id + handle          (slots: r's boundary chunks at `face`, in an order
+ *           hand the 128-byte handle to the neighbour by any means          both sides agree on; the neighbour lists ITS
+ *           dsp_seam_connect(seam, neighbour's handle)                      boundary chunks at the opposite face, same order)
+ *   per frame / epoch, on every rank:  dsp_seam_exchange_async(ctx);  dsp_mesh_*(..., DSP_MESH_HALO, ...);
+ *
+ * Exchanges are collective over a seam (both sides, once per epoch, before the halo-mode mesh calls of that epoch); a side
+ * that never shows up turns into DSP_ERR_INTERNAL after a bounded wait (~1 s), not a hang.  Seam chunks cannot be unloaded.
+ * Two contexts on the SAME device: enqueue the exchange of both before either mesh call (a spinning mesh kernel can keep a
+ * later push kernel of the same GPU from being scheduled). */
+typedef struct dsp_seam_handle { uint8_t bytes[128]; } dsp_seam_handle;
+int dsp_seam_create(dsp_ctx* ctx, int face, uint64_t n, const uint32_t* slots, uint32_t* out_seam, dsp_seam_handle* out_handle);
+int dsp_seam_connect(dsp_ctx* ctx, uint32_t seam, const dsp_seam_handle* peer_handle);
+int dsp_seam_exchange_async(dsp_ctx* ctx); /* all seams of the context; asynchronous on the context's stream */
+uint32_t dsp_seam_epoch(const dsp_ctx* ctx); /* number of exchanges started so far */
+
 /* ---- scene: GameScene::update's visible set -> load -> mesh -> unload cycle (engine/scenes/scene_game.rs:39-82) -------- */
 typedef struct dsp_scene_config {
     uint32_t horizontal_render_distance; /* "Horizonal Render Distance" of settings.json5 (engine/core/user_settings.rs:55-75) */

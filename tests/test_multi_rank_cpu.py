@@ -79,6 +79,24 @@ def _rank_main(rank, world_size, port, out_dir):
             want = halo_mesh(p, full, {})
             assert got.tobytes() == want.tobytes(), (rank, p)
             n_seam += any((p, f) in halo for f in range(6))
+        # in-library seams (dsp_seam_*): the set-up routing -- who creates which inbox, whose handle is mapped where -- is host
+        # logic shared with the GPU path; here the "handles" just name their inbox
+        created, connected = [], {}
+
+        def create(face, positions):
+            created.append((face, len(positions)))
+            return len(created) - 1, f"inbox(rank={rank},face={face},n={len(positions)})".encode().ljust(128, b"\0")
+
+        def all_gather(obj):
+            out = [None] * world_size
+            dist.all_gather_object(out, obj)
+            return out
+
+        seams = part.connect_seams(sp.seam_transfers(rank), rank, create, lambda seam, handle: connected.__setitem__(seam, handle.rstrip(b"\0").decode()), all_gather)
+        assert seams == list(range(len(sp.seam_transfers(rank))))
+        per_seam = WORLD.dims[1] * WORLD.dims[2]
+        for t, seam in zip(sp.seam_transfers(rank), seams):
+            assert connected[seam] == f"inbox(rank={t.peer},face={part.OPPOSITE_FACE[t.send_face]},n={per_seam})"
         total = torch.tensor([len(chunks), n_seam], dtype=torch.int64)
         dist.all_reduce(total)
         assert int(total[0]) == WORLD.n_chunks and int(total[1]) == 2 * (world_size - 1) * WORLD.dims[1] * WORLD.dims[2]

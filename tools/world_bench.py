@@ -31,14 +31,16 @@ def main():
     ap.add_argument("--small-output-batch", type=int, default=262144, help="chunks per launch in the halo / greedy modes (their output is 10-20x smaller)")
     ap.add_argument("--arena-gib", type=float, default=8.0)
     ap.add_argument("--quad-modes", action="store_true", help="also run the greedy + indexed modes (chunk-local and halo culling)")
-    ap.add_argument("--verify", action="store_true", help="check a sample of seam chunks against the oracle (small worlds)")
+    ap.add_argument("--verify", action="store_true", help="check a sample of seam chunks (and some interior ones) against the oracle, at any world size")
+    ap.add_argument("--seam", choices=["c", "torch"], default="c", help="c: dsp_seam_* inside the library (peer stores over NVLink, wait inside the mesh kernel); "
+                    "torch: pack -> torch.distributed isend/irecv (NCCL) -> dsp_set_halo_slabs, the multi-process fallback")
     args = ap.parse_args()
 
     import torch
     import torch.distributed as dist
     from despawnengine_b200 import capi
     from despawnengine_b200 import partition as part
-    from despawnengine_b200.halo import RegionOnDevice, exchange_region_halos
+    from despawnengine_b200.halo import RegionOnDevice, connect_region_seams, exchange_region_halos
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -73,24 +75,40 @@ def main():
     barrier()
     gen_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
 
+    seam_setup_s = 0.0
+    if world > 1 and args.seam == "c":
+        t0 = time.perf_counter()
+        connect_region_seams(dev, sp, rank, dist)  # once: inboxes, handle swap, peer mapping
+        seam_setup_s = time.perf_counter() - t0
+
     out = []
     modes = [("parity", capi.MESH_PARITY), ("halo", capi.MESH_HALO)]
     if args.quad_modes:
         modes += [("greedy_indexed", capi.MESH_GREEDY | capi.MESH_INDEXED), ("halo_greedy_indexed", capi.MESH_HALO | capi.MESH_GREEDY | capi.MESH_INDEXED)]
     for mode_name, mode in modes:
         xchg_s, xchg_bytes = 0.0, 0
-        if mode & capi.MESH_HALO:
+        c_seams = bool(mode & capi.MESH_HALO) and world > 1 and args.seam == "c"
+        if (mode & capi.MESH_HALO) and world > 1 and args.seam == "torch":
             ctx.clear_halo_slabs()
-            if world > 1:  # first exchange pays NCCL's lazy point-to-point setup; time the second
-                exchange_region_halos(dev, sp, rank, dist)
-                ctx.clear_halo_slabs()
+            exchange_region_halos(dev, sp, rank, dist)  # first exchange pays NCCL's lazy point-to-point setup; time the second
             barrier()
             t0 = time.perf_counter()
-            if world > 1:
-                xchg_bytes = exchange_region_halos(dev, sp, rank, dist)
+            xchg_bytes = exchange_region_halos(dev, sp, rank, dist)
             ctx.sync()
             barrier()
-            xchg_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+            xchg_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX)
+        if c_seams:
+            # an exchange on its own, for the record (enqueue -> all ranks' pushes complete); in the timed pass below it is
+            # enqueued in front of the mesh launches and nobody waits for it on the host
+            ctx.seam_exchange_async(); ctx.mesh_range(dev.first_slot, min(n, 1024), mode)  # epoch 1 (warm-up)
+            barrier()
+            t0 = time.perf_counter()
+            ctx.seam_exchange_async()
+            ctx.sync()
+            barrier()
+            xchg_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX)
+            ctx.mesh_range(dev.first_slot, min(n, 1024), mode)
+            xchg_bytes = sp.seam_bytes(rank)
         batch = args.batch if mode == capi.MESH_PARITY else args.small_output_batch
         # warm-up batch (also builds the neighbour table in halo mode)
         ctx.mesh_range(dev.first_slot, min(n, args.batch), mode)
@@ -98,6 +116,8 @@ def main():
         vbytes = 0
         barrier()
         t0 = time.perf_counter()
+        if c_seams:
+            ctx.seam_exchange_async()  # this epoch's border layers: on their way while the interior is meshed
         for b0 in range(0, n, batch):
             m = min(batch, n - b0)
             ctx.mesh_range_async(dev.first_slot + b0, m, mode)
@@ -110,7 +130,8 @@ def main():
         line = {"workload": f"configs[4]: {args.dims[0]}x{args.dims[2]}x{args.dims[1]}-chunk world (x,z,y-up), X-slab partition", "mode": mode_name,
                 "n_gpus": world, "chunks": W.n_chunks, "chunks_per_gpu": n, "batch": batch,
                 "terrain_fill_s": gen_s, "terrain_fill_GBps_per_gpu": n * 8192 / gen_s / 1e9,
-                "halo_exchange_s": xchg_s, "halo_bytes_sent_rank0": xchg_bytes,
+                "halo_exchange_s": xchg_s, "halo_bytes_sent_rank0": xchg_bytes, "seam_path": (args.seam if (mode & capi.MESH_HALO) and world > 1 else None),
+                "halo_exchange_inside_mesh_wall": bool(c_seams), "seam_setup_s": seam_setup_s,
                 "mesh_wall_s": mesh_s, "chunks_per_s": W.n_chunks / mesh_s, "voxels_per_s": W.n_chunks * 4096 / mesh_s,
                 "vertex_bytes": vbytes_all, "hbm_algorithmic_GBps_per_gpu": (vbytes_all / world + n * 8224) / mesh_s / 1e9,
                 "scaling": "strong", "timing": "wall clock between barriers, max over ranks; one sync per batch"}
