@@ -38,7 +38,7 @@ def test_three_slabs_on_one_gpu_match_one_context(uv_default):
     """Three contexts (a middle rank has two seams), several epochs with edits in between, greedy + indexed mode as well."""
     world = part.Region((-4, 5, 1), (7, 4, 3))
     sp = part.SlabPartition(world, 3)
-    with capi.Context(0, 256, 256 << 20) as whole, capi.Context(0, 128, 128 << 20) as c0, capi.Context(0, 128, 128 << 20) as c1, \\
+    with capi.Context(0, 256, 256 << 20) as whole, capi.Context(0, 128, 128 << 20) as c0, capi.Context(0, 128, 128 << 20) as c1, \
             capi.Context(0, 128, 128 << 20) as c2:
         ctxs = [c0, c1, c2]
         for c in [whole] + ctxs:
@@ -100,7 +100,7 @@ def test_seam_errors(uv_default):
         with pytest.raises(capi.DspError):
             a.seam_connect(sa, ha)         # same face on both sides
         with pytest.raises(capi.DspError):
-            a.seam_connect(sa, b"\\0" * 128)  # not a handle
+            a.seam_connect(sa, b"\0" * 128)  # not a handle
         a.seam_connect(sa, hb)
         with pytest.raises(capi.DspError):
             a.seam_connect(sa, hb)         # twice
