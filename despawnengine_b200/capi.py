@@ -25,6 +25,7 @@ FACE_TOP, FACE_BOTTOM, FACE_REAR, FACE_FRONT, FACE_RIGHT, FACE_LEFT = range(6)
 OPPOSITE_FACE = (1, 0, 3, 2, 5, 4)
 
 SEAM_HANDLE_BYTES = 128
+CREATE_EXPORTABLE_ARENA = 1
 MESH_ENTRY_DTYPE = np.dtype([("offset_bytes", np.uint64), ("vertex_count", np.uint32), ("index_count", np.uint32)])
 EDIT_DTYPE = np.dtype([("wx", np.int32), ("wy", np.int32), ("wz", np.int32), ("block", np.uint32)])
 VERTEX_DTYPE = np.dtype([("position", np.float32, 3), ("tex_coords", np.float32, 2)])  # vertex.rs:5-12
@@ -41,6 +42,7 @@ _vp, _u64, _u32, _i32, _int = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int32, C.c
 _P = C.POINTER
 SYMBOLS = {
     "dsp_create": (_int, [_int, _u64, _u64, _P(_vp)]),
+    "dsp_create_ex": (_int, [_int, _u64, _u64, _u32, _P(_vp)]),
     "dsp_destroy": (_int, [_vp]),
     "dsp_last_error": (C.c_char_p, [_vp]),
     "dsp_status_string": (C.c_char_p, [_int]),
@@ -58,6 +60,7 @@ SYMBOLS = {
     "dsp_mesh_chunks": (_int, [_vp, _u64, _P(_u32), _u32, _u64, _vp, _P(_u64)]),
     "dsp_mesh_range": (_int, [_vp, _u32, _u64, _u32, _u64, _vp, _P(_u64)]),
     "dsp_mesh_host_chunks": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _u32, _u64, _P(_u32), _vp, _P(_u64)]),
+    "dsp_mesh_host_chunks_to_host": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _u32, _u64, _P(_u32), _vp, _P(_u64), _vp, _u64]),
     "dsp_mesh_range_async": (_int, [_vp, _u32, _u64, _u32, _u64]),
     "dsp_mesh_chunks_async": (_int, [_vp, _u64, _P(_u32), _u32, _u64]),
     "dsp_sync": (_int, [_vp]),
@@ -78,6 +81,10 @@ SYMBOLS = {
     "dsp_scene_reset": (_int, [_vp]),
     "dsp_download_arena": (_int, [_vp, _u64, _u64, _vp]),
     "dsp_download_chunk": (_int, [_vp, _u32, _P(C.c_uint16), _P(_i32)]),
+    "dsp_arena_export_fd": (_int, [_vp, _P(_int), _P(_u64)]),
+    "dsp_arena_import_fd": (_int, [_int, _int, _u64, _P(_vp), _P(_vp)]),
+    "dsp_arena_import_read": (_int, [_vp, _u64, _u64, _vp]),
+    "dsp_arena_import_close": (_int, [_vp]),
     "dsp_arena_device_ptr": (_vp, [_vp]),
     "dsp_arena_bytes": (_u64, [_vp]),
     "dsp_voxel_device_ptr": (_vp, [_vp]),
@@ -126,6 +133,29 @@ def visible_chunks(camera_pos, horizontal: int, vertical: int) -> np.ndarray:
     return out
 
 
+class ArenaImport:
+    """CUDA-side importer of an exported arena (dsp_arena_import_fd): another process' view of the same HBM bytes."""
+
+    def __init__(self, device: int, fd: int, allocation_bytes: int):
+        self._h, ptr = C.c_void_p(), C.c_void_p()
+        rc = lib().dsp_arena_import_fd(device, fd, allocation_bytes, C.byref(self._h), C.byref(ptr))
+        if rc != OK:
+            raise DspError(rc, lib().dsp_last_error(None).decode())
+        self.device_ptr = int(ptr.value)
+
+    def read(self, offset: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        rc = lib().dsp_arena_import_read(self._h, offset, nbytes, out.ctypes.data_as(C.c_void_p))
+        if rc != OK:
+            raise DspError(rc, lib().dsp_last_error(None).decode())
+        return out
+
+    def close(self):
+        if self._h:
+            lib().dsp_arena_import_close(self._h)
+            self._h = C.c_void_p()
+
+
 class DspError(RuntimeError):
     def __init__(self, status: int, message: str):
         super().__init__(f"[{status}: {lib().dsp_status_string(status).decode()}] {message}")
@@ -139,9 +169,9 @@ def _ptr(a: np.ndarray, ctype):
 class Context:
     """Thin RAII wrapper: one context per GPU, single caller (SURVEY.md section 8b 'Threading')."""
 
-    def __init__(self, device: int = 0, max_chunks: int = 4096, arena_bytes: int = 1 << 30):
+    def __init__(self, device: int = 0, max_chunks: int = 4096, arena_bytes: int = 1 << 30, exportable_arena: bool = False):
         self._h = C.c_void_p()
-        rc = lib().dsp_create(device, max_chunks, arena_bytes, C.byref(self._h))
+        rc = lib().dsp_create_ex(device, max_chunks, arena_bytes, CREATE_EXPORTABLE_ARENA if exportable_arena else 0, C.byref(self._h))
         if rc != OK:
             raise DspError(rc, lib().dsp_last_error(None).decode())
         self.device = device
@@ -274,6 +304,26 @@ class Context:
                                                None, entries_out.ctypes.data_as(C.c_void_p), C.byref(total)))
         return int(total.value)
 
+    def mesh_host_chunks_to_host_ptr(self, n: int, pos: np.ndarray, blocks_host_ptr: int, entries_out: np.ndarray, host_vertices_ptr: int,
+                                     host_capacity: int, mode: int = MESH_PARITY, arena_offset: int = 0) -> int:
+        """dsp_mesh_host_chunks_to_host with caller-owned (pinned) host buffers; returns total bytes."""
+        total = C.c_uint64(0)
+        self._check(lib().dsp_mesh_host_chunks_to_host(self._h, n, _ptr(pos, C.c_int32), C.cast(blocks_host_ptr, C.POINTER(C.c_uint16)), mode, arena_offset,
+                                                       None, entries_out.ctypes.data_as(C.c_void_p), C.byref(total), C.c_void_p(host_vertices_ptr), host_capacity))
+        return int(total.value)
+
+    def mesh_host_chunks_to_host(self, pos, blocks, mode: int = MESH_PARITY, arena_offset: int = 0, capacity: int = 0):
+        """Returns (entries, total bytes, host mirror of the arena window as a u8 array)."""
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        n = pos.shape[0]
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(n, 4096)
+        entries = np.zeros(n, dtype=MESH_ENTRY_DTYPE)
+        host = np.empty(capacity or n * 1474560, dtype=np.uint8)
+        total = C.c_uint64(0)
+        self._check(lib().dsp_mesh_host_chunks_to_host(self._h, n, _ptr(pos, C.c_int32), _ptr(blocks, C.c_uint16), mode, arena_offset, None,
+                                                       entries.ctypes.data_as(C.c_void_p), C.byref(total), host.ctypes.data_as(C.c_void_p), host.shape[0]))
+        return entries, int(total.value), host[: int(total.value)]
+
     def mesh_range_async(self, first_slot: int, n: int, mode: int = MESH_PARITY, arena_offset: int = 0):
         self._check(lib().dsp_mesh_range_async(self._h, first_slot, n, mode, arena_offset))
 
@@ -401,6 +451,13 @@ class Context:
         pos = np.zeros(3, dtype=np.int32)
         self._check(lib().dsp_download_chunk(self._h, slot, _ptr(ids, C.c_uint16), _ptr(pos, C.c_int32)))
         return ids, pos
+
+    def arena_export_fd(self):
+        """(fd, allocation bytes) of an exportable arena: pass the fd to the importer (Vulkan external memory, another CUDA
+        process) and close it afterwards."""
+        fd, size = C.c_int(-1), C.c_uint64(0)
+        self._check(lib().dsp_arena_export_fd(self._h, C.byref(fd), C.byref(size)))
+        return int(fd.value), int(size.value)
 
     @property
     def arena_device_ptr(self) -> int:

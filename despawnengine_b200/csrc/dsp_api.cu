@@ -52,6 +52,8 @@ struct dsp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of dsp_mesh_host_chunks, overlapped with meshing on `stream`
+    cudaStream_t d2h_stream = nullptr;   // vertices -> host of dsp_mesh_host_chunks_to_host (created on first use)
+    cudaEvent_t ev_meshed[64] = {};
     static constexpr int kMaxSub = 64;   // sub-batches of one pipelined call
     cudaEvent_t ev_sub[kMaxSub] = {};
     cudaEvent_t ev_done = nullptr;
@@ -86,6 +88,8 @@ struct dsp_ctx {
     std::unordered_set<uint32_t> seam_slots;  // every slot listed by a seam (they may not be unloaded)
     uint32_t seam_epoch = 0;
     uint8_t* d_arena = nullptr;
+    unsigned long long arena_vmm_handle = 0;  // DSP_CREATE_EXPORTABLE_ARENA: CUmemGenericAllocationHandle of the arena (dsp_export.inl)
+    size_t arena_vmm_size = 0;                // ... and its size rounded to the allocation granularity (0: plain cudaMalloc arena)
     dsp::MeshEntry* d_entries = nullptr;
     uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
     uint32_t* d_slots = nullptr;
@@ -422,6 +426,8 @@ int launch_quads(dsp_ctx* ctx, const dsp::MeshParams& p, uint32_t mode) {
     return launch_quads_t<HALO, false, true>(ctx, p);
 }
 
+int alloc_exportable_arena(dsp_ctx* ctx, uint64_t bytes, std::string* err);
+void free_exportable_arena(dsp_ctx* ctx);
 int build_neighbour_table(dsp_ctx* ctx);
 int apply_halo_batches(dsp_ctx* ctx);
 int apply_seam_batches(dsp_ctx* ctx);
@@ -694,8 +700,11 @@ const char* dsp_status_string(int s) {
 
 const char* dsp_last_error(const dsp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** out_ctx) {
+int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** out_ctx) { return dsp_create_ex(device, max_chunks, arena_bytes, 0u, out_ctx); }
+
+int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_t flags, dsp_ctx** out_ctx) {
     if (!out_ctx) return fail(nullptr, DSP_ERR_BAD_ARG, "out_ctx is NULL");
+    if (flags & ~DSP_CREATE_EXPORTABLE_ARENA) return fail(nullptr, DSP_ERR_BAD_ARG, "unknown dsp_create_ex flags 0x%x", flags);
     *out_ctx = nullptr;
     if (max_chunks == 0 || max_chunks >= 0x80000000ull) return fail(nullptr, DSP_ERR_BAD_ARG, "max_chunks must be in [1, 2^31-1]");
     if (arena_bytes % DSP_SLOT_ALIGN != 0) return fail(nullptr, DSP_ERR_BAD_ARG, "arena_bytes must be a multiple of 128");
@@ -723,7 +732,10 @@ int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** 
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaMalloc(&ctx->d_voxels, max_chunks * dsp::kChunkBytes)) != cudaSuccess) return bail("cudaMalloc(voxel store)", e);
     if ((e = cudaMalloc(&ctx->d_pos, max_chunks * sizeof(int4))) != cudaSuccess) return bail("cudaMalloc(chunk positions)", e);
-    if ((e = cudaMalloc(&ctx->d_arena, std::max<uint64_t>(arena_bytes, 128))) != cudaSuccess) return bail("cudaMalloc(vertex arena)", e);
+    if (flags & DSP_CREATE_EXPORTABLE_ARENA) {
+        std::string why;
+        if (alloc_exportable_arena(ctx, arena_bytes, &why) != DSP_OK) { dsp_destroy(ctx); return fail(nullptr, DSP_ERR_CUDA, "exportable arena: %s", why.c_str()); }
+    } else if ((e = cudaMalloc(&ctx->d_arena, std::max<uint64_t>(arena_bytes, 128))) != cudaSuccess) return bail("cudaMalloc(vertex arena)", e);
     if ((e = cudaMalloc(&ctx->d_entries, max_chunks * sizeof(dsp::MeshEntry))) != cudaSuccess) return bail("cudaMalloc(entries)", e);
     if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks + 64)) != cudaSuccess) return bail("cudaMalloc(control)", e);
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
@@ -751,8 +763,11 @@ int dsp_destroy(dsp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     destroy_seams(ctx);
     cudaFree(ctx->d_halo_slots);
+    if (ctx->arena_vmm_size) free_exportable_arena(ctx);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_halo); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
+    for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_meshed[i]) cudaEventDestroy(ctx->ev_meshed[i]);
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     cudaFree(ctx->d_tickets);
@@ -1060,19 +1075,33 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
     return finish_mesh(ctx, out_entries, out_total_bytes);
 }
 
-int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
-                         uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes) {
+// dsp_mesh_host_chunks, optionally followed (pipelined) by the device->host copy of the vertices: host_vertices != NULL
+// mirrors the arena window [arena_offset, arena_offset + total) into host memory (entry offsets minus arena_offset index it).
+static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+                                 uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices, uint64_t host_capacity) {
     if (!ctx) return DSP_ERR_BAD_ARG;
     if (out_total_bytes) *out_total_bytes = 0;
     if (n && (!pos || !blocks)) return fail(ctx, DSP_ERR_BAD_ARG, "pos/blocks is NULL");
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = check_mesh_args(ctx, n, mode, arena_offset);
     if (rc != DSP_OK) return rc;
+    const bool readback = host_vertices != nullptr;
+    if (readback && !ctx->d2h_stream) {
+        DSP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < dsp_ctx::kMaxSub; ++i) DSP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_meshed[i], cudaEventDisableTiming));
+    }
     if (mode & (DSP_MESH_ORDERED | DSP_MESH_HALO)) {  // these need the whole batch resident first: plain load, then mesh
         std::vector<uint32_t> slots(n);
         if ((rc = dsp_load_chunks(ctx, n, pos, blocks, nullptr, nullptr, slots.data())) != DSP_OK) return rc;
         if (out_slots) std::memcpy(out_slots, slots.data(), n * sizeof(uint32_t));
-        return dsp_mesh_chunks(ctx, n, slots.data(), mode, arena_offset, out_entries, out_total_bytes);
+        uint64_t total = 0;
+        if ((rc = dsp_mesh_chunks(ctx, n, slots.data(), mode, arena_offset, out_entries, &total)) != DSP_OK) return rc;
+        if (out_total_bytes) *out_total_bytes = total;
+        if (readback) {
+            if (total > host_capacity) return fail(ctx, DSP_ERR_BAD_ARG, "host vertex buffer too small: %llu bytes needed, %llu given", (unsigned long long)total, (unsigned long long)host_capacity);
+            return total ? dsp_download_arena(ctx, arena_offset, total, host_vertices) : DSP_OK;
+        }
+        return DSP_OK;
     }
     ctx->last_mesh_n = n;
     const bool trace = getenv("DSP_TRACE") != nullptr;
@@ -1115,10 +1144,24 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
         ctx->stream = main_stream;
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
         release_fresh_slots(ctx, fresh_slots);
         stage_release(ctx);
         ctx->err = msg;
         return code;
+    };
+    uint64_t* const h_cursor = reinterpret_cast<uint64_t*>(ctx->h_pinned + 512);  // kMaxSub x u64 of the 4 KiB pinned block
+    int last_sub = -1;
+    uint64_t copied_to = 0;
+    const uint64_t room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
+    auto copy_out = [&](int j) -> int {  // vertices of sub-batch j: arena [copied_to, cursor(j)) -> host, on the third stream
+        DSP_CUDA(ctx, cudaEventSynchronize(ctx->ev_meshed[j]));
+        const uint64_t hi = std::min<uint64_t>(std::min<uint64_t>(h_cursor[j], room), host_capacity);
+        if (hi > copied_to) {
+            DSP_CUDA(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(host_vertices) + copied_to, ctx->d_arena + arena_offset + copied_to, hi - copied_to, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            copied_to = hi;
+        }
+        return DSP_OK;
     };
     for (int j = 0; j < subs; ++j) {
         const uint64_t i0 = sub_begin[j], m = sub_begin[j + 1] - i0;
@@ -1151,13 +1194,42 @@ int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uin
             return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the copy pipeline"));
         if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j)) != DSP_OK) return bail(rc);
         tr("sub-batch enqueued");
+        if (readback) {
+            // where the cursor stands after this sub-batch: its vertices are the arena bytes [cursor(j-1), cursor(j))
+            if (cudaMemcpyAsync(h_cursor + j, ctx->d_ctl + 16, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess)
+                return bail(fail(ctx, DSP_ERR_CUDA, "cursor read-back failed in the copy pipeline"));
+            // ... and the PREVIOUS sub-batch's vertices leave for the host now: its kernel has finished (this wait is short, the
+            // copy of sub-batch j is what the host would otherwise idle behind), the next upload is already in the DMA queue
+            if (last_sub >= 0 && (rc = copy_out(last_sub)) != DSP_OK) return bail(rc);
+            last_sub = j;
+        }
     }
+    if (readback && last_sub >= 0 && (rc = copy_out(last_sub)) != DSP_OK) return bail(rc);
     if (out_slots) std::memcpy(out_slots, h_slots, n * sizeof(uint32_t));
     if ((rc = stage_release(ctx)) != DSP_OK) return rc;
     if (trace) { cudaStreamSynchronize(ctx->copy_stream); tr("copies done"); }
-    rc = finish_mesh(ctx, out_entries, out_total_bytes);
+    uint64_t total = 0;
+    rc = finish_mesh(ctx, out_entries, &total);
+    if (out_total_bytes) *out_total_bytes = total;
+    if (readback) {
+        DSP_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
+        if (rc == DSP_OK && total > host_capacity)
+            return fail(ctx, DSP_ERR_BAD_ARG, "host vertex buffer too small: %llu bytes needed, %llu given (what fits was copied)", (unsigned long long)total, (unsigned long long)host_capacity);
+    }
     tr("finished");
     return rc;
+}
+
+int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+                         uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes) {
+    return mesh_host_chunks_impl(ctx, n, pos, blocks, mode, arena_offset, out_slots, out_entries, out_total_bytes, nullptr, 0);
+}
+
+int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+                                 uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices, uint64_t host_capacity) {
+    if (ctx && !host_vertices) return fail(ctx, DSP_ERR_BAD_ARG, "host_vertices is NULL");
+    return mesh_host_chunks_impl(ctx, n, pos, blocks, mode, arena_offset, out_slots, out_entries, out_total_bytes, host_vertices, host_capacity);
 }
 
 int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty) {
@@ -1430,3 +1502,4 @@ int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_m
 
 #include "dsp_scene.inl"
 #include "dsp_seam.inl"
+#include "dsp_export.inl"

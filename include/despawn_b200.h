@@ -102,6 +102,10 @@ typedef struct dsp_edit {
 /* Creates a context on CUDA device `device`: a voxel store of max_chunks slots (8 KiB each) and a
  * vertex arena of arena_bytes.  Replaces World::new + World::set_allocator (world.rs:18-25, 76-78). */
 int dsp_create(int device, uint64_t max_chunks, uint64_t arena_bytes, dsp_ctx** out_ctx);
+/* dsp_create with options.  DSP_CREATE_EXPORTABLE_ARENA: the vertex arena is a CUDA virtual-memory allocation that
+ * dsp_arena_export_fd can hand to another API or process (see "arena export" below); everything else is unchanged. */
+#define DSP_CREATE_EXPORTABLE_ARENA 1u
+int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_t flags, dsp_ctx** out_ctx);
 int dsp_destroy(dsp_ctx* ctx);
 const char* dsp_last_error(const dsp_ctx* ctx); /* never NULL; ctx may be NULL for create failures */
 const char* dsp_status_string(int status);
@@ -172,6 +176,17 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
  * every slot it created is released. */
 int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
                          uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes);
+
+/* The same with the vertices delivered to HOST memory, for a consumer that is not on this GPU (B200 has no raster units:
+ * whatever draws the meshes -- the reference's Vulkan device, chunk_mesh.rs:111-124 -- sits across PCIe unless it imports
+ * the arena, see dsp_arena_export_fd).  host_vertices (pinned for a truly asynchronous copy) receives a byte-for-byte mirror of
+ * the arena window [arena_offset, arena_offset + *out_total_bytes): chunk i's data is at host_vertices +
+ * (out_entries[i].offset_bytes - arena_offset).  Three streams: the upload of sub-batch k+1, the meshing of sub-batch k and the
+ * download of sub-batch k-1 overlap (PCIe is full duplex).  With 6-vertex unit quads the download is ~12x the upload and
+ * bounds the call; DSP_MESH_GREEDY | DSP_MESH_INDEXED output is ~15x smaller and the call returns to the upload's pace. */
+int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+                                 uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices,
+                                 uint64_t host_capacity);
 
 /* Asynchronous forms: enqueue on the context's stream and return; results are read with
  * dsp_mesh_result after dsp_sync.  Let a caller overlap meshing with its own work (the reference is
@@ -302,6 +317,23 @@ void* dsp_voxel_device_ptr(dsp_ctx* ctx);   /* max_chunks x 4096 u16; after writ
 void* dsp_entries_device_ptr(dsp_ctx* ctx); /* dsp_mesh_entry[n] of the last mesh call */
 void* dsp_stream(dsp_ctx* ctx);             /* cudaStream_t all work of this context is enqueued on */
 uint64_t dsp_max_chunks(const dsp_ctx* ctx);
+
+/* ---- arena export: the vertex arena as an external-memory object (zero-copy consumers) ----------------------------------
+ * The reference's mesh ends up in a Vulkan vertex buffer (chunk_mesh.rs:111-124).  A context created with
+ * DSP_CREATE_EXPORTABLE_ARENA can export its arena as a POSIX file descriptor (cuMemExportToShareableHandle): Vulkan imports
+ * it with VK_KHR_external_memory_fd (VkImportMemoryFdInfoKHR, VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT; the engine would
+ * add the extension next to khr_swapchain, engine/rendering/vulkan.rs:34-37) and binds a VERTEX_BUFFER over it -- the
+ * dsp_mesh_entry offsets index that buffer directly; another CUDA process imports it with dsp_arena_import_fd.  The fd is the
+ * caller's to pass on (SCM_RIGHTS / inheritance) and to close; each call returns a new one.  *out_allocation_bytes (>=
+ * dsp_arena_bytes, rounded to the allocation granularity) is the size an importer must map.  INTEGRATION.md has the
+ * Vulkano-side snippet. */
+int dsp_arena_export_fd(dsp_ctx* ctx, int* out_fd, uint64_t* out_allocation_bytes);
+/* CUDA-side importer: maps the allocation behind `fd` on `device` of THIS process; *out_device_ptr then aliases the exporting
+ * context's arena.  No context needed; errors through dsp_last_error(NULL). */
+typedef struct dsp_arena_import dsp_arena_import;
+int dsp_arena_import_fd(int device, int fd, uint64_t allocation_bytes, dsp_arena_import** out_import, void** out_device_ptr);
+int dsp_arena_import_read(dsp_arena_import* imp, uint64_t offset_bytes, uint64_t bytes, void* host_dst); /* blocking copy to host */
+int dsp_arena_import_close(dsp_arena_import* imp);
 
 /* Number of kernel launches this context has enqueued since creation (bench accounting). */
 uint64_t dsp_kernel_launches(const dsp_ctx* ctx);
