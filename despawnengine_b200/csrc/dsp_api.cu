@@ -94,6 +94,7 @@ struct dsp_ctx {
     uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
     uint32_t* d_slots = nullptr;
     uint8_t* d_summary = nullptr;     // per slot: dsp::kSummary* (all air / uniformly solid / unknown)
+    uint16_t* d_uid = nullptr;        // per slot, valid while the summary says "no air": the one block id of the chunk, or kUidMixed
     uint32_t* d_work_slots = nullptr; // device-built work list of halo-mode mesh calls (allocated on first use)
     uint32_t* d_work_entry = nullptr;
     float4* d_uv_rows = nullptr;
@@ -500,17 +501,34 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     ctx->ctl_clean = false;  // until the launch below is known to have been enqueued
     bool work_list = false;
     const bool halo_prepass = (mode & DSP_MESH_HALO) != 0;
-    const bool air_prepass = !halo_prepass && (mode & DSP_MESH_GREEDY) && n >= 16384;  // large merged-quad calls: drop the all-air chunks
-    if ((halo_prepass || air_prepass) && !ordered) {
+    // merged-quad calls with chunk-local culling: all-air chunks and chunks of one solid block id are finished by the pre-pass
+    // from their summaries (six quads, no tile read); worth its launch from about a thousand chunks on
+    const bool greedy_prepass = !halo_prepass && (mode & DSP_MESH_GREEDY) && n >= 1024;
+    if ((halo_prepass || greedy_prepass) && !ordered) {
         // Cross-chunk culling leaves most chunks of a large world without a single face (all air, or solid among solid
         // neighbours): a pre-pass over the chunk summaries writes their empty entries and hands the mesh kernel only the rest.
         if (!ctx->d_work_slots) {
             DSP_CUDA(ctx, cudaMalloc(&ctx->d_work_slots, ctx->max_chunks * sizeof(uint32_t)));
             DSP_CUDA(ctx, cudaMalloc(&ctx->d_work_entry, ctx->max_chunks * sizeof(uint32_t)));
         }
-        dsp::classify_chunks_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_summary, halo_prepass ? ctx->d_nbr : nullptr, d_list, first_slot, static_cast<uint32_t>(n), arena_offset, ctx->d_entries, ctx->d_work_slots, ctx->d_work_entry,
-            reinterpret_cast<uint32_t*>(ctx->d_ctl) + 3);
+        const unsigned cgrid = static_cast<unsigned>((n + 255) / 256);
+        if (greedy_prepass) {
+            dsp::ClassifyGreedyParams cp{};
+            cp.summary = ctx->d_summary; cp.uid = ctx->d_uid; cp.chunk_pos = ctx->d_pos; cp.slot_list = d_list; cp.first_slot = first_slot;
+            cp.n = static_cast<uint32_t>(n); cp.arena_offset = arena_offset;
+            cp.arena_room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
+            cp.arena = ctx->d_arena + arena_offset; cp.entries = ctx->d_entries; cp.work_slots = ctx->d_work_slots; cp.work_entry = ctx->d_work_entry;
+            cp.n_work = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 3;
+            cp.total_bytes = reinterpret_cast<unsigned long long*>(ctx->d_ctl + 16);
+            cp.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
+            cp.uvmap = ctx->d_uvmap; cp.n_blocks = ctx->n_blocks;
+            if (mode & DSP_MESH_INDEXED) dsp::classify_greedy_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(cp);
+            else dsp::classify_greedy_kernel<false><<<cgrid, 256, 0, ctx->stream>>>(cp);
+        } else {
+            dsp::classify_chunks_kernel<<<cgrid, 256, 0, ctx->stream>>>(
+                ctx->d_summary, ctx->d_nbr, d_list, first_slot, static_cast<uint32_t>(n), arena_offset, ctx->d_entries, ctx->d_work_slots, ctx->d_work_entry,
+                reinterpret_cast<uint32_t*>(ctx->d_ctl) + 3);
+        }
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
         work_list = true;
@@ -741,6 +759,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
     if ((e = cudaMalloc(&ctx->d_summary, max_chunks)) != cudaSuccess) return bail("cudaMalloc(chunk summaries)", e);
     if ((e = cudaMemset(ctx->d_summary, 0, max_chunks)) != cudaSuccess) return bail("cudaMemset(chunk summaries)", e);
+    if ((e = cudaMalloc(&ctx->d_uid, max_chunks * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc(uniform ids)", e);
     if ((e = cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
     cudaMemset(ctx->d_phase, 0, 16 * sizeof(unsigned long long));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -771,6 +790,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     cudaFree(ctx->d_tickets);
+    cudaFree(ctx->d_uid);
     cudaFree(ctx->d_summary); cudaFree(ctx->d_work_slots); cudaFree(ctx->d_work_entry);
     cudaFree(ctx->d_phase); cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -835,7 +855,7 @@ static int generate_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, in
     const uint32_t* d_list; uint32_t first;
     int rc = upload_positions_and_slots(ctx, m, todo_pos.data(), todo_slots.data(), &d_list, &first);
     if (rc != DSP_OK) { cudaStreamSynchronize(ctx->stream); release_fresh_slots(ctx, fresh_slots); return rc; }
-    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(m), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary};
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(m), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary, ctx->d_uid};
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(m, static_cast<uint64_t>(ctx->num_sms) * 64));
     dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
@@ -871,7 +891,7 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
     ctx->nbr_dirty = true;
     if (gen_kind == DSP_GEN_NOISE) {
         // heightmap computed once per chunk column and reused up the stack (terrain_fill_region_noise_kernel)
-        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed, ctx->d_summary};
+        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed, ctx->d_summary, ctx->d_uid};
         // enough CTAs to fill the machine a few times over, but as tall a run per CTA as that allows
         const uint64_t columns = static_cast<uint64_t>(dims[0]) * dims[2], want = static_cast<uint64_t>(ctx->num_sms) * 16;
         uint32_t pieces = static_cast<uint32_t>(std::min<uint64_t>(dims[1], std::max<uint64_t>(1, (want + columns - 1) / columns)));
@@ -885,7 +905,7 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
         if (n > 0xFFFFFFFFull) return fail(ctx, DSP_ERR_BAD_ARG, "region too large");
         // positions are arithmetic in a box: the fill kernel derives them from the chunk's index and records them itself
         dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed,
-                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos, ctx->d_summary};
+                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos, ctx->d_summary, ctx->d_uid};
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
         dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
         DSP_CUDA(ctx, cudaGetLastError());
@@ -917,6 +937,7 @@ int dsp_clone_region(dsp_ctx* ctx, uint32_t src_first_slot, const int32_t new_or
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_voxels + static_cast<size_t>(first) * dsp::kChunkVoxels, ctx->d_voxels + static_cast<size_t>(from.first_slot) * dsp::kChunkVoxels,
                                   n * dsp::kChunkBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_summary + first, ctx->d_summary + from.first_slot, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_uid + first, ctx->d_uid + from.first_slot, n * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
     dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
         ctx->d_pos, first, make_int3(new_origin[0], new_origin[1], new_origin[2]), make_uint3(from.dims[0], from.dims[1], from.dims[2]), n);
     DSP_CUDA(ctx, cudaGetLastError());

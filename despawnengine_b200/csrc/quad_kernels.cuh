@@ -102,10 +102,9 @@ struct QuadGeom {
     float4 uv;
     uint32_t code;
 };
-__device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox, float cbx, float cby, float cbz,
-                                              const float4* __restrict__ uvmap, uint32_t n_blocks) {
+__device__ __forceinline__ QuadGeom quad_geom_of_id(uint32_t rec, uint32_t id, float cbx, float cby, float cbz,
+                                                    const float4* __restrict__ uvmap, uint32_t n_blocks) {
     const uint32_t idx = rec & 0xFFFu, d = (rec >> 12) & 7u, w1 = (rec >> 15) & 15u, h1 = (rec >> 19) & 15u;
-    const uint32_t id = vox[idx];
     QuadGeom g;
     const uint32_t row = id < n_blocks ? id : n_blocks;  // last row = the reference's fallback (chunk_mesh.rs:53-56)
     g.uv = __ldg(&uvmap[row]);
@@ -120,6 +119,10 @@ __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox,
     g.lz = __fadd_rn(-0.5f, __fadd_rn(__uint2float_rn(az), cbz));  g.hz = __fadd_rn(0.5f, __fadd_rn(__uint2float_rn(fz), cbz));
     g.code = static_cast<uint32_t>((d < 3 ? kCodes0 >> (20 * d) : kCodes1 >> (20 * (d - 3))) & 0xFFFFFu);
     return g;
+}
+__device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox, float cbx, float cby, float cbz,
+                                              const float4* __restrict__ uvmap, uint32_t n_blocks) {
+    return quad_geom_of_id(rec, vox[rec & 0xFFFu], cbx, cby, cbz, uvmap, n_blocks);
 }
 
 template <bool HALO, bool GREEDY, bool INDEXED>
@@ -388,10 +391,6 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             }
             if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
             __syncthreads();  // records visible
-            if (tid == 0 && q0 == 0) {  // first touch of the claim's result: after the barrier, so the CTA never waits on that atomic
-                if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                *entry_of(p, cur) = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
-            }
             const uint32_t q1 = min(Q, q0 + kRecCap);
             for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {
                 if (f0 > q0) {  // (for the window's first tile the records barrier above did this)
@@ -440,6 +439,13 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
                 fence_proxy_async_smem();
                 __syncthreads();
+                // First touch of the claim's result: here, after the tile has been expanded -- the atomic's round trip (a hot
+                // address: every chunk of the launch claims from it) hides behind the record and expansion phases instead of
+                // holding the whole CTA at the barrier above (26 % of this kernel's stall samples sat on that wait in round 1).
+                if (tid == 0 && f0 == 0) {
+                    if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                    *entry_of(p, cur) = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
+                }
                 if (tid == 0 && claimed + quad_slot_bytes(Q, INDEXED) <= p.arena_room) {
                     uint8_t* const gout = p.arena + claimed;
                     uint8_t* const gidx = gout + quad_vertex_region_bytes(Q, true);

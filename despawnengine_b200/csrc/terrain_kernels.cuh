@@ -11,6 +11,7 @@
 #pragma once
 #include "dsp_common.cuh"
 #include "mesh_kernels.cuh"  // MeshEntry
+#include "quad_kernels.cuh"  // quad geometry for the uniform-chunk shortcut of classify_greedy_kernel
 
 namespace dsp {
 
@@ -28,6 +29,7 @@ struct TerrainParams {
     uint3 dims;
     int4* chunk_pos_out;
     uint8_t* summary;  // per slot: kSummaryUnknown / kSummaryAir / kSummarySolid, written where the generator knows (may be nullptr)
+    uint16_t* uid;     // per slot, meaningful only while summary has kSummarySolid: the block id every voxel has, or kUidMixed
 };
 
 // Chunk summaries let the halo-mode mesh call drop all-air chunks and chunks buried among solid neighbours before the mesh
@@ -36,6 +38,7 @@ struct TerrainParams {
 // Bits: air = every voxel is air; solid = no voxel is air; layer f = the one-voxel border layer at face f (order top,
 // bottom, rear, front, right, left) has no air.  0 = nothing known.  A solid chunk is buried, i.e. has no visible face,
 // when across every face a RESIDENT neighbour's facing layer is solid.
+constexpr uint16_t kUidMixed = 0xFFFFu;  // (uid side array) free of air, but more than one block id -- or not known
 constexpr uint8_t kSummaryUnknown = 0, kSummaryAir = 1, kSummarySolid = 2, kSummaryLayer0 = 4, kSummaryAllSolid = 2 | (63 << 2);
 
 // smoothstep-weighted bilinear value noise on a lattice whose values were hashed once per chunk
@@ -153,7 +156,17 @@ __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p
             __syncthreads();
             summary = s_red[0] & s_red[1] & s_red[2] & s_red[3] & s_red[4] & s_red[5] & s_red[6] & s_red[7];
         }
-        if (tid == 0 && p.summary != nullptr) p.summary[slot] = static_cast<uint8_t>(summary);
+        if (tid == 0 && p.summary != nullptr) {
+            p.summary[slot] = static_cast<uint8_t>(summary);
+            if (summary & kSummarySolid) {
+                // reference rule: a full chunk is all "template:dirt" = 1; noise: id 1 below the surface voxel (id 2), so the chunk
+                // is uniformly 1 when its top layer lies under every column's surface voxel: top <= h - 2 for all columns
+                uint16_t uid = kUidMixed;
+                if (p.kind == 0) uid = 1;
+                else if (p.kind == 1) { int32_t lo = s_h[0]; for (int k = 1; k < 256; ++k) lo = min(lo, s_h[k]); if (cp.y * 16 + 15 <= lo - 2) uid = 1; }
+                p.uid[slot] = uid;
+            }
+        }
         if (p.kind == 1 || p.kind == 2) __syncthreads();  // s_h / s_lat / s_red reused by the next chunk of this CTA
     }
 }
@@ -173,6 +186,7 @@ struct RegionFillParams {
     uint32_t ny;         // chunks of a column handled by one CTA
     uint32_t seed;
     uint8_t* summary;    // see TerrainParams
+    uint16_t* uid;
 };
 
 __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const RegionFillParams p) {
@@ -257,6 +271,7 @@ __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const Re
                     bits |= (top <= lo_z0 - 1 ? kSummaryLayer0 << 2 : 0u) | (top <= lo_z15 - 1 ? kSummaryLayer0 << 3 : 0u);
                     bits |= (top <= lo_x0 - 1 ? kSummaryLayer0 << 4 : 0u) | (top <= lo_x15 - 1 ? kSummaryLayer0 << 5 : 0u);
                     p.summary[slot] = static_cast<uint8_t>(bits);
+                    if (bits & kSummarySolid) p.uid[slot] = top <= lo - 2 ? uint16_t(1) : kUidMixed;  // all body blocks under every surface voxel
                 }
             }
         }
@@ -369,6 +384,98 @@ __global__ void classify_chunks_kernel(const uint8_t* summary, const uint32_t* n
         }
     }
 }
+// Pre-pass of DSP_MESH_GREEDY calls with chunk-local culling.  Most chunks of a terrain are uniform: all air (no mesh, the
+// reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20) or one solid block id throughout (exactly six 16x16 quads, one
+// per side, whatever the id).  Where the generators left a summary that says so, the chunk never reaches the mesh kernel and
+// its 8 KiB tile is never read: air chunks get their empty entry here, and a uniform solid chunk's six quads are written
+// here by one warp (slot claimed from the same cursor the mesh kernel uses, same order and arithmetic as its in-kernel
+// uniform path: BOTTOM, REAR, RIGHT at voxel 0, LEFT at (15,0,0), TOP at (0,15,0), FRONT at (0,0,15)).  Everything else --
+// surface chunks, and every chunk whose summary is unknown (host uploads, edits) -- goes to the work list.
+struct ClassifyGreedyParams {
+    const uint8_t* summary;
+    const uint16_t* uid;
+    const int4* chunk_pos;
+    const uint32_t* slot_list;
+    uint32_t first_slot, n;
+    uint64_t arena_offset, arena_room;
+    uint8_t* arena;                 // already offset by arena_offset
+    MeshEntry* entries;
+    uint32_t* work_slots;
+    uint32_t* work_entry;
+    uint32_t* n_work;
+    unsigned long long* total_bytes;  // the arena cursor of the call
+    uint32_t* status;
+    const float4* uvmap;
+    uint32_t n_blocks;
+};
+template <bool INDEXED>
+__global__ void __launch_bounds__(256) classify_greedy_kernel(const ClassifyGreedyParams p) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int kind = 0;  // 0: nothing (i >= n or skipped), 1: work list, 2: uniform solid
+    uint32_t slot = 0, uid = 0;
+    if (i < p.n) {
+        slot = p.slot_list ? p.slot_list[i] : p.first_slot + i;
+        const uint8_t s = p.summary[slot];
+        if (s & kSummaryAir) p.entries[i] = MeshEntry{p.arena_offset, 0u, 0u};
+        else if ((s & kSummarySolid) && (uid = p.uid[slot]) != kUidMixed) kind = 2;
+        else kind = 1;
+    }
+    const uint32_t b_work = __ballot_sync(0xFFFFFFFFu, kind == 1);
+    if (b_work) {
+        const int leader = __ffs(b_work) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(p.n_work, static_cast<uint32_t>(__popc(b_work)));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (kind == 1) {
+            const uint32_t k = base + __popc(b_work & ((1u << lane) - 1u));
+            p.work_slots[k] = slot;
+            p.work_entry[k] = i;
+        }
+    }
+    uint32_t b_uni = __ballot_sync(0xFFFFFFFFu, kind == 2);
+    if (b_uni == 0u) return;
+    // one slot for all uniform chunks of the warp: a single atomic, sub-allocated in lane order
+    constexpr uint32_t kSlot = INDEXED ? (512u + 256u) : 768u;  // align128(6 x 80) + align128(6 x 24) / align128(6 x 120)
+    const uint32_t n_uni = __popc(b_uni);
+    unsigned long long wbase = 0;
+    if (lane == 0) wbase = atomicAdd(p.total_bytes, static_cast<unsigned long long>(n_uni) * kSlot);
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+    const bool fits = wbase + static_cast<unsigned long long>(n_uni) * kSlot <= p.arena_room;
+    if (!fits && lane == 0) atomicOr(p.status, kStatusOverflow);
+    uint32_t ord = 0;
+    while (b_uni) {
+        const int src = __ffs(b_uni) - 1;
+        b_uni &= b_uni - 1;
+        const uint32_t c_slot = __shfl_sync(0xFFFFFFFFu, slot, src), c_i = __shfl_sync(0xFFFFFFFFu, i, src), c_id = __shfl_sync(0xFFFFFFFFu, uid, src);
+        const unsigned long long base = wbase + static_cast<unsigned long long>(ord++) * kSlot;
+        if (lane == 0) p.entries[c_i] = MeshEntry{p.arena_offset + base, INDEXED ? 24u : 36u, INDEXED ? 36u : 0u};
+        if (!fits) continue;
+        const int4 cp = __ldg(&p.chunk_pos[c_slot]);
+        const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f), cby = __fmul_rn(__int2float_rn(cp.y), 16.0f), cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
+        float* out = reinterpret_cast<float*>(p.arena + base);
+        constexpr int kVerts = INDEXED ? 4 : 6, kWordsPerQuad = kVerts * 5;
+        for (int w = lane; w < 6 * kWordsPerQuad; w += 32) {
+            const int q = w / kWordsPerQuad, rem = w - q * kWordsPerQuad, v = rem / 5, c = rem - v * 5;
+            const uint32_t rec = (q == 0 ? (0u | (1u << 12)) : q == 1 ? (0u | (2u << 12)) : q == 2 ? (0u | (4u << 12)) : q == 3 ? (15u | (5u << 12))
+                                  : q == 4 ? (240u | (0u << 12)) : (3840u | (3u << 12))) | (15u << 15) | (15u << 19);
+            const QuadGeom g = quad_geom_of_id(rec, c_id, cbx, cby, cbz, p.uvmap, p.n_blocks);
+            const int k = INDEXED ? v : (v < 3 ? v : (v == 3 ? 2 : (v == 4 ? 3 : 0)));  // stream order c0,c1,c2,c2,c3,c0
+            const uint32_t cc = g.code >> (5 * k);
+            const float val = c == 0 ? ((cc & 1u) ? g.hx : g.lx) : c == 1 ? ((cc & 2u) ? g.hy : g.ly) : c == 2 ? ((cc & 4u) ? g.hz : g.lz)
+                              : c == 3 ? ((cc & 8u) ? g.uv.z : g.uv.x) : ((cc & 16u) ? g.uv.w : g.uv.y);
+            out[w] = val;
+        }
+        if (INDEXED) {
+            uint32_t* io = reinterpret_cast<uint32_t*>(p.arena + base + 512);
+            for (int w = lane; w < 36; w += 32) {
+                const int q = w / 6, j = w - q * 6;
+                io[w] = 4u * q + (j < 3 ? j : (j == 3 ? 2 : (j == 4 ? 3 : 0)));
+            }
+        }
+    }
+}
+
 // neighbour table entry (slots[i], face) := external slab first_index + i of source `src` (0: dsp_set_halo_slabs store,
 // 1 + s: inbox of seam s), unless a resident neighbour is already there
 __global__ void apply_halo_batch_kernel(uint32_t* nbr, const uint32_t* slots, int face, uint32_t src, uint32_t first_index, uint32_t n) {
