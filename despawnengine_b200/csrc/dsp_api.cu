@@ -471,6 +471,7 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
         p.slot_list = ctx->d_work_slots;
         p.entry_map = ctx->d_work_entry;
         p.n_dev = reinterpret_cast<const uint32_t*>(ctx->d_ctl) + 3;
+        p.uid = ctx->d_uid;
     }
     if (self_reset) {
         p.done = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 2;

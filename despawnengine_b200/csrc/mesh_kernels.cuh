@@ -64,6 +64,7 @@ struct MeshParams {
     // kernel): when n_dev != nullptr the number of chunks is read from it and entry_map[i] is the entry index of chunk i.
     const uint32_t* n_dev;
     const uint32_t* entry_map;
+    const uint16_t* uid;        // per slot: the chunk's one block id where classify_greedy_kernel listed it as uniform
     // Work list layout: chunks that need nothing from another GPU fill it from the FRONT (count n_dev[0]), chunks with a
     // neighbour across a region seam from the BACK (count n_dev[3], list index n_cap - 1 - k).  Tickets run over the front
     // part first, so by the time a CTA reaches a seam chunk the neighbour GPU's border layers have usually arrived --
@@ -129,6 +130,7 @@ __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
     p.ticket[0] = 0u;
     p.ticket[3] = 0u;  // the work-list counts of classify_chunks_kernel live in the same block
     p.ticket[6] = 0u;
+    p.ticket[7] = 0u;  // (uniform-chunk count of classify_greedy_kernel)
     *p.status = 0u;
     *p.total_bytes = 0ull;
     *p.done = 0u;

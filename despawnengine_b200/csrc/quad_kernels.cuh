@@ -73,19 +73,21 @@ __device__ __forceinline__ uint32_t eq_prev_mask16(const uint4 a0, const uint4 a
 __device__ __forceinline__ uint32_t run_starts(uint32_t f, uint32_t eq) { return f & ~((f << 1) & eq); }
 __device__ __forceinline__ uint32_t run_ends(uint32_t f, uint32_t eq) { return f & ~((f >> 1) & (eq >> 1)); }
 
-// start bits of row b whose run is identical (start, end, block id) to a run of the previous row a
-__device__ __forceinline__ uint32_t continued_runs(uint32_t fa, uint32_t eqa, uint32_t fb, uint32_t eqb, uint32_t eqv) {
+// Start bits of row b whose run is identical (start, end, block id) to a run of the previous row a.  TWO directions at once:
+// the low and high halves of every argument are two independent 16-bit problems that share the id-equality masks (eqa, eqb,
+// eqv are the 16-bit masks replicated into both halves; their bit 0 / 16 is clear, so no shift below leaks across the halves,
+// and bit 15 of a half is always a run end).  Branch-free: "the two rows' end masks agree on every cell of the run" is a
+// segmented suffix-OR of the disagreement towards each run's first cell, four doubling steps over the 16 cells.
+__device__ __forceinline__ uint32_t continued_runs2(uint32_t fa, uint32_t eqa, uint32_t fb, uint32_t eqb, uint32_t eqv) {
     const uint32_t eb = run_ends(fb, eqb);
-    uint32_t cand = run_starts(fa, eqa) & run_starts(fb, eqb) & eqv;
-    const uint32_t diff = run_ends(fa, eqa) ^ eb;
-    uint32_t out = 0;
-    while (cand) {
-        const int u0 = __ffs(cand) - 1;
-        cand &= cand - 1;
-        const int len1 = __ffs(eb >> u0) - 1;  // run length - 1
-        if (((diff >> u0) & ((2u << len1) - 1u)) == 0u) out |= 1u << u0;
-    }
-    return out;
+    const uint32_t cand = run_starts(fa, eqa) & run_starts(fb, eqb) & eqv;
+    uint32_t acc = (run_ends(fa, eqa) ^ eb) & fb;   // cells of b where the rows disagree about "a run ends here"
+    uint32_t open = fb & ~eb;                       // cell x and cell x + 1 belong to the same run of b
+    acc |= (acc >> 1) & open;  open &= open >> 1;
+    acc |= (acc >> 2) & open;  open &= open >> 2;
+    acc |= (acc >> 4) & open;  open &= open >> 4;
+    acc |= (acc >> 8) & open;
+    return cand & ~acc;
 }
 
 // (Q <= 12,288, so every size below fits 32 bits)
@@ -123,6 +125,31 @@ __device__ __forceinline__ QuadGeom quad_geom_of_id(uint32_t rec, uint32_t id, f
 __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox, float cbx, float cby, float cbz,
                                               const float4* __restrict__ uvmap, uint32_t n_blocks) {
     return quad_geom_of_id(rec, vox[rec & 0xFFFu], cbx, cby, cbz, uvmap, n_blocks);
+}
+
+// A chunk of one solid block id under chunk-local culling is exactly six 16 x 16 quads, in stream order BOTTOM, REAR, RIGHT
+// anchored at voxel 0, LEFT at (15,0,0), TOP at (0,15,0), FRONT at (0,0,15).  Slot: align128(6 x 120) or align128(6 x 80) + align128(6 x 24).
+__host__ __device__ constexpr uint32_t uniform_chunk_slot_bytes(bool indexed) { return indexed ? 512u + 256u : 768u; }
+__device__ __forceinline__ uint32_t uniform_chunk_record(int q) {
+    return (q == 0 ? (0u | (1u << 12)) : q == 1 ? (0u | (2u << 12)) : q == 2 ? (0u | (4u << 12)) : q == 3 ? (15u | (5u << 12))
+            : q == 4 ? (240u | (0u << 12)) : (3840u | (3u << 12))) | (15u << 15) | (15u << 19);
+}
+// One 32-bit word per thread (t < 180 stream, t < 120 + 36 indexed) straight to the chunk's arena slot `out`.
+template <bool INDEXED>
+__device__ __forceinline__ void emit_uniform_chunk(uint8_t* out, const int4 cp, uint32_t id, const float4* __restrict__ uvmap, uint32_t n_blocks, int t) {
+    constexpr int kVerts = INDEXED ? 4 : 6, kWordsPerQuad = kVerts * 5, kWords = 6 * kWordsPerQuad;
+    if (t < kWords) {
+        const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f), cby = __fmul_rn(__int2float_rn(cp.y), 16.0f), cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
+        const int q = t / kWordsPerQuad, rem = t - q * kWordsPerQuad, v = rem / 5, c = rem - v * 5;
+        const QuadGeom g = quad_geom_of_id(uniform_chunk_record(q), id, cbx, cby, cbz, uvmap, n_blocks);
+        const int k = INDEXED ? v : (v < 3 ? v : (v == 3 ? 2 : (v == 4 ? 3 : 0)));  // stream order c0, c1, c2, c2, c3, c0
+        const uint32_t cc = g.code >> (5 * k);
+        reinterpret_cast<float*>(out)[t] = c == 0 ? ((cc & 1u) ? g.hx : g.lx) : c == 1 ? ((cc & 2u) ? g.hy : g.ly) : c == 2 ? ((cc & 4u) ? g.hz : g.lz)
+                                           : c == 3 ? ((cc & 8u) ? g.uv.z : g.uv.x) : ((cc & 16u) ? g.uv.w : g.uv.y);
+    } else if (INDEXED && t < kWords + 36) {
+        const int w = t - kWords, q = w / 6, j = w - q * 6;
+        reinterpret_cast<uint32_t*>(out + 512)[w] = 4u * q + (j < 3 ? j : (j == 3 ? 2 : (j == 4 ? 3 : 0)));
+    }
 }
 
 template <bool HALO, bool GREEDY, bool INDEXED>
@@ -171,6 +198,18 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         s_next[0] = blockIdx.x;
         if (blockIdx.x < p.n) issue_load(blockIdx.x, 0);
         pending = gridDim.x + atomicAdd(p.ticket, 1u);
+    }
+    if (GREEDY && !HALO && p.n_dev != nullptr) {
+        // chunks that classify_greedy_kernel found to be one solid block id (slot and entry are already there): their six quads,
+        // a few chunks per CTA, while the first tile is on its way
+        const uint32_t n_uni = p.n_dev[4];
+        for (uint32_t u = blockIdx.x; u < n_uni; u += gridDim.x) {
+            const uint32_t li = p.n_cap - 1u - u;
+            const uint32_t slot = __ldg(p.slot_list + li);
+            const uint64_t off = p.entries[__ldg(p.entry_map + li)].offset_bytes - p.arena_offset;
+            if (off + uniform_chunk_slot_bytes(INDEXED) <= p.arena_room)
+                emit_uniform_chunk<INDEXED>(p.arena + off, __ldg(&p.chunk_pos[slot]), p.uid[slot], p.uvmap, p.n_blocks, tid);
+        }
     }
     __syncthreads();
     uint32_t cur = s_next[0];
@@ -260,18 +299,20 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 s_SE45[r] = S45;
                 s_SE45[kRows + r] = E45;
                 __syncthreads();
-                // ---- 3. continued runs -> anchors
-                uint32_t Cm[4] = {0u, 0u, 0u, 0u};
+                // ---- 3. continued runs -> anchors (TOP | BOTTOM << 16 against the row one z below, REAR | FRONT << 16 against y - 1)
+                uint32_t Cm01 = 0u, Cm23 = 0u;
+                const uint32_t eqx2 = eqx | (eqx << 16);
                 if (z > 0) {
                     const uint32_t eqa = s_eqx[r - 16];
-                    Cm[0] = continued_runs(s_F[0 * kRows + r - 16], eqa, A[0], eqx, eqz);
-                    Cm[1] = continued_runs(s_F[1 * kRows + r - 16], eqa, A[1], eqx, eqz);
+                    Cm01 = continued_runs2(s_F[0 * kRows + r - 16] | (static_cast<uint32_t>(s_F[1 * kRows + r - 16]) << 16), eqa | (eqa << 16),
+                                           A[0] | (A[1] << 16), eqx2, eqz2);
                 }
                 if (y > 0) {
                     const uint32_t eqa = s_eqx[r - 1];
-                    Cm[2] = continued_runs(s_F[2 * kRows + r - 1], eqa, A[2], eqx, eqy);
-                    Cm[3] = continued_runs(s_F[3 * kRows + r - 1], eqa, A[3], eqx, eqy);
+                    Cm23 = continued_runs2(s_F[2 * kRows + r - 1] | (static_cast<uint32_t>(s_F[3 * kRows + r - 1]) << 16), eqa | (eqa << 16),
+                                           A[2] | (A[3] << 16), eqx2, eqy2);
                 }
+                const uint32_t Cm[4] = {Cm01 & 0xFFFFu, Cm01 >> 16, Cm23 & 0xFFFFu, Cm23 >> 16};
                 // RIGHT / LEFT: a run (lanes y0..y1 of this z-slice) continues the row one z below when that row has a run with
                 // the same start, the same id and the same end.  "Same end" = the end masks of the two rows agree on every lane
                 // of the run: OR the disagreement over the run and deliver it to the run's first lane -- a segmented suffix
@@ -354,7 +395,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
             } else if (!solid_uniform) {
                 if (cnt) {
-                    // anchors are sparse: visit only the voxels that carry one
+                    // anchors are sparse: visit only the voxels that carry one.  Only (anchor voxel, direction) is recorded here;
+                    // the quad's extent is worked out by the thread that expands it (quad_extent), ONE quad per thread -- a row
+                    // with many anchors no longer walks all their heights while the other 255 threads wait at the barrier.
                     uint32_t ord = first - q0;
                     const uint32_t rbase = static_cast<uint32_t>(r) << 4;
                     uint32_t any = A[0] | A[1] | A[2] | A[3] | A[4] | A[5];
@@ -364,26 +407,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
 #pragma unroll
                         for (uint32_t d = 0; d < 6; ++d) {
                             if (!((A[d] >> x) & 1u)) continue;
-                            if (ord < kRecCap) {
-                                uint32_t w1;
-                                int h1 = 0;
-                                if (d < 4u) {
-                                    // run length from the row's end mask; height = rows along the stack axis that continue it
-                                    const uint32_t fmask = d == 0 ? fm.top : d == 1 ? fm.bot : d == 2 ? fm.rear : fm.front;
-                                    w1 = __ffs(run_ends(fmask, eqx) >> x) - 1;
-                                    const int stride = d < 2u ? 16 : 1;
-                                    const int left = d < 2u ? 15 - z : 15 - y;
-                                    while (h1 < left && ((s_C[d * kRows + r + (h1 + 1) * stride] >> x) & 1u)) ++h1;
-                                } else {
-                                    // RIGHT / LEFT: the run climbs the rows of this z-slice until one carries its end bit; it is
-                                    // stacked along z while the rows 16 further on continue it
-                                    const int bit = x + 16 * static_cast<int>(d - 4u);
-                                    w1 = 0u;
-                                    if (!((E45 >> bit) & 1u)) { do { ++w1; } while (!((s_SE45[kRows + r + w1] >> bit) & 1u)); }
-                                    while (h1 < 15 - z && ((s_C45[r + (h1 + 1) * 16] >> bit) & 1u)) ++h1;
-                                }
-                                s_rec[ord] = (rbase + x) | (d << 12) | (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
-                            }
+                            if (ord < kRecCap) s_rec[ord] = (rbase + x) | (d << 12);
                             ++ord;
                         }
                     }
@@ -402,7 +426,31 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                     const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
                     const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
                     const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
-                    const QuadGeom g = quad_geom(s_rec[f - q0], vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
+                    uint32_t rec = s_rec[f - q0];
+                    if (GREEDY && !solid_uniform) {
+                        // extent of the quad anchored at voxel (x, row rr) in direction d: run length from the row's end mask, height =
+                        // how many following rows along the stack axis continue the run (tables of this chunk, still in shared memory)
+                        const uint32_t rr = (rec >> 4) & 0xFFu, x = rec & 15u, d = (rec >> 12) & 7u;
+                        const int zz = rr >> 4, yy = rr & 15;
+                        uint32_t w1;
+                        int h1 = 0;
+                        if (d < 4u) {
+                            w1 = __ffs(run_ends(s_F[d * kRows + rr], s_eqx[rr]) >> x) - 1;
+                            const int stride = d < 2u ? 16 : 1, left = d < 2u ? 15 - zz : 15 - yy;
+                            const uint16_t* cont = s_C + d * kRows + rr;
+                            while (h1 < left && ((cont[(h1 + 1) * stride] >> x) & 1u)) ++h1;
+                        } else {
+                            // RIGHT / LEFT: the run climbs the rows of its z-slice until one carries its end bit; it is stacked along z
+                            // while the rows 16 further on continue it
+                            const int bit = x + 16 * static_cast<int>(d - 4u);
+                            const uint32_t* ends = s_SE45 + kRows + rr;
+                            w1 = 0u;
+                            while (!((ends[w1] >> bit) & 1u)) ++w1;
+                            while (h1 < 15 - zz && ((s_C45[rr + (h1 + 1) * 16] >> bit) & 1u)) ++h1;
+                        }
+                        rec |= (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
+                    }
+                    const QuadGeom g = quad_geom(rec, vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
                     float cx[4], cy[4], cz[4], cu[4], cv[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {

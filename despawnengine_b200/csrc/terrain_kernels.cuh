@@ -387,10 +387,10 @@ __global__ void classify_chunks_kernel(const uint8_t* summary, const uint32_t* n
 // Pre-pass of DSP_MESH_GREEDY calls with chunk-local culling.  Most chunks of a terrain are uniform: all air (no mesh, the
 // reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20) or one solid block id throughout (exactly six 16x16 quads, one
 // per side, whatever the id).  Where the generators left a summary that says so, the chunk never reaches the mesh kernel and
-// its 8 KiB tile is never read: air chunks get their empty entry here, and a uniform solid chunk's six quads are written
-// here by one warp (slot claimed from the same cursor the mesh kernel uses, same order and arithmetic as its in-kernel
-// uniform path: BOTTOM, REAR, RIGHT at voxel 0, LEFT at (15,0,0), TOP at (0,15,0), FRONT at (0,0,15)).  Everything else --
-// surface chunks, and every chunk whose summary is unknown (host uploads, edits) -- goes to the work list.
+// its 8 KiB tile is never read: air chunks get their empty entry here; a uniform solid chunk gets its arena slot and entry here
+// and its six quads from the mesh kernel's prologue (emit_uniform_chunk: same order and arithmetic as the in-kernel uniform
+// path).  Everything else -- surface chunks, and every chunk whose summary is unknown (host uploads, edits) -- goes to the
+// front of the work list.
 struct ClassifyGreedyParams {
     const uint8_t* summary;
     const uint16_t* uid;
@@ -433,46 +433,29 @@ __global__ void __launch_bounds__(256) classify_greedy_kernel(const ClassifyGree
             p.work_entry[k] = i;
         }
     }
-    uint32_t b_uni = __ballot_sync(0xFFFFFFFFu, kind == 2);
+    // Uniform solid chunks: their arena slots are claimed here (one atomic per warp on the cursor the mesh kernel uses too) and
+    // their entries written; the chunks themselves go to the BACK of the work list (count n_work[4], position n - 1 - k) and
+    // the mesh kernel's CTAs write their six quads in a short prologue, spread over the whole grid, without loading a tile.
+    const uint32_t b_uni = __ballot_sync(0xFFFFFFFFu, kind == 2);
     if (b_uni == 0u) return;
-    // one slot for all uniform chunks of the warp: a single atomic, sub-allocated in lane order
-    constexpr uint32_t kSlot = INDEXED ? (512u + 256u) : 768u;  // align128(6 x 80) + align128(6 x 24) / align128(6 x 120)
+    constexpr uint32_t kSlot = uniform_chunk_slot_bytes(INDEXED);
     const uint32_t n_uni = __popc(b_uni);
+    const int leader = __ffs(b_uni) - 1;
     unsigned long long wbase = 0;
-    if (lane == 0) wbase = atomicAdd(p.total_bytes, static_cast<unsigned long long>(n_uni) * kSlot);
-    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-    const bool fits = wbase + static_cast<unsigned long long>(n_uni) * kSlot <= p.arena_room;
-    if (!fits && lane == 0) atomicOr(p.status, kStatusOverflow);
-    uint32_t ord = 0;
-    while (b_uni) {
-        const int src = __ffs(b_uni) - 1;
-        b_uni &= b_uni - 1;
-        const uint32_t c_slot = __shfl_sync(0xFFFFFFFFu, slot, src), c_i = __shfl_sync(0xFFFFFFFFu, i, src), c_id = __shfl_sync(0xFFFFFFFFu, uid, src);
-        const unsigned long long base = wbase + static_cast<unsigned long long>(ord++) * kSlot;
-        if (lane == 0) p.entries[c_i] = MeshEntry{p.arena_offset + base, INDEXED ? 24u : 36u, INDEXED ? 36u : 0u};
-        if (!fits) continue;
-        const int4 cp = __ldg(&p.chunk_pos[c_slot]);
-        const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f), cby = __fmul_rn(__int2float_rn(cp.y), 16.0f), cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
-        float* out = reinterpret_cast<float*>(p.arena + base);
-        constexpr int kVerts = INDEXED ? 4 : 6, kWordsPerQuad = kVerts * 5;
-        for (int w = lane; w < 6 * kWordsPerQuad; w += 32) {
-            const int q = w / kWordsPerQuad, rem = w - q * kWordsPerQuad, v = rem / 5, c = rem - v * 5;
-            const uint32_t rec = (q == 0 ? (0u | (1u << 12)) : q == 1 ? (0u | (2u << 12)) : q == 2 ? (0u | (4u << 12)) : q == 3 ? (15u | (5u << 12))
-                                  : q == 4 ? (240u | (0u << 12)) : (3840u | (3u << 12))) | (15u << 15) | (15u << 19);
-            const QuadGeom g = quad_geom_of_id(rec, c_id, cbx, cby, cbz, p.uvmap, p.n_blocks);
-            const int k = INDEXED ? v : (v < 3 ? v : (v == 3 ? 2 : (v == 4 ? 3 : 0)));  // stream order c0,c1,c2,c2,c3,c0
-            const uint32_t cc = g.code >> (5 * k);
-            const float val = c == 0 ? ((cc & 1u) ? g.hx : g.lx) : c == 1 ? ((cc & 2u) ? g.hy : g.ly) : c == 2 ? ((cc & 4u) ? g.hz : g.lz)
-                              : c == 3 ? ((cc & 8u) ? g.uv.z : g.uv.x) : ((cc & 16u) ? g.uv.w : g.uv.y);
-            out[w] = val;
-        }
-        if (INDEXED) {
-            uint32_t* io = reinterpret_cast<uint32_t*>(p.arena + base + 512);
-            for (int w = lane; w < 36; w += 32) {
-                const int q = w / 6, j = w - q * 6;
-                io[w] = 4u * q + (j < 3 ? j : (j == 3 ? 2 : (j == 4 ? 3 : 0)));
-            }
-        }
+    uint32_t lbase = 0;
+    if (lane == leader) {
+        wbase = atomicAdd(p.total_bytes, static_cast<unsigned long long>(n_uni) * kSlot);
+        lbase = atomicAdd(p.n_work + 4, n_uni);
+        if (wbase + static_cast<unsigned long long>(n_uni) * kSlot > p.arena_room) atomicOr(p.status, kStatusOverflow);
+    }
+    wbase = __shfl_sync(0xFFFFFFFFu, wbase, leader);
+    lbase = __shfl_sync(0xFFFFFFFFu, lbase, leader);
+    if (kind == 2) {
+        const uint32_t k = __popc(b_uni & ((1u << lane) - 1u));
+        p.entries[i] = MeshEntry{p.arena_offset + wbase + static_cast<unsigned long long>(k) * kSlot, INDEXED ? 24u : 36u, INDEXED ? 36u : 0u};
+        const uint32_t li = p.n - 1u - (lbase + k);
+        p.work_slots[li] = slot;
+        p.work_entry[li] = i;
     }
 }
 
