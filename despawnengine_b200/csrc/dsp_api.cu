@@ -465,7 +465,8 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.arena_offset = arena_offset;
     p.arena_room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
     p.entries = ctx->d_entries + entry0;
-    p.ticket = sub == 0 ? reinterpret_cast<uint32_t*>(ctx->d_ctl) : ctx->d_tickets + sub;  // control block: [ticket][status][done][-][total 8 B][-]
+    p.ticket = ctx->d_tickets + 32 * sub;  // its own cache line
+    p.ctl = reinterpret_cast<uint32_t*>(ctx->d_ctl);  // control block: [-][status][done][n_front][total 8 B][n_back][n_uniform]
     p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
     if (work_list) {  // classify_chunks_kernel left the chunks that need meshing in d_work_slots, their count in the control block
         p.slot_list = ctx->d_work_slots;
@@ -494,6 +495,7 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     const bool ordered = (mode & DSP_MESH_ORDERED) != 0;
     if (ordered || !ctx->ctl_clean || n == 0) {
         DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + (ordered ? 8 * n : 0), ctx->stream));
+        DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t), ctx->stream));
         ctx->ctl_clean = !ordered;
     }
     ctx->result_in_tail = false;
@@ -767,7 +769,10 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_sub[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
-    if ((e = cudaMalloc(&ctx->d_tickets, dsp_ctx::kMaxSub * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(tickets)", e);
+    // one 128-byte line per ticket counter, away from the control block: the ticket and the arena cursor are the two hot atomics
+    // of a launch, and on one line they queue up behind each other in the same L2 slice
+    if ((e = cudaMalloc(&ctx->d_tickets, dsp_ctx::kMaxSub * 128)) != cudaSuccess) return bail("cudaMalloc(tickets)", e);
+    if ((e = cudaMemset(ctx->d_tickets, 0, dsp_ctx::kMaxSub * 128)) != cudaSuccess) return bail("cudaMemset(tickets)", e);
     if ((e = cudaMallocHost(&ctx->h_pinned, 4096)) != cudaSuccess) return bail("cudaMallocHost", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     for (int i = 0; i < dsp_ctx::kEvRing; ++i)
@@ -1144,7 +1149,7 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     }
     const int subs = static_cast<int>(sub_begin.size()) - 1;
     DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32, ctx->stream));
-    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, dsp_ctx::kMaxSub * sizeof(uint32_t), ctx->stream));
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, dsp_ctx::kMaxSub * 128, ctx->stream));
     ctx->ctl_clean = false;  // the sub-batch launches share the cursor and leave the block as it is
     ctx->result_in_tail = false;
     if (n == 0) return finish_mesh(ctx, out_entries, out_total_bytes);

@@ -50,7 +50,8 @@ struct MeshParams {
     uint64_t arena_room;        // bytes available from arena_offset
     MeshEntry* entries;         // [n]
     uint64_t* lookback;         // [n], zeroed before launch
-    uint32_t* ticket;           // chunk ticket counter of this launch; zeroed before launch
+    uint32_t* ticket;           // chunk ticket counter of this launch (a cache line of its own); zeroed before launch
+    uint32_t* ctl;              // the context's control block (work-list counts live there)
     uint32_t* status;           // status bits (kStatus*), shared by the launches of one call
     uint64_t* total_bytes;      // out
     unsigned long long* phase_cycles;  // [16] debug: per-phase SM cycles of thread 0 summed over CTAs (DSP_PHASE_TIMERS builds)
@@ -128,9 +129,9 @@ __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
     p.result[0] = atomicOr(p.status, 0u);
     p.result[1] = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), 0ull);
     p.ticket[0] = 0u;
-    p.ticket[3] = 0u;  // the work-list counts of classify_chunks_kernel live in the same block
-    p.ticket[6] = 0u;
-    p.ticket[7] = 0u;  // (uniform-chunk count of classify_greedy_kernel)
+    p.ctl[3] = 0u;  // the work-list counts of the classify kernels: front, back (seam chunks) ...
+    p.ctl[6] = 0u;
+    p.ctl[7] = 0u;  // ... and the uniform chunks of classify_greedy_kernel
     *p.status = 0u;
     *p.total_bytes = 0ull;
     *p.done = 0u;

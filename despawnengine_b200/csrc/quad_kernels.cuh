@@ -214,6 +214,32 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     __syncthreads();
     uint32_t cur = s_next[0];
     int buf = 0, par = 0;  // ring position of `cur` and the phase parity of its barrier
+    // Thread 0 only: the LAST staging tile of a chunk is not stored the moment it is complete but one barrier into the next
+    // iteration (or at loop exit).  The store needs the slot offset, i.e. the result of the claim atomic -- a hot address every
+    // chunk of the launch hits, with a round trip that was the longest wait of this kernel (21-26 % of its stall samples, all
+    // eight warps parked behind thread 0).  Deferred, the wait overlaps the next chunk's tile wait and occupancy phase; the tile
+    // is safe meanwhile, because nothing writes the staging buffer before the next expansion, which starts with bulk_wait_read.
+    bool pend = false;
+    uint64_t pend_claimed = 0;
+    uint32_t pend_Q = 0, pend_f0 = 0, pend_cur = 0;
+    auto store_tile = [&](uint64_t claimed, uint32_t Q, uint32_t f0, uint32_t chunk) {
+        if (f0 == 0) {
+            if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
+            *entry_of(p, chunk) = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
+        }
+        if (claimed + quad_slot_bytes(Q, INDEXED) <= p.arena_room) {
+            uint8_t* const gout = p.arena + claimed;
+            uint8_t* const gidx = gout + quad_vertex_region_bytes(Q, true);
+            const uint32_t nq = min(static_cast<uint32_t>(kTile), Q - f0);
+            if (INDEXED) {
+                bulk_store(gout + static_cast<size_t>(f0) * kQuadVertexBytesIdx, s_stage, nq * kQuadVertexBytesIdx);
+                bulk_store(gidx + static_cast<size_t>(f0) * kQuadIndexBytes, s_istage, (nq * kQuadIndexBytes + 15u) & ~15u);
+            } else {
+                bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, s_stage, (nq * kFaceBytes + 15u) & ~15u);
+            }
+            bulk_commit();
+        }
+    };
     while (cur < p.n) {
         if (tid == 0) {
             const uint32_t t = pending;
@@ -243,6 +269,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         const uint32_t id0w = id0 * 0x00010001u;
         const uint32_t differs = (qa.x ^ id0w) | (qa.y ^ id0w) | (qa.z ^ id0w) | (qa.w ^ id0w) | (qb.x ^ id0w) | (qb.y ^ id0w) | (qb.z ^ id0w) | (qb.w ^ id0w);
         const bool uniform = __syncthreads_and(differs == 0u) != 0;  // also publishes s_rowmask
+        if (tid == 0 && pend) { store_tile(pend_claimed, pend_Q, pend_f0, pend_cur); pend = false; }  // the previous chunk's last tile
         if (uniform && id0 == 0u) {
             // all air: the reference's palette.len() == 1 early-out (chunk_mesh.rs:18-20)
             if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
@@ -487,24 +514,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
                 fence_proxy_async_smem();
                 __syncthreads();
-                // First touch of the claim's result: here, after the tile has been expanded -- the atomic's round trip (a hot
-                // address: every chunk of the launch claims from it) hides behind the record and expansion phases instead of
-                // holding the whole CTA at the barrier above (26 % of this kernel's stall samples sat on that wait in round 1).
-                if (tid == 0 && f0 == 0) {
-                    if (claimed + quad_slot_bytes(Q, INDEXED) > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                    *entry_of(p, cur) = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
-                }
-                if (tid == 0 && claimed + quad_slot_bytes(Q, INDEXED) <= p.arena_room) {
-                    uint8_t* const gout = p.arena + claimed;
-                    uint8_t* const gidx = gout + quad_vertex_region_bytes(Q, true);
-                    const uint32_t nq = min(static_cast<uint32_t>(kTile), Q - f0);
-                    if (INDEXED) {
-                        bulk_store(gout + static_cast<size_t>(f0) * kQuadVertexBytesIdx, s_stage, nq * kQuadVertexBytesIdx);
-                        bulk_store(gidx + static_cast<size_t>(f0) * kQuadIndexBytes, s_istage, (nq * kQuadIndexBytes + 15u) & ~15u);
-                    } else {
-                        bulk_store(gout + static_cast<size_t>(f0) * kFaceBytes, s_stage, (nq * kFaceBytes + 15u) & ~15u);
-                    }
-                    bulk_commit();
+                if (tid == 0) {
+                    if (f0 + kTile >= Q) { pend = true; pend_claimed = claimed; pend_Q = Q; pend_f0 = f0; pend_cur = cur; }  // last tile: deferred
+                    else store_tile(claimed, Q, f0, cur);
                 }
             }
         }
@@ -514,6 +526,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         if (++buf == NB) { buf = 0; par ^= 1; }
         cur = s_next[buf];
     }
+    if (tid == 0 && pend) store_tile(pend_claimed, pend_Q, pend_f0, pend_cur);
     if (tid == 0) control_block_epilogue(p);  // control words only: overlaps the drain of the last stores
     if (lane == 0) bulk_wait<0>();
 }
