@@ -476,7 +476,7 @@ class Context:
         return int(lib().dsp_stream(self._h) or 0)
 
     def debug_phase_cycles(self) -> np.ndarray:
-        out = np.zeros(16, dtype=np.uint64)
+        out = np.zeros(32, dtype=np.uint64)
         self._check(lib().dsp_debug_phase_cycles(self._h, _ptr(out, C.c_uint64)))
         return out
 

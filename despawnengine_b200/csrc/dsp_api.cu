@@ -132,6 +132,7 @@ struct dsp_ctx {
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
     bool kernel_timing = true;  // record an event pair around every mesh launch (dsp_mesh_kernel_stats)
+    bool timing_open = false;   // the start event of the current call's pair has been recorded
     bool ctl_clean = false;    // the control block is all zero (left so by a self-resetting launch): no memset needed
     bool result_in_tail = false;  // the last mesh call's {status, total} are in the result words, not in the control block
     uint64_t arena_limit = 0;  // when non-zero, a mesh call may only write below this arena offset (scene allocator)
@@ -338,6 +339,27 @@ int drain_kernel_event(dsp_ctx* ctx, int e) {
     return DSP_OK;
 }
 
+// dsp_mesh_kernel_stats times a mesh CALL's kernels: the event pair opens in front of the pre-pass (classify) launch when there
+// is one, otherwise in front of the mesh kernel, and closes behind the mesh kernel.
+int begin_kernel_timing(dsp_ctx* ctx) {
+    if (!ctx->kernel_timing || ctx->timing_open) return DSP_OK;
+    const int e = ctx->ev_next;
+    int rc = drain_kernel_event(ctx, e);  // the pair from kEvRing launches ago: long finished
+    if (rc != DSP_OK) return rc;
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k0[e], ctx->stream));
+    ctx->timing_open = true;
+    return DSP_OK;
+}
+int end_kernel_timing(dsp_ctx* ctx) {
+    if (!ctx->timing_open) return DSP_OK;
+    const int e = ctx->ev_next;
+    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k1[e], ctx->stream));
+    ctx->ev_pending[e] = true;
+    ctx->ev_next = (e + 1) % dsp_ctx::kEvRing;
+    ctx->timing_open = false;
+    return DSP_OK;
+}
+
 template <class Cfg, bool HALO, bool ORDERED>
 int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
     void (*kern)(const dsp::MeshParams);
@@ -354,23 +376,12 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
     dsp::MeshParams pp = p;
     pp.phase_cycles = ctx->d_phase;
     pp.prefetch_ahead = ctx->mesh_prefetch_mult * grid;
-    if (!ctx->kernel_timing) {
-        kern<<<grid, 256, smem, ctx->stream>>>(pp);
-        DSP_CUDA(ctx, cudaGetLastError());
-        ctx->launches++;
-        return DSP_OK;
-    }
-    const int e = ctx->ev_next;
-    int rc = drain_kernel_event(ctx, e);  // the pair from kEvRing launches ago: long finished
+    int rc = begin_kernel_timing(ctx);
     if (rc != DSP_OK) return rc;
-    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k0[e], ctx->stream));
     kern<<<grid, 256, smem, ctx->stream>>>(pp);
     DSP_CUDA(ctx, cudaGetLastError());
-    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k1[e], ctx->stream));
-    ctx->ev_pending[e] = true;
-    ctx->ev_next = (e + 1) % dsp_ctx::kEvRing;
     ctx->launches++;
-    return DSP_OK;
+    return end_kernel_timing(ctx);
 }
 
 // Kernel shapes.  0 is what ships (and what bench.py reports); DSP_MESH_VARIANT=1..3 selects the others for A/B runs:
@@ -392,7 +403,7 @@ int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
 
 // Quad modes (DSP_MESH_GREEDY / DSP_MESH_INDEXED): mesh_chunks_quads_kernel, always the atomic slot claim.
 template <bool HALO, bool GREEDY, bool INDEXED>
-int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
+int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p_in) {
     void (*kern)(const dsp::MeshParams) = dsp::mesh_chunks_quads_kernel<HALO, GREEDY, INDEXED>;
     constexpr int smem = dsp::QuadSmem<GREEDY>::kBytes;
     int& occ = ctx->quad_ctas_per_sm[(HALO ? 1 : 0) + (GREEDY ? 2 : 0) + (INDEXED ? 4 : 0)];
@@ -401,24 +412,15 @@ int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p) {
         DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         if (occ < 1) return fail(ctx, DSP_ERR_INTERNAL, "quad mesh kernel does not fit on an SM (smem %d)", smem);
     }
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, static_cast<uint64_t>(ctx->num_sms) * occ));
-    if (!ctx->kernel_timing) {
-        kern<<<grid, 256, smem, ctx->stream>>>(p);
-        DSP_CUDA(ctx, cudaGetLastError());
-        ctx->launches++;
-        return DSP_OK;
-    }
-    const int e = ctx->ev_next;
-    int rc = drain_kernel_event(ctx, e);
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p_in.n, static_cast<uint64_t>(ctx->num_sms) * occ));
+    dsp::MeshParams p = p_in;
+    p.phase_cycles = ctx->d_phase;
+    int rc = begin_kernel_timing(ctx);
     if (rc != DSP_OK) return rc;
-    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k0[e], ctx->stream));
     kern<<<grid, 256, smem, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
-    DSP_CUDA(ctx, cudaEventRecord(ctx->ev_k1[e], ctx->stream));
-    ctx->ev_pending[e] = true;
-    ctx->ev_next = (e + 1) % dsp_ctx::kEvRing;
     ctx->launches++;
-    return DSP_OK;
+    return end_kernel_timing(ctx);
 }
 template <bool HALO>
 int launch_quads(dsp_ctx* ctx, const dsp::MeshParams& p, uint32_t mode) {
@@ -515,6 +517,7 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
             DSP_CUDA(ctx, cudaMalloc(&ctx->d_work_entry, ctx->max_chunks * sizeof(uint32_t)));
         }
         const unsigned cgrid = static_cast<unsigned>((n + 255) / 256);
+        if ((rc = begin_kernel_timing(ctx)) != DSP_OK) return rc;  // the pre-pass is part of the call's kernel time
         if (greedy_prepass) {
             dsp::ClassifyGreedyParams cp{};
             cp.summary = ctx->d_summary; cp.uid = ctx->d_uid; cp.chunk_pos = ctx->d_pos; cp.slot_list = d_list; cp.first_slot = first_slot;
@@ -763,8 +766,8 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if ((e = cudaMalloc(&ctx->d_summary, max_chunks)) != cudaSuccess) return bail("cudaMalloc(chunk summaries)", e);
     if ((e = cudaMemset(ctx->d_summary, 0, max_chunks)) != cudaSuccess) return bail("cudaMemset(chunk summaries)", e);
     if ((e = cudaMalloc(&ctx->d_uid, max_chunks * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc(uniform ids)", e);
-    if ((e = cudaMalloc(&ctx->d_phase, 16 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
-    cudaMemset(ctx->d_phase, 0, 16 * sizeof(unsigned long long));
+    if ((e = cudaMalloc(&ctx->d_phase, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
+    cudaMemset(ctx->d_phase, 0, 32 * sizeof(unsigned long long));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_sub[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1502,8 +1505,8 @@ uint64_t dsp_kernel_launches(const dsp_ctx* ctx) { return ctx ? ctx->launches : 
 int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16) {
     if (!ctx || !out16) return DSP_ERR_BAD_ARG;
     DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    DSP_CUDA(ctx, cudaMemcpy(out16, ctx->d_phase, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    DSP_CUDA(ctx, cudaMemset(ctx->d_phase, 0, 16 * sizeof(uint64_t)));
+    DSP_CUDA(ctx, cudaMemcpy(out16, ctx->d_phase, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    DSP_CUDA(ctx, cudaMemset(ctx->d_phase, 0, 32 * sizeof(uint64_t)));
     return DSP_OK;
 }
 

@@ -219,6 +219,13 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     // chunk of the launch hits, with a round trip that was the longest wait of this kernel (21-26 % of its stall samples, all
     // eight warps parked behind thread 0).  Deferred, the wait overlaps the next chunk's tile wait and occupancy phase; the tile
     // is safe meanwhile, because nothing writes the staging buffer before the next expansion, which starts with bulk_wait_read.
+#ifdef DSP_PHASE_TIMERS
+    long long ph[16] = {};
+    long long tlast = clock64();
+#define QTICK(k) do { const long long t_ = clock64(); ph[k] += t_ - tlast; tlast = t_; } while (0)
+#else
+#define QTICK(k) do { } while (0)
+#endif
     bool pend = false;
     uint64_t pend_claimed = 0;
     uint32_t pend_Q = 0, pend_f0 = 0, pend_cur = 0;
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             bulk_commit();
         }
     };
+    QTICK(8);
     while (cur < p.n) {
         if (tid == 0) {
             const uint32_t t = pending;
@@ -251,6 +259,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         seam_wait<HALO>(p, cur);
         mbar_wait(&s_bar[buf], par);
+        QTICK(0);
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
 
         // ---- 1. row occupancy; is the whole chunk one block id?
@@ -269,7 +278,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         const uint32_t id0w = id0 * 0x00010001u;
         const uint32_t differs = (qa.x ^ id0w) | (qa.y ^ id0w) | (qa.z ^ id0w) | (qa.w ^ id0w) | (qb.x ^ id0w) | (qb.y ^ id0w) | (qb.z ^ id0w) | (qb.w ^ id0w);
         const bool uniform = __syncthreads_and(differs == 0u) != 0;  // also publishes s_rowmask
+        QTICK(1);
         if (tid == 0 && pend) { store_tile(pend_claimed, pend_Q, pend_f0, pend_cur); pend = false; }  // the previous chunk's last tile
+        QTICK(9);
         if (uniform && id0 == 0u) {
             // all air: the reference's palette.len() == 1 early-out (chunk_mesh.rs:18-20)
             if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
@@ -325,7 +336,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 const uint32_t joins_next = f45 & f_next & eqy_next;  // lane y + 1 belongs to the same run as lane y
                 s_SE45[r] = S45;
                 s_SE45[kRows + r] = E45;
+                QTICK(2);
                 __syncthreads();
+                QTICK(10);
                 // ---- 3. continued runs -> anchors (TOP | BOTTOM << 16 against the row one z below, REAR | FRONT << 16 against y - 1)
                 uint32_t Cm01 = 0u, Cm23 = 0u;
                 const uint32_t eqx2 = eqx | (eqx << 16);
@@ -356,12 +369,16 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                     }
                     if (z > 0) C45 = S45 & s_SE45[r - 16] & eqz2 & ~acc;
                 }
+                // Continued-run tables, laid out so that the 16 entries along a direction's STACK axis are contiguous: a quad's
+                // height is then two to four 128-bit loads and a count of trailing ones instead of a walk over up to 15 rows
+                // (quad extent below).  TOP / BOTTOM / RIGHT / LEFT stack along z: index y * 16 + z; REAR / FRONT along y: index r.
+                const int tz = y * 16 + z;
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    s_C[d * kRows + r] = static_cast<uint16_t>(Cm[d]);
+                    s_C[d * kRows + (d < 2 ? tz : r)] = static_cast<uint16_t>(Cm[d]);
                     A[d] = run_starts(A[d], eqx) & ~Cm[d];
                 }
-                s_C45[r] = C45;
+                s_C45[tz] = C45;
                 A[4] = (S45 & ~C45) & 0xFFFFu;
                 A[5] = (S45 & ~C45) >> 16;
             }
@@ -375,7 +392,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 if (lane >= o) incl += v;
             }
             if (lane == 31) s_warp[warp] = incl;
+            QTICK(3);
             __syncthreads();
+            QTICK(11);
             Q = 0;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
@@ -440,43 +459,70 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                     }
                 }
             }
+            QTICK(4);
             if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
             __syncthreads();  // records visible
+            QTICK(13);
             const uint32_t q1 = min(Q, q0 + kRecCap);
+            if (GREEDY && !solid_uniform) {
+                // Extent of every quad of the window, one quad per thread over ALL 256 threads (phase timers: with the extent
+                // worked out inside the 128-thread tile loop, expansion was 45 % of a CTA's time and half the warps idled):
+                // run length from the row's end mask, height = how many following rows along the stack axis continue the run
+                // (tables of this chunk, still in shared memory).  Written back into the record.
+                for (uint32_t i = tid; i < q1 - q0; i += 256) {
+                    const uint32_t rec = s_rec[i];
+                    const uint32_t rr = (rec >> 4) & 0xFFu, x = rec & 15u, d = (rec >> 12) & 7u;
+                    const int zz = rr >> 4, yy = rr & 15;
+                    uint32_t w1, h1;
+                    if (d < 4u) {
+                        w1 = __ffs(run_ends(s_F[d * kRows + rr], s_eqx[rr]) >> x) - 1;
+                        // the 16 continued-run masks along the stack axis of this quad's column, bit x of each -> one 16-bit word
+                        const uint4* col = reinterpret_cast<const uint4*>(s_C + d * kRows + (d < 2u ? yy : zz) * 16);
+                        const uint4 ca = col[0], cb = col[1];
+                        const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                        uint32_t T = 0u;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint32_t b = (w[j] >> x) & 0x00010001u;
+                            T |= ((b | (b >> 15)) & 3u) << (2 * j);
+                        }
+                        h1 = __ffs(~(T >> ((d < 2u ? zz : yy) + 1))) - 1;  // rows after the anchor's that continue the run, up to the first that does not
+                    } else {
+                        // RIGHT / LEFT: the run climbs the rows of its z-slice until one carries its end bit (run length along y); it is
+                        // stacked along z while the rows 16 further on continue it
+                        const uint32_t bit = x + 16u * (d - 4u);
+                        const uint4* ecol = reinterpret_cast<const uint4*>(s_SE45 + kRows + zz * 16);
+                        const uint4* ccol = reinterpret_cast<const uint4*>(s_C45 + yy * 16);
+                        uint32_t Te = 0u, Tc = 0u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 e = ecol[j], c = ccol[j];
+                            Te |= (((e.x >> bit) & 1u) | (((e.y >> bit) & 1u) << 1) | (((e.z >> bit) & 1u) << 2) | (((e.w >> bit) & 1u) << 3)) << (4 * j);
+                            Tc |= (((c.x >> bit) & 1u) | (((c.y >> bit) & 1u) << 1) | (((c.z >> bit) & 1u) << 2) | (((c.w >> bit) & 1u) << 3)) << (4 * j);
+                        }
+                        w1 = __ffs(Te >> yy) - 1;          // the run's last row always carries the end bit
+                        h1 = __ffs(~(Tc >> (zz + 1))) - 1;
+                    }
+                    s_rec[i] = rec | (w1 << 15) | (h1 << 19);
+                }
+                __syncthreads();
+            }
+            QTICK(12);
             for (uint32_t f0 = q0; f0 < q1; f0 += kTile) {
-                if (f0 > q0) {  // (for the window's first tile the records barrier above did this)
+                if (f0 > q0) {  // (for the window's first tile the barrier above did this)
                     if (tid == 0) bulk_wait_read<0>();
                     __syncthreads();
                 }
-                const uint32_t f = f0 + tid;
-                if (tid < kTile && f < Q) {
+                // one thread per quad (a thread PAIR per quad, each writing half the vertices so that all eight warps work on a
+                // 128-quad tile, measured 3-5 % slower: the kernel is issue-bound and the pair recomputes the corner geometry)
+                const int qt = tid;
+                const bool on = tid < kTile;
+                const uint32_t f = f0 + qt;
+                if (on && f < Q) {
+                    const uint32_t rec = s_rec[f - q0];
                     const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
                     const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
                     const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
-                    uint32_t rec = s_rec[f - q0];
-                    if (GREEDY && !solid_uniform) {
-                        // extent of the quad anchored at voxel (x, row rr) in direction d: run length from the row's end mask, height =
-                        // how many following rows along the stack axis continue the run (tables of this chunk, still in shared memory)
-                        const uint32_t rr = (rec >> 4) & 0xFFu, x = rec & 15u, d = (rec >> 12) & 7u;
-                        const int zz = rr >> 4, yy = rr & 15;
-                        uint32_t w1;
-                        int h1 = 0;
-                        if (d < 4u) {
-                            w1 = __ffs(run_ends(s_F[d * kRows + rr], s_eqx[rr]) >> x) - 1;
-                            const int stride = d < 2u ? 16 : 1, left = d < 2u ? 15 - zz : 15 - yy;
-                            const uint16_t* cont = s_C + d * kRows + rr;
-                            while (h1 < left && ((cont[(h1 + 1) * stride] >> x) & 1u)) ++h1;
-                        } else {
-                            // RIGHT / LEFT: the run climbs the rows of its z-slice until one carries its end bit; it is stacked along z
-                            // while the rows 16 further on continue it
-                            const int bit = x + 16 * static_cast<int>(d - 4u);
-                            const uint32_t* ends = s_SE45 + kRows + rr;
-                            w1 = 0u;
-                            while (!((ends[w1] >> bit) & 1u)) ++w1;
-                            while (h1 < 15 - zz && ((s_C45[rr + (h1 + 1) * 16] >> bit) & 1u)) ++h1;
-                        }
-                        rec |= (w1 << 15) | (static_cast<uint32_t>(h1) << 19);
-                    }
                     const QuadGeom g = quad_geom(rec, vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
                     float cx[4], cy[4], cz[4], cu[4], cv[4];
 #pragma unroll
@@ -489,31 +535,33 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                         cv[k] = (c & 16u) ? g.uv.w : g.uv.y;
                     }
                     if (INDEXED) {
-                        float4* o = reinterpret_cast<float4*>(s_stage + tid * 20);  // 80 bytes: 5 conflict-free STS.128
+                        float4* o = reinterpret_cast<float4*>(s_stage + qt * 20);  // 80 bytes: 5 conflict-free STS.128
                         o[0] = make_float4(cx[0], cy[0], cz[0], cu[0]);
                         o[1] = make_float4(cv[0], cx[1], cy[1], cz[1]);
                         o[2] = make_float4(cu[1], cv[1], cx[2], cy[2]);
                         o[3] = make_float4(cz[2], cu[2], cv[2], cx[3]);
                         o[4] = make_float4(cy[3], cz[3], cu[3], cv[3]);
-                        uint2* io = reinterpret_cast<uint2*>(s_istage + tid * 6);  // 24 bytes: 3 conflict-free STS.64
+                        uint2* io = reinterpret_cast<uint2*>(s_istage + qt * 6);  // 24 bytes: 3 conflict-free STS.64
                         const uint32_t v0 = f * 4u;
                         io[0] = make_uint2(v0, v0 + 1u);
                         io[1] = make_uint2(v0 + 2u, v0 + 2u);
                         io[2] = make_uint2(v0 + 3u, v0);
                     } else {
-                        float2* o = reinterpret_cast<float2*>(s_stage + tid * kFaceWords);
+                        float2* o = reinterpret_cast<float2*>(s_stage + qt * kFaceWords);
                         o[0] = make_float2(cx[0], cy[0]);   o[1] = make_float2(cz[0], cu[0]);   o[2] = make_float2(cv[0], cx[1]);
                         o[3] = make_float2(cy[1], cz[1]);   o[4] = make_float2(cu[1], cv[1]);   o[5] = make_float2(cx[2], cy[2]);
                         o[6] = make_float2(cz[2], cu[2]);   o[7] = make_float2(cv[2], cx[2]);   o[8] = make_float2(cy[2], cz[2]);
                         o[9] = make_float2(cu[2], cv[2]);   o[10] = make_float2(cx[3], cy[3]);  o[11] = make_float2(cz[3], cu[3]);
                         o[12] = make_float2(cv[3], cx[0]);  o[13] = make_float2(cy[0], cz[0]);  o[14] = make_float2(cu[0], cv[0]);
                     }
-                } else if (tid < kTile && f == Q && (Q & 1u)) {  // odd count: pad the last 16-byte unit with zeros (inside the slot's alignment gap)
-                    if (INDEXED) *reinterpret_cast<uint2*>(s_istage + tid * 6) = make_uint2(0u, 0u);
-                    else *reinterpret_cast<float2*>(s_stage + tid * kFaceWords) = make_float2(0.0f, 0.0f);
+                } else if (on && f == Q && (Q & 1u)) {  // odd count: pad the last 16-byte unit with zeros (inside the slot's alignment gap)
+                    if (INDEXED) *reinterpret_cast<uint2*>(s_istage + qt * 6) = make_uint2(0u, 0u);
+                    else *reinterpret_cast<float2*>(s_stage + qt * kFaceWords) = make_float2(0.0f, 0.0f);
                 }
                 fence_proxy_async_smem();
+                QTICK(5);
                 __syncthreads();
+                QTICK(14);
                 if (tid == 0) {
                     if (f0 + kTile >= Q) { pend = true; pend_claimed = claimed; pend_Q = Q; pend_f0 = f0; pend_cur = cur; }  // last tile: deferred
                     else store_tile(claimed, Q, f0, cur);
@@ -525,8 +573,14 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         // writes sits behind at least one barrier of the next iteration.
         if (++buf == NB) { buf = 0; par ^= 1; }
         cur = s_next[buf];
+        QTICK(6);
     }
     if (tid == 0 && pend) store_tile(pend_claimed, pend_Q, pend_f0, pend_cur);
+#ifdef DSP_PHASE_TIMERS
+    QTICK(7);
+    if ((tid == 0 || tid == 255) && p.phase_cycles) for (int k = 0; k < 15; ++k) atomicAdd(&p.phase_cycles[(tid ? 16 : 0) + k], static_cast<unsigned long long>(ph[k]));
+    if (tid == 0 && p.phase_cycles) atomicAdd(&p.phase_cycles[15], 1ull);
+#endif
     if (tid == 0) control_block_epilogue(p);  // control words only: overlaps the drain of the last stores
     if (lane == 0) bulk_wait<0>();
 }

@@ -337,17 +337,17 @@ int dsp_arena_import_close(dsp_arena_import* imp);
 
 /* Number of kernel launches this context has enqueued since creation (bench accounting). */
 uint64_t dsp_kernel_launches(const dsp_ctx* ctx);
-/* Device time of the mesh kernel launches alone, from CUDA events the library records around every
- * launch on the context's stream: number of launches, their summed duration, and the newest one.
- * Waits for outstanding launches. */
+/* Device time of the kernels of the mesh calls alone (the mesh kernel and, where a call has one, the classify pre-pass in
+ * front of it), from CUDA events the library records around them on the context's stream: number of calls, their summed
+ * duration, and the newest one.  Waits for outstanding launches. */
 int dsp_mesh_kernel_stats(dsp_ctx* ctx, uint64_t* out_count, double* out_total_ms, float* out_last_ms);
 /* The event pair around every mesh launch costs about 2 us of stream time per call; a caller that does not read
  * dsp_mesh_kernel_stats can switch it off (on by default). */
 int dsp_set_kernel_timing(dsp_ctx* ctx, int on);
 
-/* Debug aid: per-phase SM-cycle counters of the mesh kernel, summed over CTAs, read and cleared.  All zero
+/* Debug aid: per-phase SM-cycle counters of the mesh kernels (32 of them), summed over CTAs, read and cleared.  All zero
  * unless the library was built with -DDSP_PHASE_TIMERS (not the shipped build). */
-int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16);
+int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out32);
 
 #ifdef __cplusplus
 }
