@@ -95,6 +95,10 @@ struct dsp_ctx {
     uint32_t* d_slots = nullptr;
     uint8_t* d_summary = nullptr;     // per slot: dsp::kSummary* (all air / uniformly solid / unknown)
     uint16_t* d_uid = nullptr;        // per slot, valid while the summary says "no air": the one block id of the chunk, or kUidMixed
+    uint16_t* d_bmask = nullptr;      // per slot: 96 border occupancy masks (6 layers x 16), what cross-chunk culling reads of a neighbour
+    uint8_t* d_bvalid = nullptr;      // per slot: d_bmask up to date (bit 0) / queued for a refresh (bit 1)
+    bool bmask_stale = false;         // some resident chunk's masks may be out of date: halo-mode calls check (ensure_border_masks)
+    uint32_t* d_stale_list = nullptr; // [max_chunks] chunks whose border masks are being refreshed + [1] their count (allocated on first use)
     uint32_t* d_work_slots = nullptr; // device-built work list of halo-mode mesh calls (allocated on first use)
     uint32_t* d_work_entry = nullptr;
     float4* d_uv_rows = nullptr;
@@ -316,11 +320,14 @@ int upload_positions_and_slots(dsp_ctx* ctx, uint64_t n, const int32_t* pos, con
         if (consecutive) {
             DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_pos + *first, h, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
             DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_summary + *first, dsp::kSummaryUnknown, n, ctx->stream));  // the slots are being (re)defined
+            DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_bvalid + *first, 0, n, ctx->stream));
+            ctx->bmask_stale = true;
         } else {  // recycled slots are scattered: one copy + one scatter launch, not one copy per run of slots
             if ((rc = ensure_scratch(ctx, n * sizeof(int4))) != DSP_OK) return rc;
             DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, h, n * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream));
-            dsp::scatter_pos_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_summary, ctx->d_slots, reinterpret_cast<const int4*>(ctx->d_scratch),
-                                                                                                  static_cast<uint32_t>(n));
+            dsp::scatter_pos_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_summary, ctx->d_bvalid, ctx->d_slots,
+                                                                                                  reinterpret_cast<const int4*>(ctx->d_scratch), static_cast<uint32_t>(n));
+            ctx->bmask_stale = true;
             DSP_CUDA(ctx, cudaGetLastError());
         }
     }
@@ -457,6 +464,7 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.chunk_pos = ctx->d_pos;
     p.slot_list = d_list;
     p.nbr_slots = ctx->d_nbr;
+    p.bmask = ctx->d_bmask;
     p.halo_slabs = ctx->d_halo;
     fill_seam_params(ctx, p);
     p.uvmap = ctx->d_uvmap;
@@ -487,6 +495,26 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     return halo ? launch_mesh_variant<true, false>(ctx, p) : launch_mesh_variant<false, false>(ctx, p);
 }
 
+// Cross-chunk culling reads a neighbour through its border occupancy masks.  Where a writer could not keep them current
+// (anything but the analytic noise-region generator) the chunk's flag is clear: queue and recompute the masks of the chunks this
+// call touches -- its own and their resident neighbours -- before the mesh kernel runs.  Two small launches, and only while the
+// context knows that stale masks may exist.
+int ensure_border_masks(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot) {
+    if (!ctx->bmask_stale || n == 0) return DSP_OK;
+    if (!ctx->d_stale_list) DSP_CUDA(ctx, cudaMalloc(&ctx->d_stale_list, (ctx->max_chunks + 1) * sizeof(uint32_t)));
+    uint32_t* count = ctx->d_stale_list + ctx->max_chunks;
+    DSP_CUDA(ctx, cudaMemsetAsync(count, 0, sizeof(uint32_t), ctx->stream));
+    dsp::find_stale_masks_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_bvalid, ctx->d_nbr, d_list, first_slot, static_cast<uint32_t>(n),
+                                                                                                 ctx->d_stale_list, count);
+    DSP_CUDA(ctx, cudaGetLastError());
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(7 * n, ctx->max_chunks), static_cast<uint64_t>(ctx->num_sms) * 8));
+    dsp::refresh_border_masks_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_voxels, ctx->d_bmask, ctx->d_bvalid, ctx->d_stale_list, count);
+    DSP_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    if (n >= ctx->n_resident) ctx->bmask_stale = false;  // the call covers every resident chunk: nothing stale is left behind
+    return DSP_OK;
+}
+
 int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset) {
     int rc = check_mesh_args(ctx, n, mode, arena_offset);
     if (rc != DSP_OK) return rc;
@@ -502,7 +530,10 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     }
     ctx->result_in_tail = false;
     if (n == 0) return DSP_OK;
-    if (mode & DSP_MESH_HALO) { if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc; }
+    if (mode & DSP_MESH_HALO) {
+        if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc;
+        if ((rc = ensure_border_masks(ctx, n, d_list, first_slot)) != DSP_OK) return rc;
+    }
     ctx->ctl_clean = false;  // until the launch below is known to have been enqueued
     bool work_list = false;
     const bool halo_prepass = (mode & DSP_MESH_HALO) != 0;
@@ -654,6 +685,8 @@ int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool hal
     p.dirty_bitmap = reinterpret_cast<uint32_t*>(ctx->d_scratch + off_bitmap);
     p.nbr = nullptr;
     p.summary = ctx->d_summary;
+    p.bvalid = ctx->d_bvalid;
+    ctx->bmask_stale = true;
     if (halo) {
         if ((rc = build_neighbour_table(ctx)) != DSP_OK) return rc;
         p.nbr = ctx->d_nbr;
@@ -766,6 +799,9 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if ((e = cudaMalloc(&ctx->d_summary, max_chunks)) != cudaSuccess) return bail("cudaMalloc(chunk summaries)", e);
     if ((e = cudaMemset(ctx->d_summary, 0, max_chunks)) != cudaSuccess) return bail("cudaMemset(chunk summaries)", e);
     if ((e = cudaMalloc(&ctx->d_uid, max_chunks * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc(uniform ids)", e);
+    if ((e = cudaMalloc(&ctx->d_bmask, max_chunks * dsp::kBorderMaskStride * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc(border masks)", e);
+    if ((e = cudaMalloc(&ctx->d_bvalid, (max_chunks + 3) & ~uint64_t(3))) != cudaSuccess) return bail("cudaMalloc(border mask flags)", e);
+    if ((e = cudaMemset(ctx->d_bvalid, 0, (max_chunks + 3) & ~uint64_t(3))) != cudaSuccess) return bail("cudaMemset(border mask flags)", e);
     if ((e = cudaMalloc(&ctx->d_phase, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
     cudaMemset(ctx->d_phase, 0, 32 * sizeof(unsigned long long));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
@@ -799,7 +835,8 @@ int dsp_destroy(dsp_ctx* ctx) {
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     cudaFree(ctx->d_tickets);
-    cudaFree(ctx->d_uid);
+    cudaFree(ctx->d_uid); cudaFree(ctx->d_bmask); cudaFree(ctx->d_bvalid);
+    cudaFree(ctx->d_stale_list);
     cudaFree(ctx->d_summary); cudaFree(ctx->d_work_slots); cudaFree(ctx->d_work_entry);
     cudaFree(ctx->d_phase); cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -864,7 +901,8 @@ static int generate_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, in
     const uint32_t* d_list; uint32_t first;
     int rc = upload_positions_and_slots(ctx, m, todo_pos.data(), todo_slots.data(), &d_list, &first);
     if (rc != DSP_OK) { cudaStreamSynchronize(ctx->stream); release_fresh_slots(ctx, fresh_slots); return rc; }
-    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(m), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary, ctx->d_uid};
+    dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, d_list, first, static_cast<uint32_t>(m), gen_kind, seed, make_int3(0, 0, 0), make_uint3(0, 0, 0), nullptr, ctx->d_summary, ctx->d_uid, ctx->d_bvalid};
+    ctx->bmask_stale = true;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(m, static_cast<uint64_t>(ctx->num_sms) * 64));
     dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
     DSP_CUDA(ctx, cudaGetLastError());
@@ -900,7 +938,7 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
     ctx->nbr_dirty = true;
     if (gen_kind == DSP_GEN_NOISE) {
         // heightmap computed once per chunk column and reused up the stack (terrain_fill_region_noise_kernel)
-        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed, ctx->d_summary, ctx->d_uid};
+        dsp::RegionFillParams rp{ctx->d_voxels, ctx->d_pos, first, make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), 0u, seed, ctx->d_summary, ctx->d_uid, ctx->d_bmask, ctx->d_bvalid};
         // enough CTAs to fill the machine a few times over, but as tall a run per CTA as that allows
         const uint64_t columns = static_cast<uint64_t>(dims[0]) * dims[2], want = static_cast<uint64_t>(ctx->num_sms) * 16;
         uint32_t pieces = static_cast<uint32_t>(std::min<uint64_t>(dims[1], std::max<uint64_t>(1, (want + columns - 1) / columns)));
@@ -914,7 +952,8 @@ int dsp_generate_region(dsp_ctx* ctx, const int32_t origin[3], const uint32_t di
         if (n > 0xFFFFFFFFull) return fail(ctx, DSP_ERR_BAD_ARG, "region too large");
         // positions are arithmetic in a box: the fill kernel derives them from the chunk's index and records them itself
         dsp::TerrainParams p{ctx->d_voxels, ctx->d_pos, nullptr, first, static_cast<uint32_t>(n), gen_kind, seed,
-                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos, ctx->d_summary, ctx->d_uid};
+                             make_int3(origin[0], origin[1], origin[2]), make_uint3(dims[0], dims[1], dims[2]), ctx->d_pos, ctx->d_summary, ctx->d_uid, ctx->d_bvalid};
+        ctx->bmask_stale = true;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n, static_cast<uint64_t>(ctx->num_sms) * 64));
         dsp::terrain_fill_kernel<<<grid, 256, 0, ctx->stream>>>(p);
         DSP_CUDA(ctx, cudaGetLastError());
@@ -947,6 +986,10 @@ int dsp_clone_region(dsp_ctx* ctx, uint32_t src_first_slot, const int32_t new_or
                                   n * dsp::kChunkBytes, cudaMemcpyDeviceToDevice, ctx->stream));
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_summary + first, ctx->d_summary + from.first_slot, n, cudaMemcpyDeviceToDevice, ctx->stream));
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_uid + first, ctx->d_uid + from.first_slot, n * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_bmask + static_cast<size_t>(first) * dsp::kBorderMaskStride, ctx->d_bmask + static_cast<size_t>(from.first_slot) * dsp::kBorderMaskStride,
+                                  n * dsp::kBorderMaskStride * sizeof(uint16_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_bvalid + first, 0, n, ctx->stream));  // (re-derived on demand; the copied masks are only overwritten with the same values)
+    ctx->bmask_stale = true;
     dsp::region_positions_kernel<<<static_cast<unsigned>(std::min<uint64_t>((n + 255) / 256, 65535)), 256, 0, ctx->stream>>>(
         ctx->d_pos, first, make_int3(new_origin[0], new_origin[1], new_origin[2]), make_uint3(from.dims[0], from.dims[1], from.dims[2]), n);
     DSP_CUDA(ctx, cudaGetLastError());
@@ -968,7 +1011,8 @@ int dsp_invalidate_chunks(dsp_ctx* ctx, uint64_t n, const uint32_t* slots) {
     if ((rc = ensure_scratch(ctx, n * sizeof(uint32_t))) != DSP_OK) return rc;
     DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, h, n * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = stage_release(ctx)) != DSP_OK) return rc;
-    dsp::invalidate_summaries_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_summary, reinterpret_cast<const uint32_t*>(ctx->d_scratch), static_cast<uint32_t>(n));
+    dsp::invalidate_summaries_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_summary, ctx->d_bvalid, reinterpret_cast<const uint32_t*>(ctx->d_scratch), static_cast<uint32_t>(n));
+    ctx->bmask_stale = true;
     DSP_CUDA(ctx, cudaGetLastError());
     ctx->launches++;
     return DSP_OK;
@@ -1212,7 +1256,8 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
         // DMA engine until all tile copies are through (0.73 -> 0.93 ms).  So positions and the slot list do not use a copy
         // engine at all: a small kernel on the main stream reads them straight from the pinned staging block (UVA).
         dsp::stage_positions_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
+            ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_bvalid, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
+        ctx->bmask_stale = true;
         if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "stage_positions_kernel launch failed"));
         const uint32_t* d_list = consecutive ? nullptr : ctx->d_slots + i0;
         ctx->stream = ctx->copy_stream;  // upload_by_runs enqueues on ctx->stream
@@ -1313,7 +1358,8 @@ int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* o
         if (rc != DSP_OK) return rc;
         DSP_CUDA(ctx, cudaMemcpyAsync(ctx->d_scratch, packed.data(), packed.size() * sizeof(uint2), cudaMemcpyHostToDevice, ctx->stream));
         dsp::edit_scatter_kernel<<<static_cast<unsigned>((packed.size() + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_voxels, ctx->d_summary, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(packed.size()));
+            ctx->d_voxels, ctx->d_summary, ctx->d_bvalid, reinterpret_cast<const uint2*>(ctx->d_scratch), static_cast<uint32_t>(packed.size()));
+        ctx->bmask_stale = true;
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
     }

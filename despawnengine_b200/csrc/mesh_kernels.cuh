@@ -40,6 +40,7 @@ struct MeshParams {
     const int4* chunk_pos;      // per slot
     const uint32_t* slot_list;  // nullable
     const uint32_t* nbr_slots;  // [max_chunks][6] (halo mode) or nullptr: neighbour slot, kNbrExternal | slab index, or none
+    const uint16_t* bmask;      // [max_chunks][96] border occupancy masks (halo mode): 6 one-voxel border layers x 16 masks per chunk
     const uint16_t* halo_slabs; // [n_slabs][256] border layers received from other devices (halo mode)
     const float4* uvmap;        // [n_blocks + 1], last row = fallback
     uint32_t n_blocks;
@@ -137,6 +138,8 @@ __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
     *p.done = 0u;
 }
 
+constexpr int kNbrMasks = 96;           // 6 neighbours x 16 border masks (see fetch_nbr_mask)
+constexpr int kBorderMaskStride = 96;   // u16 per chunk in MeshParams::bmask
 constexpr int kTileFaces = 256;
 constexpr int kTileBytes = kTileFaces * kFaceBytes;  // 30,720
 constexpr int kWarpSlotWords = 32 * kFaceWords;      // 3,840 bytes: one warp's 32 faces
@@ -212,13 +215,39 @@ struct MeshCfg {
     static constexpr int kVox = 0;                                   // 2 x 8192
     static constexpr int kStage = 2 * kChunkBytes;                   // NSTAGE x 30720
     static constexpr int kRec = kStage + NSTAGE * kTileBytes;        // kRecCap x u16
-    static constexpr int kRowMask = kRec + kRecCap * 2;              // 256 x u16
-    static constexpr int kWarpTot = kRowMask + kRows * 2;            // 8 x u32 (+8 pad)
+    static constexpr int kRowMask = kRec + kRecCap * 2;              // 256 x u16 row masks + 96 x u16 neighbour border masks
+    static constexpr int kWarpTot = kRowMask + (kRows + kNbrMasks) * 2;  // 8 x u32 (+8 pad)
     static constexpr int kBar = kWarpTot + 64;                       // 2 x u64
     static constexpr int kBase = kBar + 16;                          // u64
     static constexpr int kNext = kBase + 8;                          // 2 x u32
     static constexpr int kBytes = kNext + 8;
 };
+
+// Border occupancy masks.  Every chunk has a 192-byte side record: for each of its six one-voxel border layers (face order top,
+// bottom, rear, front, right, left) 16 masks of 16 bits -- +-Y layers: mask[z] bit x, +-Z layers: mask[y] bit x, +-X layers:
+// mask[z] bit y (the layouts of dsp_pack_border_slabs, one bit per voxel instead of its u16 id).  Cross-chunk culling needs
+// nothing else of a neighbour, so a chunk's six neighbours cost six 32-byte reads instead of strided reads all over their
+// voxel tiles (round 1: the +-X neighbours alone touched 512 sectors for 64 useful bytes).
+
+// Thread t < 96 of a CTA fetches mask k = t % 16 of the neighbour across face f = t / 16 of chunk `slot`: from the neighbour's
+// side record when it is resident, from the received border layer (16 voxels -> 16 bits) when it lives on another GPU,
+// 0 (air: the border face is emitted, chunk_mesh.rs:46-51) when there is none.
+__device__ __forceinline__ uint32_t fetch_nbr_mask(const MeshParams& p, uint32_t slot, int t) {
+    if (t >= kNbrMasks) return 0u;
+    const int f = t >> 4, k = t & 15;
+    const uint32_t code = __ldg(p.nbr_slots + static_cast<size_t>(slot) * 6 + f);
+    if (code == kNbrNone) return 0u;
+    if (code & kNbrExternal) {
+        // (read through L2 only: a seam's inbox is written by the neighbour GPU while this kernel runs)
+        const uint32_t src = (code >> kNbrSrcShift) & 7u;
+        const uint16_t* base = p.ext_base[0];
+#pragma unroll
+        for (uint32_t j = 1; j < 8u; ++j) base = src == j ? p.ext_base[j] : base;  // selects, not a dynamic index (see seam_wait)
+        const uint4* q = reinterpret_cast<const uint4*>(base + static_cast<size_t>(code & kNbrIndexMask) * 256 + k * 16);
+        return nonzero_mask8(ld_cg_u4(q)) | (nonzero_mask8(ld_cg_u4(q + 1)) << 8);
+    }
+    return __ldg(p.bmask + static_cast<size_t>(code) * kBorderMaskStride + (f ^ 1) * 16 + k);  // the layer that faces us
+}
 
 // The six 16-bit face masks of x-row r = y + 16 z (bit x set: that face of voxel (x, y, z) is emitted), from the row
 // occupancy masks of the chunk in shared memory.  chunk_mesh.rs:46-51.
@@ -226,7 +255,7 @@ struct FaceMasks {
     uint32_t top, bot, rear, front, right, left;
 };
 template <bool HALO>
-__device__ __forceinline__ FaceMasks row_face_masks(const MeshParams& p, uint32_t slot, const uint16_t* s_rowmask, int r, int y, int z, uint32_t m) {
+__device__ __forceinline__ FaceMasks row_face_masks(const uint16_t* s_rowmask, int r, int y, int z, uint32_t m) {
     // chunk_mesh.rs:46-51: outside the chunk counts as air (mask 0) in parity mode
     uint32_t up = y < 15 ? s_rowmask[r + 1] : 0u;
     uint32_t dn = y > 0 ? s_rowmask[r - 1] : 0u;
@@ -234,38 +263,15 @@ __device__ __forceinline__ FaceMasks row_face_masks(const MeshParams& p, uint32_
     uint32_t fr = z < 15 ? s_rowmask[r + 16] : 0u;
     uint32_t xm = 0u, xp = 0u;  // occupancy of the voxel beyond x = 0 / x = 15
     if (HALO) {
-        // extension: consult the resident neighbour across each border (DSP_MESH_HALO)
-        const uint32_t* nb = p.nbr_slots + static_cast<size_t>(slot) * 6;
-        uint32_t code[6];
-#pragma unroll
-        for (int f = 0; f < 6; ++f) code[f] = __ldg(nb + f);  // (arithmetic neighbour slots for box worlds measured no faster)
-        // occupancy of 16 consecutive voxels: row `nr` of a resident neighbour chunk, or row `sr` of a received slab
-        // (external layers are read through L2 only: a seam's inbox is written by the neighbour GPU while this kernel runs)
-        auto ext_slab = [&](uint32_t code) -> const uint16_t* {
-            const uint32_t src = (code >> kNbrSrcShift) & 7u;
-            const uint16_t* base = p.ext_base[0];
-#pragma unroll
-            for (uint32_t k = 1; k < 8u; ++k) base = src == k ? p.ext_base[k] : base;  // selects, not a dynamic index (see seam_wait)
-            return base + static_cast<size_t>(code & kNbrIndexMask) * 256;
-        };
-        auto row_mask_of = [&](uint32_t code, int nr, int sr) -> uint32_t {
-            if (code & kNbrExternal) {
-                const uint4* q = reinterpret_cast<const uint4*>(ext_slab(code) + sr * 16);
-                return nonzero_mask8(ld_cg_u4(q)) | (nonzero_mask8(ld_cg_u4(q + 1)) << 8);
-            }
-            const uint4* q = reinterpret_cast<const uint4*>(p.voxels + static_cast<size_t>(code) * kChunkVoxels + nr * 16);
-            return nonzero_mask8(__ldg(q)) | (nonzero_mask8(__ldg(q + 1)) << 8);
-        };
-        auto voxel_of = [&](uint32_t code, int vidx, int sidx) -> uint32_t {
-            return (code & kNbrExternal) ? ld_cg_u16(ext_slab(code) + sidx) : __ldg(p.voxels + static_cast<size_t>(code) * kChunkVoxels + vidx);
-        };
-        // slab layouts: +-Y faces [z][x], +-Z faces [y][x], +-X faces [z][y] (== row index r)
-        if (y == 15) { const uint32_t s = code[0]; if (s != kNbrNone) up = row_mask_of(s, 0 + 16 * z, z); }
-        if (y == 0) { const uint32_t s = code[1]; if (s != kNbrNone) dn = row_mask_of(s, 15 + 16 * z, z); }
-        if (z == 0) { const uint32_t s = code[2]; if (s != kNbrNone) re = row_mask_of(s, y + 16 * 15, y); }
-        if (z == 15) { const uint32_t s = code[3]; if (s != kNbrNone) fr = row_mask_of(s, y, y); }
-        { const uint32_t s = code[4]; if (s != kNbrNone) xm = voxel_of(s, r * 16 + 15, r) != 0; }
-        { const uint32_t s = code[5]; if (s != kNbrNone) xp = voxel_of(s, r * 16, r) != 0; }
+        // extension (DSP_MESH_HALO): the border rows consult the neighbour chunk across each face -- its border masks are in
+        // shared memory behind the row masks (fetch_nbr_mask, stored by count_phase / the quad kernel before the barrier)
+        const uint16_t* nb = s_rowmask + kRows;
+        if (y == 15) up = nb[0 * 16 + z];
+        if (y == 0) dn = nb[1 * 16 + z];
+        if (z == 0) re = nb[2 * 16 + y];
+        if (z == 15) fr = nb[3 * 16 + y];
+        xm = (nb[4 * 16 + z] >> y) & 1u;
+        xp = (nb[5 * 16 + z] >> y) & 1u;
     }
     FaceMasks f;
     f.top = m & ~up; f.bot = m & ~dn; f.rear = m & ~re; f.front = m & ~fr;
@@ -337,6 +343,8 @@ struct MeshCta {
     // first barrier is executed and total = cnt = 0 is returned with *empty = true; the caller then does nothing else.
     __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish, bool* empty = nullptr) const {
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
+        uint32_t nbv = 0u;
+        if (HALO) nbv = fetch_nbr_mask(p, slot_of(chunk), tid);  // (global loads: issued before the tile is touched)
         uint32_t m;
         {
             const uint4* rowp = reinterpret_cast<const uint4*>(vox + r * 16);
@@ -345,6 +353,7 @@ struct MeshCta {
             m = (nonzero_mask8(qa) << (8 * h)) | (nonzero_mask8(qb) << (8 * (h ^ 1)));
         }
         s_rowmask[r] = static_cast<uint16_t>(m);
+        if (HALO && tid < kNbrMasks) s_rowmask[kRows + tid] = static_cast<uint16_t>(nbv);
         if (empty != nullptr) {
             *empty = __syncthreads_or(m != 0u) == 0;
             if (*empty) return RowFaces{};
@@ -353,7 +362,7 @@ struct MeshCta {
         }
         RowFaces f;
         {
-            const FaceMasks fm = row_face_masks<HALO>(p, HALO ? slot_of(chunk) : 0u, s_rowmask, r, y, z, m);
+            const FaceMasks fm = row_face_masks<HALO>(s_rowmask, r, y, z, m);
             f.top = fm.top; f.bot = fm.bot; f.rear = fm.rear; f.front = fm.front; f.right = fm.right; f.left = fm.left;
         }
         f.cnt = __popc(f.top) + __popc(f.bot) + __popc(f.rear) + __popc(f.front) + __popc(f.right) + __popc(f.left);

@@ -43,8 +43,8 @@ struct QuadSmem {
     static constexpr int kVox = 0;                                    // kVoxBufs x 8192
     static constexpr int kStage = kVoxBufs * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
     static constexpr int kRec = kStage + kTileQuads * kFaceBytes;     // kRecCap x u32
-    static constexpr int kRowMask = kRec + kRecCap * 4;               // 256 x u16
-    static constexpr int kF = kRowMask + kRows * 2;                   // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
+    static constexpr int kRowMask = kRec + kRecCap * 4;               // 256 x u16 row masks + 96 x u16 neighbour border masks (halo mode) + pad
+    static constexpr int kF = kRowMask + kRows * 2 + 256;             // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
     static constexpr int kEqx = kF + 4 * kT;                          // [256] u16
     static constexpr int kSE45 = kEqx + kT;                           // [2][256] u32: run starts / ends along y of RIGHT (low half) and LEFT (high half)
     static constexpr int kC = kSE45 + 4 * kT;                         // [4][256] u16 continued-run masks per row (TOP, BOTTOM, REAR, FRONT)
@@ -258,6 +258,8 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
         seam_wait<HALO>(p, cur);
+        uint32_t nbv = 0u;
+        if (HALO) nbv = fetch_nbr_mask(p, slot_of(cur), tid);  // the neighbours' border masks (global loads in flight during the tile wait)
         mbar_wait(&s_bar[buf], par);
         QTICK(0);
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
@@ -274,6 +276,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             m = nonzero_mask8(qa) | (nonzero_mask8(qb) << 8);
         }
         s_rowmask[r] = static_cast<uint16_t>(m);
+        if (HALO && tid < kNbrMasks) s_rowmask[kRows + tid] = static_cast<uint16_t>(nbv);
         const uint32_t id0 = vox[0];
         const uint32_t id0w = id0 * 0x00010001u;
         const uint32_t differs = (qa.x ^ id0w) | (qa.y ^ id0w) | (qa.z ^ id0w) | (qa.w ^ id0w) | (qb.x ^ id0w) | (qb.y ^ id0w) | (qb.z ^ id0w) | (qb.w ^ id0w);
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
             }
         } else {
             // ---- 2. face masks (chunk_mesh.rs:46-51); anchors = faces unless merging
-            fm = row_face_masks<HALO>(p, HALO ? slot_of(cur) : 0u, s_rowmask, r, y, z, m);
+            fm = row_face_masks<HALO>(s_rowmask, r, y, z, m);
             A[0] = fm.top; A[1] = fm.bot; A[2] = fm.rear; A[3] = fm.front; A[4] = fm.right; A[5] = fm.left;
             if (HALO && GREEDY) {
                 // cross-chunk culling buries most solid chunks completely: find that out before the merge machinery runs

@@ -30,6 +30,7 @@ struct TerrainParams {
     int4* chunk_pos_out;
     uint8_t* summary;  // per slot: kSummaryUnknown / kSummaryAir / kSummarySolid, written where the generator knows (may be nullptr)
     uint16_t* uid;     // per slot, meaningful only while summary has kSummarySolid: the block id every voxel has, or kUidMixed
+    uint8_t* bvalid;   // per slot: border masks (MeshParams::bmask) up to date?  Reset here: they are recomputed on demand
 };
 
 // Chunk summaries let the halo-mode mesh call drop all-air chunks and chunks buried among solid neighbours before the mesh
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(256) terrain_fill_kernel(const TerrainParams p
             summary = s_red[0] & s_red[1] & s_red[2] & s_red[3] & s_red[4] & s_red[5] & s_red[6] & s_red[7];
         }
         if (tid == 0 && p.summary != nullptr) {
+            p.bvalid[slot] = 0;
             p.summary[slot] = static_cast<uint8_t>(summary);
             if (summary & kSummarySolid) {
                 // reference rule: a full chunk is all "template:dirt" = 1; noise: id 1 below the surface voxel (id 2), so the chunk
@@ -187,6 +189,8 @@ struct RegionFillParams {
     uint32_t seed;
     uint8_t* summary;    // see TerrainParams
     uint16_t* uid;
+    uint16_t* bmask;     // [slot][96] border occupancy masks, written here from the heightmap (kBorderMaskStride)
+    uint8_t* bvalid;
 };
 
 __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const RegionFillParams p) {
@@ -256,6 +260,27 @@ __global__ void __launch_bounds__(256) terrain_fill_region_noise_kernel(const Re
                 }
                 dst[hr] = make_uint4(w[0], w[1], w[2], w[3]);
             }
+            {
+                // border occupancy masks straight from the heightmap: voxel (x, y, z) is solid iff cy * 16 + y <= h(x, z) - 1.
+                // +-Y layers: thread (x = tid & 15, z = tid >> 4), half-warp ballot = mask[z]; +-Z and +-X layers: thread
+                // (bit = tid & 15, k = tid >> 4) = (x, y) resp. (y, z).
+                const int lo4 = tid & 15, hi4 = tid >> 4, lane = tid & 31;
+                const int32_t top = cy * 16 + 15, bot = cy * 16;
+                const int32_t h_xz = s_h[tid];
+                const uint32_t b_top = __ballot_sync(0xFFFFFFFFu, top <= h_xz - 1), b_bot = __ballot_sync(0xFFFFFFFFu, bot <= h_xz - 1);
+                const int32_t wy_k = cy * 16 + hi4;   // (x = lo4, y = hi4)
+                const uint32_t b_rear = __ballot_sync(0xFFFFFFFFu, wy_k <= s_h[lo4] - 1), b_front = __ballot_sync(0xFFFFFFFFu, wy_k <= s_h[15 * 16 + lo4] - 1);
+                const int32_t wy_b = cy * 16 + lo4;   // (y = lo4, z = hi4)
+                const uint32_t b_right = __ballot_sync(0xFFFFFFFFu, wy_b <= s_h[hi4 * 16] - 1), b_left = __ballot_sync(0xFFFFFFFFu, wy_b <= s_h[hi4 * 16 + 15] - 1);
+                if ((lane & 15) == 0) {
+                    uint16_t* bm = p.bmask + static_cast<size_t>(slot) * kBorderMaskStride + hi4;
+                    const int sh = lane & 16;
+                    bm[0] = static_cast<uint16_t>(b_top >> sh);    bm[16] = static_cast<uint16_t>(b_bot >> sh);
+                    bm[32] = static_cast<uint16_t>(b_rear >> sh);  bm[48] = static_cast<uint16_t>(b_front >> sh);
+                    bm[64] = static_cast<uint16_t>(b_right >> sh); bm[80] = static_cast<uint16_t>(b_left >> sh);
+                }
+                if (tid == 0) p.bvalid[slot] = 1;
+            }
             if (tid == 0) {
                 p.chunk_pos[slot] = make_int4(cx, cy, cz, 0);
                 if (p.summary != nullptr) {
@@ -308,25 +333,71 @@ __global__ void region_neighbours_kernel(uint32_t* nbr, uint32_t first_slot, uin
     }
 }
 // positions and slot list of a sub-batch, read directly from pinned host memory (no copy engine involved)
-__global__ void stage_positions_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, const int4* host_pos, const uint32_t* host_slots, uint32_t n) {
+__global__ void stage_positions_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, uint8_t* bvalid, const int4* host_pos, const uint32_t* host_slots, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t s = host_slots[i];
     chunk_pos[s] = host_pos[i];
     slot_list_out[i] = s;
     summary[s] = kSummaryUnknown;  // host voxels are about to land in this slot
+    bvalid[s] = 0;
 }
-__global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, const uint32_t* slots, const int4* src, uint32_t n) {
+__global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, uint8_t* bvalid, const uint32_t* slots, const int4* src, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     chunk_pos[slots[i]] = src[i];
     summary[slots[i]] = kSummaryUnknown;  // the slot is being (re)defined; a generator that follows sets it again
+    bvalid[slots[i]] = 0;
 }
 
 // dsp_invalidate_chunks: the caller wrote voxels behind the library's back (dsp_voxel_device_ptr); forget what is known
-__global__ void invalidate_summaries_kernel(uint8_t* summary, const uint32_t* slots, uint32_t n) {
+__global__ void invalidate_summaries_kernel(uint8_t* summary, uint8_t* bvalid, const uint32_t* slots, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) summary[slots[i]] = kSummaryUnknown;
+    if (i < n) { summary[slots[i]] = kSummaryUnknown; bvalid[slots[i]] = 0; }
+}
+
+// ---- border occupancy masks (MeshParams::bmask) on demand ------------------------------------------------------------------
+// Writers that know the terrain analytically fill a chunk's masks as they go (terrain_fill_region_noise_kernel); everybody else
+// -- the other generators, host uploads, edits, dsp_invalidate_chunks -- clears the chunk's `bvalid` byte, and a halo-mode mesh
+// call first brings the masks of the chunks it touches (its own and their resident neighbours) up to date:
+//   find_stale_masks_kernel   one thread per chunk of the call: every chunk among {self, 6 neighbours} whose byte is 0 is queued
+//                             once (atomicOr of a "queued" bit on the byte's word) into a list;
+//   refresh_border_masks_kernel   one CTA per queued chunk: row occupancy of the 256 x-rows from the voxel tile -> the six layers.
+// bvalid byte: bit 0 = masks valid, bit 1 = queued.
+__global__ void find_stale_masks_kernel(uint8_t* bvalid, const uint32_t* nbr, const uint32_t* slot_list, uint32_t first_slot, uint32_t n, uint32_t* list,
+                                        uint32_t* count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t slot = slot_list ? slot_list[i] : first_slot + i;
+#pragma unroll
+    for (int f = -1; f < 6; ++f) {
+        const uint32_t s = f < 0 ? slot : nbr[static_cast<size_t>(slot) * 6 + f];
+        if (s == 0xFFFFFFFFu || (s & 0x80000000u)) continue;  // none / lives on another GPU (its layer arrives through the seam)
+        if (bvalid[s] != 0) continue;                          // valid, or queued by somebody else
+        uint32_t* word = reinterpret_cast<uint32_t*>(bvalid + (s & ~3u));
+        const uint32_t bit = 2u << (8u * (s & 3u));
+        if ((atomicOr(word, bit) & (3u << (8u * (s & 3u)))) == 0u) list[atomicAdd(count, 1u)] = s;
+    }
+}
+__global__ void __launch_bounds__(256) refresh_border_masks_kernel(const uint16_t* voxels, uint16_t* bmask, uint8_t* bvalid, const uint32_t* list, const uint32_t* count) {
+    const int tid = threadIdx.x, y = tid & 15, z = tid >> 4, lane = tid & 31;
+    const uint32_t n = *count;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t slot = list[i];
+        const uint4* rowp = reinterpret_cast<const uint4*>(voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
+        const uint32_t m = nonzero_mask8(rowp[0]) | (nonzero_mask8(rowp[1]) << 8);  // occupancy of x-row (y, z)
+        uint16_t* bm = bmask + static_cast<size_t>(slot) * kBorderMaskStride;
+        if (y == 15) bm[0 * 16 + z] = static_cast<uint16_t>(m);
+        if (y == 0) bm[1 * 16 + z] = static_cast<uint16_t>(m);
+        if (z == 0) bm[2 * 16 + y] = static_cast<uint16_t>(m);
+        if (z == 15) bm[3 * 16 + y] = static_cast<uint16_t>(m);
+        const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, m & 1u), b15 = __ballot_sync(0xFFFFFFFFu, (m >> 15) & 1u);  // bit y of mask[z], two z per warp
+        if ((lane & 15) == 0) {
+            bm[4 * 16 + z] = static_cast<uint16_t>(b0 >> (lane & 16));
+            bm[5 * 16 + z] = static_cast<uint16_t>(b15 >> (lane & 16));
+        }
+        if (tid == 0) bvalid[slot] = 1;
+    }
 }
 
 // Halo-mode pre-pass: chunk i of the call needs no meshing when it is all air, or free of air with six RESIDENT neighbours
@@ -562,12 +633,13 @@ __global__ void __launch_bounds__(256) palette_remap_kernel(uint16_t* voxels, co
 // Chunk::set_block on resident chunks (chunk.rs:49-68).  The host has already resolved world
 // coordinates to (slot, voxel index) and kept only the last edit per voxel, so the scatter is
 // race-free.  packed = slot (u32), idx | block << 16 (u32).
-__global__ void edit_scatter_kernel(uint16_t* voxels, uint8_t* summary, const uint2* edits, uint32_t n) {
+__global__ void edit_scatter_kernel(uint16_t* voxels, uint8_t* summary, uint8_t* bvalid, const uint2* edits, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint2 e = edits[i];
     voxels[static_cast<size_t>(e.x) * kChunkVoxels + (e.y & 0xFFFu)] = static_cast<uint16_t>(e.y >> 16);
     summary[e.x] = kSummaryUnknown;
+    bvalid[e.x] = 0;
 }
 
 // ---- device-side edit pipeline for worlds made of box regions (dsp_apply_edits / dsp_apply_edits_and_remesh) ------------
@@ -593,6 +665,7 @@ struct EditParams {
     uint32_t* dirty_bitmap;   // one bit per slot; zeroed before the call
     const uint32_t* nbr;      // halo mode: [slot][6] neighbour table; an edit on a chunk border also dirties the resident neighbour
     uint8_t* summary;         // edited chunks become kSummaryUnknown
+    uint8_t* bvalid;          // ... and their border masks stale
 };
 
 __device__ __forceinline__ bool edit_key(const EditParams& p, const int4 e, uint64_t* key) {
@@ -643,6 +716,7 @@ __global__ void edit_apply_kernel(const EditParams p) {
             const uint32_t slot = static_cast<uint32_t>(key >> 12);
             atomicOr(&p.dirty_bitmap[slot >> 5], 1u << (slot & 31u));
             p.summary[slot] = kSummaryUnknown;
+            p.bvalid[slot] = 0;
             if (p.nbr != nullptr) {  // cross-chunk culling: the neighbour's border faces depend on this voxel
                 const int lx = e.x & 15, ly = e.y & 15, lz = e.z & 15;
                 const int faces[3] = {ly == 15 ? 0 : (ly == 0 ? 1 : -1), lz == 0 ? 2 : (lz == 15 ? 3 : -1), lx == 0 ? 4 : (lx == 15 ? 5 : -1)};
