@@ -1225,6 +1225,19 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
         return code;
     };
     uint64_t* const h_cursor = reinterpret_cast<uint64_t*>(ctx->h_pinned + 512);  // kMaxSub x u64 of the 4 KiB pinned block
+    // Is the destination pinned (device-accessible) host memory?  Then the download needs no host in the loop (see below).
+    uint8_t* zero_copy_dst = nullptr;
+    unsigned long long* d_cursors = nullptr;
+    if (readback) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, host_vertices) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr) {
+            zero_copy_dst = static_cast<uint8_t*>(attr.devicePointer);
+            if ((rc = ensure_scratch(ctx, dsp_ctx::kMaxSub * sizeof(unsigned long long))) != DSP_OK) return rc;
+            d_cursors = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+        } else {
+            cudaGetLastError();
+        }
+    }
     int last_sub = -1;
     uint64_t copied_to = 0;
     const uint64_t room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
@@ -1271,8 +1284,23 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
         tr("sub-batch enqueued");
         if (readback) {
             // where the cursor stands after this sub-batch: its vertices are the arena bytes [cursor(j-1), cursor(j))
-            if (cudaMemcpyAsync(h_cursor + j, ctx->d_ctl + 16, 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
-                cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess)
+            if (zero_copy_dst != nullptr) {
+                // pinned destination: the device keeps the cursor history itself and a copy kernel on the third stream, ordered
+                // behind this sub-batch by an event, stores the window into host memory -- the host enqueues and moves on
+                dsp::publish_u64_kernel<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long*>(ctx->d_ctl + 16), d_cursors + j);
+                if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess ||
+                    cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_meshed[j], 0) != cudaSuccess)
+                    return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the download pipeline"));
+                dsp::copy_window_to_host_kernel<<<ctx->num_sms * 2, 256, 0, ctx->d2h_stream>>>(ctx->d_arena + arena_offset, zero_copy_dst, last_sub >= 0 ? d_cursors + last_sub : nullptr,
+                                                                                               d_cursors + j, std::min<uint64_t>(room, host_capacity));
+                if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "copy_window_to_host_kernel launch failed"));
+                ctx->launches += 2;
+                last_sub = j;
+                continue;
+            }
+            // pageable destination: the copy engine needs sizes on the host -- read the cursor back, wait for the previous sub-batch
+            dsp::publish_u64_kernel<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long*>(ctx->d_ctl + 16), reinterpret_cast<unsigned long long*>(h_cursor + j));
+            if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess)
                 return bail(fail(ctx, DSP_ERR_CUDA, "cursor read-back failed in the copy pipeline"));
             // ... and the PREVIOUS sub-batch's vertices leave for the host now: its kernel has finished (this wait is short, the
             // copy of sub-batch j is what the host would otherwise idle behind), the next upload is already in the DMA queue
@@ -1280,7 +1308,7 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
             last_sub = j;
         }
     }
-    if (readback && last_sub >= 0 && (rc = copy_out(last_sub)) != DSP_OK) return bail(rc);
+    if (readback && zero_copy_dst == nullptr && last_sub >= 0 && (rc = copy_out(last_sub)) != DSP_OK) return bail(rc);
     if (out_slots) std::memcpy(out_slots, h_slots, n * sizeof(uint32_t));
     if ((rc = stage_release(ctx)) != DSP_OK) return rc;
     if (trace) { cudaStreamSynchronize(ctx->copy_stream); tr("copies done"); }

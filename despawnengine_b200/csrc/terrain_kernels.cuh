@@ -602,6 +602,25 @@ __global__ void __launch_bounds__(256) seam_push_kernel(const SeamPushParams p) 
         }
     }
 }
+// one 64-bit word device -> pinned host memory by a store over PCIe (UVA), not by a copy engine: a small copy would queue
+// behind the bulk uploads that keep the DMA engines busy during a pipelined call
+__global__ void publish_u64_kernel(const unsigned long long* src, unsigned long long* host_dst) {
+    *host_dst = *src;
+    __threadfence_system();
+}
+// dsp_mesh_host_chunks_to_host, device-driven: the arena bytes [*lo_p, *hi_p) of a sub-batch -- bounds that only the device knows
+// when the launch is enqueued (they are the cursor after the previous and after this sub-batch) -- stored straight into
+// pinned host memory over PCIe (UVA), 16 bytes per thread and iteration.  No host round trip sits between the sub-batches.
+__global__ void __launch_bounds__(256) copy_window_to_host_kernel(const uint8_t* arena, uint8_t* host, const unsigned long long* lo_p, const unsigned long long* hi_p,
+                                                                  unsigned long long cap) {
+    const unsigned long long lo = lo_p ? *lo_p : 0ull, hi = min(*hi_p, cap);
+    if (hi <= lo) return;
+    const uint4* src = reinterpret_cast<const uint4*>(arena + lo);
+    uint4* dst = reinterpret_cast<uint4*>(host + lo);
+    const unsigned long long n16 = (hi - lo) >> 4;  // cursors are multiples of 128
+    for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+        dst[i] = __ldcs(src + i);
+}
 __global__ void scatter_u32_kernel(uint32_t* dst, const uint2* idx_val, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[idx_val[i].x] = idx_val[i].y;

@@ -97,3 +97,30 @@ def test_mesh_host_chunks_to_host_mirrors_the_arena(uv_default, mode):
         with pytest.raises(capi.DspError) as ei:
             ctx.mesh_host_chunks_to_host(pos, ids, mode, capacity=4096)
         assert ei.value.status == capi.ERR_BAD_ARG and str(total) in str(ei.value)
+
+
+def test_mesh_host_chunks_to_host_pinned_destination_is_device_driven(uv_default):
+    """Pinned host buffers: the sub-batch windows are stored by a copy kernel over PCIe, no host round trip between sub-batches;
+    same bytes as the arena, for the reference layout and for merged indexed quads."""
+    import torch
+    dims = (16, 12, 16)  # 3,072 chunks
+    pos = np.array([(a, 2 + b, c) for c in range(dims[2]) for b in range(dims[1]) for a in range(dims[0])], dtype=np.int32)
+    n = len(pos)
+    vox = torch.empty((n, 4096), dtype=torch.int16).pin_memory()
+    vox.numpy().view(np.uint16)[:] = orc.generate_batch(orc.GEN_NOISE, SEED, pos)
+    cap = 400 << 20
+    host = torch.zeros(cap, dtype=torch.uint8).pin_memory()
+    entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
+    with capi.Context(0, 4096, 1 << 30) as ctx:
+        ctx.set_uv_table(uv_default)
+        for mode in (capi.MESH_PARITY, capi.MESH_GREEDY | capi.MESH_INDEXED):
+            launches0 = ctx.kernel_launches
+            total = ctx.mesh_host_chunks_to_host_ptr(n, pos, vox.data_ptr(), entries, host.data_ptr(), cap, mode, arena_offset=256)
+            assert ctx.kernel_launches - launches0 >= 4 * 3  # per sub-batch: positions, mesh, cursor, copy-out
+            assert total > 0 and host.numpy()[:total].tobytes() == ctx.download_arena(256, total).tobytes()
+            e = entries[n // 2]
+            o = int(e["offset_bytes"]) - 256
+            if mode == capi.MESH_PARITY:
+                want = orc.mesh_chunk(pos[n // 2], vox.numpy().view(np.uint16)[n // 2], uv_default)
+                assert host.numpy()[o:o + want.nbytes].tobytes() == want.tobytes()
+            ctx.unload_chunks(np.arange(n, dtype=np.uint32))
