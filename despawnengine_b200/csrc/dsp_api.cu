@@ -135,6 +135,7 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
+    bool use_pdl = true;        // programmatic dependent launch of the mesh kernels (DSP_PDL=0 switches it off for A/B runs)
     bool kernel_timing = true;  // record an event pair around every mesh launch (dsp_mesh_kernel_stats)
     bool timing_open = false;   // the start event of the current call's pair has been recorded
     bool ctl_clean = false;    // the control block is all zero (left so by a self-resetting launch): no memset needed
@@ -367,6 +368,20 @@ int end_kernel_timing(dsp_ctx* ctx) {
     return DSP_OK;
 }
 
+// Launch with the programmatic-stream-serialization attribute (the kernels start with griddepcontrol.wait, so the only thing
+// that overlaps the previous kernel's tail is CTA scheduling and launch latency -- safe behind any predecessor).
+template <class Kern>
+cudaError_t launch_pdl(dsp_ctx* ctx, Kern kern, unsigned grid, int smem, const dsp::MeshParams& p) {
+    if (!ctx->use_pdl) { kern<<<grid, 256, smem, ctx->stream>>>(p); return cudaGetLastError(); }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = static_cast<size_t>(smem); cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
 template <class Cfg, bool HALO, bool ORDERED>
 int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
     void (*kern)(const dsp::MeshParams);
@@ -385,8 +400,8 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
     pp.prefetch_ahead = ctx->mesh_prefetch_mult * grid;
     int rc = begin_kernel_timing(ctx);
     if (rc != DSP_OK) return rc;
-    kern<<<grid, 256, smem, ctx->stream>>>(pp);
-    DSP_CUDA(ctx, cudaGetLastError());
+    if (ORDERED) { kern<<<grid, 256, smem, ctx->stream>>>(pp); DSP_CUDA(ctx, cudaGetLastError()); }
+    else DSP_CUDA(ctx, launch_pdl(ctx, kern, grid, smem, pp));
     ctx->launches++;
     return end_kernel_timing(ctx);
 }
@@ -424,8 +439,7 @@ int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p_in) {
     p.phase_cycles = ctx->d_phase;
     int rc = begin_kernel_timing(ctx);
     if (rc != DSP_OK) return rc;
-    kern<<<grid, 256, smem, ctx->stream>>>(p);
-    DSP_CUDA(ctx, cudaGetLastError());
+    DSP_CUDA(ctx, launch_pdl(ctx, kern, grid, smem, p));
     ctx->launches++;
     return end_kernel_timing(ctx);
 }
@@ -778,6 +792,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     ctx->max_chunks = max_chunks;
     ctx->arena_bytes = arena_bytes;
     ctx->num_sms = prop.multiProcessorCount;
+    if (const char* s = getenv("DSP_PDL")) ctx->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
     auto bail = [&](const char* what, cudaError_t err) {

@@ -82,6 +82,12 @@ __device__ __forceinline__ void st_volatile_u64(uint64_t* p, uint64_t v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Programmatic dependent launch: when the host launches a kernel with the "programmatic stream serialization" attribute, its
+// CTAs may be scheduled while the previous kernel of the stream is still draining; pdl_wait() then blocks until that kernel has
+// completed and its memory is visible.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // system-scope acquire / release on 32-bit flags: region-seam hand-shake between GPUs (the writer sits across NVLink)
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
     uint32_t v;

@@ -662,6 +662,10 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const
 // look-back organisation when a reproducible layout matters).
 template <class Cfg, bool HALO>
 __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p_in) {
+    // Back-to-back mesh calls (a frame loop; bench.py's steps): the next launch's CTAs take their SM slots while this launch's
+    // last CTAs drain, and wait here -- before the first global access -- until it has completed (control block reset included).
+    pdl_launch_dependents();
+    pdl_wait();
     MeshParams p = p_in;
     adopt_work_list(p);  // device-built work list (written by an earlier kernel of the same stream)
     extern __shared__ __align__(128) uint8_t smem[];

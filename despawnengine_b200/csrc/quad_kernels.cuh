@@ -154,6 +154,8 @@ __device__ __forceinline__ void emit_uniform_chunk(uint8_t* out, const int4 cp, 
 
 template <bool HALO, bool GREEDY, bool INDEXED>
 __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p_in) {
+    pdl_launch_dependents();  // (see mesh_chunks_bump_kernel)
+    pdl_wait();
     MeshParams p = p_in;
     adopt_work_list(p);  // device-built work list (see classify_chunks_kernel)
     using L = QuadSmem<GREEDY>;
