@@ -75,6 +75,9 @@ SYMBOLS = {
     "dsp_seam_connect": (_int, [_vp, _u32, _vp]),
     "dsp_seam_exchange_async": (_int, [_vp]),
     "dsp_seam_epoch": (_u32, [_vp]),
+    "dsp_comm_unique_id": (_int, [_vp]),
+    "dsp_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "dsp_seam_connect_nccl": (_int, [_vp, _u32, _int]),
     "dsp_visible_chunks": (_int, [_P(C.c_float), _u32, _u32, _u64, _P(_i32), _P(_u64)]),
     "dsp_scene_update": (_int, [_vp, _P(C.c_float), _vp, _vp]),
     "dsp_scene_draw_list": (_int, [_vp, _u64, _P(_i32), _vp, _P(_u64)]),
@@ -116,6 +119,15 @@ def lib() -> C.CDLL:
             raise RuntimeError("ABI version mismatch between capi.py and libdespawn_b200.so")
         _lib = L
     return _lib
+
+
+def comm_unique_id() -> bytes:
+    """A fresh NCCL unique id (128 bytes) for dsp_comm_init: made on one rank, handed to all."""
+    buf = C.create_string_buffer(128)
+    rc = lib().dsp_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc != OK:
+        raise DspError(rc, lib().dsp_last_error(None).decode())
+    return buf.raw
 
 
 def visible_chunks(camera_pos, horizontal: int, vertical: int) -> np.ndarray:
@@ -367,6 +379,14 @@ class Context:
         assert len(peer_handle) == SEAM_HANDLE_BYTES
         buf = C.create_string_buffer(peer_handle, SEAM_HANDLE_BYTES)
         self._check(lib().dsp_seam_connect(self._h, seam, C.cast(buf, C.c_void_p)))
+
+    def comm_init(self, rank: int, n_ranks: int, unique_id: bytes):
+        """NCCL communicator for the fallback seam transport (collective over the ranks)."""
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(lib().dsp_comm_init(self._h, rank, n_ranks, C.cast(buf, C.c_void_p)))
+
+    def seam_connect_nccl(self, seam: int, peer_rank: int):
+        self._check(lib().dsp_seam_connect_nccl(self._h, seam, peer_rank))
 
     def seam_exchange_async(self):
         self._check(lib().dsp_seam_exchange_async(self._h))

@@ -83,7 +83,10 @@ struct dsp_ctx {
         uint8_t* inbox = nullptr; size_t inbox_bytes = 0;           // ours: {flag, ack, data[2][n][256]}
         uint8_t* peer = nullptr; bool peer_ipc = false, connected = false;  // the neighbour's inbox, mapped
         uint32_t* d_done = nullptr;
+        int nccl_peer = -1; uint8_t* outbox = nullptr;                       // NCCL route (fallback): peer rank and the local send buffer
     };
+    void* nccl_comm = nullptr;  // ncclComm_t of dsp_comm_init
+    int nccl_rank = -1;
     std::vector<Seam> seams;
     std::unordered_set<uint32_t> seam_slots;  // every slot listed by a seam (they may not be unloaded)
     uint32_t seam_epoch = 0;

@@ -17,7 +17,55 @@
 //     never overwrite layers its neighbour is still reading, and nobody waits for anybody in steady state.
 // Exchanges are collective over a seam: both sides call dsp_seam_exchange_async once per epoch.
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved at run time (dlopen), there is no link-time dependency
+
 namespace {
+
+// ---- NCCL transport (fallback where a neighbour's memory cannot be mapped: no P2P path, separate PID namespaces) ------------
+// The product path above needs nothing but CUDA.  Where peer mapping is not available, a seam can be given a NCCL route instead:
+// the same push kernel packs the border layers into a LOCAL send buffer, and one grouped ncclSend / ncclRecv per seam on the
+// context's stream moves them into the inbox; a one-thread kernel then raises the inbox flag, so the mesh kernel's wait is the
+// same as on the peer-memory route.  libnccl.so.2 is looked up with dlopen when dsp_comm_init is called (the copy torch has
+// already loaded, else the system one); without it the call fails with a clear message and nothing else is affected.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+const NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the one already in the process (torch's), if any
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { a.why = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return a; }
+        bool all = true;
+        auto get = [&](const char* name, void** fn) { *fn = dlsym(h, name); if (!*fn) { all = false; a.why = std::string("libnccl.so.2 lacks ") + name; } };
+        get("ncclGetUniqueId", reinterpret_cast<void**>(&a.GetUniqueId));
+        get("ncclCommInitRank", reinterpret_cast<void**>(&a.CommInitRank));
+        get("ncclCommDestroy", reinterpret_cast<void**>(&a.CommDestroy));
+        get("ncclGroupStart", reinterpret_cast<void**>(&a.GroupStart));
+        get("ncclGroupEnd", reinterpret_cast<void**>(&a.GroupEnd));
+        get("ncclSend", reinterpret_cast<void**>(&a.Send));
+        get("ncclRecv", reinterpret_cast<void**>(&a.Recv));
+        get("ncclGetErrorString", reinterpret_cast<void**>(&a.GetErrorString));
+        a.ok = all;
+        return a;
+    }();
+    return api;
+}
+#define DSP_NCCL(ctx, call)                                                                                                   \
+    do {                                                                                                                      \
+        ncclResult_t r_ = (call);                                                                                             \
+        if (r_ != ncclSuccess) return fail(ctx, DSP_ERR_CUDA, "%s failed: %s", #call, nccl_api().GetErrorString(r_));         \
+    } while (0)
 
 constexpr uint32_t kSeamMagic = 0x4D535344u;  // "DSSM"
 struct SeamWire {  // what dsp_seam_handle carries (128 bytes)
@@ -60,8 +108,10 @@ void fill_seam_params(const dsp_ctx* ctx, dsp::MeshParams& p) {
 }
 
 void destroy_seams(dsp_ctx* ctx) {
+    if (ctx->nccl_comm) { nccl_api().CommDestroy(static_cast<ncclComm_t>(ctx->nccl_comm)); ctx->nccl_comm = nullptr; }
     for (auto& sm : ctx->seams) {
         if (sm.peer && sm.peer_ipc) cudaIpcCloseMemHandle(sm.peer);
+        cudaFree(sm.outbox);
         cudaFree(sm.inbox);
         cudaFree(sm.d_slots);
         cudaFree(sm.d_done);
@@ -143,10 +193,11 @@ int dsp_seam_exchange_async(dsp_ctx* ctx) {
     if (!ctx) return DSP_ERR_BAD_ARG;
     if (ctx->seams.empty()) return DSP_OK;
     for (size_t s = 0; s < ctx->seams.size(); ++s)
-        if (!ctx->seams[s].connected) return fail(ctx, DSP_ERR_BAD_ARG, "seam %zu has no peer yet (dsp_seam_connect)", s);
+        if (!ctx->seams[s].connected) return fail(ctx, DSP_ERR_BAD_ARG, "seam %zu has no peer yet (dsp_seam_connect / dsp_seam_connect_nccl)", s);
     DSP_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t epoch = ++ctx->seam_epoch;
     if (epoch == 1) ctx->nbr_dirty = true;  // from now on the seam faces have a neighbour
+    bool any_nccl = false;
     for (auto& sm : ctx->seams) {
         dsp::SeamPushParams p{};
         p.voxels = ctx->d_voxels;
@@ -154,15 +205,78 @@ int dsp_seam_exchange_async(dsp_ctx* ctx) {
         p.n = sm.n;
         p.face = sm.face;
         p.epoch = epoch;
-        p.peer = reinterpret_cast<dsp::SeamInbox*>(sm.peer);
-        p.mine = reinterpret_cast<const dsp::SeamInbox*>(sm.inbox);
+        // peer-memory route: straight into the neighbour's inbox; NCCL route: into our own outbox (same layout), shipped below
+        p.peer = reinterpret_cast<dsp::SeamInbox*>(sm.nccl_peer >= 0 ? sm.outbox : sm.peer);
+        p.mine = reinterpret_cast<const dsp::SeamInbox*>(sm.nccl_peer >= 0 ? sm.outbox : sm.inbox);  // (NCCL is stream-ordered: no ack to wait for)
+        if (sm.nccl_peer >= 0) p.epoch_for_ack_wait_off = 1u;
         p.done = sm.d_done;
         p.status = reinterpret_cast<uint32_t*>(ctx->d_ctl) + 1;
         const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(sm.n, static_cast<uint64_t>(ctx->num_sms) * 8));
         dsp::seam_push_kernel<<<grid, 256, 0, ctx->stream>>>(p);
         DSP_CUDA(ctx, cudaGetLastError());
         ctx->launches++;
+        any_nccl = any_nccl || sm.nccl_peer >= 0;
     }
+    if (any_nccl) {
+        const NcclApi& nc = nccl_api();
+        ncclComm_t comm = static_cast<ncclComm_t>(ctx->nccl_comm);
+        DSP_NCCL(ctx, nc.GroupStart());
+        for (auto& sm : ctx->seams) {
+            if (sm.nccl_peer < 0) continue;
+            const size_t bytes = static_cast<size_t>(sm.n) * 512, off = dsp::kSeamInboxHeader + static_cast<size_t>(epoch & 1u) * bytes;
+            DSP_NCCL(ctx, nc.Send(sm.outbox + off, bytes, ncclUint8, sm.nccl_peer, comm, ctx->stream));
+            DSP_NCCL(ctx, nc.Recv(sm.inbox + off, bytes, ncclUint8, sm.nccl_peer, comm, ctx->stream));
+        }
+        DSP_NCCL(ctx, nc.GroupEnd());
+        for (auto& sm : ctx->seams) {
+            if (sm.nccl_peer < 0) continue;
+            dsp::seam_flag_kernel<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<dsp::SeamInbox*>(sm.inbox), epoch);
+            DSP_CUDA(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+    }
+    return DSP_OK;
+}
+
+int dsp_comm_unique_id(uint8_t* out_id128) {
+    if (!out_id128) return fail(nullptr, DSP_ERR_BAD_ARG, "out_id128 is NULL");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(nullptr, DSP_ERR_CUDA, "NCCL is not available: %s", nc.why.c_str());
+    ncclUniqueId id;
+    DSP_NCCL(nullptr, nc.GetUniqueId(&id));
+    static_assert(sizeof id == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out_id128, &id, sizeof id);
+    return DSP_OK;
+}
+
+int dsp_comm_init(dsp_ctx* ctx, int rank, int n_ranks, const uint8_t* id128) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (!id128 || rank < 0 || rank >= n_ranks) return fail(ctx, DSP_ERR_BAD_ARG, "bad communicator arguments");
+    if (ctx->nccl_comm) return fail(ctx, DSP_ERR_BAD_ARG, "the context has a communicator already");
+    const NcclApi& nc = nccl_api();
+    if (!nc.ok) return fail(ctx, DSP_ERR_CUDA, "NCCL is not available: %s", nc.why.c_str());
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    ncclComm_t comm = nullptr;
+    DSP_NCCL(ctx, nc.CommInitRank(&comm, n_ranks, id, rank));
+    ctx->nccl_comm = comm;
+    ctx->nccl_rank = rank;
+    return DSP_OK;
+}
+
+int dsp_seam_connect_nccl(dsp_ctx* ctx, uint32_t seam, int peer_rank) {
+    if (!ctx) return DSP_ERR_BAD_ARG;
+    if (seam >= ctx->seams.size()) return fail(ctx, DSP_ERR_BAD_ARG, "no such seam");
+    if (!ctx->nccl_comm) return fail(ctx, DSP_ERR_BAD_ARG, "dsp_comm_init has not been called on this context");
+    dsp_ctx::Seam& sm = ctx->seams[seam];
+    if (sm.connected) return fail(ctx, DSP_ERR_BAD_ARG, "seam %u is connected already", seam);
+    if (peer_rank < 0 || peer_rank == ctx->nccl_rank) return fail(ctx, DSP_ERR_BAD_ARG, "bad peer rank %d", peer_rank);
+    DSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DSP_CUDA(ctx, cudaMalloc(&sm.outbox, sm.inbox_bytes));
+    DSP_CUDA(ctx, cudaMemset(sm.outbox, 0, sm.inbox_bytes));
+    sm.nccl_peer = peer_rank;
+    sm.connected = true;
     return DSP_OK;
 }
 

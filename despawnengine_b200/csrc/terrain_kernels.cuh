@@ -569,11 +569,13 @@ struct SeamPushParams {
     const SeamInbox* mine;    // our inbox: the peer writes `ack` here
     uint32_t* done;           // CTA counter (local), zeroed by the last CTA
     uint32_t* status;         // context status word: kStatusSeam on time-out
+    uint32_t epoch_for_ack_wait_off;  // non-zero: `peer` is a local send buffer for a stream-ordered transport (NCCL): no ack protocol
 };
+__global__ void seam_flag_kernel(SeamInbox* inbox, uint32_t epoch) { st_release_sys_u32(&inbox->flag, epoch); }
 __global__ void __launch_bounds__(256) seam_push_kernel(const SeamPushParams p) {
     const int t = threadIdx.x, a = t >> 4, b = t & 15;
     if (blockIdx.x == 0 && t == 0) st_release_sys_u32(&p.peer->ack, p.epoch - 1u);
-    if (p.epoch >= 3u) {
+    if (p.epoch >= 3u && p.epoch_for_ack_wait_off == 0u) {
         uint32_t spins = 0;
         while (static_cast<int32_t>(ld_acquire_sys_u32(&p.mine->ack) - (p.epoch - 2u)) < 0) {
             __nanosleep(200);

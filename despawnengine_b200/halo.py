@@ -72,3 +72,19 @@ def connect_region_seams(dev: RegionOnDevice, partition: SlabPartition, rank: in
 
     return connect_seams(transfers, rank, lambda face, positions: dev.ctx.seam_create(face, dev.slots_of(positions)),
                          dev.ctx.seam_connect, all_gather)
+
+
+def connect_region_seams_nccl(dev: RegionOnDevice, partition: SlabPartition, rank: int, dist):
+    """The same seams over the library's NCCL fallback transport (dsp_comm_init + dsp_seam_connect_nccl): for GPUs whose memory
+    cannot be mapped into each other.  The unique id is made on rank 0 and broadcast once; ncclSend / ncclRecv are issued from
+    inside the library on the context's stream."""
+    from . import capi
+    box = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    dev.ctx.comm_init(rank, dist.get_world_size(), box[0])
+    seams = []
+    for t in partition.seam_transfers(rank):
+        seam, _ = dev.ctx.seam_create(t.send_face, dev.slots_of(t.positions))
+        dev.ctx.seam_connect_nccl(seam, t.peer)
+        seams.append(seam)
+    return seams

@@ -268,6 +268,16 @@ int dsp_seam_create(dsp_ctx* ctx, int face, uint64_t n, const uint32_t* slots, u
 int dsp_seam_connect(dsp_ctx* ctx, uint32_t seam, const dsp_seam_handle* peer_handle);
 int dsp_seam_exchange_async(dsp_ctx* ctx); /* all seams of the context; asynchronous on the context's stream */
 uint32_t dsp_seam_epoch(const dsp_ctx* ctx); /* number of exchanges started so far */
+/* Fallback transport for a seam whose neighbour's memory cannot be mapped (no peer path between the GPUs, processes in separate
+ * PID namespaces): NCCL send/recv, called from inside the library on the context's stream.  libnccl.so.2 is resolved with dlopen
+ * when first needed (no link-time dependency).  Rank 0 makes an id with dsp_comm_unique_id and distributes the 128 bytes; every
+ * rank calls dsp_comm_init (collective, like ncclCommInitRank); a seam is then connected with dsp_seam_connect_nccl(seam, rank of
+ * the neighbour) instead of dsp_seam_connect.  dsp_seam_exchange_async and the halo-mode mesh calls are used exactly as above
+ * (both routes may be mixed in one context).  The exchange is then not hidden behind the interior chunks to the same degree: the
+ * receive completes in stream order before the mesh kernel starts. */
+int dsp_comm_unique_id(uint8_t* out_id128);
+int dsp_comm_init(dsp_ctx* ctx, int rank, int n_ranks, const uint8_t* id128);
+int dsp_seam_connect_nccl(dsp_ctx* ctx, uint32_t seam, int peer_rank);
 
 /* ---- scene: GameScene::update's visible set -> load -> mesh -> unload cycle (engine/scenes/scene_game.rs:39-82) -------- */
 typedef struct dsp_scene_config {

@@ -32,15 +32,16 @@ def main():
     ap.add_argument("--arena-gib", type=float, default=8.0)
     ap.add_argument("--quad-modes", action="store_true", help="also run the greedy + indexed modes (chunk-local and halo culling)")
     ap.add_argument("--verify", action="store_true", help="check a sample of seam chunks (and some interior ones) against the oracle, at any world size")
-    ap.add_argument("--seam", choices=["c", "torch"], default="c", help="c: dsp_seam_* inside the library (peer stores over NVLink, wait inside the mesh kernel); "
-                    "torch: pack -> torch.distributed isend/irecv (NCCL) -> dsp_set_halo_slabs, the multi-process fallback")
+    ap.add_argument("--seam", choices=["c", "nccl", "torch"], default="c", help="c: dsp_seam_* inside the library over peer memory (stores over NVLink, wait inside the "
+                    "mesh kernel); nccl: the library's own NCCL fallback transport (ncclSend/ncclRecv from C); torch: pack -> torch.distributed isend/irecv -> "
+                    "dsp_set_halo_slabs (round 1's route)")
     args = ap.parse_args()
 
     import torch
     import torch.distributed as dist
     from despawnengine_b200 import capi
     from despawnengine_b200 import partition as part
-    from despawnengine_b200.halo import RegionOnDevice, connect_region_seams, exchange_region_halos
+    from despawnengine_b200.halo import RegionOnDevice, connect_region_seams, connect_region_seams_nccl, exchange_region_halos
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -76,9 +77,12 @@ def main():
     gen_s = reduce(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
 
     seam_setup_s = 0.0
-    if world > 1 and args.seam == "c":
+    if world > 1 and args.seam in ("c", "nccl"):
         t0 = time.perf_counter()
-        connect_region_seams(dev, sp, rank, dist)  # once: inboxes, handle swap, peer mapping
+        if args.seam == "c":
+            connect_region_seams(dev, sp, rank, dist)  # once: inboxes, handle swap, peer mapping
+        else:
+            connect_region_seams_nccl(dev, sp, rank, dist)  # once: communicator, inboxes + send buffers
         seam_setup_s = time.perf_counter() - t0
 
     out = []
@@ -87,7 +91,7 @@ def main():
         modes += [("greedy_indexed", capi.MESH_GREEDY | capi.MESH_INDEXED), ("halo_greedy_indexed", capi.MESH_HALO | capi.MESH_GREEDY | capi.MESH_INDEXED)]
     for mode_name, mode in modes:
         xchg_s, xchg_bytes = 0.0, 0
-        c_seams = bool(mode & capi.MESH_HALO) and world > 1 and args.seam == "c"
+        c_seams = bool(mode & capi.MESH_HALO) and world > 1 and args.seam in ("c", "nccl")
         if (mode & capi.MESH_HALO) and world > 1 and args.seam == "torch":
             ctx.clear_halo_slabs()
             exchange_region_halos(dev, sp, rank, dist)  # first exchange pays NCCL's lazy point-to-point setup; time the second
