@@ -47,12 +47,12 @@ N_CHUNKS = DIMS[0] * DIMS[1] * DIMS[2]
 UV = np.array([[0, 0, 0, 0], [0.0, 0.0, 0.5, 1.0], [0.5, 0.0, 1.0, 1.0]], dtype=np.float32)
 WORKLOAD = "configs[1]: 16x16x16-chunk region (256^3 voxels) of seeded integer value-noise terrain, reference cull semantics, unit quads"
 METRIC = "chunks meshed/sec"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE mesh_chunks_bump_kernel launch of this exact workload, from the
-# `ncu --set full` capture summarised in profiles/r01_final_bump_ncu_summary.csv (33.65 MB read + 337.92 MB written; the
-# remaining ~59 MB of the 397 MB vertex stream was still dirty in the 126 MB L2 when the kernel ended).  Below the
-# algorithmic 430.5 MB, i.e. no wasted re-reads.
-NCU_TRAFFIC_BYTES = 33_651_968 + 337_916_928
-NCU_TRAFFIC_SOURCE = "profiles/r01_final_bump_ncu_summary.csv (ncu --set full, one launch, same workload)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE mesh_chunks_bump_kernel launch of this exact workload, from the round-2
+# `ncu --set full` capture summarised in profiles/r02_kernels_ncu_summary.csv (launch1: 33.66 MB read + 340.96 MB written; the
+# remaining ~56 MB of the 397 MB vertex stream was still dirty in the 126 MB L2 when the kernel ended).  Below the algorithmic
+# 430.5 MB, i.e. no wasted re-reads.
+NCU_TRAFFIC_BYTES = 33_655_040 + 340_957_952
+NCU_TRAFFIC_SOURCE = "profiles/r02_kernels_ncu_summary.csv (ncu --set full, tools/prof_r02.py, launch1 of mesh_chunks_bump_kernel, same workload)"
 
 
 def workload_config(n_gpus: int) -> dict:
