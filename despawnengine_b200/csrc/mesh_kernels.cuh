@@ -219,8 +219,8 @@ struct MeshCfg {
     static constexpr int kWarpTot = kRowMask + (kRows + kNbrMasks) * 2;  // 8 x u32 (+8 pad)
     static constexpr int kBar = kWarpTot + 64;                       // 2 x u64
     static constexpr int kBase = kBar + 16;                          // u64
-    static constexpr int kNext = kBase + 8;                          // 2 x u32
-    static constexpr int kBytes = kNext + 8;
+    static constexpr int kNext = kBase + 8;                          // 2 x u32 next tickets + 2 x u32 their slots
+    static constexpr int kBytes = kNext + 16;
 };
 
 // Border occupancy masks.  Every chunk has a 192-byte side record: for each of its six one-voxel border layers (face order top,
@@ -247,6 +247,20 @@ __device__ __forceinline__ uint32_t fetch_nbr_mask(const MeshParams& p, uint32_t
         return nonzero_mask8(ld_cg_u4(q)) | (nonzero_mask8(ld_cg_u4(q + 1)) << 8);
     }
     return __ldg(p.bmask + static_cast<size_t>(code) * kBorderMaskStride + (f ^ 1) * 16 + k);  // the layer that faces us
+}
+
+// The same fetch in two stages, for prefetching the NEXT chunk's masks while the current one is processed (each stage is one
+// global load whose latency hides behind a phase of the current chunk): the neighbour code first, the mask later.  Masks of
+// neighbours on other GPUs are not prefetched -- their inbox may only be read after seam_wait -- `*ready` stays false then and the
+// consumer falls back to fetch_nbr_mask.
+__device__ __forceinline__ uint32_t prefetch_nbr_code(const MeshParams& p, uint32_t slot, int t) {
+    return t < kNbrMasks ? __ldg(p.nbr_slots + static_cast<size_t>(slot) * 6 + (t >> 4)) : kNbrNone;
+}
+__device__ __forceinline__ uint32_t prefetch_nbr_mask(const MeshParams& p, uint32_t code, int t, bool* ready) {
+    *ready = true;
+    if (t >= kNbrMasks || code == kNbrNone) return 0u;
+    if (code & kNbrExternal) { *ready = false; return 0u; }
+    return __ldg(p.bmask + static_cast<size_t>(code) * kBorderMaskStride + ((t >> 4) ^ 1) * 16 + (t & 15));
 }
 
 // The six 16-bit face masks of x-row r = y + 16 z (bit x set: that face of voxel (x, y, z) is emitted), from the row
@@ -310,6 +324,9 @@ struct MeshCta {
     uint32_t* s_next;
     int tid, lane, warp, r, y, z;
     uint32_t stage_ctr = 0;
+    // halo mode: the neighbour masks of the chunk that comes next, fetched in two stages during the current chunk
+    uint32_t pf_code = kNbrNone, pf_val = 0u;
+    bool pf_ready = false;
 
     __device__ __forceinline__ MeshCta(const MeshParams& params, uint8_t* smem) : p(params) {
         s_vox = reinterpret_cast<uint16_t*>(smem + Cfg::kVox);
@@ -326,10 +343,22 @@ struct MeshCta {
 
     __device__ __forceinline__ uint32_t slot_of(uint32_t chunk) const { return p.slot_list ? __ldg(p.slot_list + work_index(p, chunk)) : p.first_slot + chunk; }
 
+    // stage A / stage B of the neighbour-mask prefetch for ticket `nxt`, whose slot thread 0 left in s_next[2 + ...] when it issued the tile
+    __device__ __forceinline__ void prefetch_codes(uint32_t nxt, int nxt_buf) {
+        pf_ready = false;
+        pf_code = kNbrNone;
+        if (HALO && nxt < p.n && tid < kNbrMasks) pf_code = prefetch_nbr_code(p, s_next[2 + nxt_buf], tid);
+    }
+    __device__ __forceinline__ void prefetch_masks() {
+        if (HALO) pf_val = prefetch_nbr_mask(p, pf_code, tid, &pf_ready);
+    }
+
     // thread 0 only: 8 KiB voxel tile of `chunk` -> voxel buffer `buf`, completion on s_bar[buf]
     __device__ __forceinline__ void issue_load(uint32_t chunk, int buf) const {
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
-        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
+        const uint32_t slot = slot_of(chunk);
+        s_next[2 + buf] = slot;  // (read by prefetch_codes after the next barrier)
+        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
 #ifdef DSP_L2_PREFETCH
         // tickets are handed out in order, so the tile of chunk + prefetch_ahead will be wanted by some CTA soon: pull it into L2
         const uint64_t ahead = static_cast<uint64_t>(chunk) + p.prefetch_ahead;
@@ -341,10 +370,11 @@ struct MeshCta {
     //      With `publish`, thread 0 posts the chunk's byte size for the look-back of later chunks.
     // `skip_empty`: when the chunk is all air (the reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20) only the
     // first barrier is executed and total = cnt = 0 is returned with *empty = true; the caller then does nothing else.
-    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish, bool* empty = nullptr) const {
+    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish, bool* empty = nullptr, bool use_prefetch = false) const {
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
         uint32_t nbv = 0u;
-        if (HALO) nbv = fetch_nbr_mask(p, slot_of(chunk), tid);  // (global loads: issued before the tile is touched)
+        if (HALO) nbv = (use_prefetch && pf_ready) ? pf_val : fetch_nbr_mask(p, slot_of(chunk), tid);  // prefetched during the previous chunk, or fetched now
+        (void)use_prefetch;
         uint32_t m;
         {
             const uint4* rowp = reinterpret_cast<const uint4*>(vox + r * 16);
@@ -700,9 +730,13 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         c.tick(2);
 #ifndef DSP_NO_EMPTY_SKIP
         bool empty;
-        const RowFaces fc = c.count_phase(cur, buf, false, &empty);
+        const RowFaces fc = c.count_phase(cur, buf, false, &empty, true);
         c.tick(3);
+        // the next ticket (written by thread 0 at the top of this iteration) is visible behind count_phase's barrier: its
+        // neighbour codes start their trip now, its masks after the records -- both land before the next iteration needs them
+        c.prefetch_codes(c.s_next[(it + 1) & 1], buf ^ 1);
         if (empty || fc.total == 0u) {
+            c.prefetch_masks();
             // Nothing to emit and no slot to claim (all air; or, with cross-chunk culling, a chunk buried among solid
             // neighbours).  No further barrier is needed: every read of vox(buf), the row masks and the warp totals precedes a
             // barrier inside count_phase that all threads have passed, and s_next[(it + 1) & 1] was written before it.
@@ -719,9 +753,10 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
             // claim the chunk's arena slot now; the result is not touched until the records are written (see records_and_emit)
             uint64_t claimed = 0;
             if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(slot_bytes_of(fc.total)));
-            c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, []() {}, &claimed);
+            c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() { c.prefetch_masks(); }, &claimed);
         } else {
             c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
+                c.prefetch_masks();
                 if (tid == 0) {  // every warp issues its own stores: the offset goes through shared memory
                     const uint64_t bytes = slot_bytes_of(fc.total);
                     const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
