@@ -389,6 +389,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the mesh path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # Host side of the end-to-end legs: keep this rank's thread -- and with it the pinned buffers it allocates below -- on the CPUs
+    # (NUMA node) the GPU hangs off, so that eight ranks do not all pull their uploads across one socket's memory.
+    affinity = "not set"
+    if os.environ.get("DSP_BENCH_NO_AFFINITY") is None:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+            affinity = f"{len(os.sched_getaffinity(0))} CPUs local to GPU {local_rank} (nvmlDeviceSetCpuAffinity)"
+        except Exception as e:  # pragma: no cover
+            affinity = f"not set ({type(e).__name__})"
     distributed = world > 1
     if distributed:
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
@@ -663,6 +674,7 @@ def main():
                                    "what": "dsp_regenerate_chunks(host positions) + dsp_mesh_chunks -> entry table on the host: the reference's load loop "
                                            "(World::load_chunk generates the chunk, scene_game.rs:56-64), voxels never cross PCIe"},
             "modes_per_gpu": modes_out,
+            "host_affinity_rank0": affinity,
             "configs": configs,
             "clocks": sampler.summary("sampled every 20 ms over the continuous run that contains the timed steps"),
         }

@@ -111,3 +111,24 @@ def test_seam_errors(uv_default):
         with pytest.raises(capi.DspError) as ei:
             a.mesh_range(fa, 8, capi.MESH_HALO)
         assert ei.value.status == capi.ERR_INTERNAL and "seam" in str(ei.value)
+
+
+def test_nccl_fallback_entry_points(uv_default):
+    """The NCCL transport is exercised across processes by tools/world_bench.py --seam nccl (2 GPUs); here: the library finds
+    libnccl.so.2 by itself (no link-time dependency), makes unique ids, and refuses misuse."""
+    a, b = capi.comm_unique_id(), capi.comm_unique_id()
+    assert len(a) == 128 and a != b
+    with capi.Context(0, 64, 16 << 20) as ctx:
+        ctx.set_uv_table(uv_default)
+        f = ctx.generate_region((0, 6, 0), (2, 2, 2), capi.GEN_NOISE, SEED)
+        seam, _ = ctx.seam_create(capi.FACE_LEFT, [f + 1, f + 3, f + 5, f + 7])
+        with pytest.raises(capi.DspError) as ei:
+            ctx.seam_connect_nccl(seam, 1)     # no communicator yet
+        assert ei.value.status == capi.ERR_BAD_ARG
+        ctx.comm_init(0, 1, a)                 # a communicator of one rank: enough to check the plumbing
+        with pytest.raises(capi.DspError):
+            ctx.comm_init(0, 1, b)             # twice
+        with pytest.raises(capi.DspError):
+            ctx.seam_connect_nccl(seam, 0)     # a seam with oneself
+        with pytest.raises(capi.DspError):
+            ctx.seam_connect_nccl(99, 1)
