@@ -82,7 +82,7 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock, power and throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = float(os.environ.get("DSP_BENCH_SAMPLE_PERIOD", "0.02"))):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.power = [], set(), []
