@@ -63,7 +63,7 @@ typedef enum dsp_gen_kind {
 #define DSP_MESH_PARITY 0u /* chunk-local cull, border faces always emitted (chunk_mesh.rs:46-51) */
 #define DSP_MESH_HALO 1u   /* extension: border faces tested against resident neighbour chunks */
 #define DSP_MESH_ORDERED 2u /* pack the chunks' arena slots back to back in the order of the call (reproducible
-                             * layout, ~10 % slower); without it slots are claimed in completion order */
+                             * layout, ~25 % slower: 96 vs 77 us on the bench region); without it slots are claimed in completion order */
 
 /* Quad modes (extensions; spec with the oracle, oracle/mesher_oracle.cpp).  Not available with
  * DSP_MESH_ORDERED. */
