@@ -138,6 +138,7 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
+    int summary_skip = 3;       // parity mesh calls use the chunk summaries: bit 0 all-air chunks end at the ticket, bit 1 chunks of one known solid id skip their tile (DSP_SUMMARY_SKIP=0..3 for A/B runs)
     bool use_pdl = true;        // programmatic dependent launch of the mesh kernels (DSP_PDL=0 switches it off for A/B runs)
     bool kernel_timing = true;  // record an event pair around every mesh launch (dsp_mesh_kernel_stats)
     bool timing_open = false;   // the start event of the current call's pair has been recorded
@@ -507,6 +508,11 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     }
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
     p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
+    if (!halo && !work_list && !(mode & (DSP_MESH_ORDERED | DSP_MESH_GREEDY | DSP_MESH_INDEXED)) && ctx->summary_skip) {
+        p.summary = ctx->d_summary;
+        p.uid = (ctx->summary_skip & 2) ? ctx->d_uid : nullptr;
+        p.summary_air_skip = (ctx->summary_skip & 1) != 0;
+    }
     if (mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return halo ? launch_quads<true>(ctx, p, mode) : launch_quads<false>(ctx, p, mode);
     if (mode & DSP_MESH_ORDERED) return halo ? launch_mesh_variant<true, true>(ctx, p) : launch_mesh_variant<false, true>(ctx, p);
     return halo ? launch_mesh_variant<true, false>(ctx, p) : launch_mesh_variant<false, false>(ctx, p);
@@ -796,6 +802,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     ctx->arena_bytes = arena_bytes;
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* s = getenv("DSP_PDL")) ctx->use_pdl = atoi(s) != 0;
+    if (const char* s = getenv("DSP_SUMMARY_SKIP")) ctx->summary_skip = atoi(s) & 3;
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
     auto bail = [&](const char* what, cudaError_t err) {

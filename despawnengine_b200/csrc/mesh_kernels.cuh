@@ -67,6 +67,11 @@ struct MeshParams {
     const uint32_t* n_dev;
     const uint32_t* entry_map;
     const uint16_t* uid;        // per slot: the chunk's one block id where classify_greedy_kernel listed it as uniform
+    // Chunk-local culling without a pre-pass (mesh_chunks_bump_kernel): per-slot summary bytes, or nullptr.  A chunk whose summary
+    // says "all air" is finished by the thread that takes its ticket -- empty entry, no tile load, no CTA iteration; a chunk of one
+    // known solid block id is meshed from that id without its tile being read (uid above).
+    const uint8_t* summary;
+    bool summary_air_skip;
     // Work list layout: chunks that need nothing from another GPU fill it from the FRONT (count n_dev[0]), chunks with a
     // neighbour across a region seam from the BACK (count n_dev[3], list index n_cap - 1 - k).  Tickets run over the front
     // part first, so by the time a CTA reaches a seam chunk the neighbour GPU's border layers have usually arrived --
@@ -79,6 +84,11 @@ struct MeshParams {
     const uint32_t* seam_flag[7];
     uint32_t n_seams, seam_epoch;
 };
+
+// Chunk summaries (one byte per slot, written by the generators, reset to "unknown" by edits / uploads / dsp_invalidate_chunks;
+// terrain_kernels.cuh has the full story) and the uniform-id side array.
+constexpr uint16_t kUidMixed = 0xFFFFu;  // (uid side array) free of air, but more than one block id -- or not known
+constexpr uint8_t kSummaryUnknown = 0, kSummaryAir = 1, kSummarySolid = 2, kSummaryLayer0 = 4, kSummaryAllSolid = 2 | (63 << 2);
 
 constexpr uint32_t kNbrNone = 0xFFFFFFFFu;
 constexpr uint32_t kNbrExternal = 0x80000000u;  // neighbour lives on another device: bits 28-30 = source (0: dsp_set_halo_slabs,
@@ -219,8 +229,8 @@ struct MeshCfg {
     static constexpr int kWarpTot = kRowMask + (kRows + kNbrMasks) * 2;  // 8 x u32 (+8 pad)
     static constexpr int kBar = kWarpTot + 64;                       // 2 x u64
     static constexpr int kBase = kBar + 16;                          // u64
-    static constexpr int kNext = kBase + 8;                          // 2 x u32 next tickets + 2 x u32 their slots
-    static constexpr int kBytes = kNext + 16;
+    static constexpr int kNext = kBase + 8;                          // 2 x u32 next tickets + 2 x u32 their slots + 2 x u32 "uniform chunk of block id" words
+    static constexpr int kBytes = kNext + 32;
 };
 
 // Border occupancy masks.  Every chunk has a 192-byte side record: for each of its six one-voxel border layers (face order top,
@@ -353,11 +363,32 @@ struct MeshCta {
         if (HALO) pf_val = prefetch_nbr_mask(p, pf_code, tid, &pf_ready);
     }
 
+    // thread 0 only: the first ticket from `t` on that needs the CTA.  Where the chunk summaries are at hand (parity mode, no
+    // pre-pass) an all-air chunk -- the reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20 -- ends right here: empty
+    // entry, next ticket.  Its tile is never read and the CTA spends no iteration (two barriers, a tile wait) on it.
+    __device__ __forceinline__ uint32_t claim_ticket(uint32_t t) const {
+        if (p.summary == nullptr || !p.summary_air_skip) return t;
+        while (t < p.n && (__ldg(p.summary + slot_of(t)) & kSummaryAir)) {
+            *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
+            t = gridDim.x + atomicAdd(p.ticket, 1u);
+        }
+        return t;
+    }
+
     // thread 0 only: 8 KiB voxel tile of `chunk` -> voxel buffer `buf`, completion on s_bar[buf]
     __device__ __forceinline__ void issue_load(uint32_t chunk, int buf) const {
-        mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
         const uint32_t slot = slot_of(chunk);
         s_next[2 + buf] = slot;  // (read by prefetch_codes after the next barrier)
+        // A chunk known to be one solid block id throughout needs no tile: every row mask is 0xFFFF and every voxel is that id.
+        // count_phase rebuilds the tile in shared memory (two STS.128 per thread); the barrier phase completes without bytes.
+        uint32_t uni = 0u;
+        if (p.summary != nullptr && p.uid != nullptr && (__ldg(p.summary + slot) & kSummarySolid)) {
+            const uint32_t id = __ldg(p.uid + slot);
+            if (id != kUidMixed) uni = 0x10000u | id;
+        }
+        s_next[4 + buf] = uni;
+        if (uni) { mbar_arrive(&s_bar[buf]); return; }
+        mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
         bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
 #ifdef DSP_L2_PREFETCH
         // tickets are handed out in order, so the tile of chunk + prefetch_ahead will be wanted by some CTA soon: pull it into L2
@@ -376,7 +407,17 @@ struct MeshCta {
         if (HALO) nbv = (use_prefetch && pf_ready) ? pf_val : fetch_nbr_mask(p, slot_of(chunk), tid);  // prefetched during the previous chunk, or fetched now
         (void)use_prefetch;
         uint32_t m;
-        {
+        const uint32_t uni = s_next[4 + buf];  // written by thread 0 when it "loaded" this buffer, at least one barrier ago
+        if (uni) {
+            // one solid block id (by the chunk's summary): the tile was not loaded -- this thread writes its row of it for emit_face
+            const uint32_t w = (uni & 0xFFFFu) * 0x00010001u;
+            uint4* rowp = reinterpret_cast<uint4*>(s_vox + buf * kChunkVoxels + r * 16);
+            const int h = (r >> 2) & 1;
+            rowp[h] = make_uint4(w, w, w, w);
+            rowp[h ^ 1] = make_uint4(w, w, w, w);
+            fence_proxy_async_smem();  // the next tile load into this buffer is an async-proxy write behind these generic ones
+            m = 0xFFFFu;
+        } else {
             const uint4* rowp = reinterpret_cast<const uint4*>(vox + r * 16);
             const int h = (r >> 2) & 1;  // alternate which half is read first: conflict-free LDS.128
             const uint4 qa = rowp[h], qb = rowp[h ^ 1];
@@ -705,7 +746,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         mbar_init(&c.s_bar[0], 1);
         mbar_init(&c.s_bar[1], 1);
         fence_mbar_init();
-        const uint32_t t0 = blockIdx.x;  // first chunk = block index: the tile load starts without waiting for an atomic
+        const uint32_t t0 = c.claim_ticket(blockIdx.x);  // first chunk = block index: the tile load starts without waiting for an atomic
         c.s_next[0] = t0;
         if (t0 < p.n) c.issue_load(t0, 0);
     }
@@ -720,7 +761,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
     while (cur < p.n) {
         const int buf = it & 1;
         if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
-            const uint32_t t = gridDim.x + atomicAdd(p.ticket, 1u);
+            const uint32_t t = c.claim_ticket(gridDim.x + atomicAdd(p.ticket, 1u));
             c.s_next[(it + 1) & 1] = t;
             if (t < p.n) c.issue_load(t, buf ^ 1);  // buf^1 was released by the barrier that ended the previous iteration
         }

@@ -127,6 +127,47 @@ __device__ __forceinline__ QuadGeom quad_geom(uint32_t rec, const uint16_t* vox,
     return quad_geom_of_id(rec, vox[rec & 0xFFFu], cbx, cby, cbz, uvmap, n_blocks);
 }
 
+// Extent bits (w - 1) << 15 | (h - 1) << 19 of the quad anchored at voxel (x, row rr) in direction d, from the chunk's tables in
+// shared memory: run length from the row's end mask (RIGHT / LEFT: from the end masks of the rows above it in its z-slice), height =
+// how many following rows along the stack axis continue the run -- the continued-run tables hold the 16 entries along the stack
+// axis contiguously, so that is a few 128-bit loads, a bit gather and a count of trailing ones; no walk over rows.
+__device__ __forceinline__ uint32_t quad_extent(uint32_t rec, const uint16_t* s_F, const uint16_t* s_eqx, const uint32_t* s_SE45, const uint16_t* s_C,
+                                                const uint32_t* s_C45) {
+    const uint32_t rr = (rec >> 4) & 0xFFu, x = rec & 15u, d = (rec >> 12) & 7u;
+    const int zz = rr >> 4, yy = rr & 15;
+    uint32_t w1, h1;
+    if (d < 4u) {
+        w1 = __ffs(run_ends(s_F[d * kRows + rr], s_eqx[rr]) >> x) - 1;
+        // the 16 continued-run masks along the stack axis of this quad's column, bit x of each -> one 16-bit word
+        const uint4* col = reinterpret_cast<const uint4*>(s_C + d * kRows + (d < 2u ? yy : zz) * 16);
+        const uint4 ca = col[0], cb = col[1];
+        const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+        uint32_t T = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t b = (w[j] >> x) & 0x00010001u;
+            T |= ((b | (b >> 15)) & 3u) << (2 * j);
+        }
+        h1 = __ffs(~(T >> ((d < 2u ? zz : yy) + 1))) - 1;  // rows after the anchor's that continue the run, up to the first that does not
+    } else {
+        // RIGHT / LEFT: the run climbs the rows of its z-slice until one carries its end bit (run length along y); it is stacked
+        // along z while the rows 16 further on continue it
+        const uint32_t bit = x + 16u * (d - 4u);
+        const uint4* ecol = reinterpret_cast<const uint4*>(s_SE45 + kRows + zz * 16);
+        const uint4* ccol = reinterpret_cast<const uint4*>(s_C45 + yy * 16);
+        uint32_t Te = 0u, Tc = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 e = ecol[j], c = ccol[j];
+            Te |= (((e.x >> bit) & 1u) | (((e.y >> bit) & 1u) << 1) | (((e.z >> bit) & 1u) << 2) | (((e.w >> bit) & 1u) << 3)) << (4 * j);
+            Tc |= (((c.x >> bit) & 1u) | (((c.y >> bit) & 1u) << 1) | (((c.z >> bit) & 1u) << 2) | (((c.w >> bit) & 1u) << 3)) << (4 * j);
+        }
+        w1 = __ffs(Te >> yy) - 1;  // the run's last row always carries the end bit
+        h1 = __ffs(~(Tc >> (zz + 1))) - 1;
+    }
+    return (w1 << 15) | (h1 << 19);
+}
+
 // A chunk of one solid block id under chunk-local culling is exactly six 16 x 16 quads, in stream order BOTTOM, REAR, RIGHT
 // anchored at voxel 0, LEFT at (15,0,0), TOP at (0,15,0), FRONT at (0,0,15).  Slot: align128(6 x 120) or align128(6 x 80) + align128(6 x 24).
 __host__ __device__ constexpr uint32_t uniform_chunk_slot_bytes(bool indexed) { return indexed ? 512u + 256u : 768u; }
@@ -161,6 +202,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     using L = QuadSmem<GREEDY>;
     constexpr uint32_t kRecCap = L::kRecCap;
     constexpr int kTile = L::kTileQuads;
+    constexpr bool DIRECT = GREEDY && INDEXED;  // merged quads in the indexed layout are stored straight to the arena (see the expansion)
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t* const s_vox = reinterpret_cast<uint16_t*>(smem + L::kVox);
     float* const s_stage = reinterpret_cast<float*>(smem + L::kStage);
@@ -173,6 +215,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     uint32_t* const s_C45 = reinterpret_cast<uint32_t*>(smem + L::kC45);
     uint32_t* const s_warp = reinterpret_cast<uint32_t*>(smem + L::kWarpTot);
     uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
+    uint64_t* const s_base = reinterpret_cast<uint64_t*>(smem + L::kBase);
     uint32_t* const s_next = reinterpret_cast<uint32_t*>(smem + L::kNext);
     float* const s_istage = s_stage + kTile * 20;  // indexed layout: the tile's indices follow its vertices
 
@@ -251,11 +294,11 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
     };
     QTICK(8);
     while (cur < p.n) {
+        const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
+        uint32_t tnext = 0;
         if (tid == 0) {
-            const uint32_t t = pending;
-            const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
-            s_next[nb] = t;
-            if (t < p.n) issue_load(t, nb);
+            tnext = pending;
+            s_next[nb] = tnext;
             pending = gridDim.x + atomicAdd(p.ticket, 1u);
         }
         const int4 cp = __ldg(&p.chunk_pos[slot_of(cur)]);
@@ -283,6 +326,10 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
         const uint32_t id0w = id0 * 0x00010001u;
         const uint32_t differs = (qa.x ^ id0w) | (qa.y ^ id0w) | (qa.z ^ id0w) | (qa.w ^ id0w) | (qb.x ^ id0w) | (qb.y ^ id0w) | (qb.z ^ id0w) | (qb.w ^ id0w);
         const bool uniform = __syncthreads_and(differs == 0u) != 0;  // also publishes s_rowmask
+        // The next ticket's tile goes into the buffer of the PREVIOUS iteration only now: merged quads are expanded straight
+        // from the tables and the tile with no barrier behind them, so the barrier above is the first point at which every thread
+        // is known to have finished with that buffer.
+        if (tid == 0 && tnext < p.n) issue_load(tnext, nb);
         QTICK(1);
         if (tid == 0 && pend) { store_tile(pend_claimed, pend_Q, pend_f0, pend_cur); pend = false; }  // the previous chunk's last tile
         QTICK(9);
@@ -465,51 +512,68 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks
                 }
             }
             QTICK(4);
-            if (tid == 0) bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
+            if (DIRECT) {
+                // Merged quads are few (a couple of hundred per surface chunk): in the indexed layout they go STRAIGHT to the arena
+                // from the thread that expands them (five 16-byte stores per quad + its indices) -- no staging tile, no bulk store to
+                // wait for between tiles, no barrier per tile; 35.4-36.7 -> 34.3 us on the bench region in one A/B call.  (The
+                // six-vertex stream form stays on the staging tile: its 120-byte quads are only 8-byte aligned, and fifteen scattered
+                // 8-byte stores per thread cost 12 us more than the bulk store.)  All that is shared is the slot offset: thread 0
+                // publishes it (first touch of the claim's result; the atomic has had the record phase to come back), writes the
+                // entry, and the barrier that publishes the records publishes it too.
+                if (tid == 0 && q0 == 0) {
+                    const bool fits = claimed + quad_slot_bytes(Q, INDEXED) <= p.arena_room;
+                    if (!fits) atomicOr(p.status, kStatusOverflow);
+                    *entry_of(p, cur) = MeshEntry{p.arena_offset + claimed, INDEXED ? Q * 4u : Q * 6u, INDEXED ? Q * 6u : 0u};
+                    *s_base = fits ? claimed : ~0ull;
+                }
+            } else if (tid == 0) {
+                bulk_wait_read<0>();  // the stores that last used the staging tile have drained it
+            }
             __syncthreads();  // records visible
             QTICK(13);
             const uint32_t q1 = min(Q, q0 + kRecCap);
+            if (DIRECT) {
+                const uint64_t base = *s_base;
+                const float cbx = __fmul_rn(__int2float_rn(cp.x), 16.0f);  // math.rs:135-139,166-170
+                const float cby = __fmul_rn(__int2float_rn(cp.y), 16.0f);
+                const float cbz = __fmul_rn(__int2float_rn(cp.z), 16.0f);
+                uint8_t* const gout = p.arena + base;
+                uint8_t* const gidx = gout + quad_vertex_region_bytes(Q, true);
+                for (uint32_t i = tid; i < q1 - q0 && base != ~0ull; i += 256) {
+                    uint32_t rec = s_rec[i];
+                    if (!solid_uniform) rec |= quad_extent(rec, s_F, s_eqx, s_SE45, s_C, s_C45);
+                    const QuadGeom g = quad_geom(rec, vox, cbx, cby, cbz, p.uvmap, p.n_blocks);
+                    float cx[4], cy[4], cz[4], cu[4], cv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t c = g.code >> (5 * k);
+                        cx[k] = (c & 1u) ? g.hx : g.lx;
+                        cy[k] = (c & 2u) ? g.hy : g.ly;
+                        cz[k] = (c & 4u) ? g.hz : g.lz;
+                        cu[k] = (c & 8u) ? g.uv.z : g.uv.x;
+                        cv[k] = (c & 16u) ? g.uv.w : g.uv.y;
+                    }
+                    const uint32_t f = q0 + i;
+                    float4* o = reinterpret_cast<float4*>(gout + static_cast<size_t>(f) * kQuadVertexBytesIdx);  // 80 bytes, 16-byte aligned
+                    o[0] = make_float4(cx[0], cy[0], cz[0], cu[0]);
+                    o[1] = make_float4(cv[0], cx[1], cy[1], cz[1]);
+                    o[2] = make_float4(cu[1], cv[1], cx[2], cy[2]);
+                    o[3] = make_float4(cz[2], cu[2], cv[2], cx[3]);
+                    o[4] = make_float4(cy[3], cz[3], cu[3], cv[3]);
+                    uint2* io = reinterpret_cast<uint2*>(gidx + static_cast<size_t>(f) * kQuadIndexBytes);      // 24 bytes, 8-byte aligned
+                    const uint32_t v0 = f * 4u;
+                    io[0] = make_uint2(v0, v0 + 1u);
+                    io[1] = make_uint2(v0 + 2u, v0 + 2u);
+                    io[2] = make_uint2(v0 + 3u, v0);
+                }
+                QTICK(5);
+                continue;  // next record window (the barrier at its top separates this window's reads of s_rec from the next one's writes)
+            }
             if (GREEDY && !solid_uniform) {
                 // Extent of every quad of the window, one quad per thread over ALL 256 threads (phase timers: with the extent
-                // worked out inside the 128-thread tile loop, expansion was 45 % of a CTA's time and half the warps idled):
-                // run length from the row's end mask, height = how many following rows along the stack axis continue the run
-                // (tables of this chunk, still in shared memory).  Written back into the record.
-                for (uint32_t i = tid; i < q1 - q0; i += 256) {
-                    const uint32_t rec = s_rec[i];
-                    const uint32_t rr = (rec >> 4) & 0xFFu, x = rec & 15u, d = (rec >> 12) & 7u;
-                    const int zz = rr >> 4, yy = rr & 15;
-                    uint32_t w1, h1;
-                    if (d < 4u) {
-                        w1 = __ffs(run_ends(s_F[d * kRows + rr], s_eqx[rr]) >> x) - 1;
-                        // the 16 continued-run masks along the stack axis of this quad's column, bit x of each -> one 16-bit word
-                        const uint4* col = reinterpret_cast<const uint4*>(s_C + d * kRows + (d < 2u ? yy : zz) * 16);
-                        const uint4 ca = col[0], cb = col[1];
-                        const uint32_t w[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
-                        uint32_t T = 0u;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const uint32_t b = (w[j] >> x) & 0x00010001u;
-                            T |= ((b | (b >> 15)) & 3u) << (2 * j);
-                        }
-                        h1 = __ffs(~(T >> ((d < 2u ? zz : yy) + 1))) - 1;  // rows after the anchor's that continue the run, up to the first that does not
-                    } else {
-                        // RIGHT / LEFT: the run climbs the rows of its z-slice until one carries its end bit (run length along y); it is
-                        // stacked along z while the rows 16 further on continue it
-                        const uint32_t bit = x + 16u * (d - 4u);
-                        const uint4* ecol = reinterpret_cast<const uint4*>(s_SE45 + kRows + zz * 16);
-                        const uint4* ccol = reinterpret_cast<const uint4*>(s_C45 + yy * 16);
-                        uint32_t Te = 0u, Tc = 0u;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 e = ecol[j], c = ccol[j];
-                            Te |= (((e.x >> bit) & 1u) | (((e.y >> bit) & 1u) << 1) | (((e.z >> bit) & 1u) << 2) | (((e.w >> bit) & 1u) << 3)) << (4 * j);
-                            Tc |= (((c.x >> bit) & 1u) | (((c.y >> bit) & 1u) << 1) | (((c.z >> bit) & 1u) << 2) | (((c.w >> bit) & 1u) << 3)) << (4 * j);
-                        }
-                        w1 = __ffs(Te >> yy) - 1;          // the run's last row always carries the end bit
-                        h1 = __ffs(~(Tc >> (zz + 1))) - 1;
-                    }
-                    s_rec[i] = rec | (w1 << 15) | (h1 << 19);
-                }
+                // worked out inside the 128-thread tile loop, expansion was 45 % of a CTA's time and half the warps idled).
+                // Written back into the record.
+                for (uint32_t i = tid; i < q1 - q0; i += 256) s_rec[i] |= quad_extent(s_rec[i], s_F, s_eqx, s_SE45, s_C, s_C45);
                 __syncthreads();
             }
             QTICK(12);

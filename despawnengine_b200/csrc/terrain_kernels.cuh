@@ -39,8 +39,7 @@ struct TerrainParams {
 // Bits: air = every voxel is air; solid = no voxel is air; layer f = the one-voxel border layer at face f (order top,
 // bottom, rear, front, right, left) has no air.  0 = nothing known.  A solid chunk is buried, i.e. has no visible face,
 // when across every face a RESIDENT neighbour's facing layer is solid.
-constexpr uint16_t kUidMixed = 0xFFFFu;  // (uid side array) free of air, but more than one block id -- or not known
-constexpr uint8_t kSummaryUnknown = 0, kSummaryAir = 1, kSummarySolid = 2, kSummaryLayer0 = 4, kSummaryAllSolid = 2 | (63 << 2);
+// (the constants kSummary*, kUidMixed are in mesh_kernels.cuh: the mesh kernels consult the summaries too)
 
 // smoothstep-weighted bilinear value noise on a lattice whose values were hashed once per chunk
 // into `lat` (3x3 per octave, [dz][dx]); identical arithmetic to oracle/mesher_oracle.cpp.
