@@ -51,8 +51,8 @@ METRIC = "chunks meshed/sec"
 # `ncu --set full` capture summarised in profiles/r02_kernels_ncu_summary.csv (launch1: 33.66 MB read + 340.96 MB written; the
 # remaining ~56 MB of the 397 MB vertex stream was still dirty in the 126 MB L2 when the kernel ended).  Below the algorithmic
 # 430.5 MB, i.e. no wasted re-reads.
-NCU_TRAFFIC_BYTES = 33_655_040 + 340_957_952
-NCU_TRAFFIC_SOURCE = "profiles/r02_kernels_ncu_summary.csv (ncu --set full, tools/prof_r02.py, launch1 of mesh_chunks_bump_kernel, same workload)"
+NCU_TRAFFIC_BYTES = 10_231_040 + 338_869_248
+NCU_TRAFFIC_SOURCE = "profiles/r02b_kernels_ncu_summary.csv (ncu --set full, tools/prof_r02b.py, launch1 of mesh_chunks_bump_kernel, same workload; the rest of the 396.8 MB vertex stream is still dirty in L2 at kernel exit)"
 
 
 def workload_config(n_gpus: int) -> dict:
@@ -522,6 +522,24 @@ def main():
              "what": "the K steps alone, enqueued on an idle GPU (clocks not yet settled under load)"}
     ctx.set_kernel_timing(True)
 
+    # ---- other kernels on the same region (kernel time from the library's own events, 12 calls back to back;
+    #      before the end-to-end legs, whose uploads reset the chunk summaries of the first copy) ----------
+    modes_out = {}
+    for mname, m in (("ordered", capi.MESH_ORDERED), ("indexed", capi.MESH_INDEXED), ("greedy", capi.MESH_GREEDY), ("greedy_indexed", capi.MESH_GREEDY | capi.MESH_INDEXED)):
+        e_m, tot_m = ctx.mesh_range(first, N_CHUNKS, m)
+        per = 4 if m & capi.MESH_INDEXED else 6
+        quads = int(e_m["vertex_count"].astype(np.int64).sum()) // per
+        ctx.sync()
+        k0, t0ms, _ = ctx.mesh_kernel_stats()
+        for j in range(12):
+            ctx.mesh_range_async(firsts[j % COPIES], N_CHUNKS, m, (j % COPIES) * SLICE)
+        ctx.sync()
+        k1, t1ms, _ = ctx.mesh_kernel_stats()
+        kms = (t1ms - t0ms) / max(1, k1 - k0)
+        ab = N_CHUNKS * (8192 + 32) + (104 if m & capi.MESH_INDEXED else 120) * quads
+        modes_out[mname] = {"quads": quads, "arena_bytes": int(tot_m), "kernel_ms": kms, "chunks_per_s_per_gpu": N_CHUNKS / (kms * 1e-3),
+                            "algorithmic_GBps": ab / (kms * 1e-3) / 1e9, "frac_of_measured_peak": ab / (kms * 1e-3) / 1e9 / peak}
+
     # ---- end-to-end legs: host voxel buffers -> C ABI -> results on the host ---------------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 40)
     pos = region_positions(origin)
@@ -529,6 +547,9 @@ def main():
     hv = host_vox.numpy().view(np.uint16)
     for i in range(N_CHUNKS):  # setup, untimed: host copies of the chunks, as a host caller would hold them (Chunk.blocks)
         hv[i] = ctx.download_chunk(first + i)[0]
+    # chunks whose tile the parity kernel does not read: all air (ended at the ticket) / one solid block id (rebuilt from the id), by the generator's chunk summaries
+    n_air = int((hv == 0).all(axis=1).sum())
+    n_uniform = int(((hv == hv[:, :1]).all(axis=1) & (hv[:, 0] != 0)).sum())
     entries_host = torch.empty(N_CHUNKS * 16, dtype=torch.uint8).pin_memory()
     entries_np = entries_host.numpy().view(capi.MESH_ENTRY_DTYPE)
     h2d = N_CHUNKS * (8192 + 16)
@@ -590,22 +611,26 @@ def main():
 
     gp_value, gp_ms = timed_calls(positions_step, gp_steps)
 
-    # ---- other kernels on the same region (kernel time from the library's own events, 10 launches back to back) ----------
-    modes_out = {}
-    for mname, m in (("ordered", capi.MESH_ORDERED), ("indexed", capi.MESH_INDEXED), ("greedy", capi.MESH_GREEDY), ("greedy_indexed", capi.MESH_GREEDY | capi.MESH_INDEXED)):
-        e_m, tot_m = ctx.mesh_range(first, N_CHUNKS, m)
-        per = 4 if m & capi.MESH_INDEXED else 6
-        quads = int(e_m["vertex_count"].astype(np.int64).sum()) // per
-        ctx.sync()
-        k0, t0ms, _ = ctx.mesh_kernel_stats()
-        for j in range(12):
-            ctx.mesh_range_async(firsts[j % COPIES], N_CHUNKS, m, (j % COPIES) * SLICE)
-        ctx.sync()
-        k1, t1ms, _ = ctx.mesh_kernel_stats()
-        kms = (t1ms - t0ms) / max(1, k1 - k0)
-        ab = N_CHUNKS * (8192 + 32) + (104 if m & capi.MESH_INDEXED else 120) * quads
-        modes_out[mname] = {"quads": quads, "arena_bytes": int(tot_m), "kernel_ms": kms, "chunks_per_s_per_gpu": N_CHUNKS / (kms * 1e-3),
-                            "algorithmic_GBps": ab / (kms * 1e-3) / 1e9, "frac_of_measured_peak": ab / (kms * 1e-3) / 1e9 / peak}
+    # ---- the headline step on a world WITHOUT chunk summaries (what a host-uploaded or freshly edited world looks like): every tile
+    #      is read, all-air chunks cost a CTA iteration.  Same rotating step, 64 launches back to back, one event pair.
+    ctx.set_kernel_timing(False)
+    for f in firsts:
+        ctx.invalidate_chunks(np.arange(f, f + N_CHUNKS, dtype=np.uint32))
+    for k in range(COPIES):
+        step(k)
+    ctx.sync()
+    n0, n1 = _events(torch, stream)
+    barrier()
+    n0.record(stream)
+    for k in range(64):
+        step(k)
+    n1.record(stream)
+    ctx.sync()
+    nosum_ms = max_over_ranks(n0.elapsed_time(n1)) / 64
+    no_summaries = {"ms_per_step": nosum_ms, "chunks_per_s": world * N_CHUNKS / (nosum_ms * 1e-3), "algorithmic_GBps_per_gpu": algo_bytes / (nosum_ms * 1e-3) / 1e9,
+                    "frac_of_measured_peak": algo_bytes / (nosum_ms * 1e-3) / 1e9 / peak,
+                    "what": "the same step after dsp_invalidate_chunks on every chunk (summaries unknown, as after a host upload or an edit): all 4,096 tiles are read"}
+    ctx.set_kernel_timing(True)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------------------------------
     cpu = None
@@ -646,18 +671,22 @@ def main():
                              "voxels and 397 MB of vertices were last touched 1.7 GB of traffic earlier (L2 is 126 MB)",
                        "timing": f"the K timed steps (one kernel launch each, back to back, one CUDA event pair on the context's stream) sit inside a continuous "
                                  f"{sus_total * 1e-3:.2f} s run of the same rotating step ({n_side} steps before, {n_side} after); NVML sampled every 20 ms over the whole run; max over ranks",
-                       "slot_order": "completion order (atomic slot claim); DSP_MESH_ORDERED is under modes_per_gpu.ordered"},
+                       "slot_order": "completion order (atomic slot claim); DSP_MESH_ORDERED (count + scan pass, then the same kernel at preset offsets) is under modes_per_gpu.ordered"},
             "faces_per_step": int(faces_all), "vertex_bytes_per_step_per_gpu": int(total_bytes),
             "voxels_per_s": value * 4096,
             "faces_per_s": faces_all * args.steps / (dev_ms_total * 1e-3),
             "gpu_launches": int(args.steps),
             "gpu_launches_whole_sustained_run": int(launches_total),
             "wall_s_sustained_run": wall1 - wall0,
-            "sustained": sustained, "burst": burst,
+            "sustained": sustained, "burst": burst, "no_summaries": no_summaries,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
                          "kernel": "mesh_chunks_bump_kernel", "kernel_ms_avg": kernel_ms_avg,
                          "algorithmic_bytes_per_launch": int(algo_bytes), "peak_source": peak_src,
+                         "bytes_moved_per_launch": int(algo_bytes - 8192 * (n_air + n_uniform)),
+                         "bytes_moved_note": f"the generator's chunk summaries let the kernel skip the tile of {n_air} all-air and {n_uniform} one-solid-id chunks "
+                                             f"({8192 * (n_air + n_uniform)} B of the algorithmic bytes are not read); `no_summaries` is the same step with every tile read",
+                         "moved_GBps": (algo_bytes - 8192 * (n_air + n_uniform)) / (kernel_ms_avg * 1e-3) / 1e9,
                          "frac_of_8TBs_datasheet": achieved / 8000.0},
             "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps,
                     "ms_per_step": e2e_ms, "h2d_copy_alone_ms": h2d_only_ms,

@@ -94,7 +94,7 @@ struct dsp_ctx {
     unsigned long long arena_vmm_handle = 0;  // DSP_CREATE_EXPORTABLE_ARENA: CUmemGenericAllocationHandle of the arena (dsp_export.inl)
     size_t arena_vmm_size = 0;                // ... and its size rounded to the allocation granularity (0: plain cudaMalloc arena)
     dsp::MeshEntry* d_entries = nullptr;
-    uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][lookback 8 B x max_chunks]
+    uint8_t* d_ctl = nullptr;  // [ctrl 16 B][total 16 B][face counts of the DSP_MESH_ORDERED count pass: 8 B x max_chunks reserved, u32 used][result 16 B]
     uint32_t* d_slots = nullptr;
     uint8_t* d_summary = nullptr;     // per slot: dsp::kSummary* (all air / uniformly solid / unknown)
     uint16_t* d_uid = nullptr;        // per slot, valid while the summary says "no air": the one block id of the chunk, or kUidMixed
@@ -138,6 +138,7 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
+    uint64_t e2e_head_chunks = 128;  // first sub-batch of the pipelined host-chunk calls (DSP_E2E_HEAD=0 switches it off for A/B runs)
     int summary_skip = 3;       // parity mesh calls use the chunk summaries: bit 0 all-air chunks end at the ticket, bit 1 chunks of one known solid id skip their tile (DSP_SUMMARY_SKIP=0..3 for A/B runs)
     bool use_pdl = true;        // programmatic dependent launch of the mesh kernels (DSP_PDL=0 switches it off for A/B runs)
     bool kernel_timing = true;  // record an event pair around every mesh launch (dsp_mesh_kernel_stats)
@@ -375,10 +376,10 @@ int end_kernel_timing(dsp_ctx* ctx) {
 // Launch with the programmatic-stream-serialization attribute (the kernels start with griddepcontrol.wait, so the only thing
 // that overlaps the previous kernel's tail is CTA scheduling and launch latency -- safe behind any predecessor).
 template <class Kern>
-cudaError_t launch_pdl(dsp_ctx* ctx, Kern kern, unsigned grid, int smem, const dsp::MeshParams& p) {
-    if (!ctx->use_pdl) { kern<<<grid, 256, smem, ctx->stream>>>(p); return cudaGetLastError(); }
+cudaError_t launch_pdl(dsp_ctx* ctx, Kern kern, unsigned grid, int smem, const dsp::MeshParams& p, unsigned block = 256) {
+    if (!ctx->use_pdl) { kern<<<grid, block, smem, ctx->stream>>>(p); return cudaGetLastError(); }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = static_cast<size_t>(smem); cfg.stream = ctx->stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = static_cast<size_t>(smem); cfg.stream = ctx->stream;
     cudaLaunchAttribute attr{};
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
@@ -386,12 +387,11 @@ cudaError_t launch_pdl(dsp_ctx* ctx, Kern kern, unsigned grid, int smem, const d
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
-template <class Cfg, bool HALO, bool ORDERED>
+template <class Cfg, bool HALO>
 int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
-    void (*kern)(const dsp::MeshParams);
-    if constexpr (ORDERED) kern = dsp::mesh_chunks_kernel<Cfg, HALO>; else kern = dsp::mesh_chunks_bump_kernel<Cfg, HALO>;
+    void (*kern)(const dsp::MeshParams) = dsp::mesh_chunks_bump_kernel<Cfg, HALO>;
     constexpr int smem = Cfg::kBytes;
-    int& occ = ctx->mesh_ctas_per_sm[variant][(HALO ? 1 : 0) + (ORDERED ? 2 : 0)];
+    int& occ = ctx->mesh_ctas_per_sm[variant][HALO ? 1 : 0];
     if (occ == 0) {
         DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
@@ -404,8 +404,16 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
     pp.prefetch_ahead = ctx->mesh_prefetch_mult * grid;
     int rc = begin_kernel_timing(ctx);
     if (rc != DSP_OK) return rc;
-    if (ORDERED) { kern<<<grid, 256, smem, ctx->stream>>>(pp); DSP_CUDA(ctx, cudaGetLastError()); }
-    else DSP_CUDA(ctx, launch_pdl(ctx, kern, grid, smem, pp));
+    if (pp.preset) {
+        // DSP_MESH_ORDERED, pass 1: sizes and offsets of all chunks in call order (one warp per chunk; the second ticket line counts its CTAs out)
+        dsp::MeshParams cp = pp;
+        cp.ticket = pp.ticket + 32;
+        void (*count_kern)(const dsp::MeshParams) = dsp::count_chunks_scan_kernel<HALO>;
+        const unsigned cgrid = static_cast<unsigned>((p.n + dsp::kCountChunksPerCta - 1) / dsp::kCountChunksPerCta);
+        DSP_CUDA(ctx, launch_pdl(ctx, count_kern, cgrid, 0, cp, dsp::kCountThreads));
+        ctx->launches++;
+    }
+    DSP_CUDA(ctx, launch_pdl(ctx, kern, grid, smem, pp));
     ctx->launches++;
     return end_kernel_timing(ctx);
 }
@@ -414,16 +422,16 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
 //   0: 3 CTAs/SM, one bulk store per 256-face tile     1: 3 CTAs/SM, one bulk store per warp (32 faces)
 //   2: 4 CTAs/SM (8 KiB record window), tile           3: 4 CTAs/SM, warp
 constexpr int kMeshVariants = 4;
-template <bool HALO, bool ORDERED>
+template <bool HALO>
 int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
     // Cross-chunk culling leaves little to emit per chunk and adds dependent neighbour reads: what it needs is more CTAs in
     // flight, so its default is the 4-CTAs/SM shape (config-5 world: 28.4 -> 24.1 ms); DSP_MESH_VARIANT still overrides.
     const int variant = (HALO && !ctx->mesh_variant_forced) ? 2 : ctx->mesh_variant;
     switch (variant) {
-        case 1: return launch_mesh_t<dsp::MeshCfg<3, 1, true>, HALO, ORDERED>(ctx, p, 1);
-        case 2: return launch_mesh_t<dsp::MeshCfg<4, 1, false>, HALO, ORDERED>(ctx, p, 2);
-        case 3: return launch_mesh_t<dsp::MeshCfg<4, 1, true>, HALO, ORDERED>(ctx, p, 3);
-        default: return launch_mesh_t<dsp::MeshCfg<3, 1, false>, HALO, ORDERED>(ctx, p, 0);
+        case 1: return launch_mesh_t<dsp::MeshCfg<3, 1, true>, HALO>(ctx, p, 1);
+        case 2: return launch_mesh_t<dsp::MeshCfg<4, 1, false>, HALO>(ctx, p, 2);
+        case 3: return launch_mesh_t<dsp::MeshCfg<4, 1, true>, HALO>(ctx, p, 3);
+        default: return launch_mesh_t<dsp::MeshCfg<3, 1, false>, HALO>(ctx, p, 0);
     }
 }
 
@@ -507,15 +515,15 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
         p.result = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32 + 8 * ctx->max_chunks);
     }
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
-    p.lookback = reinterpret_cast<uint64_t*>(ctx->d_ctl + 32);
-    if (!halo && !work_list && !(mode & (DSP_MESH_ORDERED | DSP_MESH_GREEDY | DSP_MESH_INDEXED)) && ctx->summary_skip) {
+    p.face_counts = reinterpret_cast<uint32_t*>(ctx->d_ctl + 32);
+    p.preset = (mode & DSP_MESH_ORDERED) != 0;
+    if (!halo && !work_list && !(mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) && ctx->summary_skip) {
         p.summary = ctx->d_summary;
         p.uid = (ctx->summary_skip & 2) ? ctx->d_uid : nullptr;
         p.summary_air_skip = (ctx->summary_skip & 1) != 0;
     }
     if (mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return halo ? launch_quads<true>(ctx, p, mode) : launch_quads<false>(ctx, p, mode);
-    if (mode & DSP_MESH_ORDERED) return halo ? launch_mesh_variant<true, true>(ctx, p) : launch_mesh_variant<false, true>(ctx, p);
-    return halo ? launch_mesh_variant<true, false>(ctx, p) : launch_mesh_variant<false, false>(ctx, p);
+    return halo ? launch_mesh_variant<true>(ctx, p) : launch_mesh_variant<false>(ctx, p);
 }
 
 // Cross-chunk culling reads a neighbour through its border occupancy masks.  Where a writer could not keep them current
@@ -542,15 +550,16 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
     int rc = check_mesh_args(ctx, n, mode, arena_offset);
     if (rc != DSP_OK) return rc;
     ctx->last_mesh_n = n;
-    // Control block.  The atomic-claim kernels reset it themselves at their end (control_block_epilogue), so in steady state a
-    // mesh call is one kernel launch and nothing else; a memset is only needed for the first call, after a multi-launch or
-    // look-back call, and for the look-back words of DSP_MESH_ORDERED.
+    // Control block.  The mesh kernels reset it themselves at their end (control_block_epilogue), so in steady state a mesh call
+    // is one kernel launch (two with DSP_MESH_ORDERED: the count + scan pass) and nothing else; a memset is only needed for the
+    // first call and after a multi-launch call.
     const bool ordered = (mode & DSP_MESH_ORDERED) != 0;
-    if (ordered || !ctx->ctl_clean || n == 0) {
-        DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32 + (ordered ? 8 * n : 0), ctx->stream));
-        DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, sizeof(uint32_t), ctx->stream));
-        ctx->ctl_clean = !ordered;
+    if (!ctx->ctl_clean || n == 0) {
+        DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_ctl, 0, 32, ctx->stream));
+        DSP_CUDA(ctx, cudaMemsetAsync(ctx->d_tickets, 0, 256, ctx->stream));  // (the count pass of DSP_MESH_ORDERED has the second ticket line)
+        ctx->ctl_clean = true;
     }
+
     ctx->result_in_tail = false;
     if (n == 0) return DSP_OK;
     if (mode & DSP_MESH_HALO) {
@@ -593,8 +602,8 @@ int enqueue_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t firs
         ctx->launches++;
         work_list = true;
     }
-    rc = launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0, !ordered, work_list);
-    if (rc == DSP_OK && !ordered) { ctx->ctl_clean = true; ctx->result_in_tail = true; }
+    rc = launch_mesh(ctx, n, d_list, first_slot, mode, arena_offset, 0, 0, true, work_list);
+    if (rc == DSP_OK) { ctx->ctl_clean = true; ctx->result_in_tail = true; }
     return rc;
 }
 
@@ -730,11 +739,12 @@ int apply_edits_device(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, bool hal
     return DSP_OK;
 }
 
-int finish_mesh(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total) {
+// `first_entry`: entries below it have already been copied out (sub-batch pipeline of the host-chunk calls)
+int finish_mesh(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total, uint64_t first_entry = 0) {
     const uint64_t n = ctx->last_mesh_n;
     if (out_total) *out_total = 0;
-    if (n && out_entries)
-        DSP_CUDA(ctx, cudaMemcpyAsync(out_entries, ctx->d_entries, n * sizeof(dsp_mesh_entry), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n > first_entry && out_entries)
+        DSP_CUDA(ctx, cudaMemcpyAsync(out_entries + first_entry, ctx->d_entries + first_entry, (n - first_entry) * sizeof(dsp_mesh_entry), cudaMemcpyDeviceToHost, ctx->stream));
     uint32_t status;
     uint64_t total;
     if (ctx->result_in_tail) {  // written by the last CTA of a self-resetting launch
@@ -803,6 +813,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* s = getenv("DSP_PDL")) ctx->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("DSP_SUMMARY_SKIP")) ctx->summary_skip = atoi(s) & 3;
+    if (const char* s = getenv("DSP_E2E_HEAD")) ctx->e2e_head_chunks = static_cast<uint64_t>(std::min(512, std::max(0, atoi(s))));
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
     auto bail = [&](const char* what, cudaError_t err) {
@@ -820,6 +831,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     } else if ((e = cudaMalloc(&ctx->d_arena, std::max<uint64_t>(arena_bytes, 128))) != cudaSuccess) return bail("cudaMalloc(vertex arena)", e);
     if ((e = cudaMalloc(&ctx->d_entries, max_chunks * sizeof(dsp::MeshEntry))) != cudaSuccess) return bail("cudaMalloc(entries)", e);
     if ((e = cudaMalloc(&ctx->d_ctl, 32 + 8 * max_chunks + 64)) != cudaSuccess) return bail("cudaMalloc(control)", e);
+    if ((e = cudaMemset(ctx->d_ctl, 0, 32 + 8 * max_chunks + 64)) != cudaSuccess) return bail("cudaMemset(control)", e);  // (scan words: epoch 0 is never used)
     if ((e = cudaMalloc(&ctx->d_slots, max_chunks * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc(slot list)", e);
     if ((e = cudaMalloc(&ctx->d_summary, max_chunks)) != cudaSuccess) return bail("cudaMalloc(chunk summaries)", e);
     if ((e = cudaMemset(ctx->d_summary, 0, max_chunks)) != cudaSuccess) return bail("cudaMemset(chunk summaries)", e);
@@ -1185,7 +1197,15 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     int rc = check_mesh_args(ctx, n, mode, arena_offset);
     if (rc != DSP_OK) return rc;
     const bool readback = host_vertices != nullptr;
-    if (readback && !ctx->d2h_stream) {
+    // Entry table in pinned host memory: the entries of every sub-batch but the last leave on the download stream as soon as the
+    // sub-batch is meshed (the D2H engine is idle while the voxels come up), so only the last piece's few KB remain for the tail.
+    bool early_entries = false;
+    if (!readback && out_entries && n > 1024) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, out_entries) == cudaSuccess && attr.type == cudaMemoryTypeHost) early_entries = true;
+        else cudaGetLastError();
+    }
+    if ((readback || early_entries) && !ctx->d2h_stream) {
         DSP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         for (int i = 0; i < dsp_ctx::kMaxSub; ++i) DSP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_meshed[i], cudaEventDisableTiming));
     }
@@ -1210,13 +1230,16 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     // Sub-batch plan.  Every copy costs a few microseconds of gap on the DMA engine, so the body is cut into pieces of about
     // 1,024 chunks (8 MiB); the LAST piece is small (256 chunks) because its kernel and the entry read-back are the only work
     // that cannot hide behind a copy.
+    // The FIRST piece is small too (128 chunks): the host resolves a piece's positions to slots before it can enqueue the
+    // piece's copy, and nothing crosses PCIe while it does that for the first one.
     std::vector<uint64_t> sub_begin;
     {
-        const uint64_t tail = n > 512 ? 256 : 0, body = n - tail;
+        const uint64_t tail = n > 512 ? 256 : 0, head = n > 1024 ? ctx->e2e_head_chunks : 0, body = n - tail - head;
         uint64_t pieces = std::max<uint64_t>(1, (body + 1023) / 1024);
-        pieces = std::min<uint64_t>(pieces, dsp_ctx::kMaxSub - 1);
-        for (uint64_t k = 0; k < pieces; ++k) sub_begin.push_back(body * k / pieces);
-        if (tail) sub_begin.push_back(body);
+        pieces = std::min<uint64_t>(pieces, dsp_ctx::kMaxSub - 2);
+        if (head) sub_begin.push_back(0);
+        for (uint64_t k = 0; k < pieces; ++k) sub_begin.push_back(head + body * k / pieces);
+        if (tail) sub_begin.push_back(head + body);
         sub_begin.push_back(n);
     }
     const int subs = static_cast<int>(sub_begin.size()) - 1;
@@ -1264,7 +1287,7 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
         }
     }
     int last_sub = -1;
-    uint64_t copied_to = 0;
+    uint64_t copied_to = 0, entries_out = 0;
     const uint64_t room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
     auto copy_out = [&](int j) -> int {  // vertices of sub-batch j: arena [copied_to, cursor(j)) -> host, on the third stream
         DSP_CUDA(ctx, cudaEventSynchronize(ctx->ev_meshed[j]));
@@ -1307,6 +1330,12 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
             return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the copy pipeline"));
         if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j)) != DSP_OK) return bail(rc);
         tr("sub-batch enqueued");
+        if (early_entries && j + 1 < subs) {
+            if (cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_meshed[j], 0) != cudaSuccess ||
+                cudaMemcpyAsync(out_entries + i0, ctx->d_entries + i0, m * sizeof(dsp_mesh_entry), cudaMemcpyDeviceToHost, ctx->d2h_stream) != cudaSuccess)
+                return bail(fail(ctx, DSP_ERR_CUDA, "entry download failed in the copy pipeline"));
+            entries_out = i0 + m;
+        }
         if (readback) {
             // where the cursor stands after this sub-batch: its vertices are the arena bytes [cursor(j-1), cursor(j))
             if (zero_copy_dst != nullptr) {
@@ -1338,8 +1367,9 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     if ((rc = stage_release(ctx)) != DSP_OK) return rc;
     if (trace) { cudaStreamSynchronize(ctx->copy_stream); tr("copies done"); }
     uint64_t total = 0;
-    rc = finish_mesh(ctx, out_entries, &total);
+    rc = finish_mesh(ctx, out_entries, &total, entries_out);
     if (out_total_bytes) *out_total_bytes = total;
+    if (early_entries) DSP_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));  // (long finished: those copies ran under the uploads)
     if (readback) {
         DSP_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
         if (rc == DSP_OK && total > host_capacity)

@@ -15,10 +15,9 @@
 //   2. thread r builds the occupancy mask of x-row r, derives the six face masks and its face
 //      count; a warp-shuffle + 8-way scan gives every row its first face ordinal and the CTA the
 //      chunk's face total F (all-air chunks, and chunks with no visible face, leave here);
-//   3. the chunk's arena slot of align128(120*F) bytes:
-//        mesh_chunks_bump_kernel (default)  one 64-bit atomicAdd on a cursor -- slots gap-free, in completion order;
-//        mesh_chunks_kernel (DSP_MESH_ORDERED)  decoupled look-back over the earlier tickets, the count phase of chunk
-//        k+1 running before the emission of chunk k so that sizes are published early -- slots in call order;
+//   3. the chunk's arena slot of align128(120*F) bytes: one 64-bit atomicAdd on a cursor -- slots gap-free, in completion
+//      order; with DSP_MESH_ORDERED a count + scan pass (count_chunks_scan_kernel) has fixed every chunk's offset in call
+//      order beforehand and the kernel takes it from the chunk's entry (p.preset);
 //      meanwhile all rows write 16-bit face records (voxel index, direction) in stream order;
 //   4. faces are expanded one thread per face into a 30,720-byte staging tile (256 faces) that leaves with ONE bulk
 //      shared->global copy (cp.async.bulk), so only full-line writes reach L2/HBM (MeshCfg variants: per-warp tiles);
@@ -50,7 +49,7 @@ struct MeshParams {
     uint64_t arena_offset;
     uint64_t arena_room;        // bytes available from arena_offset
     MeshEntry* entries;         // [n]
-    uint64_t* lookback;         // [n], zeroed before launch
+    uint32_t* face_counts;      // [n] per-chunk face counts of count_chunks_scan_kernel (DSP_MESH_ORDERED)
     uint32_t* ticket;           // chunk ticket counter of this launch (a cache line of its own); zeroed before launch
     uint32_t* ctl;              // the context's control block (work-list counts live there)
     uint32_t* status;           // status bits (kStatus*), shared by the launches of one call
@@ -72,6 +71,9 @@ struct MeshParams {
     // known solid block id is meshed from that id without its tile being read (uid above).
     const uint8_t* summary;
     bool summary_air_skip;
+    // DSP_MESH_ORDERED: count_chunks_scan_kernel has already written every chunk's entry (slots packed in call order); the mesh
+    // kernel takes each chunk's offset from its entry instead of claiming one, and writes neither entries nor the total.
+    bool preset;
     // Work list layout: chunks that need nothing from another GPU fill it from the FRONT (count n_dev[0]), chunks with a
     // neighbour across a region seam from the BACK (count n_dev[3], list index n_cap - 1 - k).  Tickets run over the front
     // part first, so by the time a CTA reaches a seam chunk the neighbour GPU's border layers have usually arrived --
@@ -95,7 +97,7 @@ constexpr uint32_t kNbrExternal = 0x80000000u;  // neighbour lives on another de
 constexpr uint32_t kNbrSrcShift = 28u;          // 1 + s: seam s), bits 0-27 = slab index within that source
 constexpr uint32_t kNbrIndexMask = 0x0FFFFFFFu;
 constexpr uint32_t kStatusOverflow = 1u;
-constexpr uint32_t kStatusSpin = 2u;
+constexpr uint32_t kStatusSpin = 2u;  // (unused since the look-back organisation went; kept so that the bit is not reassigned)
 constexpr uint32_t kStatusSeam = 4u;  // a neighbour GPU's border layers did not arrive (dsp_seam_exchange_async missing on the peer?)
 
 // position in the work list of ticket `chunk` (identity without a device-built list)
@@ -140,6 +142,7 @@ __device__ __forceinline__ void control_block_epilogue(const MeshParams& p) {
     p.result[0] = atomicOr(p.status, 0u);
     p.result[1] = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), 0ull);
     p.ticket[0] = 0u;
+    if (p.preset) p.ticket[32] = 0u;  // the count pass's "CTAs done" counter (DSP_MESH_ORDERED)
     p.ctl[3] = 0u;  // the work-list counts of the classify kernels: front, back (seam chunks) ...
     p.ctl[6] = 0u;
     p.ctl[7] = 0u;  // ... and the uniform chunks of classify_greedy_kernel
@@ -316,9 +319,126 @@ __device__ __forceinline__ uint64_t slot_bytes_of(uint32_t faces) {
     return (static_cast<uint64_t>(faces) * kFaceBytes + (kSlotAlign - 1)) & ~static_cast<uint64_t>(kSlotAlign - 1);
 }
 
-constexpr uint64_t kLbAgg = 1ull << 62, kLbPrefix = 2ull << 62, kLbVal = (1ull << 62) - 1;
+// ===== DSP_MESH_ORDERED, pass 1: face count of every chunk + exclusive scan of the slot sizes, in call order ==================
+// CTA b counts chunks [16 b, 16 b + 16), one per warp: the 8 KiB tile is read with sixteen fully coalesced 128-bit loads per
+// lane (none at all where the chunk's summary says all air or no air: 0 / 1,536 faces), the 256 row masks go to a 704-byte
+// shared-memory strip of the warp and every lane counts the faces of eight rows (chunk_mesh.rs:46-51, the same row_face_masks as
+// the mesh kernel).  Counts go to a u32 array; CTAs count themselves out, and the LAST one to finish scans the array (512
+// threads, 2,048 chunks per sweep with a running carry) and writes every chunk's entry -- no CTA ever waits for another.  The
+// mesh kernel that follows (mesh_chunks_bump_kernel with p.preset) emits every chunk at the offset found here: slots packed back
+// to back in call order.  History: rounds 1-2 did this in ONE pass with a decoupled look-back inside the mesh kernel (97 us
+// against 78 us for the atomic claim: a chunk's predecessors were busy emitting when it wanted their sizes); a look-back inside
+// this count pass measured 14-16 us for the pass (every CTA finishes counting in the same microsecond, so the chain of waits
+// IS the kernel); the last-CTA scan has no chain.
+constexpr int kCountChunksPerCta = 16;
+constexpr int kCountThreads = kCountChunksPerCta * 32;
+template <bool HALO>
+__global__ void __launch_bounds__(kCountThreads, 2) count_chunks_scan_kernel(const MeshParams p_in) {
+    pdl_launch_dependents();
+    pdl_wait();
+    MeshParams p = p_in;
+    p.n_front = 0u;  // no device-built work list in this mode
+    __shared__ __align__(16) uint16_t s_masks[kCountChunksPerCta][kRows + kNbrMasks];
+    __shared__ unsigned long long s_warp_tot[kCountChunksPerCta];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* const rm = s_masks[warp];
+    {
+        const uint64_t chunk64 = static_cast<uint64_t>(blockIdx.x) * kCountChunksPerCta + warp;
+        if (chunk64 < p.n) {
+            const uint32_t chunk = static_cast<uint32_t>(chunk64);
+            const uint32_t slot = p.slot_list ? __ldg(p.slot_list + chunk) : p.first_slot + chunk;
+            const uint32_t summary = (!HALO && p.summary != nullptr) ? __ldg(p.summary + slot) : 0u;
+            uint32_t faces;
+            if (summary & kSummaryAir) {
+                faces = 0u;  // palette.len() == 1 (chunk_mesh.rs:18-20)
+            } else if (summary & kSummarySolid) {
+                faces = 6u * 256u;  // no air anywhere, chunk-local cull: exactly the six outer layers
+            } else {
+                seam_wait<HALO>(p, chunk);
+                const uint4* tile = reinterpret_cast<const uint4*>(p.voxels + static_cast<size_t>(slot) * kChunkVoxels);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint4 q[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) q[i] = __ldg(tile + (half * 8 + i) * 32 + lane);  // 16-byte unit u = 32 i + lane: half (u & 1) of row u >> 1
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint32_t b = nonzero_mask8(q[i]);
+                        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, b, 1);
+                        if (!(lane & 1)) rm[(half * 8 + i) * 16 + (lane >> 1)] = static_cast<uint16_t>(b | (o << 8));
+                    }
+                }
+                if (HALO) {
+#pragma unroll
+                    for (int j = 0; j < kNbrMasks / 32; ++j) rm[kRows + lane + 32 * j] = static_cast<uint16_t>(fetch_nbr_mask(p, slot, lane + 32 * j));
+                }
+                __syncwarp();
+                uint32_t cnt = 0u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = lane + 32 * j;
+                    const FaceMasks fm = row_face_masks<HALO>(rm, r, r & 15, r >> 4, rm[r]);
+                    cnt += __popc(fm.top) + __popc(fm.bot) + __popc(fm.rear) + __popc(fm.front) + __popc(fm.right) + __popc(fm.left);
+                }
+                faces = __reduce_add_sync(0xFFFFFFFFu, cnt);
+            }
+            if (lane == 0) p.face_counts[chunk] = faces;
+        }
+    }
+    // count this CTA out; the last one does the scan
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.ticket, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    unsigned long long carry = 0ull;
+    bool overflow = false;
+    for (uint64_t base = 0; base < p.n; base += kCountThreads * 4) {
+        const uint64_t c0 = base + threadIdx.x * 4;
+        uint4 f = make_uint4(0u, 0u, 0u, 0u);
+        if (c0 + 3 < p.n) f = __ldcg(reinterpret_cast<const uint4*>(p.face_counts + c0));
+        else if (c0 < p.n) {
+            f.x = __ldcg(p.face_counts + c0);
+            if (c0 + 1 < p.n) f.y = __ldcg(p.face_counts + c0 + 1);
+            if (c0 + 2 < p.n) f.z = __ldcg(p.face_counts + c0 + 2);
+        }
+        const unsigned long long b0 = slot_bytes_of(f.x), b1 = slot_bytes_of(f.y), b2 = slot_bytes_of(f.z), b3 = slot_bytes_of(f.w);
+        unsigned long long incl = b0 + b1 + b2 + b3;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long wpre = 0ull, sweep = 0ull;
+#pragma unroll
+        for (int w = 0; w < kCountChunksPerCta; ++w) {
+            const unsigned long long v = s_warp_tot[w];
+            wpre += w < warp ? v : 0ull;
+            sweep += v;
+        }
+        unsigned long long off = carry + wpre + incl - (b0 + b1 + b2 + b3);
+        const uint32_t fv[4] = {f.x, f.y, f.z, f.w};
+        const unsigned long long bv[4] = {b0, b1, b2, b3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (c0 + k < p.n) {
+                overflow |= off + bv[k] > p.arena_room;
+                p.entries[c0 + k] = MeshEntry{p.arena_offset + off, fv[k] * 6u, 0u};
+            }
+            off += bv[k];
+        }
+        carry += sweep;
+        __syncthreads();  // s_warp_tot is rewritten by the next sweep
+    }
+    if (overflow) atomicOr(p.status, kStatusOverflow);
+    if (threadIdx.x == 0) *p.total_bytes = carry;
+}
 
-// Per-CTA working set shared by the two kernel organisations below.
+// Per-CTA working set of the mesh kernel.
 template <class Cfg, bool HALO>
 struct MeshCta {
     static constexpr int NSTAGE = Cfg::NSTAGE;
@@ -369,7 +489,7 @@ struct MeshCta {
     __device__ __forceinline__ uint32_t claim_ticket(uint32_t t) const {
         if (p.summary == nullptr || !p.summary_air_skip) return t;
         while (t < p.n && (__ldg(p.summary + slot_of(t)) & kSummaryAir)) {
-            *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
+            if (!p.preset) *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
             t = gridDim.x + atomicAdd(p.ticket, 1u);
         }
         return t;
@@ -398,10 +518,9 @@ struct MeshCta {
     }
 
     // ---- count phase: row occupancy -> six face masks -> per-row count -> block scan.  2 CTA barriers.
-    //      With `publish`, thread 0 posts the chunk's byte size for the look-back of later chunks.
     // `skip_empty`: when the chunk is all air (the reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20) only the
     // first barrier is executed and total = cnt = 0 is returned with *empty = true; the caller then does nothing else.
-    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool publish, bool* empty = nullptr, bool use_prefetch = false) const {
+    __device__ __forceinline__ RowFaces count_phase(uint32_t chunk, int buf, bool* empty = nullptr, bool use_prefetch = false) const {
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
         uint32_t nbv = 0u;
         if (HALO) nbv = (use_prefetch && pf_ready) ? pf_val : fetch_nbr_mask(p, slot_of(chunk), tid);  // prefetched during the previous chunk, or fetched now
@@ -454,65 +573,7 @@ struct MeshCta {
         }
         f.first = wpre + incl - f.cnt;
         f.total = total;
-        if (publish && tid == 0) st_volatile_u64(&p.lookback[chunk], (chunk == 0 ? kLbPrefix : kLbAgg) | slot_bytes_of(total));
         return f;
-    }
-
-    // ---- decoupled look-back (one warp): exclusive prefix of the byte sizes of all earlier chunks; also writes the
-    //      chunk's mesh entry, the overflow flag and (last chunk) the batch total.  Result in *s_base.
-    //      Each probe covers 128 predecessors (lane l reads the aligned quad of entries (j >> 2) - l with two 128-bit
-    //      loads): with ~500 chunks in flight the walk back to the nearest resolved prefix must be a couple of L2 round
-    //      trips, not a dozen -- at 32 entries per probe the look-back chain itself capped the whole kernel.
-    __device__ __forceinline__ void look_back(uint32_t chunk, uint32_t faces) const {
-        const uint64_t bytes = slot_bytes_of(faces);
-        uint64_t excl = 0;
-        if (chunk > 0) {
-            int64_t j = static_cast<int64_t>(chunk) - 1;  // nearest predecessor not yet accounted for
-            uint32_t spins = 0;
-            for (;;) {
-                const int64_t quad = (j >> 2) - lane;  // entries 4*quad .. 4*quad+3
-                uint64_t e[4];
-                if (quad >= 0) ld_volatile_u64x4(&p.lookback[quad * 4], e);
-                // walk this lane's entries from the highest index down, stopping at the first resolved prefix
-                uint64_t sum = 0;
-                bool has_pref = quad < 0, invalid = false;  // below index 0: an implicit prefix of 0
-                if (quad >= 0) {
-#pragma unroll
-                    for (int k = 3; k >= 0; --k) {
-                        const int64_t idx = quad * 4 + k;
-                        const uint32_t flag = static_cast<uint32_t>(e[k] >> 62);
-                        const bool take = idx <= j && !has_pref;
-                        if (take) {
-                            invalid |= flag == 0u;
-                            sum += e[k] & kLbVal;
-                            has_pref = flag == 2u;
-                        }
-                    }
-                }
-                const uint32_t pref = __ballot_sync(0xFFFFFFFFu, has_pref);
-                const uint32_t inval = __ballot_sync(0xFFFFFFFFu, invalid);
-                const int first = pref ? __ffs(pref) - 1 : 31;  // lanes 0..first are needed
-                const uint32_t need = first == 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
-                if (inval & need) {  // a predecessor has not published yet
-                    if (++spins > (1u << 24)) { if (lane == 0) atomicOr(p.status, kStatusSpin); break; }
-                    __nanosleep(20);
-                    continue;
-                }
-                uint64_t part = (need >> lane) & 1u ? sum : 0ull;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
-                excl += part;
-                if (pref) break;
-                j = ((j >> 2) - 32) * 4 + 3;  // continue below the 32 quads just covered
-            }
-            if (lane == 0) st_volatile_u64(&p.lookback[chunk], kLbPrefix | (excl + bytes));
-        }
-        if (lane == 0) {
-            *s_base = excl;
-            if (excl + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
-            p.entries[chunk] = MeshEntry{p.arena_offset + excl, faces * 6u, 0u};
-            if (chunk == p.n - 1) *p.total_bytes = excl + bytes;
-        }
     }
 
     // ---- face records in stream order for the window [q0, q0 + kRecCap): rec = (voxel index << 3) | direction
@@ -598,7 +659,7 @@ struct MeshCta {
     }
 
     // records + emission of one counted chunk; `between` runs once after the (first round of) records and before the
-    // barrier that publishes them (the single-pass kernel counts the next chunk and does its look-back there)
+    // barrier that publishes them (the halo-mode mask prefetch lives there)
 #ifdef DSP_PHASE_TIMERS
     long long ph[16] = {};
     long long tlast = 0;
@@ -629,8 +690,10 @@ struct MeshCta {
         if (claimed != nullptr) {
             if (tid == 0) {
                 base = *claimed;
-                if (base + slot_bytes_of(F) > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                *entry_of(p, chunk) = MeshEntry{p.arena_offset + base, F * 6u, 0u};
+                if (!p.preset) {
+                    if (base + slot_bytes_of(F) > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                    *entry_of(p, chunk) = MeshEntry{p.arena_offset + base, F * 6u, 0u};
+                }
             }
         } else {
             base = *s_base;
@@ -657,80 +720,12 @@ struct MeshCta {
     }
 };
 
-// ===== organisation A (DSP_MESH_ORDERED): single pass, slots packed in call order by decoupled look-back ================
-// Voxels are read from HBM exactly once.  The count phase of chunk k+1 runs before the emission of chunk k, so every
-// ticket's size is published within (tile latency + count) of the ticket being taken.  The price of the reproducible
-// layout is the look-back itself: ~1.3 us per chunk on the critical path of the CTA (profiles/README.md).
-template <class Cfg, bool HALO>
-__global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_kernel(const MeshParams p_in) {
-    MeshParams p = p_in;
-    adopt_work_list(p);
-    extern __shared__ __align__(128) uint8_t smem[];
-    MeshCta<Cfg, HALO> c(p, smem);
-    const int tid = c.tid;
-
-    if (tid == 0) {
-        mbar_init(&c.s_bar[0], 1);
-        mbar_init(&c.s_bar[1], 1);
-        fence_mbar_init();
-        const uint32_t t0 = atomicAdd(p.ticket, 1u);
-        c.s_next[0] = t0;
-        if (t0 < p.n) c.issue_load(t0, 0);
-        uint32_t t1 = 0xFFFFFFFFu;
-        if (t0 < p.n) { t1 = atomicAdd(p.ticket, 1u); if (t1 < p.n) c.issue_load(t1, 1); }
-        c.s_next[1] = t1;
-    }
-    __syncthreads();
-    uint32_t cur = c.s_next[0];
-    if (cur >= p.n) return;
-    seam_wait<HALO>(p, cur);  // no work list in this organisation (n_front == 0): every CTA waits for the seams first
-    mbar_wait(&c.s_bar[0], 0);
-    RowFaces fc = c.count_phase(cur, 0, true);
-    uint32_t it = 0;
-#ifdef DSP_PHASE_TIMERS
-    c.tlast = clock64();
-#endif
-
-    // Invariant at the top of iteration `it`: chunk `cur` is in voxel buffer it&1 with its count phase done and
-    // its size published; the ticket after it is in s_next[(it+1)&1] and its tile is in flight to the other buffer.
-    for (;;) {
-        const int buf = it & 1;
-        const uint32_t nxt = c.s_next[(it + 1) & 1];
-        RowFaces fn{};
-        c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
-            if (nxt < p.n) {
-                mbar_wait(&c.s_bar[buf ^ 1], ((it + 1) >> 1) & 1);
-                c.tick(2);
-                fn = c.count_phase(nxt, buf ^ 1, true);
-                c.tick(3);
-            }
-            if (c.warp == 0) c.look_back(cur, fc.total);
-        });
-        if (nxt >= p.n) break;
-        uint32_t t2 = 0;
-        if (tid == 0) { t2 = atomicAdd(p.ticket, 1u); c.s_next[it & 1] = t2; }
-        c.tick(7);
-        __syncthreads();  // everyone is done with vox(buf), s_rec and s_base; s_next visible
-        c.tick(8);
-        if (tid == 0 && t2 < p.n) c.issue_load(t2, buf);
-        cur = nxt;
-        fc = fn;
-        ++it;
-    }
-    if (c.lane == 0) bulk_wait<0>();  // lane 0 of every warp may own bulk stores
-#ifdef DSP_PHASE_TIMERS
-    c.tick(9);
-    if (tid == 0 && p.phase_cycles) for (int k = 0; k < 16; ++k) atomicAdd(&p.phase_cycles[k], static_cast<unsigned long long>(c.ph[k]));
-    if (tid == 255 && p.phase_cycles) atomicAdd(&p.phase_cycles[15], 1ull);
-#endif
-}
-
-// ===== organisation B: single pass, arena space claimed with one atomic per chunk ========================================
+// ===== the mesh kernel: single pass, arena space claimed with one atomic per chunk ========================================
 // No ordering between chunks at all: thread 0 claims align128(120*F) bytes from a global cursor as soon as the chunk
-// is counted, so there is no look-back, tickets can be taken a whole chunk early (deep tile prefetch) and nothing ever
-// waits on another CTA.  Every chunk's stream is still byte-exact and the entry table says where it landed; only the
-// ORDER of the slots in the arena follows completion order instead of call order (DSP_MESH_ORDERED selects the
-// look-back organisation when a reproducible layout matters).
+// is counted, tickets can be taken a whole chunk early (deep tile prefetch) and nothing ever waits on another CTA.  Every
+// chunk's stream is byte-exact and the entry table says where it landed; only the ORDER of the slots in the arena follows
+// completion order instead of call order.  DSP_MESH_ORDERED runs count_chunks_scan_kernel first and this kernel with p.preset:
+// same emission, offsets taken from the entries.
 template <class Cfg, bool HALO>
 __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p_in) {
     // Back-to-back mesh calls (a frame loop; bench.py's steps): the next launch's CTAs take their SM slots while this launch's
@@ -771,7 +766,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         c.tick(2);
 #ifndef DSP_NO_EMPTY_SKIP
         bool empty;
-        const RowFaces fc = c.count_phase(cur, buf, false, &empty, true);
+        const RowFaces fc = c.count_phase(cur, buf, &empty, true);
         c.tick(3);
         // the next ticket (written by thread 0 at the top of this iteration) is visible behind count_phase's barrier: its
         // neighbour codes start their trip now, its masks after the records -- both land before the next iteration needs them
@@ -781,29 +776,36 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
             // Nothing to emit and no slot to claim (all air; or, with cross-chunk culling, a chunk buried among solid
             // neighbours).  No further barrier is needed: every read of vox(buf), the row masks and the warp totals precedes a
             // barrier inside count_phase that all threads have passed, and s_next[(it + 1) & 1] was written before it.
-            if (tid == 0) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
+            if (tid == 0 && !p.preset) *entry_of(p, cur) = MeshEntry{p.arena_offset, 0u, 0u};
             ++it;
             cur = c.s_next[it & 1];
             continue;
         }
 #else
-        const RowFaces fc = c.count_phase(cur, buf, false);
+        const RowFaces fc = c.count_phase(cur, buf);
         c.tick(3);
 #endif
         if (!Cfg::WARP_EMIT) {
             // claim the chunk's arena slot now; the result is not touched until the records are written (see records_and_emit)
             uint64_t claimed = 0;
-            if (tid == 0) claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(slot_bytes_of(fc.total)));
+            if (tid == 0) {
+                if (p.preset) claimed = ld_volatile_u64(&entry_of(p, cur)->offset_bytes) - p.arena_offset;  // packed in call order by count_chunks_scan_kernel
+                else claimed = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(slot_bytes_of(fc.total)));
+            }
             c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() { c.prefetch_masks(); }, &claimed);
         } else {
             c.records_and_emit(cur, fc, c.s_vox + buf * kChunkVoxels, [&]() {
                 c.prefetch_masks();
                 if (tid == 0) {  // every warp issues its own stores: the offset goes through shared memory
                     const uint64_t bytes = slot_bytes_of(fc.total);
-                    const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
-                    *c.s_base = base;
-                    if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
-                    *entry_of(p, cur) = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
+                    if (p.preset) {
+                        *c.s_base = ld_volatile_u64(&entry_of(p, cur)->offset_bytes) - p.arena_offset;
+                    } else {
+                        const uint64_t base = atomicAdd(reinterpret_cast<unsigned long long*>(p.total_bytes), static_cast<unsigned long long>(bytes));
+                        *c.s_base = base;
+                        if (base + bytes > p.arena_room) atomicOr(p.status, kStatusOverflow);
+                        *entry_of(p, cur) = MeshEntry{p.arena_offset + base, fc.total * 6u, 0u};
+                    }
                 }
             });
         }

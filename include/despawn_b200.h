@@ -62,8 +62,9 @@ typedef enum dsp_gen_kind {
 /* Mesh modes (bit flags).  0 is the reference's behaviour and the only bit-exact-to-reference mode. */
 #define DSP_MESH_PARITY 0u /* chunk-local cull, border faces always emitted (chunk_mesh.rs:46-51) */
 #define DSP_MESH_HALO 1u   /* extension: border faces tested against resident neighbour chunks */
-#define DSP_MESH_ORDERED 2u /* pack the chunks' arena slots back to back in the order of the call (reproducible
-                             * layout, ~25 % slower: 96 vs 77 us on the bench region); without it slots are claimed in completion order */
+#define DSP_MESH_ORDERED 2u /* pack the chunks' arena slots back to back in the order of the call (reproducible layout: a count +
+                             * scan pass fixes every offset first; 89 vs 72 us on the bench region); without it slots are claimed
+                             * in completion order */
 
 /* Quad modes (extensions; spec with the oracle, oracle/mesher_oracle.cpp).  Not available with
  * DSP_MESH_ORDERED. */
