@@ -149,9 +149,11 @@ struct dsp_ctx {
     std::string err;
 
     // ---- scene state (dsp_scene_update): World.loaded_chunks + GameScene.chunk_meshes + last_chunk_pos
-    struct SceneChunk { uint32_t slot; uint32_t batch; dsp_mesh_entry entry; };
+    struct SceneChunk { uint32_t loaded; uint32_t batch; dsp_mesh_entry entry; };
     struct SceneBatch { uint64_t offset, bytes; uint32_t live; };
-    std::unordered_map<PosKey, SceneChunk, PosHash> scene_loaded;
+    std::vector<SceneChunk> scene_chunks;  // by voxel slot (position: slot_pos): the loaded set is the previous update's visible set, so no map by position is needed
+    uint64_t scene_n_loaded = 0;
+    uint32_t scene_last_h = 0, scene_last_v = 0;  // render distances of the update that produced the loaded set
     std::vector<SceneBatch> scene_batches;
     std::vector<uint32_t> scene_free_batch_ids;
     std::map<uint64_t, uint64_t> scene_free;  // free arena intervals: offset -> bytes
@@ -439,7 +441,7 @@ int launch_mesh_variant(dsp_ctx* ctx, const dsp::MeshParams& p) {
 template <bool HALO, bool GREEDY, bool INDEXED>
 int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p_in) {
     void (*kern)(const dsp::MeshParams) = dsp::mesh_chunks_quads_kernel<HALO, GREEDY, INDEXED>;
-    constexpr int smem = dsp::QuadSmem<GREEDY>::kBytes;
+    constexpr int smem = dsp::QuadSmem<GREEDY, GREEDY && INDEXED>::kBytes;
     int& occ = ctx->quad_ctas_per_sm[(HALO ? 1 : 0) + (GREEDY ? 2 : 0) + (INDEXED ? 4 : 0)];
     if (occ == 0) {
         DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -26,6 +26,9 @@
 
 namespace dsp {
 
+#ifndef DSP_QUAD_DIRECT_CTAS
+#define DSP_QUAD_DIRECT_CTAS 5
+#endif
 constexpr int kQuadVertexBytesIdx = 80;   // 4 vertices
 constexpr int kQuadIndexBytes = 24;       // 6 x u32
 
@@ -33,16 +36,16 @@ constexpr int kQuadIndexBytes = 24;       // 6 x u32
 // staging space for residency and tile prefetch depth: 128-quad tiles and a 2,048-record window make room for 4 CTAs per SM, which is what
 // hides the per-chunk latencies (tile, barriers, the slot atomic) once there is little emission to hide them behind.
 // The unit-quad indexed kernel keeps the 256-quad tile / 4,096-record window of the parity kernel (3 CTAs per SM).
-template <bool GREEDY>
+template <bool GREEDY, bool DIRECT = false>  // DIRECT: merged quads in the indexed layout are stored straight to the arena -- no staging tile
 struct QuadSmem {
-    static constexpr int kCtasPerSm = GREEDY ? 4 : 3;
+    static constexpr int kCtasPerSm = DIRECT ? DSP_QUAD_DIRECT_CTAS : (GREEDY ? 4 : 3);
     static constexpr int kTileQuads = GREEDY ? 128 : 256;
     static constexpr uint32_t kRecCap = GREEDY ? 2048 : 4096;         // records per window (u32 each)
     static constexpr int kVoxBufs = 2;                                // voxel tile ring: kVoxBufs - 1 tiles in flight per CTA (3 measured slower)
     static constexpr int kT = GREEDY ? kRows * 2 : 0;                 // bytes of one [256] u16 table (none without merging)
     static constexpr int kVox = 0;                                    // kVoxBufs x 8192
     static constexpr int kStage = kVoxBufs * kChunkBytes;                    // kTileQuads x 120 (stream) or x 80 + x 24 (indexed)
-    static constexpr int kRec = kStage + kTileQuads * kFaceBytes;     // kRecCap x u32
+    static constexpr int kRec = kStage + (DIRECT ? 0 : kTileQuads * kFaceBytes);  // kRecCap x u32
     static constexpr int kRowMask = kRec + kRecCap * 4;               // 256 x u16 row masks + 96 x u16 neighbour border masks (halo mode) + pad
     static constexpr int kF = kRowMask + kRows * 2 + 256;             // [4][256] u16: TOP, BOTTOM, REAR, FRONT masks per row
     static constexpr int kEqx = kF + 4 * kT;                          // [256] u16
@@ -55,7 +58,7 @@ struct QuadSmem {
     static constexpr int kNext = kBase + 8;                           // kVoxBufs (<= 4) x u32
     static constexpr int kBytes = kNext + 16;
 };
-static_assert(QuadSmem<true>::kBytes <= 57344 && QuadSmem<false>::kBytes <= 76800, "4 / 3 CTAs per SM");
+static_assert(QuadSmem<true>::kBytes <= 57344 && QuadSmem<false>::kBytes <= 76800 && QuadSmem<true, true>::kBytes <= 45056, "4 / 3 / 5 CTAs per SM");
 
 // bit x = ids equal at position x of two rows of 16 u16 (held as 8 words each): "differs" is nonzero_mask8 of the XOR
 __device__ __forceinline__ uint32_t eq_mask16(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
@@ -194,15 +197,15 @@ __device__ __forceinline__ void emit_uniform_chunk(uint8_t* out, const int4 cp, 
 }
 
 template <bool HALO, bool GREEDY, bool INDEXED>
-__global__ void __launch_bounds__(256, QuadSmem<GREEDY>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p_in) {
+__global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCtasPerSm) mesh_chunks_quads_kernel(const MeshParams p_in) {
     pdl_launch_dependents();  // (see mesh_chunks_bump_kernel)
     pdl_wait();
     MeshParams p = p_in;
     adopt_work_list(p);  // device-built work list (see classify_chunks_kernel)
-    using L = QuadSmem<GREEDY>;
+    constexpr bool DIRECT = GREEDY && INDEXED;  // merged quads in the indexed layout are stored straight to the arena (see the expansion)
+    using L = QuadSmem<GREEDY, DIRECT>;
     constexpr uint32_t kRecCap = L::kRecCap;
     constexpr int kTile = L::kTileQuads;
-    constexpr bool DIRECT = GREEDY && INDEXED;  // merged quads in the indexed layout are stored straight to the arena (see the expansion)
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t* const s_vox = reinterpret_cast<uint16_t*>(smem + L::kVox);
     float* const s_stage = reinterpret_cast<float*>(smem + L::kStage);

@@ -95,3 +95,39 @@ def test_repeated_shuffled_batches_are_stable_with_cross_chunk_culling(uv_defaul
                     o = int(e["offset_bytes"])
                     oi = o + ((nv * 20 + 127) & ~127)
                     assert hashlib.sha256(blob[o:o + nv * 20].tobytes() + blob[oi:oi + ni * 4].tobytes()).digest() == digest, (rep, m, worlds[int(j)][0])
+
+
+def test_repeated_shuffled_batches_are_stable_on_generated_regions(uv_default):
+    """The chunk-summary paths of the parity kernel under the same treatment: generated boxes (so summaries exist) that mix
+    all-air chunks (finished at the ticket), chunks of one solid id (tile rebuilt in shared memory behind a byte-less barrier
+    phase) and surface chunks (tile loaded), in shuffled orders with repeats -- a tile load landing in a buffer that was just
+    written by hand, or a ticket skipped twice, would show up as an intermittent mismatch.  Default and ordered mode."""
+    rng = np.random.default_rng(31)
+    with capi.Context(0, 4096, 2 << 30) as ctx:
+        ctx.set_uv_table(uv_default)
+        worlds = []
+        for origin, dims, kind, seed in (((0, 2, 0), (2, 12, 2), capi.GEN_NOISE, 0xD5E50001), ((40, -2, 0), (2, 4, 2), capi.GEN_REFERENCE, 0)):
+            first = ctx.generate_region(origin, dims, kind, seed)
+            for c in range(dims[2]):
+                for b in range(dims[1]):
+                    for a in range(dims[0]):
+                        p = (origin[0] + a, origin[1] + b, origin[2] + c)
+                        worlds.append((p, first + a + dims[0] * (b + dims[1] * c), orc.generate(kind, seed, p)))
+        slots = np.array([s for _, s, _ in worlds], dtype=np.uint32)
+        want = []
+        kinds = {"air": 0, "uniform": 0, "mixed": 0}
+        for p, _, ids in worlds:
+            v = orc.mesh_chunk(p, ids, uv_default)
+            want.append((v.shape[0], hashlib.sha256(v.tobytes()).digest()))
+            kinds["air" if not ids.any() else ("uniform" if (ids == ids[0]).all() else "mixed")] += 1
+        assert min(kinds.values()) >= 4, kinds
+        for rep in range(int(os.environ.get("DSP_STRESS_REPS", "12"))):
+            for m in (capi.MESH_PARITY, capi.MESH_ORDERED):
+                order = rng.permutation(np.tile(np.arange(len(worlds)), int(rng.integers(8, 40))))
+                entries, total = ctx.mesh_chunks(slots[order], m)
+                blob = ctx.download_arena(0, total)
+                for j, e in zip(order, entries):
+                    nv, digest = want[int(j)]
+                    assert int(e["vertex_count"]) == nv, (rep, m, j)
+                    o = int(e["offset_bytes"])
+                    assert hashlib.sha256(blob[o:o + nv * 20].tobytes()).digest() == digest, (rep, m, worlds[int(j)][0])

@@ -172,3 +172,39 @@ def test_first_frame_with_cross_chunk_culling(uv_default, kind, seed, cam):
                 n_meshes += 1
                 assert ctx.download_vertices(got[p]).tobytes() == want.tobytes(), p
         assert n_meshes == len(got) == int(st["n_meshes"]) and 0 < n_meshes < len(vis)
+
+
+@pytest.mark.gpu
+def test_crossings_at_a_larger_render_distance_and_a_changing_one(uv_default):
+    """The loaded set is kept as arithmetic on (position - previous centre): unit crossings, a diagonal step, a far jump and
+    a change of the render distances between updates must load exactly visible(now) - visible(before) and unload exactly
+    visible(before) - visible(now) (scene_game.rs:56-73), at a distance where the set has tens of thousands of chunks."""
+    kind, seed = capi.GEN_NOISE, 0xD5E50001
+    steps = [((8.0, 120.0, 8.0), 20, 6), ((24.0, 120.0, 8.0), 20, 6), ((40.0, 136.0, -8.0), 20, 6), ((40.0, 136.0, -8.0), 12, 3),  # same chunk: nothing happens,
+             ((56.0, 136.0, -8.0), 12, 3),                                                                                          # the new distances apply at the next crossing
+             ((72.0, 136.0, -8.0), 22, 2), ((5000.0, 100.0, -5000.0), 22, 2), ((5016.0, 100.0, -5000.0), 3, 1)]
+    with capi.Context(0, 40000, 6 << 30) as ctx:
+        ctx.set_uv_table(uv_default)
+        before, last_chunk = set(), None
+        for cam, h, v in steps:
+            st = ctx.scene_update(cam, h, v, kind, seed)
+            cur = sco.current_chunk(cam)
+            if cur == last_chunk:
+                assert st["changed"] == 0 and int(st["n_loaded_total"]) == len(before)
+                continue
+            now = set(sco.visible_chunks(cam, h, v))
+            assert (int(st["n_visible"]), int(st["n_loaded_now"]), int(st["n_unloaded_now"]), int(st["n_loaded_total"])) == \
+                   (len(now), len(now - before), len(before - now), len(now)), (cam, h, v)
+            assert ctx.resident_chunks == len(now)
+            pos, entries = ctx.scene_draw_list()
+            drawn = {tuple(p) for p in pos.tolist()}
+            assert drawn <= now and len(drawn) == int(st["n_meshes"])
+            for p in list(now)[::997]:  # residency by position, and a sampled mesh against the oracle
+                assert ctx.find_chunk(p) is not None
+            sample = [p for p in sorted(drawn)[::701]]
+            got = {tuple(p): e for p, e in zip(pos.tolist(), entries)}
+            for p in sample:
+                assert ctx.download_vertices(got[p]).tobytes() == orc.mesh_chunk(p, orc.generate(kind, seed, p), uv_default).tobytes(), p
+            for p in list(before - now)[::499]:
+                assert ctx.find_chunk(p) is None
+            before, last_chunk = now, cur
