@@ -550,9 +550,15 @@ def main():
     # chunks whose tile the parity kernel does not read: all air (ended at the ticket) / one solid block id (rebuilt from the id), by the generator's chunk summaries
     n_air = int((hv == 0).all(axis=1).sum())
     n_uniform = int(((hv == hv[:, :1]).all(axis=1) & (hv[:, 0] != 0)).sum())
+    # Chunk::palette.len() of every chunk as the reference's World would hold it (chunk.rs:11,58-65): 1 for a chunk that has never held
+    # anything but air, else air + the block ids present.  Part of the host-side chunk, like `blocks`; the CPU arm's restatement uses it too
+    # (its build_chunk_mesh returns None on palette.len() == 1 without looking at a voxel, chunk_mesh.rs:18-20).
+    palette_lens = np.array([1 + len(np.setdiff1d(np.unique(hv[i]), [0])) for i in range(N_CHUNKS)], dtype=np.uint32)
+    assert int((palette_lens == 1).sum()) == n_air
     entries_host = torch.empty(N_CHUNKS * 16, dtype=torch.uint8).pin_memory()
     entries_np = entries_host.numpy().view(capi.MESH_ENTRY_DTYPE)
-    h2d = N_CHUNKS * (8192 + 16)
+    h2d = N_CHUNKS * (8192 + 16)                        # every tile + position (calls without palette lengths)
+    h2d_pal = (N_CHUNKS - n_air) * 8192 + N_CHUNKS * 21   # tiles of the chunks that hold something + position, slot, flag per chunk
     d2h_entries = N_CHUNKS * 16 + 32
     # PCIe floor for context: the same 32 MiB pinned host buffer copied to the device, nothing else
     dev_tmp = torch.empty((N_CHUNKS, 4096), dtype=torch.int16, device="cuda")
@@ -584,9 +590,13 @@ def main():
         ms = max_over_ranks(max(s_ev.elapsed_time(e_ev), (t1 - t0) * 1e3))
         return world * N_CHUNKS * steps / (ms * 1e-3), ms / steps
 
-    # (1) `e2e`: voxels in, entry table out, vertices stay in HBM (the reference's result is a device buffer too)
-    e2e_value, e2e_ms = timed_calls(lambda: ctx.mesh_host_chunks_ptr(N_CHUNKS, pos, host_vox.data_ptr(), entries_np, mode), e2e_steps)
+    # (1) `e2e`: host chunks (voxels + palette lengths) in, entry table out, vertices stay in HBM (the reference's result is a device
+    #     buffer too).  dsp_mesh_host_chunks_ex: the mesh kernel pulls the tiles out of the pinned buffer itself, all-air chunks never cross.
+    e2e_value, e2e_ms = timed_calls(lambda: ctx.mesh_host_chunks_ex_ptr(N_CHUNKS, pos, host_vox.data_ptr(), palette_lens, entries_np, mode), e2e_steps)
     assert int(entries_np["vertex_count"].astype(np.int64).sum()) == faces * 6  # the result really came back
+    # (1b) the same chunks without the palette lengths (dsp_mesh_host_chunks): every tile crosses, copy-engine pipeline
+    nopal_value, nopal_ms = timed_calls(lambda: ctx.mesh_host_chunks_ptr(N_CHUNKS, pos, host_vox.data_ptr(), entries_np, mode), e2e_steps)
+    assert int(entries_np["vertex_count"].astype(np.int64).sum()) == faces * 6
     # (2) vertices delivered to pinned HOST memory (a consumer that is not on this GPU), reference layout: PCIe D2H bound
     host_verts = torch.empty(SLICE, dtype=torch.uint8).pin_memory()
     rb_steps = max(3, min(10, e2e_steps))
@@ -688,10 +698,15 @@ def main():
                                              f"({8192 * (n_air + n_uniform)} B of the algorithmic bytes are not read); `no_summaries` is the same step with every tile read",
                          "moved_GBps": (algo_bytes - 8192 * (n_air + n_uniform)) / (kernel_ms_avg * 1e-3) / 1e9,
                          "frac_of_8TBs_datasheet": achieved / 8000.0},
-            "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms, "h2d_copy_alone_ms": h2d_only_ms,
-                    "what": "dsp_mesh_host_chunks(host u16 voxels, pinned; copy/mesh pipelined in ~1,024-chunk sub-batches) -> dsp_mesh_entry table on the host; vertices stay in HBM "
-                            "(the reference's result is a device buffer too, chunk_mesh.rs:111-124; dsp_arena_export_fd hands that buffer to the renderer)"},
+            "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d_pal, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms, "h2d_copy_alone_ms": h2d_only_ms, "all_air_chunks_not_fetched": n_air,
+                    "what": "dsp_mesh_host_chunks_ex(host u16 voxels in pinned memory + Chunk::palette.len() per chunk) -> dsp_mesh_entry table on the host; the mesh kernel "
+                            "pulls each tile over PCIe itself (1-D bulk / TMA copies from host memory) and files it in the voxel store; chunks whose palette is only air are "
+                            "never fetched (the reference's early-out, chunk_mesh.rs:18-20, which the CPU arm takes too); vertices stay in HBM (the reference's result is a "
+                            "device buffer too, chunk_mesh.rs:111-124; dsp_arena_export_fd hands that buffer to the renderer)"},
+            "e2e_without_palette_lens": {"value": nopal_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps, "ms_per_step": nopal_ms,
+                                         "what": "dsp_mesh_host_chunks: the same chunks without their palette lengths -- all 4,096 tiles cross PCIe, copy/mesh pipelined in "
+                                                 "~1,024-chunk sub-batches on the copy engine (round 1's and the first session's `e2e`)"},
             "e2e_vertices_to_host": {"value": rb_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(total_bytes) + d2h_entries, "steps": rb_steps, "ms_per_step": rb_ms,
                                      "what": "dsp_mesh_host_chunks_to_host, reference layout (6 vertices per face): vertices end in pinned host memory; upload, meshing and download "
                                              "overlap on three streams; bound by PCIe device-to-host (397 MB per step)"},

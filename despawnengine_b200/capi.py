@@ -61,6 +61,7 @@ SYMBOLS = {
     "dsp_mesh_range": (_int, [_vp, _u32, _u64, _u32, _u64, _vp, _P(_u64)]),
     "dsp_mesh_host_chunks": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _u32, _u64, _P(_u32), _vp, _P(_u64)]),
     "dsp_mesh_host_chunks_to_host": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _u32, _u64, _P(_u32), _vp, _P(_u64), _vp, _u64]),
+    "dsp_mesh_host_chunks_ex": (_int, [_vp, _u64, _P(_i32), _P(C.c_uint16), _P(_u32), _u32, _u64, _P(_u32), _vp, _P(_u64), _vp, _u64]),
     "dsp_mesh_range_async": (_int, [_vp, _u32, _u64, _u32, _u64]),
     "dsp_mesh_chunks_async": (_int, [_vp, _u64, _P(_u32), _u32, _u64]),
     "dsp_sync": (_int, [_vp]),
@@ -323,6 +324,27 @@ class Context:
         self._check(lib().dsp_mesh_host_chunks_to_host(self._h, n, _ptr(pos, C.c_int32), C.cast(blocks_host_ptr, C.POINTER(C.c_uint16)), mode, arena_offset,
                                                        None, entries_out.ctypes.data_as(C.c_void_p), C.byref(total), C.c_void_p(host_vertices_ptr), host_capacity))
         return int(total.value)
+
+    def mesh_host_chunks_ex_ptr(self, n: int, pos: np.ndarray, blocks_host_ptr: int, palette_lens, entries_out: np.ndarray, mode: int = MESH_PARITY,
+                                arena_offset: int = 0, host_vertices_ptr: int = 0, host_capacity: int = 0, slots_out=None) -> int:
+        """dsp_mesh_host_chunks_ex with caller-owned host buffers (pinned: the mesh kernel pulls the tiles itself); palette_lens: u32[n]
+        or None; returns total bytes."""
+        total = C.c_uint64(0)
+        pl = None if palette_lens is None else _ptr(np.ascontiguousarray(palette_lens, dtype=np.uint32), C.c_uint32)
+        self._check(lib().dsp_mesh_host_chunks_ex(self._h, n, _ptr(pos, C.c_int32), C.cast(blocks_host_ptr, C.POINTER(C.c_uint16)), pl, mode, arena_offset,
+                                                  None if slots_out is None else _ptr(slots_out, C.c_uint32), entries_out.ctypes.data_as(C.c_void_p), C.byref(total),
+                                                  C.c_void_p(host_vertices_ptr) if host_vertices_ptr else None, host_capacity))
+        return int(total.value)
+
+    def mesh_host_chunks_ex(self, pos, blocks, palette_lens=None, mode: int = MESH_PARITY, arena_offset: int = 0):
+        """dsp_mesh_host_chunks_ex on a numpy array (pageable memory unless the caller pinned it); returns (slots, entries, total_bytes)."""
+        pos = np.ascontiguousarray(pos, dtype=np.int32).reshape(-1, 3)
+        n = pos.shape[0]
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(n, 4096)
+        slots = np.empty(n, dtype=np.uint32)
+        entries = np.zeros(n, dtype=MESH_ENTRY_DTYPE)
+        total = self.mesh_host_chunks_ex_ptr(n, pos, blocks.ctypes.data, palette_lens, entries, mode, arena_offset, slots_out=slots)
+        return slots, entries, total
 
     def mesh_host_chunks_to_host(self, pos, blocks, mode: int = MESH_PARITY, arena_offset: int = 0, capacity: int = 0):
         """Returns (entries, total bytes, host mirror of the arena window as a u8 array)."""

@@ -138,6 +138,8 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
+    uint64_t e2e_pull_first_div = 8; // kernel pull: the first launch takes n / this chunks (DSP_E2E_PULL_DIV, for A/B runs)
+    int e2e_pull = 1;            // host-chunk calls on pinned memory: the mesh kernel pulls the tiles itself (DSP_E2E_PULL=0: copy-engine pipeline, for A/B runs)
     uint64_t e2e_head_chunks = 128;  // first sub-batch of the pipelined host-chunk calls (DSP_E2E_HEAD=0 switches it off for A/B runs)
     int summary_skip = 3;       // parity mesh calls use the chunk summaries: bit 0 all-air chunks end at the ticket, bit 1 chunks of one known solid id skip their tile (DSP_SUMMARY_SKIP=0..3 for A/B runs)
     bool use_pdl = true;        // programmatic dependent launch of the mesh kernels (DSP_PDL=0 switches it off for A/B runs)
@@ -485,10 +487,12 @@ int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offs
 
 // One mesh launch over `n` chunks whose entries start at entry index `entry0`; `sub` picks the ticket counter.
 int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub, bool self_reset = false,
-                bool work_list = false) {
+                bool work_list = false, const uint16_t* host_tiles = nullptr) {
     const bool halo = (mode & DSP_MESH_HALO) != 0;
     dsp::MeshParams p{};
     p.voxels = ctx->d_voxels;
+    p.host_tiles = host_tiles;  // the chunks of this launch are pulled out of (pinned) host memory by the kernel itself
+    p.voxels_out = ctx->d_voxels;
     p.chunk_pos = ctx->d_pos;
     p.slot_list = d_list;
     p.nbr_slots = ctx->d_nbr;
@@ -519,9 +523,9 @@ int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first
     p.total_bytes = reinterpret_cast<uint64_t*>(ctx->d_ctl + 16);
     p.face_counts = reinterpret_cast<uint32_t*>(ctx->d_ctl + 32);
     p.preset = (mode & DSP_MESH_ORDERED) != 0;
-    if (!halo && !work_list && !(mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) && ctx->summary_skip) {
+    if (!halo && !work_list && ctx->summary_skip) {
         p.summary = ctx->d_summary;
-        p.uid = (ctx->summary_skip & 2) ? ctx->d_uid : nullptr;
+        p.uid = ((ctx->summary_skip & 2) && !(mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED))) ? ctx->d_uid : nullptr;  // (the quad kernels only use the all-air bit)
         p.summary_air_skip = (ctx->summary_skip & 1) != 0;
     }
     if (mode & (DSP_MESH_GREEDY | DSP_MESH_INDEXED)) return halo ? launch_quads<true>(ctx, p, mode) : launch_quads<false>(ctx, p, mode);
@@ -815,6 +819,8 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     ctx->num_sms = prop.multiProcessorCount;
     if (const char* s = getenv("DSP_PDL")) ctx->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("DSP_SUMMARY_SKIP")) ctx->summary_skip = atoi(s) & 3;
+    if (const char* s = getenv("DSP_E2E_PULL")) ctx->e2e_pull = std::min(2, std::max(0, atoi(s)));
+    if (const char* s = getenv("DSP_E2E_PULL_DIV")) ctx->e2e_pull_first_div = static_cast<uint64_t>(std::min(64, std::max(2, atoi(s))));
     if (const char* s = getenv("DSP_E2E_HEAD")) ctx->e2e_head_chunks = static_cast<uint64_t>(std::min(512, std::max(0, atoi(s))));
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
@@ -1190,7 +1196,7 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
 
 // dsp_mesh_host_chunks, optionally followed (pipelined) by the device->host copy of the vertices: host_vertices != NULL
 // mirrors the arena window [arena_offset, arena_offset + total) into host memory (entry offsets minus arena_offset index it).
-static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
+static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode, uint64_t arena_offset,
                                  uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices, uint64_t host_capacity) {
     if (!ctx) return DSP_ERR_BAD_ARG;
     if (out_total_bytes) *out_total_bytes = 0;
@@ -1228,6 +1234,26 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     const bool trace = getenv("DSP_TRACE") != nullptr;
     const auto tr0 = std::chrono::steady_clock::now();
     auto tr = [&](const char* what) { if (trace) fprintf(stderr, "[trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count()); };
+    // Are the voxels in pinned / registered host memory that the device can read?  Then no copy engine is involved at all: the mesh
+    // kernel pulls every tile over PCIe with the bulk (TMA) copy that otherwise reads the voxel store, meshes it and files it in the
+    // store on the way (MeshParams::host_tiles).  Chunks whose palette has one entry are never fetched (stage_host_chunks_kernel).
+    // Pageable memory takes the copy-engine pipeline below.
+    // Which is faster depends on how many tiles need not cross the bus: SM pulls reach 50.7 GB/s, the copy engine 55.1 GB/s
+    // (tools/pcie_pull_probe.cu), so the pull is taken when the palette lengths spare at least a tenth of the chunks
+    // (DSP_E2E_PULL=2 forces it, 0 switches it off).
+    const uint16_t* dev_blocks = nullptr;
+    if (ctx->e2e_pull && n && (!readback || ctx->e2e_pull >= 2)) {  // (with the download behind it the copy-engine pipeline measured faster: 1.09 against 1.23 ms)
+        uint64_t n_air = 0;
+        if (palette_lens != nullptr)
+            for (uint64_t i = 0; i < n; ++i) n_air += palette_lens[i] == 1u;
+        if (ctx->e2e_pull >= 2 || n_air * 10 >= n) {
+            cudaPointerAttributes attr{};
+            if (cudaPointerGetAttributes(&attr, blocks) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr)
+                dev_blocks = static_cast<const uint16_t*>(attr.devicePointer);
+            else cudaGetLastError();
+        }
+    }
+    const bool pull = dev_blocks != nullptr;
     // sub-batches: copy k+1 crosses PCIe while sub-batch k is meshed
     // Sub-batch plan.  Every copy costs a few microseconds of gap on the DMA engine, so the body is cut into pieces of about
     // 1,024 chunks (8 MiB); the LAST piece is small (256 chunks) because its kernel and the entry read-back are the only work
@@ -1235,7 +1261,14 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     // The FIRST piece is small too (128 chunks): the host resolves a piece's positions to slots before it can enqueue the
     // piece's copy, and nothing crosses PCIe while it does that for the first one.
     std::vector<uint64_t> sub_begin;
-    {
+    if (pull && !readback) {  // (with a download behind it the finer plan below keeps the three directions overlapped)
+        // Kernel pull: a kernel boundary is a PCIe bubble (the next launch's CTAs wait for the previous one to drain), so there
+        // are only two pieces -- a first eighth that starts pulling while the host still resolves the slots of the rest (the host
+        // resolves a chunk in about a sixth of the time its tile takes to cross the bus), then everything else in one launch.
+        sub_begin.push_back(0);
+        if (n > 1024) sub_begin.push_back((n / ctx->e2e_pull_first_div + 63) & ~uint64_t(63));
+        sub_begin.push_back(n);
+    } else {
         const uint64_t tail = n > 512 ? 256 : 0, head = n > 1024 ? ctx->e2e_head_chunks : 0, body = n - tail - head;
         uint64_t pieces = std::max<uint64_t>(1, (body + 1023) / 1024);
         pieces = std::min<uint64_t>(pieces, dsp_ctx::kMaxSub - 2);
@@ -1251,9 +1284,10 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     ctx->result_in_tail = false;
     if (n == 0) return finish_mesh(ctx, out_entries, out_total_bytes);
     uint8_t* h;
-    if ((rc = stage_host(ctx, n * (sizeof(int4) + sizeof(uint32_t)), &h)) != DSP_OK) return rc;
+    if ((rc = stage_host(ctx, n * (sizeof(int4) + sizeof(uint32_t) + 1), &h)) != DSP_OK) return rc;
     int4* h_pos = reinterpret_cast<int4*>(h);
     uint32_t* h_slots = reinterpret_cast<uint32_t*>(h + n * sizeof(int4));
+    uint8_t* h_air = h + n * (sizeof(int4) + sizeof(uint32_t));
     tr("staging ready");
     // the copy stream must not overtake earlier work of the main stream that still reads the voxel store
     DSP_CUDA(ctx, cudaEventRecord(ctx->ev_done, ctx->stream));
@@ -1312,25 +1346,33 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
                 return bail(fail(ctx, DSP_ERR_BAD_ARG, "position (%d, %d, %d) appears twice in the batch (entry %llu): one chunk per position",
                                  pos[3 * (i0 + i)], pos[3 * (i0 + i) + 1], pos[3 * (i0 + i) + 2], (unsigned long long)(i0 + i)));
             h_pos[i0 + i] = make_int4(pos[3 * (i0 + i)], pos[3 * (i0 + i) + 1], pos[3 * (i0 + i) + 2], 0);
+            h_air[i0 + i] = (pull && palette_lens != nullptr && palette_lens[i0 + i] == 1u) ? 1 : 0;
             if (i && h_slots[i0 + i] != h_slots[i0 + i - 1] + 1) consecutive = false;
         }
         // The copy stream carries nothing but the voxel tiles, back to back: small copies between them cost more in gaps than
         // in bytes (16 copies took 0.68 ms where 32 MiB alone take 0.61 ms), and small copies on ANOTHER stream wait in the
         // DMA engine until all tile copies are through (0.73 -> 0.93 ms).  So positions and the slot list do not use a copy
         // engine at all: a small kernel on the main stream reads them straight from the pinned staging block (UVA).
-        dsp::stage_positions_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
-            ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_bvalid, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
+        if (pull && palette_lens != nullptr)
+            dsp::stage_host_chunks_kernel<<<static_cast<unsigned>((m + dsp::kStageChunksPerCta - 1) / dsp::kStageChunksPerCta), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_bvalid, ctx->d_voxels,
+                                                                                             h_pos + i0, h_slots + i0, h_air + i0, static_cast<uint32_t>(m));
+        else
+            dsp::stage_positions_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
+                ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_bvalid, h_pos + i0, h_slots + i0, static_cast<uint32_t>(m));
         ctx->bmask_stale = true;
-        if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "stage_positions_kernel launch failed"));
+        if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "staging kernel launch failed"));
+        ctx->launches++;
         const uint32_t* d_list = consecutive ? nullptr : ctx->d_slots + i0;
-        ctx->stream = ctx->copy_stream;  // upload_by_runs enqueues on ctx->stream
-        rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, h_slots + i0, m,
-                            reinterpret_cast<const uint8_t*>(blocks + (i0 * dsp::kChunkVoxels)));
-        ctx->stream = main_stream;
-        if (rc != DSP_OK) return bail(rc);
-        if (cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
-            return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the copy pipeline"));
-        if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j)) != DSP_OK) return bail(rc);
+        if (!pull) {
+            ctx->stream = ctx->copy_stream;  // upload_by_runs enqueues on ctx->stream
+            rc = upload_by_runs(ctx, reinterpret_cast<uint8_t*>(ctx->d_voxels), dsp::kChunkBytes, h_slots + i0, m,
+                                reinterpret_cast<const uint8_t*>(blocks + (i0 * dsp::kChunkVoxels)));
+            ctx->stream = main_stream;
+            if (rc != DSP_OK) return bail(rc);
+            if (cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
+                return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the copy pipeline"));
+        }
+        if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j, false, false, pull ? dev_blocks + i0 * dsp::kChunkVoxels : nullptr)) != DSP_OK) return bail(rc);
         tr("sub-batch enqueued");
         if (early_entries && j + 1 < subs) {
             if (cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_meshed[j], 0) != cudaSuccess ||
@@ -1383,13 +1425,18 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
 
 int dsp_mesh_host_chunks(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
                          uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes) {
-    return mesh_host_chunks_impl(ctx, n, pos, blocks, mode, arena_offset, out_slots, out_entries, out_total_bytes, nullptr, 0);
+    return mesh_host_chunks_impl(ctx, n, pos, blocks, nullptr, mode, arena_offset, out_slots, out_entries, out_total_bytes, nullptr, 0);
+}
+
+int dsp_mesh_host_chunks_ex(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode, uint64_t arena_offset,
+                            uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices, uint64_t host_capacity) {
+    return mesh_host_chunks_impl(ctx, n, pos, blocks, palette_lens, mode, arena_offset, out_slots, out_entries, out_total_bytes, host_vertices, host_capacity);
 }
 
 int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, uint32_t mode, uint64_t arena_offset,
                                  uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices, uint64_t host_capacity) {
     if (ctx && !host_vertices) return fail(ctx, DSP_ERR_BAD_ARG, "host_vertices is NULL");
-    return mesh_host_chunks_impl(ctx, n, pos, blocks, mode, arena_offset, out_slots, out_entries, out_total_bytes, host_vertices, host_capacity);
+    return mesh_host_chunks_impl(ctx, n, pos, blocks, nullptr, mode, arena_offset, out_slots, out_entries, out_total_bytes, host_vertices, host_capacity);
 }
 
 int dsp_apply_edits(dsp_ctx* ctx, uint64_t n, const dsp_edit* edits, uint32_t* out_dirty_slots, uint64_t cap_dirty, uint64_t* out_n_dirty) {

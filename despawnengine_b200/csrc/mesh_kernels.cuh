@@ -71,6 +71,12 @@ struct MeshParams {
     // known solid block id is meshed from that id without its tile being read (uid above).
     const uint8_t* summary;
     bool summary_air_skip;
+    // Host-resident chunks (dsp_mesh_host_chunks*, pinned / registered memory): tile of ticket i = host_tiles + i * 4096, pulled over
+    // PCIe by the same 1-D bulk (TMA) copy that otherwise reads the voxel store -- no copy engine, no staging buffer, no separate
+    // upload kernel; once it is in shared memory the tile is also stored to the chunk's slot of the voxel store (voxels_out), so
+    // the chunk is resident afterwards like any other.  nullptr: tiles come from the voxel store.
+    const uint16_t* host_tiles;
+    uint16_t* voxels_out;
     // DSP_MESH_ORDERED: count_chunks_scan_kernel has already written every chunk's entry (slots packed in call order); the mesh
     // kernel takes each chunk's offset from its entry instead of claiming one, and writes neither entries nor the total.
     bool preset;
@@ -509,7 +515,8 @@ struct MeshCta {
         s_next[4 + buf] = uni;
         if (uni) { mbar_arrive(&s_bar[buf]); return; }
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
-        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
+        const uint16_t* src = p.host_tiles != nullptr ? p.host_tiles + static_cast<size_t>(chunk) * kChunkVoxels : p.voxels + static_cast<size_t>(slot) * kChunkVoxels;
+        bulk_load(s_vox + buf * kChunkVoxels, src, kChunkBytes, &s_bar[buf]);
 #ifdef DSP_L2_PREFETCH
         // tickets are handed out in order, so the tile of chunk + prefetch_ahead will be wanted by some CTA soon: pull it into L2
         const uint64_t ahead = static_cast<uint64_t>(chunk) + p.prefetch_ahead;
@@ -758,12 +765,19 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
         if (tid == 0) {  // next ticket now: its tile lands while this chunk is processed
             const uint32_t t = c.claim_ticket(gridDim.x + atomicAdd(p.ticket, 1u));
             c.s_next[(it + 1) & 1] = t;
+            if (p.host_tiles != nullptr) bulk_wait_read<0>();  // the previous chunk's tile has left buf^1 for the voxel store (see below)
             if (t < p.n) c.issue_load(t, buf ^ 1);  // buf^1 was released by the barrier that ended the previous iteration
         }
         c.tick(7);
         seam_wait<HALO>(p, cur);
         mbar_wait(&c.s_bar[buf], (it >> 1) & 1);
         c.tick(2);
+        if (p.host_tiles != nullptr && tid == 0) {
+            // the tile came straight from host memory: it also becomes the chunk's copy in the voxel store (shared -> global bulk copy,
+            // async proxy on both sides; its read of the buffer is awaited before the buffer's next load, at the top of the next iteration)
+            bulk_store(p.voxels_out + static_cast<size_t>(c.s_next[2 + buf]) * kChunkVoxels, c.s_vox + buf * kChunkVoxels, kChunkBytes);
+            bulk_commit();
+        }
 #ifndef DSP_NO_EMPTY_SKIP
         bool empty;
         const RowFaces fc = c.count_phase(cur, buf, &empty, true);

@@ -227,7 +227,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
     auto slot_of = [&](uint32_t chunk) -> uint32_t { return p.slot_list ? __ldg(p.slot_list + work_index(p, chunk)) : p.first_slot + chunk; };
     auto issue_load = [&](uint32_t chunk, int buf) {
         mbar_arrive_expect_tx(&s_bar[buf], kChunkBytes);
-        bulk_load(s_vox + buf * kChunkVoxels, p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels, kChunkBytes, &s_bar[buf]);
+        // (host-resident chunks: the tile of ticket i is pulled straight out of pinned host memory, see MeshParams::host_tiles)
+        const uint16_t* src = p.host_tiles != nullptr ? p.host_tiles + static_cast<size_t>(chunk) * kChunkVoxels : p.voxels + static_cast<size_t>(slot_of(chunk)) * kChunkVoxels;
+        bulk_load(s_vox + buf * kChunkVoxels, src, kChunkBytes, &s_bar[buf]);
     };
 
     // Tickets.  The first chunk of a CTA is its block index (no atomic: hundreds of CTAs hitting one counter in the same
@@ -238,13 +240,24 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
     // latency is not what bounds short chunks), static striding itself (no atomics, but 15 % slower on uneven regions).
     constexpr int NB = L::kVoxBufs;
     static_assert(NB == 2, "the prologue assigns one buffer");
+    // thread 0 only: where the chunk summaries are at hand (no pre-pass), an all-air chunk ends at the ticket -- empty entry, next
+    // ticket, no tile (chunk_mesh.rs:18-20; see MeshCta::claim_ticket)
+    auto skip_air = [&](uint32_t t) -> uint32_t {
+        if (p.summary == nullptr || !p.summary_air_skip) return t;
+        while (t < p.n && (__ldg(p.summary + slot_of(t)) & kSummaryAir)) {
+            *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
+            t = gridDim.x + atomicAdd(p.ticket, 1u);
+        }
+        return t;
+    };
     uint32_t pending = 0;  // thread 0: the ticket after the one whose tile is in flight
     if (tid == 0) {
 #pragma unroll
         for (int b = 0; b < NB; ++b) mbar_init(&s_bar[b], 1);
         fence_mbar_init();
-        s_next[0] = blockIdx.x;
-        if (blockIdx.x < p.n) issue_load(blockIdx.x, 0);
+        const uint32_t t0 = skip_air(blockIdx.x);
+        s_next[0] = t0;
+        if (t0 < p.n) issue_load(t0, 0);
         pending = gridDim.x + atomicAdd(p.ticket, 1u);
     }
     if (GREEDY && !HALO && p.n_dev != nullptr) {
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
         const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
         uint32_t tnext = 0;
         if (tid == 0) {
-            tnext = pending;
+            tnext = skip_air(pending);
             s_next[nb] = tnext;
             pending = gridDim.x + atomicAdd(p.ticket, 1u);
         }
@@ -332,7 +345,16 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
         // The next ticket's tile goes into the buffer of the PREVIOUS iteration only now: merged quads are expanded straight
         // from the tables and the tile with no barrier behind them, so the barrier above is the first point at which every thread
         // is known to have finished with that buffer.
-        if (tid == 0 && tnext < p.n) issue_load(tnext, nb);
+        if (tid == 0) {
+            if (p.host_tiles != nullptr) {
+                // the tile that has just arrived from host memory also becomes the chunk's copy in the voxel store; the previous
+                // chunk's copy has left buffer nb before that buffer is loaded again
+                bulk_wait_read<0>();
+                bulk_store(p.voxels_out + static_cast<size_t>(slot_of(cur)) * kChunkVoxels, s_vox + buf * kChunkVoxels, kChunkBytes);
+                bulk_commit();
+            }
+            if (tnext < p.n) issue_load(tnext, nb);
+        }
         QTICK(1);
         if (tid == 0 && pend) { store_tile(pend_claimed, pend_Q, pend_f0, pend_cur); pend = false; }  // the previous chunk's last tile
         QTICK(9);

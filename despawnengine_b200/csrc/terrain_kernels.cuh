@@ -341,6 +341,37 @@ __global__ void stage_positions_kernel(int4* chunk_pos, uint32_t* slot_list_out,
     summary[s] = kSummaryUnknown;  // host voxels are about to land in this slot
     bvalid[s] = 0;
 }
+// The same for a sub-batch whose chunks carry the reference's palette length (dsp_mesh_host_chunks_ex).  A chunk
+// with palette.len() == 1 has never held anything but air (chunk.rs:58-65; build_chunk_mesh returns None for it without looking at
+// a voxel, chunk_mesh.rs:18-20): its host voxels are not fetched at all -- the slot is zero-filled here and its summary says so,
+// which is what lets the mesh kernel finish it at the ticket.
+constexpr int kStageChunksPerCta = 64;
+__global__ void __launch_bounds__(256) stage_host_chunks_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, uint8_t* bvalid, uint16_t* voxels,
+                                                                const int4* host_pos, const uint32_t* host_slots, const uint8_t* host_air, uint32_t n) {
+    // 64 chunks per CTA: their positions / slots / flags are read from the pinned staging block with coalesced loads (one PCIe
+    // request per warp, not per chunk), then the CTA zero-fills the slots of the flagged ones, 8 KiB each
+    __shared__ uint32_t s_air_slot[kStageChunksPerCta];
+    __shared__ uint32_t s_n_air;
+    if (threadIdx.x == 0) s_n_air = 0u;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * kStageChunksPerCta + threadIdx.x;
+    if (threadIdx.x < kStageChunksPerCta && i < n) {
+        const uint32_t s = host_slots[i];
+        const bool air = host_air[i] != 0;
+        chunk_pos[s] = host_pos[i];
+        slot_list_out[i] = s;
+        summary[s] = air ? kSummaryAir : kSummaryUnknown;
+        bvalid[s] = 0;
+        if (air) s_air_slot[atomicAdd(&s_n_air, 1u)] = s;
+    }
+    __syncthreads();
+    const uint32_t n_air = s_n_air;
+    for (uint32_t k = 0; k < n_air; ++k) {
+        uint4* d = reinterpret_cast<uint4*>(voxels + static_cast<size_t>(s_air_slot[k]) * kChunkVoxels);
+        d[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+        d[threadIdx.x + 256] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
 __global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, uint8_t* bvalid, const uint32_t* slots, const int4* src, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -189,6 +189,21 @@ int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
                                  uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices,
                                  uint64_t host_capacity);
 
+/* The general form of the two calls above, with what the reference's Chunk also carries: palette_lens[i] = Chunk::palette.len()
+ * of chunk i (chunks/chunk.rs:11,58-65; NULL: not known).  A chunk whose palette has ONE entry has never held anything but air:
+ * build_chunk_mesh returns None for it without looking at a voxel (chunk_mesh.rs:18-20), and so does this call -- the chunk's
+ * `blocks` are not fetched (they must still be addressable; by the reference's invariant they are all zero), its slot of the voxel
+ * store is zero-filled on the device and its entry is empty.  host_vertices may be NULL (then host_capacity is ignored and the
+ * call is dsp_mesh_host_chunks with palette lengths).
+ * When `blocks` is pinned or registered host memory that the device can address (cudaHostAlloc / cudaHostRegister), host_vertices
+ * is NULL and the palette lengths spare at least a tenth of the chunks, no copy engine is involved: the mesh kernel itself pulls each remaining chunk's
+ * 8 KiB tile over PCIe with the bulk (TMA) copy that otherwise reads the voxel store, meshes it and files it in the store on the
+ * way -- two launches per call, nothing staged, nothing copied twice.  Otherwise (pageable memory, no palette lengths) the
+ * copy-engine pipeline described above is used.  Both give identical results. */
+int dsp_mesh_host_chunks_ex(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode,
+                            uint64_t arena_offset, uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes,
+                            void* host_vertices, uint64_t host_capacity);
+
 /* Asynchronous forms: enqueue on the context's stream and return; results are read with
  * dsp_mesh_result after dsp_sync.  Let a caller overlap meshing with its own work (the reference is
  * synchronous inside GameScene::update, scene_game.rs:56-64). */
