@@ -1247,9 +1247,13 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
         if (palette_lens != nullptr)
             for (uint64_t i = 0; i < n; ++i) n_air += palette_lens[i] == 1u;
         if (ctx->e2e_pull >= 2 || n_air * 10 >= n) {
-            cudaPointerAttributes attr{};
-            if (cudaPointerGetAttributes(&attr, blocks) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr)
-                dev_blocks = static_cast<const uint16_t*>(attr.devicePointer);
+            // first and last byte of the array must lie in one device-addressable host allocation
+            cudaPointerAttributes a0{}, a1{};
+            const uint8_t* last = reinterpret_cast<const uint8_t*>(blocks) + n * dsp::kChunkBytes - 1;
+            if (cudaPointerGetAttributes(&a0, blocks) == cudaSuccess && a0.type == cudaMemoryTypeHost && a0.devicePointer != nullptr &&
+                cudaPointerGetAttributes(&a1, last) == cudaSuccess && a1.type == cudaMemoryTypeHost && a1.devicePointer != nullptr &&
+                static_cast<const uint8_t*>(a1.devicePointer) - static_cast<const uint8_t*>(a0.devicePointer) == last - reinterpret_cast<const uint8_t*>(blocks))
+                dev_blocks = static_cast<const uint16_t*>(a0.devicePointer);
             else cudaGetLastError();
         }
     }
