@@ -138,7 +138,8 @@ struct dsp_ctx {
 
     uint64_t last_mesh_n = 0;
     uint64_t launches = 0;
-    uint64_t e2e_pull_first_div = 8; // kernel pull: the first launch takes n / this chunks (DSP_E2E_PULL_DIV, for A/B runs)
+    uint64_t e2e_pull_first_div = 5; // kernel pull: the first launch takes n / this chunks (DSP_E2E_PULL_DIV, for A/B runs)
+    int e2e_pull_pieces = 2;         // (DSP_E2E_PULL_PIECES=3: a smaller launch in front, all on one stream; 1: two launches on one stream -- for A/B runs)
     int e2e_pull = 1;            // host-chunk calls on pinned memory: the mesh kernel pulls the tiles itself (DSP_E2E_PULL=0: copy-engine pipeline, for A/B runs)
     uint64_t e2e_head_chunks = 128;  // first sub-batch of the pipelined host-chunk calls (DSP_E2E_HEAD=0 switches it off for A/B runs)
     int summary_skip = 3;       // parity mesh calls use the chunk summaries: bit 0 all-air chunks end at the ticket, bit 1 chunks of one known solid id skip their tile (DSP_SUMMARY_SKIP=0..3 for A/B runs)
@@ -820,6 +821,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if (const char* s = getenv("DSP_PDL")) ctx->use_pdl = atoi(s) != 0;
     if (const char* s = getenv("DSP_SUMMARY_SKIP")) ctx->summary_skip = atoi(s) & 3;
     if (const char* s = getenv("DSP_E2E_PULL")) ctx->e2e_pull = std::min(2, std::max(0, atoi(s)));
+    if (const char* s = getenv("DSP_E2E_PULL_PIECES")) ctx->e2e_pull_pieces = atoi(s);
     if (const char* s = getenv("DSP_E2E_PULL_DIV")) ctx->e2e_pull_first_div = static_cast<uint64_t>(std::min(64, std::max(2, atoi(s))));
     if (const char* s = getenv("DSP_E2E_HEAD")) ctx->e2e_head_chunks = static_cast<uint64_t>(std::min(512, std::max(0, atoi(s))));
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
@@ -1267,9 +1269,10 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     std::vector<uint64_t> sub_begin;
     if (pull && !readback) {  // (with a download behind it the finer plan below keeps the three directions overlapped)
         // Kernel pull: a kernel boundary is a PCIe bubble (the next launch's CTAs wait for the previous one to drain), so there
-        // are only two pieces -- a first eighth that starts pulling while the host still resolves the slots of the rest (the host
-        // resolves a chunk in about a sixth of the time its tile takes to cross the bus), then everything else in one launch.
+        // are only two pieces -- a first fifth that starts pulling while the host still resolves the slots of the rest (the host
+        // resolves a chunk in about a quarter of the time an average tile takes to cross the bus), then everything else in one launch.
         sub_begin.push_back(0);
+        if (n > 1024 && ctx->e2e_pull_pieces >= 3) sub_begin.push_back((n / (4 * ctx->e2e_pull_first_div) + 63) & ~uint64_t(63));
         if (n > 1024) sub_begin.push_back((n / ctx->e2e_pull_first_div + 63) & ~uint64_t(63));
         sub_begin.push_back(n);
     } else {
@@ -1357,6 +1360,11 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
         // in bytes (16 copies took 0.68 ms where 32 MiB alone take 0.61 ms), and small copies on ANOTHER stream wait in the
         // DMA engine until all tile copies are through (0.73 -> 0.93 ms).  So positions and the slot list do not use a copy
         // engine at all: a small kernel on the main stream reads them straight from the pinned staging block (UVA).
+        // Kernel pull: the second launch goes to the side stream.  Behind the first one on the same stream its CTAs would wait
+        // (griddepcontrol.wait) until the LAST tile of the first launch has crossed the bus and been meshed -- a PCIe bubble;
+        // on its own stream each of its CTAs starts pulling the moment a CTA of the first launch retires.
+        const bool side = pull && !readback && j >= 1 && ctx->e2e_pull_pieces == 2;
+        if (side) ctx->stream = ctx->copy_stream;
         if (pull && palette_lens != nullptr)
             dsp::stage_host_chunks_kernel<<<static_cast<unsigned>((m + dsp::kStageChunksPerCta - 1) / dsp::kStageChunksPerCta), 256, 0, ctx->stream>>>(ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_bvalid, ctx->d_voxels,
                                                                                              h_pos + i0, h_slots + i0, h_air + i0, static_cast<uint32_t>(m));
@@ -1376,7 +1384,13 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
             if (cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
                 return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the copy pipeline"));
         }
-        if ((rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j, false, false, pull ? dev_blocks + i0 * dsp::kChunkVoxels : nullptr)) != DSP_OK) return bail(rc);
+        rc = launch_mesh(ctx, m, d_list, h_slots[i0], mode, arena_offset, i0, j, false, false, pull ? dev_blocks + i0 * dsp::kChunkVoxels : nullptr);
+        if (side) {
+            ctx->stream = main_stream;
+            if (rc == DSP_OK && (cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess))
+                rc = fail(ctx, DSP_ERR_CUDA, "event record / wait failed behind the side-stream launch");
+        }
+        if (rc != DSP_OK) return bail(rc);
         tr("sub-batch enqueued");
         if (early_entries && j + 1 < subs) {
             if (cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_meshed[j], 0) != cudaSuccess ||

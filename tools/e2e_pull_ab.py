@@ -18,10 +18,12 @@ ent = torch.empty(N * 16, dtype=torch.uint8).pin_memory()
 ent_np = ent.numpy().view(capi.MESH_ENTRY_DTYPE)
 out = {"air_chunks": int((pal == 1).sum())}
 cases = [("copy_engine", "0", None, "8"), ("pull", "2", None, "8"), ("pull_palette_lens", "1", pal, "8"), ("copy_engine_again", "0", None, "8")]
+cases += [("pull_palette_lens_one_stream", "1", pal, "8")] + [(f"pull_palette_lens_div{d}", "1", pal, str(d)) for d in (4, 6, 12, 16)] + [("pull_palette_lens_again", "1", pal, "8")]
 host = torch.empty(448 << 20, dtype=torch.uint8).pin_memory()
 for label, pull, pl, div in cases:
     os.environ["DSP_E2E_PULL"] = pull
     os.environ["DSP_E2E_PULL_DIV"] = div
+    os.environ["DSP_E2E_PULL_PIECES"] = "1" if "one_stream" in label else "2"
     with capi.Context(0, N, 1 << 30) as ctx:
         ctx.set_uv_table(syn.UV_DEFAULT)
         fn = lambda: ctx.mesh_host_chunks_ex_ptr(N, pos, vox.data_ptr(), pl, ent_np)
