@@ -4,6 +4,7 @@
   2. DSP_MESH_ORDERED: count_chunks_scan_kernel + mesh_chunks_bump_kernel at preset offsets, 2 calls
   3. merged quads, indexed layout (classify_greedy_kernel + mesh_chunks_quads_kernel with direct stores), 2 calls
   4. parity mesh with the summaries invalidated (every tile read), 2 launches
+  5. dsp_mesh_host_chunks_ex on pinned voxels with palette lengths: stage_host_chunks_kernel + the mesh kernel pulling host tiles, 2 + 2 launches
 python tools/prof_r02b.py"""
 import os, sys
 import numpy as np
@@ -24,4 +25,14 @@ with capi.Context(0, 4096 * 4, 4 * SL) as ctx:
     ctx.invalidate_chunks(np.arange(firsts[2], firsts[2] + 8192, dtype=np.uint32))
     for k in (2, 3):
         ctx.mesh_range(firsts[k], 4096, capi.MESH_PARITY, k * SL)
+    # 5. host-resident chunks through dsp_mesh_host_chunks_ex: staging kernel + mesh kernel pulling its tiles out of pinned host memory, two launches
+    import torch
+    pos = syn.box_positions((0, 0, 0), (16, 16, 16))
+    vox = torch.empty((4096, 4096), dtype=torch.int16).pin_memory()
+    hv = vox.numpy().view(np.uint16)
+    for i in range(4096):
+        hv[i] = ctx.download_chunk(first + i)[0]
+    pal = np.where((hv == 0).all(axis=1), 1, 3).astype(np.uint32)
+    ent = np.zeros(4096, dtype=capi.MESH_ENTRY_DTYPE)
+    ctx.mesh_host_chunks_ex_ptr(4096, pos, vox.data_ptr(), pal, ent)
 print("done")
