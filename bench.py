@@ -295,7 +295,8 @@ def config5(torch, dist, capi, rank, world, local_rank, peak):
         if world > 1:
             connect_region_seams(dev, sp, rank, dist)
         res = {}
-        for mode_name, mode, batch in (("parity", capi.MESH_PARITY, 32768), ("halo", capi.MESH_HALO, 262144)):
+        # (parity: 98,304 chunks = three x-y slabs per launch write ~5 GB of the 8 GiB arena; each launch is followed by a host sync that reads its total)
+        for mode_name, mode, batch in (("parity", capi.MESH_PARITY, 98304), ("halo", capi.MESH_HALO, 262144)):
             xchg_ms = 0.0
             if mode == capi.MESH_HALO and world > 1:
                 ctx.seam_exchange_async(); ctx.mesh_range(dev.first_slot, min(n, 4096), mode)  # epoch 1: warm-up

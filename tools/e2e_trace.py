@@ -26,3 +26,14 @@ with capi.Context(0, N, 1 << 30) as ctx:
     print("untraced step us:", [round(t * 1e6) for t in ts])
     os.environ["DSP_TRACE"] = "1"
     ctx.mesh_host_chunks_ptr(N, pos, host.data_ptr(), ent_np, 0)
+    # the same chunks with their palette lengths: kernel pull (dsp_mesh_host_chunks_ex)
+    os.environ.pop("DSP_TRACE", None)
+    pal = np.where((hv == 0).all(axis=1), 1, 3).astype(np.uint32)
+    for _ in range(3):
+        ctx.mesh_host_chunks_ex_ptr(N, pos, host.data_ptr(), pal, ent_np)
+    ts = []
+    for _ in range(10):
+        t0 = time.perf_counter(); ctx.mesh_host_chunks_ex_ptr(N, pos, host.data_ptr(), pal, ent_np); ts.append(time.perf_counter() - t0)
+    print("untraced step us, kernel pull with palette lengths:", [round(t * 1e6) for t in ts])
+    os.environ["DSP_TRACE"] = "1"
+    ctx.mesh_host_chunks_ex_ptr(N, pos, host.data_ptr(), pal, ent_np)
