@@ -295,8 +295,9 @@ def config5(torch, dist, capi, rank, world, local_rank, peak):
         if world > 1:
             connect_region_seams(dev, sp, rank, dist)
         res = {}
-        # (parity: 98,304 chunks = three x-y slabs per launch write ~5 GB of the 8 GiB arena; each launch is followed by a host sync that reads its total)
-        for mode_name, mode, batch in (("parity", capi.MESH_PARITY, 98304), ("halo", capi.MESH_HALO, 262144)):
+        # (chunks per launch sized for ~5 GB of the 8 GiB arena: parity 98,304 chunks at ~50 KB each, halo 786,432 at ~6 KB each; every launch
+        #  is followed by a host sync that reads its total)
+        for mode_name, mode, batch in (("parity", capi.MESH_PARITY, 98304), ("halo", capi.MESH_HALO, 786432)):
             xchg_ms = 0.0
             if mode == capi.MESH_HALO and world > 1:
                 ctx.seam_exchange_async(); ctx.mesh_range(dev.first_slot, min(n, 4096), mode)  # epoch 1: warm-up

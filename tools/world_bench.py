@@ -27,8 +27,8 @@ UV = np.array([[0, 0, 0, 0], [0.0, 0.0, 0.5, 1.0], [0.5, 0.0, 1.0, 1.0]], dtype=
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--dims", type=int, nargs=3, default=[512, 32, 512], help="world size in chunks: x y z (y is up)")
-    ap.add_argument("--batch", type=int, default=32768, help="chunks per mesh launch (arena is reused between launches)")
-    ap.add_argument("--small-output-batch", type=int, default=262144, help="chunks per launch in the halo / greedy modes (their output is 10-20x smaller)")
+    ap.add_argument("--batch", type=int, default=98304, help="chunks per mesh launch (arena is reused between launches)")
+    ap.add_argument("--small-output-batch", type=int, default=786432, help="chunks per launch in the halo / greedy modes (their output is 10-20x smaller)")
     ap.add_argument("--arena-gib", type=float, default=8.0)
     ap.add_argument("--quad-modes", action="store_true", help="also run the greedy + indexed modes (chunk-local and halo culling)")
     ap.add_argument("--verify", action="store_true", help="check a sample of seam chunks (and some interior ones) against the oracle, at any world size")
