@@ -222,3 +222,35 @@ def test_quad_modes_pull_equals_copy_engine_and_the_extension_oracle(uv_default,
         if mode & capi.MESH_INDEXED:
             assert got["pull"][1][i][1] == ix.tobytes()
     del keep
+
+
+def test_bench_region_through_the_e2e_call_at_full_size(uv_default):
+    """BASELINE config 2 (the bench's workload) through the call bench.py times as `e2e`: all 4,096 host-resident chunks of the
+    16x16x16-chunk noise region, pinned, with their palette lengths -- kernel pull, all-air chunks never fetched.  Checksum of
+    per-chunk checksums against the oracle; every chunk resident afterwards with its voxels."""
+    import hashlib
+    pos = box_positions((0, 0, 0), (16, 16, 16))
+    ids = orc.generate_batch(orc.GEN_NOISE, SEED_NOISE, pos)
+    counts, want = orc.mesh_batch(pos, ids, uv_default, flavour=orc.FAIR)
+    pal = np.array([1 + len(np.setdiff1d(np.unique(c), [0])) for c in ids], dtype=np.uint32)
+    assert int((pal == 1).sum()) == 1540
+    keep, host = pinned_copy(ids)
+    with capi.Context(0, 4096, 1 << 30) as c:
+        c.set_uv_table(uv_default)
+        entries = np.zeros(4096, dtype=capi.MESH_ENTRY_DTYPE)
+        slots = np.zeros(4096, dtype=np.uint32)
+        for rep in range(2):  # the second call finds every position resident
+            total = c.mesh_host_chunks_ex_ptr(4096, pos, host.ctypes.data, pal, entries, slots_out=slots)
+            assert np.array_equal(entries["vertex_count"].astype(np.int64), counts) and total == 396_833_664
+            blob = c.download_arena(0, total)
+            hg, hw, w0 = hashlib.sha256(), hashlib.sha256(), 0
+            wb = want.view(np.uint8).reshape(-1)
+            for e, k in zip(entries, counts):
+                nb, o = int(k) * 20, int(e["offset_bytes"])
+                hg.update(hashlib.sha256(blob[o:o + nb].tobytes()).digest())
+                hw.update(hashlib.sha256(wb[w0:w0 + nb].tobytes()).digest())
+                w0 += nb
+            assert hg.hexdigest() == hw.hexdigest(), rep
+        for i in range(0, 4096, 97):
+            assert np.array_equal(c.download_chunk(int(slots[i]))[0], ids[i])
+    del keep
