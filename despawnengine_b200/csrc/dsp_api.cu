@@ -1431,6 +1431,14 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     uint64_t total = 0;
     rc = finish_mesh(ctx, out_entries, &total, entries_out);
     if (out_total_bytes) *out_total_bytes = total;
+    if (rc != DSP_OK) {  // arena too small, seam time-out: the call did not happen -- the slots it created are given back (the bytes needed stay in *out_total_bytes)
+        const std::string msg = ctx->err;
+        cudaStreamSynchronize(ctx->copy_stream);
+        if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
+        release_fresh_slots(ctx, fresh_slots);
+        ctx->err = msg;
+        return rc;
+    }
     if (early_entries) DSP_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));  // (long finished: those copies ran under the uploads)
     if (readback) {
         DSP_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));

@@ -190,7 +190,7 @@ def test_pull_path_rejects_duplicates_and_rolls_back(uv_default):
             small.set_uv_table(uv_default)
             with pytest.raises(capi.DspError) as e2:
                 small.mesh_host_chunks_ex_ptr(600, pos, host.ctypes.data, None, entries)
-            assert e2.value.status == capi.ERR_ARENA_FULL
+            assert e2.value.status == capi.ERR_ARENA_FULL and small.resident_chunks == 0
         total = c.mesh_host_chunks_ex_ptr(600, pos, host.ctypes.data, None, entries)  # the context is usable afterwards
         assert total > 0 and c.resident_chunks == 600
     del keep
