@@ -522,6 +522,18 @@ def main():
     burst_ms = max_over_ranks(b0.elapsed_time(b1))
     burst = {"ms_per_step": burst_ms / args.steps, "chunks_per_s": world * N_CHUNKS * args.steps / (burst_ms * 1e-3),
              "what": "the K steps alone, enqueued on an idle GPU (clocks not yet settled under load)"}
+    # per-step figures as SURVEY.md 8(d) words them: every step bracketed by its own CUDA event pair, median and best of 30
+    # (an event between two launches keeps the next step's CTAs from taking their places early, so these sit a little above `value`)
+    pairs = [_events(torch, stream) for _ in range(30)]
+    barrier()
+    for kk, (ea, eb) in enumerate(pairs):
+        ea.record(stream)
+        step(kk)
+        eb.record(stream)
+    ctx.sync()
+    per = sorted(ea.elapsed_time(eb) for ea, eb in pairs)
+    per_step = {"median_ms": max_over_ranks(per[len(per) // 2]), "best_ms": max_over_ranks(per[0]), "steps": len(per),
+                "what": "each of 30 steps bracketed by its own CUDA event pair on the context's stream (max over ranks of the per-rank median / best)"}
     ctx.set_kernel_timing(True)
 
     # ---- other kernels on the same region (kernel time from the library's own events, 12 calls back to back;
@@ -690,7 +702,7 @@ def main():
             "gpu_launches": int(args.steps),
             "gpu_launches_whole_sustained_run": int(launches_total),
             "wall_s_sustained_run": wall1 - wall0,
-            "sustained": sustained, "burst": burst, "no_summaries": no_summaries,
+            "sustained": sustained, "burst": burst, "per_step_events": per_step, "no_summaries": no_summaries,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_BYTES, "traffic_source": NCU_TRAFFIC_SOURCE,
                          "kernel": "mesh_chunks_bump_kernel", "kernel_ms_avg": kernel_ms_avg,
