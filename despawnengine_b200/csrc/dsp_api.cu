@@ -546,7 +546,7 @@ int ensure_border_masks(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32
                                                                                                  ctx->d_stale_list, count);
     DSP_CUDA(ctx, cudaGetLastError());
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(std::min<uint64_t>(7 * n, ctx->max_chunks), static_cast<uint64_t>(ctx->num_sms) * 8));
-    dsp::refresh_border_masks_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_voxels, ctx->d_bmask, ctx->d_bvalid, ctx->d_stale_list, count);
+    dsp::refresh_border_masks_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_voxels, ctx->d_bmask, ctx->d_bvalid, ctx->d_summary, ctx->d_uid, ctx->d_stale_list, count);
     DSP_CUDA(ctx, cudaGetLastError());
     ctx->launches += 2;
     if (n >= ctx->n_resident) ctx->bmask_stale = false;  // the call covers every resident chunk: nothing stale is left behind

@@ -409,13 +409,38 @@ __global__ void find_stale_masks_kernel(uint8_t* bvalid, const uint32_t* nbr, co
         if ((atomicOr(word, bit) & (3u << (8u * (s & 3u)))) == 0u) list[atomicAdd(count, 1u)] = s;
     }
 }
-__global__ void __launch_bounds__(256) refresh_border_masks_kernel(const uint16_t* voxels, uint16_t* bmask, uint8_t* bvalid, const uint32_t* list, const uint32_t* count) {
+// The kernel reads the whole tile for that, so it also leaves the chunk's SUMMARY (all air / no air / which border layers are free
+// of air) and, for a chunk without air, its one block id: a world that came from the host (dsp_load_chunks, dsp_mesh_host_chunks*)
+// or was edited has no summaries, and without them the halo pre-pass could drop nothing -- after the first halo-mode call over
+// it, such a world is classified like a generated one (all-air and buried chunks never reach the mesh kernel).
+__global__ void __launch_bounds__(256) refresh_border_masks_kernel(const uint16_t* voxels, uint16_t* bmask, uint8_t* bvalid, uint8_t* summary, uint16_t* uid,
+                                                                   const uint32_t* list, const uint32_t* count) {
+    __shared__ uint32_t s_red[8];
     const int tid = threadIdx.x, y = tid & 15, z = tid >> 4, lane = tid & 31;
     const uint32_t n = *count;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
         const uint32_t slot = list[i];
         const uint4* rowp = reinterpret_cast<const uint4*>(voxels + static_cast<size_t>(slot) * kChunkVoxels + tid * 16);
-        const uint32_t m = nonzero_mask8(rowp[0]) | (nonzero_mask8(rowp[1]) << 8);  // occupancy of x-row (y, z)
+        const uint4 q0 = rowp[0], q1 = rowp[1];
+        const uint32_t m = nonzero_mask8(q0) | (nonzero_mask8(q1) << 8);  // occupancy of x-row (y, z)
+        {
+            const uint32_t id0 = voxels[static_cast<size_t>(slot) * kChunkVoxels], w = id0 * 0x00010001u;
+            const uint32_t differs = (q0.x ^ w) | (q0.y ^ w) | (q0.z ^ w) | (q0.w ^ w) | (q1.x ^ w) | (q1.y ^ w) | (q1.z ^ w) | (q1.w ^ w);
+            const bool full = m == 0xFFFFu;
+            // one bit per statement that must hold for EVERY row: all air, no air, layer f (top, bottom, rear, front, right = x 0, left = x 15) free of air, one id
+            uint32_t bits = (m == 0u ? kSummaryAir : 0u) | (full ? kSummarySolid : 0u) | ((y != 15 || full) ? kSummaryLayer0 : 0u) | ((y != 0 || full) ? kSummaryLayer0 << 1 : 0u) |
+                            ((z != 0 || full) ? kSummaryLayer0 << 2 : 0u) | ((z != 15 || full) ? kSummaryLayer0 << 3 : 0u) | ((m & 1u) ? kSummaryLayer0 << 4 : 0u) |
+                            ((m >> 15) & 1u ? kSummaryLayer0 << 5 : 0u) | (differs == 0u ? 0x100u : 0u);
+            bits = __reduce_and_sync(0xFFFFFFFFu, bits);
+            if (lane == 0) s_red[tid >> 5] = bits;
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t all = s_red[0] & s_red[1] & s_red[2] & s_red[3] & s_red[4] & s_red[5] & s_red[6] & s_red[7];
+                summary[slot] = static_cast<uint8_t>(all & 0xFFu);
+                if (all & kSummarySolid) uid[slot] = (all & 0x100u) ? static_cast<uint16_t>(id0) : kUidMixed;
+            }
+            __syncthreads();  // s_red is rewritten for the CTA's next chunk
+        }
         uint16_t* bm = bmask + static_cast<size_t>(slot) * kBorderMaskStride;
         if (y == 15) bm[0 * 16 + z] = static_cast<uint16_t>(m);
         if (y == 0) bm[1 * 16 + z] = static_cast<uint16_t>(m);
