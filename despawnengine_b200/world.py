@@ -194,3 +194,28 @@ def build_chunk_meshes(world: World, positions: Sequence[Sequence[int]], block_u
 def build_chunk_mesh(world: World, chunk_pos, block_uvs: Dict[str, AtlasUV]) -> Optional[ChunkMesh]:
     """chunk_mesh.rs:13-17 -- None when the chunk is all air / produces no faces."""
     return build_chunk_meshes(world, [chunk_pos], block_uvs)[0]
+
+
+def build_all_host_chunks(world: World, chunks: Sequence[Chunk], block_uvs: Dict[str, AtlasUV], mode: int = capi.MESH_PARITY,
+                          blocks_out: Optional[np.ndarray] = None) -> List[Optional[ChunkMesh]]:
+    """GameScene::build_all_loaded_chunks (scene_game.rs:231-244) for chunks the caller holds on the HOST: every `Chunk` (blocks +
+    string palette, chunk.rs:15-20) is loaded and meshed by one dsp_mesh_host_chunks_ex call.  The host does what the reference's
+    host does around the loop -- palette strings to numbers -- and hands over the palette lengths, so that a chunk whose palette
+    is just "base:air" is never fetched (chunk_mesh.rs:18-20).  `blocks_out` (n x 4096 u16, e.g. a pinned torch buffer's numpy
+    view) receives the global-id voxels; with pinned memory the mesh kernel pulls the tiles itself."""
+    world.set_block_uvs(block_uvs)
+    n = len(chunks)
+    gids = blocks_out if blocks_out is not None else np.empty((n, 4096), dtype=np.uint16)
+    pos = np.empty((n, 3), dtype=np.int32)
+    palette_lens = np.empty(n, dtype=np.uint32)
+    for i, c in enumerate(chunks):
+        pos[i] = c.position
+        palette_lens[i] = len(c.palette)
+        gids[i] = np.array([world.registry.id_of(b) for b in c.palette], dtype=np.uint16)[c.blocks]  # per-chunk palette index -> global id (chunk.rs:58-65)
+    entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
+    slots = np.zeros(n, dtype=np.uint32)
+    total = world.ctx.mesh_host_chunks_ex_ptr(n, pos, gids.ctypes.data, palette_lens, entries, mode, world._arena_top, slots_out=slots)
+    for c, s in zip(chunks, slots):
+        world.chunks[tuple(int(k) for k in c.position)] = int(s)
+    world._arena_top += total
+    return [ChunkMesh(world, int(e["offset_bytes"]), int(e["vertex_count"]), int(e["index_count"])) if e["vertex_count"] else None for e in entries]

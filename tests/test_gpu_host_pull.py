@@ -254,3 +254,58 @@ def test_bench_region_through_the_e2e_call_at_full_size(uv_default):
         for i in range(0, 4096, 97):
             assert np.array_equal(c.download_chunk(int(slots[i]))[0], ids[i])
     del keep
+
+
+def test_host_mirror_builds_all_host_chunks_like_the_reference(uv_default):
+    """despawnengine_b200.world: `Chunk`s filled with Chunk::set_block as the reference's generators do (chunk.rs:86-120: flat,
+    full, empty) plus a few hand-edited ones, meshed in bulk through build_all_host_chunks -- against the oracle's faithful
+    flavour (string palettes and all) and against chunk-at-a-time build_chunk_mesh over put_chunk."""
+    import torch
+    from despawnengine_b200 import world as w
+    uvs = {"template:dirt": w.AtlasUV((0.0, 0.0), (0.5, 1.0)), "template:engine": w.AtlasUV((0.5, 0.0), (1.0, 1.0))}
+    rng = np.random.default_rng(2)
+    chunks = []
+    for k in range(60):
+        c = w.Chunk(position=(k % 7 - 3, k // 7 - 4, 5 - k % 3))
+        kind = k % 5
+        if kind == 0:      # generate_flat
+            for x in range(16):
+                for y in range(8):
+                    for z in range(16):
+                        c.set_block(x, y, z, "template:dirt")
+        elif kind == 1:    # generate_full, in the other block
+            for x in range(16):
+                for y in range(16):
+                    for z in range(16):
+                        c.set_block(x, y, z, "template:engine")
+        elif kind == 2:    # generate_empty: palette stays ["base:air"]
+            pass
+        elif kind == 3:    # sparse, engine first: the palette order differs from the registry's
+            for _ in range(200):
+                x, y, z = (int(v) for v in rng.integers(0, 16, 3))
+                c.set_block(x, y, z, "template:engine" if rng.random() < 0.5 else "template:dirt")
+        else:              # placed and removed again: all air, but the palette has grown -- no early-out, and no faces
+            c.set_block(1, 2, 3, "template:dirt")
+            c.set_block(1, 2, 3, w.AIR_BLOCK_ID)
+        chunks.append(c)
+    pinned = torch.empty((len(chunks), 4096), dtype=torch.int16).pin_memory()
+    world = w.World(0, 256, 256 << 20)
+    try:
+        meshes = w.build_all_host_chunks(world, chunks, uvs, blocks_out=pinned.numpy().view(np.uint16))
+        for c, m in zip(chunks, meshes):
+            gid = np.array([world.registry.id_of(b) for b in c.palette], dtype=np.uint16)[c.blocks]
+            want = orc.mesh_chunk(c.position, gid, world.registry.uv_table(uvs), flavour=orc.FAITHFUL)
+            assert (m is None) == (want.shape[0] == 0), c.position
+            if m is not None:
+                assert m.to_host().tobytes() == want.tobytes(), c.position
+        assert sum(m is None for m in meshes) == 24  # the 12 never-touched chunks and the 12 emptied ones
+        world2 = w.World(0, 256, 256 << 20)
+        try:
+            for c, m in zip(chunks[:20], meshes[:20]):
+                world2.put_chunk(c)
+                one = w.build_chunk_mesh(world2, c.position, uvs)
+                assert (one is None) == (m is None) and (one is None or one.to_host().tobytes() == m.to_host().tobytes())
+        finally:
+            world2.close()
+    finally:
+        world.close()
