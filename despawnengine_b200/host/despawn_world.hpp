@@ -172,6 +172,39 @@ inline std::vector<std::optional<ChunkMesh>> build_chunk_meshes(World& world, co
 inline std::optional<ChunkMesh> build_chunk_mesh(World& world, const ChunkPos& chunk_pos, const BlockUvs& block_uvs) {
     return build_chunk_meshes(world, {chunk_pos}, block_uvs)[0];
 }
+// GameScene::build_all_loaded_chunks (scene_game.rs:231-244) for chunks the caller holds on the HOST: every Chunk (blocks + string
+// palette) is loaded and meshed by ONE dsp_mesh_host_chunks_ex call.  The host resolves palette indices to registry ids (what the
+// reference's host does around the loop too) and hands over the palette lengths: a chunk whose palette is only "base:air" is never
+// fetched (chunk_mesh.rs:18-20).  Hand in `staging` registered with cudaHostRegister and the mesh kernel pulls the tiles itself.
+inline std::vector<std::optional<ChunkMesh>> build_all_host_chunks(World& world, const std::vector<Chunk>& host_chunks, const BlockUvs& block_uvs,
+                                                                   uint32_t mode = DSP_MESH_PARITY, std::vector<uint16_t>* staging = nullptr) {
+    world.set_block_uvs(block_uvs);
+    const std::size_t n = host_chunks.size();
+    std::vector<uint16_t> local;
+    std::vector<uint16_t>& gids = staging ? *staging : local;
+    gids.resize(n * 4096);
+    std::vector<int32_t> pos(3 * n);
+    std::vector<uint32_t> palette_lens(n), slots(n);
+    for (std::size_t i = 0; i < n; ++i) {
+        const Chunk& c = host_chunks[i];
+        std::copy(c.position.begin(), c.position.end(), pos.begin() + 3 * i);
+        palette_lens[i] = static_cast<uint32_t>(c.palette.size());
+        std::vector<uint16_t> pal;
+        for (const std::string& b : c.palette) pal.push_back(world.register_block(b));
+        for (std::size_t v = 0; v < 4096; ++v) gids[i * 4096 + v] = pal[c.blocks[v]];  // per-chunk palette index -> registry id (chunk.rs:58-65)
+    }
+    std::vector<dsp_mesh_entry> entries(n);
+    uint64_t total = 0;
+    world.check(dsp_mesh_host_chunks_ex(world.ctx(), n, pos.data(), gids.data(), palette_lens.data(), mode, world.arena_top, slots.data(), entries.data(), &total,
+                                        nullptr, 0));
+    world.arena_top += total;
+    std::vector<std::optional<ChunkMesh>> out;
+    for (std::size_t i = 0; i < n; ++i) {
+        world.chunks[host_chunks[i].position] = slots[i];
+        out.push_back(entries[i].vertex_count ? std::optional<ChunkMesh>(ChunkMesh{entries[i].offset_bytes, entries[i].vertex_count, entries[i].index_count}) : std::nullopt);
+    }
+    return out;
+}
 
 // scene_game.rs:170-223 get_all_chunk_pos_in_render: cylinder around the camera chunk; loop bounds min-1 .. max+1 (exclusive)
 inline std::vector<ChunkPos> visible_chunks(const ChunkPos& cam, int32_t hori_dist, int32_t vert_dist) {

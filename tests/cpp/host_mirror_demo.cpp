@@ -32,6 +32,20 @@ int main(int argc, char** argv) {
             std::printf("%llu %llu %llu %llu %llu %zu\n", (unsigned long long)a.n_loaded_total, (unsigned long long)a.n_meshes, (unsigned long long)a.vertex_total,
                         (unsigned long long)b.n_loaded_now, (unsigned long long)b.n_unloaded_now, scene.amount_of_chunk_meshes());
         }
+        {   // host-resident chunks in bulk (build_all_loaded_chunks over Chunk structs): flat / full / empty as the reference's
+            // generators fill them (chunk.rs:86-120), one emptied again -- 1,024 + 1,536 + 0 + 0 faces
+            World w3(64, 64ull << 20);
+            std::vector<Chunk> host(4, Chunk({0, 0, 0}));
+            for (int i = 0; i < 4; ++i) host[i].position = {100 + i, 0, 0};
+            for (int x = 0; x < 16; ++x) for (int z = 0; z < 16; ++z) for (int y = 0; y < 16; ++y) {
+                if (y < 8) host[0].set_block(x, y, z, "template:dirt");
+                host[1].set_block(x, y, z, "template:engine");
+            }
+            host[3].set_block(5, 5, 5, "template:dirt");
+            host[3].set_block(5, 5, 5, AIR_BLOCK_ID);
+            const auto hm = build_all_host_chunks(w3, host, block_uvs);
+            std::printf("%u %u %u %u\n", hm[0] ? hm[0]->len() : 0u, hm[1] ? hm[1]->len() : 0u, hm[2] ? hm[2]->len() : 0u, hm[3] ? hm[3]->len() : 0u);
+        }
         if (argc > 1) {
             const auto origin = build_chunk_mesh(world, {0, 0, 0}, block_uvs);
             const auto v = world.download(*origin);

@@ -42,5 +42,6 @@ def test_cpp_host_mirror_first_frame(tmp_path):
     assert lines[1] == "72"  # two isolated voxels: 12 faces
     # GameScene::update: same first frame; one chunk to +x swaps 21 columns x 9 layers in and out, mesh count unchanged
     assert lines[2].split() == ["2853", "1268", "10712064", "189", "189", "1268"]
+    assert lines[3].split() == ["6144", "9216", "0", "0"]  # build_all_host_chunks: flat 1,024 faces, full 1,536, never touched, emptied again
     golden = np.fromfile(os.path.join(ROOT, "tests", "golden", "flat_chunk_origin.bin"), dtype=np.uint8)
     assert np.fromfile(dump, dtype=np.uint8).tobytes() == golden.tobytes()
