@@ -108,6 +108,7 @@ struct dsp_ctx {
     float4* d_uvmap = nullptr;
     uint32_t n_blocks = 0, uv_cap = 0;
     uint8_t* d_scratch = nullptr;
+    int quad_ctas_cap = 0;  // DSP_QUAD_CTAS: upper bound on the quad kernels' CTAs per SM (0: whatever fits)
     unsigned long long* d_phase = nullptr;  // debug phase timers (16 counters)
     size_t scratch_bytes = 0;
     uint8_t* h_pinned = nullptr;  // 4 KiB of pinned host memory for small read-backs
@@ -345,6 +346,12 @@ int upload_positions_and_slots(dsp_ctx* ctx, uint64_t n, const int32_t* pos, con
     return stage_release(ctx);
 }
 
+#ifdef DSP_PHASE_TIMERS
+constexpr size_t kPhaseWords = 32 + 1024 * 16;  // + a 16-word timeline per CTA (debug builds only)
+#else
+constexpr size_t kPhaseWords = 32;
+#endif
+
 int drain_kernel_event(dsp_ctx* ctx, int e) {
     if (!ctx->ev_pending[e]) return DSP_OK;
     float ms = 0.0f;
@@ -451,7 +458,8 @@ int launch_quads_t(dsp_ctx* ctx, const dsp::MeshParams& p_in) {
         DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         if (occ < 1) return fail(ctx, DSP_ERR_INTERNAL, "quad mesh kernel does not fit on an SM (smem %d)", smem);
     }
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p_in.n, static_cast<uint64_t>(ctx->num_sms) * occ));
+    const int ctas = ctx->quad_ctas_cap > 0 ? std::min(occ, ctx->quad_ctas_cap) : occ;  // (DSP_QUAD_CTAS: A/B runs)
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p_in.n, static_cast<uint64_t>(ctx->num_sms) * ctas));
     dsp::MeshParams p = p_in;
     p.phase_cycles = ctx->d_phase;
     int rc = begin_kernel_timing(ctx);
@@ -824,6 +832,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if (const char* s = getenv("DSP_E2E_PULL_PIECES")) ctx->e2e_pull_pieces = atoi(s);
     if (const char* s = getenv("DSP_E2E_PULL_DIV")) ctx->e2e_pull_first_div = static_cast<uint64_t>(std::min(64, std::max(2, atoi(s))));
     if (const char* s = getenv("DSP_E2E_HEAD")) ctx->e2e_head_chunks = static_cast<uint64_t>(std::min(512, std::max(0, atoi(s))));
+    if (const char* s = getenv("DSP_QUAD_CTAS")) ctx->quad_ctas_cap = atoi(s);
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
     auto bail = [&](const char* what, cudaError_t err) {
@@ -849,8 +858,8 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if ((e = cudaMalloc(&ctx->d_bmask, max_chunks * dsp::kBorderMaskStride * sizeof(uint16_t))) != cudaSuccess) return bail("cudaMalloc(border masks)", e);
     if ((e = cudaMalloc(&ctx->d_bvalid, (max_chunks + 3) & ~uint64_t(3))) != cudaSuccess) return bail("cudaMalloc(border mask flags)", e);
     if ((e = cudaMemset(ctx->d_bvalid, 0, (max_chunks + 3) & ~uint64_t(3))) != cudaSuccess) return bail("cudaMemset(border mask flags)", e);
-    if ((e = cudaMalloc(&ctx->d_phase, 32 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
-    cudaMemset(ctx->d_phase, 0, 32 * sizeof(unsigned long long));
+    if ((e = cudaMalloc(&ctx->d_phase, kPhaseWords * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
+    cudaMemset(ctx->d_phase, 0, kPhaseWords * sizeof(unsigned long long));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_sub[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1713,6 +1722,17 @@ int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16) {
     DSP_CUDA(ctx, cudaMemset(ctx->d_phase, 0, 32 * sizeof(uint64_t)));
     return DSP_OK;
 }
+
+#ifdef DSP_PHASE_TIMERS
+// debug builds only (not in the header, not in the shipped library): the per-CTA timelines of the last quad-kernel launch
+int dsp_debug_timeline(dsp_ctx* ctx, uint64_t* out, uint64_t words) {
+    if (!ctx || !out || words > kPhaseWords - 32) return DSP_ERR_BAD_ARG;
+    DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    DSP_CUDA(ctx, cudaMemcpy(out, ctx->d_phase + 32, words * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    DSP_CUDA(ctx, cudaMemset(ctx->d_phase + 32, 0, words * sizeof(uint64_t)));
+    return DSP_OK;
+}
+#endif
 
 int dsp_set_kernel_timing(dsp_ctx* ctx, int on) {
     if (!ctx) return DSP_ERR_BAD_ARG;

@@ -284,8 +284,15 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
     long long ph[16] = {};
     long long tlast = clock64();
 #define QTICK(k) do { const long long t_ = clock64(); ph[k] += t_ - tlast; tlast = t_; } while (0)
+    // per-CTA timeline (ns, globaltimer): [0] start, [1] prologue done, [2..7] chunk k done, [8] exit, [9] SM, [10] chunks, [11] first tile in
+    unsigned long long* const tl = (p.phase_cycles && blockIdx.x < 1024u && tid == 0) ? p.phase_cycles + 32 + blockIdx.x * 16 : nullptr;
+    uint32_t tl_chunks = 0;
+    auto gtime = [] { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; };
+    if (tl) { tl[0] = gtime(); unsigned sm; asm("mov.u32 %0, %smid;" : "=r"(sm)); tl[9] = sm; }
+#define QTL(k) do { if (tl) tl[k] = gtime(); } while (0)
 #else
 #define QTICK(k) do { } while (0)
+#define QTL(k) do { } while (0)
 #endif
     bool pend = false;
     uint64_t pend_claimed = 0;
@@ -309,6 +316,7 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
         }
     };
     QTICK(8);
+    QTL(1);
     while (cur < p.n) {
         const int nb = buf == 0 ? NB - 1 : buf - 1;  // the buffer the previous iteration has just finished with
         uint32_t tnext = 0;
@@ -323,6 +331,9 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
         if (HALO) nbv = fetch_nbr_mask(p, slot_of(cur), tid);  // the neighbours' border masks (global loads in flight during the tile wait)
         mbar_wait(&s_bar[buf], par);
         QTICK(0);
+#ifdef DSP_PHASE_TIMERS
+        if (tl && tl_chunks == 0) tl[11] = gtime();
+#endif
         const uint16_t* vox = s_vox + buf * kChunkVoxels;
 
         // ---- 1. row occupancy; is the whole chunk one block id?
@@ -668,10 +679,14 @@ __global__ void __launch_bounds__(256, QuadSmem<GREEDY, GREEDY && INDEXED>::kCta
         if (++buf == NB) { buf = 0; par ^= 1; }
         cur = s_next[buf];
         QTICK(6);
+#ifdef DSP_PHASE_TIMERS
+        if (tl) { if (tl_chunks < 6) tl[2 + tl_chunks] = gtime(); tl[10] = ++tl_chunks; }
+#endif
     }
     if (tid == 0 && pend) store_tile(pend_claimed, pend_Q, pend_f0, pend_cur);
 #ifdef DSP_PHASE_TIMERS
     QTICK(7);
+    QTL(8);
     if ((tid == 0 || tid == 255) && p.phase_cycles) for (int k = 0; k < 15; ++k) atomicAdd(&p.phase_cycles[(tid ? 16 : 0) + k], static_cast<unsigned long long>(ph[k]));
     if (tid == 0 && p.phase_cycles) atomicAdd(&p.phase_cycles[15], 1ull);
 #endif
