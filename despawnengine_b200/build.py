@@ -14,8 +14,8 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libdespawn_b200.so")
-SOURCES = [os.path.join(CSRC, "dsp_api.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("dsp_common.cuh", "mesh_kernels.cuh", "quad_kernels.cuh", "terrain_kernels.cuh", "dsp_scene.inl", "dsp_seam.inl", "dsp_export.inl")] + [
+SOURCES = [os.path.join(CSRC, "dsp_api.cu"), os.path.join(CSRC, "host_pack.cpp")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("dsp_common.cuh", "mesh_kernels.cuh", "quad_kernels.cuh", "terrain_kernels.cuh", "dsp_scene.inl", "dsp_seam.inl", "dsp_export.inl", "host_pack.hpp")] + [
     os.path.join(ROOT, "include", "despawn_b200.h")]
 
 NVCC_FLAGS = [

@@ -96,10 +96,27 @@ SYMBOLS = {
     "dsp_stream": (_vp, [_vp]),
     "dsp_max_chunks": (_u64, [_vp]),
     "dsp_kernel_launches": (_u64, [_vp]),
+    "dsp_host_upload_stats": (_int, [_vp, _P(_u64)]),
+    "dsp_debug_pack_chunk": (_int, [_P(C.c_uint16), _P(C.c_uint8), _P(_u32), _int]),
     "dsp_debug_phase_cycles": (_int, [_vp, _P(_u64)]),
     "dsp_set_kernel_timing": (_int, [_vp, _int]),
     "dsp_mesh_kernel_stats": (_int, [_vp, _P(_u64), _P(C.c_double), _P(C.c_float)]),
 }
+
+PACK_FORMS = ("air", "uniform", "bits2", "bits4", "bits8", "raw")
+
+
+def debug_pack_chunk(blocks: np.ndarray, portable: bool = False):
+    """(descriptor, packed bytes of the form's size) of the host-side packer on one chunk (dsp_debug_pack_chunk; no GPU needed)."""
+    b = np.ascontiguousarray(blocks, dtype=np.uint16).reshape(4096)
+    out = np.zeros(8192, dtype=np.uint8)
+    desc = C.c_uint32(0)
+    rc = lib().dsp_debug_pack_chunk(b.ctypes.data_as(C.POINTER(C.c_uint16)), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(desc), 1 if portable else 0)
+    if rc != 0:
+        raise RuntimeError(f"dsp_debug_pack_chunk failed: {rc}")
+    size = (0, 0, 1024, 2048, 4096, 8192)[desc.value & 7]
+    return int(desc.value), out[:size].copy()
+
 
 _lib = None
 
@@ -516,6 +533,13 @@ class Context:
     @property
     def stream(self) -> int:
         return int(lib().dsp_stream(self._h) or 0)
+
+    def host_upload_stats(self) -> dict:
+        """How the chunks of the last host-chunk call crossed the bus (dsp_host_upload_stats)."""
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(lib().dsp_host_upload_stats(self._h, _ptr(out, C.c_uint64)))
+        keys = ("air", "uniform", "bits2", "bits4", "bits8", "raw", "host_threads", "device_read_bytes")
+        return {k: int(v) for k, v in zip(keys, out)}
 
     def debug_phase_cycles(self) -> np.ndarray:
         out = np.zeros(32, dtype=np.uint64)

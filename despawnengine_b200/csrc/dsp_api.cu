@@ -18,10 +18,13 @@
 #include <map>
 #include <vector>
 #include <unistd.h>
+#include <sched.h>
+#include <thread>
 
 #include "mesh_kernels.cuh"
 #include "quad_kernels.cuh"
 #include "terrain_kernels.cuh"
+#include "host_pack.hpp"
 
 namespace {
 
@@ -108,6 +111,14 @@ struct dsp_ctx {
     float4* d_uvmap = nullptr;
     uint32_t n_blocks = 0, uv_cap = 0;
     uint8_t* d_scratch = nullptr;
+    // packed upload of host-resident chunks (csrc/host_pack.hpp): worker threads, pinned staging (8 KiB per chunk of the largest call so far)
+    dsp_host::PackPool* pack_pool = nullptr;
+    uint8_t* h_pack = nullptr;
+    size_t h_pack_bytes = 0;
+    int e2e_pack = 1;         // DSP_E2E_PACK=0: host-chunk calls never pack (kernel pull / copy-engine pipeline as before)
+    int host_threads = -1;    // DSP_HOST_THREADS: worker threads of the packer (-1: the CPUs this thread may run on, minus one; at most 15)
+    uint64_t upload_stats[8] = {};  // dsp_host_upload_stats
+    int e2e_pack_pieces = 3;  // DSP_E2E_PACK_PIECES: launches per call (pack / unpack + mesh pipeline)
     int quad_ctas_cap = 0;  // DSP_QUAD_CTAS: upper bound on the quad kernels' CTAs per SM (0: whatever fits)
     unsigned long long* d_phase = nullptr;  // debug phase timers (16 counters)
     size_t scratch_bytes = 0;
@@ -832,6 +843,9 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if (const char* s = getenv("DSP_E2E_PULL_PIECES")) ctx->e2e_pull_pieces = atoi(s);
     if (const char* s = getenv("DSP_E2E_PULL_DIV")) ctx->e2e_pull_first_div = static_cast<uint64_t>(std::min(64, std::max(2, atoi(s))));
     if (const char* s = getenv("DSP_E2E_HEAD")) ctx->e2e_head_chunks = static_cast<uint64_t>(std::min(512, std::max(0, atoi(s))));
+    if (const char* s = getenv("DSP_E2E_PACK")) ctx->e2e_pack = atoi(s);
+    if (const char* s = getenv("DSP_HOST_THREADS")) ctx->host_threads = std::min(63, std::max(-1, atoi(s)));
+    if (const char* s = getenv("DSP_E2E_PACK_PIECES")) ctx->e2e_pack_pieces = std::min(16, std::max(1, atoi(s)));
     if (const char* s = getenv("DSP_QUAD_CTAS")) ctx->quad_ctas_cap = atoi(s);
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
@@ -896,6 +910,8 @@ int dsp_destroy(dsp_ctx* ctx) {
     cudaFree(ctx->d_summary); cudaFree(ctx->d_work_slots); cudaFree(ctx->d_work_entry);
     cudaFree(ctx->d_phase); cudaFree(ctx->d_ctl); cudaFree(ctx->d_slots); cudaFree(ctx->d_uv_rows); cudaFree(ctx->d_uvmap); cudaFree(ctx->d_scratch);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    delete ctx->pack_pool;  // (joins the workers)
+    if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
     for (int i = 0; i < dsp_ctx::kEvRing; ++i) {
@@ -1205,6 +1221,151 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
     return finish_mesh(ctx, out_entries, out_total_bytes);
 }
 
+// Packed upload (csrc/host_pack.hpp): worker threads reduce every chunk to the smallest of five lossless forms in pinned staging,
+// unpack_host_chunks_kernel expands them into the voxel store (and leaves the summaries of air / uniform chunks), the ordinary mesh
+// kernel follows -- in a few pieces, so that the GPU works on piece k while the host packs piece k + 1.  The caller's memory is only
+// ever read by the host: pageable memory works as well as pinned.  Same contract as the other host-chunk paths (a failing call
+// leaves no trace).  *handled = false: the call is not one for this path (nothing has been done).
+static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode,
+                                   uint64_t arena_offset, uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, bool* handled) {
+    *handled = false;
+    if (!ctx->e2e_pack || n < 256 || n > (1u << 17) || (mode & (DSP_MESH_ORDERED | DSP_MESH_HALO))) return DSP_OK;
+    if (!ctx->pack_pool) {
+        int workers = ctx->host_threads;
+        if (workers < 0) {
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            const int cpus = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : static_cast<int>(std::thread::hardware_concurrency());
+            workers = std::min(15, std::max(0, cpus - 1));
+        }
+        if (workers < 1) { ctx->e2e_pack = 0; return DSP_OK; }  // a single CPU packs slower than PCIe copies
+        ctx->pack_pool = new dsp_host::PackPool(workers);
+    }
+    if (n * dsp_host::kPackSlotBytes > ctx->h_pack_bytes) {
+        if (ctx->h_pack) { DSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); DSP_CUDA(ctx, cudaFreeHost(ctx->h_pack)); ctx->h_pack = nullptr; ctx->h_pack_bytes = 0; }
+        const size_t cap = std::max<size_t>(n * dsp_host::kPackSlotBytes, 4096 * dsp_host::kPackSlotBytes);
+        if (cudaMallocHost(&ctx->h_pack, cap) != cudaSuccess) { cudaGetLastError(); ctx->e2e_pack = 0; return DSP_OK; }  // no pinned memory to spare: the other paths
+        ctx->h_pack_bytes = cap;
+    }
+    *handled = true;
+    ctx->last_mesh_n = n;
+    const bool trace = getenv("DSP_TRACE") != nullptr;
+    const auto tr0 = std::chrono::steady_clock::now();
+    auto tr = [&](const char* what) { if (trace) fprintf(stderr, "[trace] %-28s %8.1f us\n", what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tr0).count()); };
+    int rc;
+    uint8_t* h;
+    if ((rc = stage_host(ctx, n * (sizeof(int4) + 2 * sizeof(uint32_t)), &h)) != DSP_OK) return rc;
+    int4* h_pos = reinterpret_cast<int4*>(h);
+    uint32_t* h_slots = reinterpret_cast<uint32_t*>(h + n * sizeof(int4));
+    uint32_t* h_desc = h_slots + n;
+    dsp_host::PackPool& pool = *ctx->pack_pool;
+    pool.start(blocks, palette_lens, n, h_desc, ctx->h_pack);  // the workers are off; this thread resolves positions to slots meanwhile
+    tr("packing started");
+    std::vector<uint32_t> fresh_slots;
+    auto bail = [&](int code) {
+        const std::string msg = ctx->err;
+        pool.finish();  // nobody may still be reading the caller's voxels or writing the staging buffers
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        release_fresh_slots(ctx, fresh_slots);
+        stage_release(ctx);
+        ctx->err = msg;
+        return code;
+    };
+    if (cudaMemsetAsync(ctx->d_ctl, 0, 32, ctx->stream) != cudaSuccess || cudaMemsetAsync(ctx->d_tickets, 0, dsp_ctx::kMaxSub * 128, ctx->stream) != cudaSuccess)
+        return bail(fail(ctx, DSP_ERR_CUDA, "control block reset failed: %s", cudaGetErrorString(cudaGetLastError())));
+    ctx->ctl_clean = false;  // the pieces share the cursor and leave the block as it is
+    ctx->result_in_tail = false;
+    // the side stream must not overtake earlier work of the main stream that still reads the voxel store
+    if (cudaEventRecord(ctx->ev_done, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0) != cudaSuccess)
+        return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed"));
+    new_stamp(ctx);
+    // pieces: a small first one (the GPU starts while most of the packing is still to do), the rest even
+    std::vector<uint64_t> piece_begin;
+    {
+        const int pieces = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(ctx->e2e_pack_pieces), std::max<uint64_t>(1, n / 256)));
+        piece_begin.push_back(0);
+        if (pieces > 1) {
+            const uint64_t head = ((n / (2 * static_cast<uint64_t>(pieces))) + 15) & ~uint64_t(15);
+            piece_begin.push_back(head);
+            for (int k = 1; k < pieces - 1; ++k) piece_begin.push_back((head + (n - head) * static_cast<uint64_t>(k) / static_cast<uint64_t>(pieces - 1) + 15) & ~uint64_t(15));
+        }
+        piece_begin.push_back(n);
+    }
+    uint64_t resolved = 0;
+    std::vector<cudaEvent_t> tev;  // DSP_TRACE: device-side timeline (start, then after every kernel)
+    auto tev_mark = [&] { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, ctx->stream); tev.push_back(e); } };
+    tev_mark();
+    for (size_t j = 0; j + 1 < piece_begin.size(); ++j) {
+        const uint64_t i0 = piece_begin[j], i1 = piece_begin[j + 1], m = i1 - i0;
+        if (m == 0) continue;
+        bool consecutive = true;
+        for (; resolved < i1; ++resolved) {
+            bool fresh = false;
+            if ((rc = acquire_slot(ctx, pos + 3 * resolved, &h_slots[resolved], &fresh)) != DSP_OK) return bail(rc);
+            if (fresh) fresh_slots.push_back(h_slots[resolved]);
+            if (!stamp_slot(ctx, h_slots[resolved]))
+                return bail(fail(ctx, DSP_ERR_BAD_ARG, "position (%d, %d, %d) appears twice in the batch (entry %llu): one chunk per position", pos[3 * resolved],
+                                 pos[3 * resolved + 1], pos[3 * resolved + 2], (unsigned long long)resolved));
+            h_pos[resolved] = make_int4(pos[3 * resolved], pos[3 * resolved + 1], pos[3 * resolved + 2], 0);
+        }
+        for (uint64_t i = i0 + 1; i < i1 && consecutive; ++i) consecutive = h_slots[i] == h_slots[i - 1] + 1;
+        tr("piece resolved");
+        if (j + 2 == piece_begin.size()) pool.help();  // last piece: nothing else for this thread to do but pack along
+        while (pool.packed_upto() < i1) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        tr("piece packed");
+        // the expansion of piece j runs on the side stream, next to the mesh kernel of piece j - 1 (it is a handful of PCIe round
+        // trips, not bandwidth); the mesh kernel of piece j waits for it through an event
+        dsp::unpack_host_chunks_kernel<<<static_cast<unsigned>((m + dsp::kUnpackChunksPerCta - 1) / dsp::kUnpackChunksPerCta), dsp::kUnpackChunksPerCta * 32, 0, ctx->copy_stream>>>(
+            ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_uid, ctx->d_bvalid, ctx->d_voxels, h_pos + i0, h_slots + i0, h_desc + i0, ctx->h_pack + i0 * dsp_host::kPackSlotBytes,
+            static_cast<uint32_t>(m));
+        if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
+            return bail(fail(ctx, DSP_ERR_CUDA, "unpack kernel launch failed"));
+        ctx->bmask_stale = true;
+        ctx->launches++;
+        tev_mark();
+        if ((rc = launch_mesh(ctx, m, consecutive ? nullptr : ctx->d_slots + i0, h_slots[i0], mode, arena_offset, i0, static_cast<int>(j), false, false, nullptr)) != DSP_OK) return bail(rc);
+        tev_mark();
+        tr("piece enqueued");
+    }
+    pool.finish();
+    if (out_slots) std::memcpy(out_slots, h_slots, n * sizeof(uint32_t));
+    {
+        static const uint64_t form_bytes[6] = {0, 0, 1024, 2048, 4096, 8192};
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t form = std::min<uint32_t>(h_desc[i] & 7u, 5u);
+            ctx->upload_stats[form]++;
+            ctx->upload_stats[7] += form_bytes[form] + sizeof(int4) + 2 * sizeof(uint32_t);
+        }
+        ctx->upload_stats[6] = static_cast<uint64_t>(pool.workers());
+    }
+    if ((rc = stage_release(ctx)) != DSP_OK) return rc;
+    uint64_t total = 0;
+    tr("all enqueued");
+    rc = finish_mesh(ctx, out_entries, &total, 0);
+    if (out_total_bytes) *out_total_bytes = total;
+    if (rc != DSP_OK) {  // arena too small: the call did not happen -- the slots it created are given back (the bytes needed stay in *out_total_bytes)
+        const std::string msg = ctx->err;
+        release_fresh_slots(ctx, fresh_slots);
+        ctx->err = msg;
+        return rc;
+    }
+    tr("finished");
+    if (trace) {
+        for (size_t k = 1; k < tev.size(); ++k) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tev[0], tev[k - 1]); cudaEventElapsedTime(&b, tev[0], tev[k]);
+            fprintf(stderr, "[trace] device: %s %zu  %7.1f -> %7.1f us after the first event\n", (k & 1) ? "unpack" : "mesh  ", (k - 1) / 2, a * 1e3, b * 1e3);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
+    return rc;
+}
+
 // dsp_mesh_host_chunks, optionally followed (pipelined) by the device->host copy of the vertices: host_vertices != NULL
 // mirrors the arena window [arena_offset, arena_offset + total) into host memory (entry offsets minus arena_offset index it).
 static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode, uint64_t arena_offset,
@@ -1216,6 +1377,12 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     int rc = check_mesh_args(ctx, n, mode, arena_offset);
     if (rc != DSP_OK) return rc;
     const bool readback = host_vertices != nullptr;
+    std::memset(ctx->upload_stats, 0, sizeof(ctx->upload_stats));
+    if (!readback && n) {  // bulk calls: pack on the host, expand on the device (the bus carries a fraction of the voxels' bytes)
+        bool handled = false;
+        rc = mesh_host_chunks_packed(ctx, n, pos, blocks, palette_lens, mode, arena_offset, out_slots, out_entries, out_total_bytes, &handled);
+        if (handled || rc != DSP_OK) return rc;
+    }
     // Entry table in pinned host memory: the entries of every sub-batch but the last leave on the download stream as soon as the
     // sub-batch is meshed (the D2H engine is idle while the voxels come up), so only the last piece's few KB remain for the tail.
     bool early_entries = false;
@@ -1713,6 +1880,18 @@ void* dsp_voxel_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_voxels : nullptr;
 void* dsp_entries_device_ptr(dsp_ctx* ctx) { return ctx ? ctx->d_entries : nullptr; }
 void* dsp_stream(dsp_ctx* ctx) { return ctx ? ctx->stream : nullptr; }
 uint64_t dsp_kernel_launches(const dsp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dsp_host_upload_stats(dsp_ctx* ctx, uint64_t out[8]) {
+    if (!ctx || !out) return DSP_ERR_BAD_ARG;
+    std::memcpy(out, ctx->upload_stats, sizeof(ctx->upload_stats));
+    return DSP_OK;
+}
+
+int dsp_debug_pack_chunk(const uint16_t* blocks, uint8_t* packed, uint32_t* desc, int portable) {
+    if (!blocks || !packed || !desc) return DSP_ERR_BAD_ARG;
+    *desc = portable ? dsp_host::pack_chunk_portable(blocks, packed) : dsp_host::pack_chunk(blocks, packed);
+    return DSP_OK;
+}
 
 // debug: reads and clears the 16 phase counters (all zero unless the library was built with -DDSP_PHASE_TIMERS)
 int dsp_debug_phase_cycles(dsp_ctx* ctx, uint64_t* out16) {

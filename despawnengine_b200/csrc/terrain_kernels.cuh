@@ -372,6 +372,96 @@ __global__ void __launch_bounds__(256) stage_host_chunks_kernel(int4* chunk_pos,
         d[threadIdx.x + 256] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
+// ---- packed upload of host-resident chunks (csrc/host_pack.hpp has the five forms) ------------------------------------------------
+// The host's worker threads have packed each chunk into its slot of a pinned staging buffer; this kernel reads what is there over
+// PCIe -- nothing for air and uniform chunks, 1 / 2 / 4 KiB for chunks whose ids fit 2 / 4 / 8 bits, 8 KiB otherwise -- and writes the
+// 8 KiB u16 tile the mesh kernels read into the chunk's slot of the voxel store.  One warp per chunk, 16 chunks per CTA; the
+// per-chunk words (position, slot, descriptor) are read coalesced by the CTA's first 16 threads.  Air and uniform chunks get the
+// summary the generators would have left (all air / no air + the one block id), so the parity kernel finishes them at the ticket.
+constexpr int kUnpackChunksPerCta = 16;
+__device__ __forceinline__ uint4 ldcv_u4(const uint4* p) {  // system memory that the host rewrites between calls: never a stale line
+    uint4 v;
+    asm volatile("ld.global.cv.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldcv_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.cv.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__global__ void __launch_bounds__(kUnpackChunksPerCta * 32) unpack_host_chunks_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, uint16_t* uid, uint8_t* bvalid,
+                                                                                       uint16_t* voxels, const int4* host_pos, const uint32_t* host_slots,
+                                                                                       const uint32_t* host_desc, const uint8_t* host_packed, uint32_t n) {
+    __shared__ uint32_t s_slot[kUnpackChunksPerCta], s_desc[kUnpackChunksPerCta];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    {
+        const uint32_t i = blockIdx.x * kUnpackChunksPerCta + threadIdx.x;
+        if (threadIdx.x < kUnpackChunksPerCta && i < n) {
+            const uint32_t s = ldcv_u32(host_slots + i), d = ldcv_u32(host_desc + i);
+            const uint4 pq = ldcv_u4(reinterpret_cast<const uint4*>(host_pos + i));
+            chunk_pos[s] = make_int4(static_cast<int>(pq.x), static_cast<int>(pq.y), static_cast<int>(pq.z), 0);
+            slot_list_out[i] = s;
+            const uint32_t form = d & 7u;
+            summary[s] = form == 0u ? kSummaryAir : form == 1u ? kSummaryAllSolid : kSummaryUnknown;
+            if (form == 1u) uid[s] = static_cast<uint16_t>(d >> 16);
+            bvalid[s] = 0;
+            s_slot[threadIdx.x] = s;
+            s_desc[threadIdx.x] = d;
+        }
+    }
+    __syncthreads();
+    const uint32_t i = blockIdx.x * kUnpackChunksPerCta + warp;
+    if (i >= n) return;
+    const uint32_t d = s_desc[warp], form = d & 7u;
+    uint4* tile = reinterpret_cast<uint4*>(voxels + static_cast<size_t>(s_slot[warp]) * kChunkVoxels);  // 512 x 16 bytes
+    const uint8_t* src = host_packed + static_cast<size_t>(i) * 8192;
+    if (form <= 1u) {
+        const uint32_t w = form == 0u ? 0u : (d >> 16) * 0x00010001u;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) tile[lane + 32 * j] = make_uint4(w, w, w, w);
+    } else if (form == 2u) {  // 2 bits per voxel: 16 bytes = 64 voxels = 8 tile units
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int u = lane + 32 * j;
+            const uint4 q = ldcv_u4(reinterpret_cast<const uint4*>(src) + u);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 32 bits = 16 voxels = two tile units
+                uint32_t o[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) o[t] = ((w[k] >> (4 * t)) & 3u) | (((w[k] >> (4 * t + 2)) & 3u) << 16);
+                tile[u * 8 + k * 2] = make_uint4(o[0], o[1], o[2], o[3]);
+                tile[u * 8 + k * 2 + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    } else if (form == 3u) {  // 4 bits per voxel: 16 bytes = 32 voxels = 4 tile units
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int u = lane + 32 * j;
+            const uint4 q = ldcv_u4(reinterpret_cast<const uint4*>(src) + u);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {  // 32 bits = 8 voxels = one tile unit
+                uint32_t o[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o[t] = ((w[k] >> (8 * t)) & 15u) | (((w[k] >> (8 * t + 4)) & 15u) << 16);
+                tile[u * 4 + k] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    } else if (form == 4u) {  // 8 bits per voxel: 16 bytes = 16 voxels = 2 tile units
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int u = lane + 32 * j;
+            const uint4 q = ldcv_u4(reinterpret_cast<const uint4*>(src) + u);
+            tile[u * 2] = make_uint4(__byte_perm(q.x, 0u, 0x4140), __byte_perm(q.x, 0u, 0x4342), __byte_perm(q.y, 0u, 0x4140), __byte_perm(q.y, 0u, 0x4342));
+            tile[u * 2 + 1] = make_uint4(__byte_perm(q.z, 0u, 0x4140), __byte_perm(q.z, 0u, 0x4342), __byte_perm(q.w, 0u, 0x4140), __byte_perm(q.w, 0u, 0x4342));
+        }
+    } else {  // raw
+#pragma unroll 4
+        for (int j = 0; j < 16; ++j) tile[lane + 32 * j] = ldcv_u4(reinterpret_cast<const uint4*>(src) + lane + 32 * j);
+    }
+}
+
 __global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, uint8_t* bvalid, const uint32_t* slots, const int4* src, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -3,8 +3,9 @@ itself, and the reference's palette length as the all-air early-out.
 
 Reference: World::load_chunk + build_chunk_mesh over Chunk.blocks held in host memory (/root/reference/src/content/world/
 chunks/chunk.rs:17, engine/scenes/scene_game.rs:56-64); palette.len() == 1 => None without looking at a voxel
-(chunks/chunk_mesh.rs:18-20).  Every path -- kernel pull from pinned memory, copy-engine pipeline (DSP_E2E_PULL=0), pageable
-memory -- must give the oracle's streams byte for byte and leave the chunks resident with the caller's voxels."""
+(chunks/chunk_mesh.rs:18-20).  Every path -- packed upload (the default for bulk calls; tests/test_gpu_packed_upload.py has its own
+cases), kernel pull from pinned memory, copy-engine pipeline (DSP_E2E_PULL=0), pageable memory -- must give the oracle's streams byte
+for byte and leave the chunks resident with the caller's voxels."""
 import os
 
 import numpy as np
@@ -81,14 +82,15 @@ def world(n_extra_random=6):
 
 
 @pytest.mark.parametrize("with_palette_lens", [False, True])
-@pytest.mark.parametrize("path", ["pull", "copy engine", "pageable"])
+@pytest.mark.parametrize("path", ["packed", "packed pageable", "pull", "copy engine", "pageable"])
 def test_host_chunks_every_path_equals_the_oracle(uv_default, path, with_palette_lens):
     pos, ids = world()
     n = len(pos)
     counts, want = oracle_streams(pos, ids, uv_default)
     pal = np.where((ids == 0).all(axis=1), 1, 3).astype(np.uint32) if with_palette_lens else None
-    keep, host = pinned_copy(ids) if path != "pageable" else (None, ids.copy())
-    with env(DSP_E2E_PULL="0" if path == "copy engine" else "2"):  # 2: pull whatever the share of all-air chunks (the default wants a tenth)
+    keep, host = pinned_copy(ids) if "pageable" not in path else (None, ids.copy())
+    # (DSP_E2E_PULL 2: pull whatever the share of all-air chunks -- the default wants a tenth; DSP_E2E_PACK 0: no packed upload)
+    with env(DSP_E2E_PULL="0" if path == "copy engine" else "2", DSP_E2E_PACK="1" if path.startswith("packed") else "0"):
         with capi.Context(0, n + 64, 1 << 30) as c:
             c.set_uv_table(uv_default)
             entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
@@ -99,6 +101,8 @@ def test_host_chunks_every_path_equals_the_oracle(uv_default, path, with_palette
             assert total == sum(align128(int(k) * 20) for k in counts)
             assert [c.download_vertices(e).tobytes() for e in entries] == want
             assert c.kernel_launches > launches0
+            st = c.host_upload_stats()
+            assert (sum(st[k] for k in capi.PACK_FORMS) == n) == path.startswith("packed"), st
             # the chunks are resident with the caller's voxels, whichever way they came
             assert c.resident_chunks == n
             for i in range(0, n, 37):
@@ -117,7 +121,8 @@ def test_host_chunks_every_path_equals_the_oracle(uv_default, path, with_palette
     del keep
 
 
-def test_palette_length_one_means_the_voxels_are_never_fetched(uv_default):
+@pytest.mark.parametrize("packed", ["1", "0"])
+def test_palette_length_one_means_the_voxels_are_never_fetched(uv_default, packed):
     """chunk_mesh.rs:18-20: palette.len() == 1 => None.  The slot is zero-filled on the device: whatever was resident at that
     position before is gone, and what the (unread) host array holds does not matter."""
     pos = box_positions((0, 0, 0), (40, 1, 40))  # 1,600 chunks: several sub-batches
@@ -128,7 +133,7 @@ def test_palette_length_one_means_the_voxels_are_never_fetched(uv_default):
     air = rng.random(n) < 0.4
     pal[air] = 1
     keep, host = pinned_copy(ids)  # the air-flagged chunks still hold voxels here: a caller that broke the invariant
-    with capi.Context(0, n, 512 << 20) as c:
+    with env(DSP_E2E_PACK=packed), capi.Context(0, n, 512 << 20) as c:
         c.set_uv_table(uv_default)
         first_slots = c.load_chunks(pos, np.full((n, 4096), 1, dtype=np.uint16))  # every position resident and solid beforehand
         entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
@@ -173,12 +178,13 @@ def test_pull_path_small_and_ragged_batches_with_vertices_to_host(uv_default, n)
     del keep
 
 
-def test_pull_path_rejects_duplicates_and_rolls_back(uv_default):
+@pytest.mark.parametrize("packed", ["1", "0"])
+def test_pull_path_rejects_duplicates_and_rolls_back(uv_default, packed):
     pos, ids = world()
     pos, ids = pos[:600].copy(), ids[:600]
     pos[577] = pos[12]
     keep, host = pinned_copy(ids)
-    with capi.Context(0, 1024, 64 << 20) as c:
+    with env(DSP_E2E_PACK=packed), capi.Context(0, 1024, 64 << 20) as c:
         c.set_uv_table(uv_default)
         entries = np.zeros(600, dtype=capi.MESH_ENTRY_DTYPE)
         with pytest.raises(capi.DspError) as ei:
@@ -203,8 +209,8 @@ def test_quad_modes_pull_equals_copy_engine_and_the_extension_oracle(uv_default,
     pal = np.where((ids == 0).all(axis=1), 1, 3).astype(np.uint32)
     keep, host = pinned_copy(ids)
     got = {}
-    for label, e in (("pull", "2"), ("copy engine", "0")):
-        with env(DSP_E2E_PULL=e):
+    for label, e, pk in (("pull", "2", "0"), ("copy engine", "0", "0"), ("packed", "2", "1")):
+        with env(DSP_E2E_PULL=e, DSP_E2E_PACK=pk):
             with capi.Context(0, n + 64, 1 << 30) as c:
                 c.set_uv_table(uv_default)
                 entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
@@ -216,6 +222,7 @@ def test_quad_modes_pull_equals_copy_engine_and_the_extension_oracle(uv_default,
     assert np.array_equal(got["pull"][0]["vertex_count"], got["copy engine"][0]["vertex_count"])
     assert np.array_equal(got["pull"][0]["index_count"], got["copy engine"][0]["index_count"])
     assert got["pull"][1] == got["copy engine"][1]
+    assert np.array_equal(got["pull"][0]["vertex_count"], got["packed"][0]["vertex_count"]) and got["pull"][1] == got["packed"][1]
     for i in range(0, n, 29):
         v, ix, _ = orc.mesh_chunk_ext(tuple(int(k) for k in pos[i]), ids[i], uv_default, greedy=bool(mode & capi.MESH_GREEDY), indexed=bool(mode & capi.MESH_INDEXED))
         assert got["pull"][1][i][0] == v.tobytes()
