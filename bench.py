@@ -398,8 +398,18 @@ def main():
         try:
             import pynvml
             pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-            affinity = f"{len(os.sched_getaffinity(0))} CPUs local to GPU {local_rank} (nvmlDeviceSetCpuAffinity)"
+            # the CPU set of every GPU of this job; ranks whose GPUs share a set (one NUMA node) take equal slices of it, so that each
+            # rank's host threads -- the library's upload packers are as many as the CPUs the calling thread may run on, minus one --
+            # have cores of their own
+            sets = []
+            for g in range(world):
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(g))
+                sets.append(tuple(sorted(os.sched_getaffinity(0))))
+            mine = sets[local_rank]
+            sharers = [g for g in range(world) if sets[g] == mine]
+            k, idx = len(mine) // len(sharers), sharers.index(local_rank)
+            os.sched_setaffinity(0, set(mine[idx * k:(idx + 1) * k]) if k >= 1 else set(mine))
+            affinity = f"{len(os.sched_getaffinity(0))} of the {len(mine)} CPUs local to GPU {local_rank} (nvmlDeviceSetCpuAffinity; {len(sharers)} rank(s) share them)"
         except Exception as e:  # pragma: no cover
             affinity = f"not set ({type(e).__name__})"
     distributed = world > 1
@@ -605,12 +615,28 @@ def main():
         return world * N_CHUNKS * steps / (ms * 1e-3), ms / steps
 
     # (1) `e2e`: host chunks (voxels + palette lengths) in, entry table out, vertices stay in HBM (the reference's result is a device
-    #     buffer too).  dsp_mesh_host_chunks_ex: the mesh kernel pulls the tiles out of the pinned buffer itself, all-air chunks never cross.
+    #     buffer too).  dsp_mesh_host_chunks_ex, packed upload: host worker threads reduce every chunk to its smallest lossless form
+    #     (nothing for air / one-id chunks, 2 bits per voxel for most of the rest), a kernel expands them on the device, the mesh kernel follows.
     e2e_value, e2e_ms = timed_calls(lambda: ctx.mesh_host_chunks_ex_ptr(N_CHUNKS, pos, host_vox.data_ptr(), palette_lens, entries_np, mode), e2e_steps)
     assert int(entries_np["vertex_count"].astype(np.int64).sum()) == faces * 6  # the result really came back
-    # (1b) the same chunks without the palette lengths (dsp_mesh_host_chunks): every tile crosses, copy-engine pipeline
+    up = ctx.host_upload_stats()
+    packed = sum(up[k] for k in capi.PACK_FORMS) == N_CHUNKS  # (not with DSP_E2E_PACK=0 or on a one-CPU box: then this leg is the kernel pull)
+    assert not packed or up["air"] == n_air, up  # all-air chunks by their palette length
+    # (1b) the same chunks without the palette lengths (dsp_mesh_host_chunks): the packer reads the all-air chunks too
     nopal_value, nopal_ms = timed_calls(lambda: ctx.mesh_host_chunks_ptr(N_CHUNKS, pos, host_vox.data_ptr(), entries_np, mode), e2e_steps)
     assert int(entries_np["vertex_count"].astype(np.int64).sum()) == faces * 6
+    up_nopal = ctx.host_upload_stats()
+    # (1c) the former paths, for comparison (a second context created under DSP_E2E_PACK=0): kernel pull with palette lengths (the
+    #      previous `e2e`), copy-engine pipeline without them
+    os.environ["DSP_E2E_PACK"] = "0"
+    ctx2 = capi.Context(local_rank, N_CHUNKS, SLICE)
+    os.environ.pop("DSP_E2E_PACK")
+    ctx2.set_uv_table(UV)
+    ctx2.set_kernel_timing(False)
+    pull_value, pull_ms = timed_calls(lambda: ctx2.mesh_host_chunks_ex_ptr(N_CHUNKS, pos, host_vox.data_ptr(), palette_lens, entries_np, mode), e2e_steps)
+    assert int(entries_np["vertex_count"].astype(np.int64).sum()) == faces * 6 and sum(ctx2.host_upload_stats().values()) == 0
+    ce_value, ce_ms = timed_calls(lambda: ctx2.mesh_host_chunks_ptr(N_CHUNKS, pos, host_vox.data_ptr(), entries_np, mode), e2e_steps)
+    ctx2.close()
     # (2) vertices delivered to pinned HOST memory (a consumer that is not on this GPU), reference layout: PCIe D2H bound
     host_verts = torch.empty(SLICE, dtype=torch.uint8).pin_memory()
     rb_steps = max(3, min(10, e2e_steps))
@@ -712,15 +738,25 @@ def main():
                                              f"({8192 * (n_air + n_uniform)} B of the algorithmic bytes are not read); `no_summaries` is the same step with every tile read",
                          "moved_GBps": (algo_bytes - 8192 * (n_air + n_uniform)) / (kernel_ms_avg * 1e-3) / 1e9,
                          "frac_of_8TBs_datasheet": achieved / 8000.0},
-            "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d_pal, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps,
-                    "ms_per_step": e2e_ms, "h2d_copy_alone_ms": h2d_only_ms, "all_air_chunks_not_fetched": n_air,
-                    "what": "dsp_mesh_host_chunks_ex(host u16 voxels in pinned memory + Chunk::palette.len() per chunk) -> dsp_mesh_entry table on the host; the mesh kernel "
-                            "pulls each tile over PCIe itself (1-D bulk / TMA copies from host memory) and files it in the voxel store; chunks whose palette is only air are "
-                            "never fetched (the reference's early-out, chunk_mesh.rs:18-20, which the CPU arm takes too); vertices stay in HBM (the reference's result is a "
-                            "device buffer too, chunk_mesh.rs:111-124; dsp_arena_export_fd hands that buffer to the renderer)"},
-            "e2e_without_palette_lens": {"value": nopal_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps, "ms_per_step": nopal_ms,
-                                         "what": "dsp_mesh_host_chunks: the same chunks without their palette lengths -- all 4,096 tiles cross PCIe, copy/mesh pipelined in "
-                                                 "~1,024-chunk sub-batches on the copy engine (round 1's and the first session's `e2e`)"},
+            "e2e": {"value": e2e_value, "unit": "chunks/s", "h2d_bytes_per_step": up["device_read_bytes"] if packed else h2d_pal, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps,
+                    "ms_per_step": e2e_ms, "h2d_copy_alone_ms": h2d_only_ms, "host_voxel_bytes_per_step": N_CHUNKS * 8192, "host_threads": up["host_threads"],
+                    "path": ("packed upload" + (f", shared with the bus: {up['raw']} chunks fetched as they are ({up['host_threads']} host worker threads per rank)" if up["raw"] else ""))
+                            if packed else "kernel pull (see e2e_kernel_pull)",
+                    "chunks_by_form": {k: up[k] for k in capi.PACK_FORMS},
+                    "what": "dsp_mesh_host_chunks_ex(host u16 voxels in pinned memory + Chunk::palette.len() per chunk) -> dsp_mesh_entry table on the host, PACKED UPLOAD: "
+                            "host worker threads (host_threads; this rank's share of the CPUs local to the GPU) reduce every chunk to the smallest lossless form that holds it -- "
+                            "nothing for all-air (by palette length, chunk_mesh.rs:18-20, which the CPU arm takes too) and one-id chunks, 2 / 4 / 8 bits per voxel where the ids "
+                            "fit, raw otherwise -- in pinned staging; unpack_host_chunks_kernel reads that over PCIe (h2d_bytes_per_step: what the device actually read) and "
+                            "expands it into the voxel store, the mesh kernel follows, three pieces per call; chunks are resident afterwards bit for bit; vertices stay in HBM "
+                            "(the reference's result is a device buffer too, chunk_mesh.rs:111-124; dsp_arena_export_fd hands that buffer to the renderer)"},
+            "e2e_without_palette_lens": {"value": nopal_value, "unit": "chunks/s", "h2d_bytes_per_step": up_nopal["device_read_bytes"] if packed else h2d, "d2h_bytes_per_step": d2h_entries,
+                                         "steps": e2e_steps, "ms_per_step": nopal_ms,
+                                         "what": "dsp_mesh_host_chunks: the same chunks without their palette lengths -- packed upload too, the packer reads the all-air chunks as well"},
+            "e2e_kernel_pull": {"value": pull_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d_pal, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps, "ms_per_step": pull_ms,
+                                "what": "DSP_E2E_PACK=0, with palette lengths (the `e2e` of the earlier sessions of this round): the mesh kernel pulls each non-air tile over PCIe itself "
+                                        "(1-D bulk / TMA copies from pinned host memory), no host threads"},
+            "e2e_copy_engine": {"value": ce_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_entries, "steps": e2e_steps, "ms_per_step": ce_ms,
+                                "what": "DSP_E2E_PACK=0, without palette lengths (round 1's `e2e`): all 4,096 tiles cross PCIe, copy/mesh pipelined in ~1,024-chunk sub-batches on the copy engine"},
             "e2e_vertices_to_host": {"value": rb_value, "unit": "chunks/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(total_bytes) + d2h_entries, "steps": rb_steps, "ms_per_step": rb_ms,
                                      "what": "dsp_mesh_host_chunks_to_host, reference layout (6 vertices per face): vertices end in pinned host memory; upload, meshing and download "
                                              "overlap on three streams; bound by PCIe device-to-host (397 MB per step)"},

@@ -118,6 +118,7 @@ struct dsp_ctx {
     int e2e_pack = 1;         // DSP_E2E_PACK=0: host-chunk calls never pack (kernel pull / copy-engine pipeline as before)
     int host_threads = -1;    // DSP_HOST_THREADS: worker threads of the packer (-1: the CPUs this thread may run on, minus one; at most 15)
     uint64_t upload_stats[8] = {};  // dsp_host_upload_stats
+    int e2e_pack_keep = 0;    // DSP_E2E_PACK_KEEP=1..16: of every 16 chunks, how many the host packs (0: from the number of workers)
     int e2e_pack_pieces = 3;  // DSP_E2E_PACK_PIECES: launches per call (pack / unpack + mesh pipeline)
     int quad_ctas_cap = 0;  // DSP_QUAD_CTAS: upper bound on the quad kernels' CTAs per SM (0: whatever fits)
     unsigned long long* d_phase = nullptr;  // debug phase timers (16 counters)
@@ -845,6 +846,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if (const char* s = getenv("DSP_E2E_HEAD")) ctx->e2e_head_chunks = static_cast<uint64_t>(std::min(512, std::max(0, atoi(s))));
     if (const char* s = getenv("DSP_E2E_PACK")) ctx->e2e_pack = atoi(s);
     if (const char* s = getenv("DSP_HOST_THREADS")) ctx->host_threads = std::min(63, std::max(-1, atoi(s)));
+    if (const char* s = getenv("DSP_E2E_PACK_KEEP")) ctx->e2e_pack_keep = std::min(16, std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_E2E_PACK_PIECES")) ctx->e2e_pack_pieces = std::min(16, std::max(1, atoi(s)));
     if (const char* s = getenv("DSP_QUAD_CTAS")) ctx->quad_ctas_cap = atoi(s);
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
@@ -1238,7 +1240,7 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
             const int cpus = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : static_cast<int>(std::thread::hardware_concurrency());
             workers = std::min(15, std::max(0, cpus - 1));
         }
-        if (workers < 1) { ctx->e2e_pack = 0; return DSP_OK; }  // a single CPU packs slower than PCIe copies
+        if (workers < 1) { ctx->e2e_pack = 0; return DSP_OK; }
         ctx->pack_pool = new dsp_host::PackPool(workers);
     }
     if (n * dsp_host::kPackSlotBytes > ctx->h_pack_bytes) {
@@ -1247,6 +1249,25 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
         if (cudaMallocHost(&ctx->h_pack, cap) != cudaSuccess) { cudaGetLastError(); ctx->e2e_pack = 0; return DSP_OK; }  // no pinned memory to spare: the other paths
         ctx->h_pack_bytes = cap;
     }
+    // How much of the work the host cores take.  With many cores everything is packed: 2.4x / 2.1x faster than the kernel pull with
+    // 15 / 11 workers (one / two ranks per box).  With few -- eight ranks on a 32-CPU box, 3 workers each, all of them reading host
+    // memory at once -- packing everything is slower than the pull (0.73-0.98 against 0.64-0.83 ms per call) and sharing the chunks out
+    // between the cores and the bus is faster than either (0.42-0.52 ms): of every 16 chunks `keep` are packed, the others cross the
+    // bus as they are, fetched by the unpack kernel from the caller's array.  That needs an array the device can address; pageable
+    // memory is packed whole (the alternative there is a pageable copy).  tools/e2e_pack_sweep.py has the sweep.
+    uint32_t keep_of_16 = 16;
+    const uint8_t* dev_blocks = nullptr;
+    if (ctx->pack_pool->workers() <= 8 || ctx->e2e_pack_keep > 0) {
+        cudaPointerAttributes a0{}, a1{};
+        const uint8_t* last = reinterpret_cast<const uint8_t*>(blocks) + n * dsp::kChunkBytes - 1;
+        if (cudaPointerGetAttributes(&a0, blocks) == cudaSuccess && a0.type == cudaMemoryTypeHost && a0.devicePointer != nullptr &&
+            cudaPointerGetAttributes(&a1, last) == cudaSuccess && a1.type == cudaMemoryTypeHost && a1.devicePointer != nullptr &&
+            static_cast<const uint8_t*>(a1.devicePointer) - static_cast<const uint8_t*>(a0.devicePointer) == last - reinterpret_cast<const uint8_t*>(blocks))
+            dev_blocks = static_cast<const uint8_t*>(a0.devicePointer);
+        else cudaGetLastError();
+        if (dev_blocks != nullptr && ctx->e2e_pack < 2) keep_of_16 = ctx->pack_pool->workers() <= 4 ? 8u : 12u;
+    }
+    if (ctx->e2e_pack_keep > 0) keep_of_16 = dev_blocks != nullptr ? static_cast<uint32_t>(std::min(16, ctx->e2e_pack_keep)) : 16u;  // DSP_E2E_PACK_KEEP (A/B runs)
     *handled = true;
     ctx->last_mesh_n = n;
     const bool trace = getenv("DSP_TRACE") != nullptr;
@@ -1259,7 +1280,7 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     uint32_t* h_slots = reinterpret_cast<uint32_t*>(h + n * sizeof(int4));
     uint32_t* h_desc = h_slots + n;
     dsp_host::PackPool& pool = *ctx->pack_pool;
-    pool.start(blocks, palette_lens, n, h_desc, ctx->h_pack);  // the workers are off; this thread resolves positions to slots meanwhile
+    pool.start(blocks, palette_lens, n, h_desc, ctx->h_pack, keep_of_16);  // the workers are off; this thread resolves positions to slots meanwhile
     tr("packing started");
     std::vector<uint32_t> fresh_slots;
     auto bail = [&](int code) {
@@ -1322,7 +1343,7 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
         // trips, not bandwidth); the mesh kernel of piece j waits for it through an event
         dsp::unpack_host_chunks_kernel<<<static_cast<unsigned>((m + dsp::kUnpackChunksPerCta - 1) / dsp::kUnpackChunksPerCta), dsp::kUnpackChunksPerCta * 32, 0, ctx->copy_stream>>>(
             ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_uid, ctx->d_bvalid, ctx->d_voxels, h_pos + i0, h_slots + i0, h_desc + i0, ctx->h_pack + i0 * dsp_host::kPackSlotBytes,
-            static_cast<uint32_t>(m));
+            dev_blocks != nullptr ? dev_blocks + i0 * dsp::kChunkBytes : nullptr, static_cast<uint32_t>(m));
         if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
             return bail(fail(ctx, DSP_ERR_CUDA, "unpack kernel launch failed"));
         ctx->bmask_stale = true;
@@ -1337,7 +1358,7 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     {
         static const uint64_t form_bytes[6] = {0, 0, 1024, 2048, 4096, 8192};
         for (uint64_t i = 0; i < n; ++i) {
-            const uint32_t form = std::min<uint32_t>(h_desc[i] & 7u, 5u);
+            const uint32_t form = std::min<uint32_t>(h_desc[i] & 7u, 5u);  // (chunks left in place count as raw: they cross the bus as they are)
             ctx->upload_stats[form]++;
             ctx->upload_stats[7] += form_bytes[form] + sizeof(int4) + 2 * sizeof(uint32_t);
         }

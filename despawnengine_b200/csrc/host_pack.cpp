@@ -116,7 +116,7 @@ PackPool::~PackPool() {
     for (auto& t : threads_) t.join();
 }
 
-void PackPool::start(const uint16_t* blocks, const uint32_t* palette_lens, uint64_t n, uint32_t* desc, uint8_t* staging) {
+void PackPool::start(const uint16_t* blocks, const uint32_t* palette_lens, uint64_t n, uint32_t* desc, uint8_t* staging, uint32_t keep_of_16) {
     const uint64_t nb = (n + kBlock - 1) / kBlock;
     if (nb > block_cap_) {
         block_cap_ = nb * 2;
@@ -128,6 +128,7 @@ void PackPool::start(const uint16_t* blocks, const uint32_t* palette_lens, uint6
     {
         std::lock_guard<std::mutex> g(m_);
         job_.blocks = blocks; job_.lens = palette_lens; job_.desc = desc; job_.staging = staging; job_.n = n; job_.n_blocks = nb;
+        job_.keep_of_16 = keep_of_16;
         job_.generation = generation_.load() + 1;
         next_.store(static_cast<uint64_t>(job_.generation) << 32, std::memory_order_release);
         generation_.store(job_.generation, std::memory_order_release);
@@ -149,6 +150,7 @@ void PackPool::work(const Job& job) {
         for (uint64_t i = i0; i < i1; ++i) {
             // Chunk::palette.len() == 1: the chunk has never held anything but air (chunk.rs:58-65) -- not even read
             if (job.lens != nullptr && job.lens[i] == 1u) { job.desc[i] = kPackAir; continue; }
+            if ((i & 15u) >= job.keep_of_16) { job.desc[i] = kPackInPlace; continue; }
             job.desc[i] = pack_chunk(job.blocks + i * 4096, job.staging + i * kPackSlotBytes);
         }
         block_done_[b].store(1, std::memory_order_release);

@@ -21,6 +21,7 @@
 namespace dsp_host {
 
 constexpr uint32_t kPackAir = 0, kPackUniform = 1, kPack2 = 2, kPack4 = 3, kPack8 = 4, kPackRaw = 5;
+constexpr uint32_t kPackInPlace = 6;  // not touched by the host at all: the device reads the chunk's 8 KiB where the caller holds them
 constexpr uint32_t kPackSlotBytes = 8192;  // staging stride per chunk (the raw form fills it)
 
 // descriptor: bits 0-2 form, bits 16-31 the block id of a uniform chunk
@@ -36,8 +37,10 @@ public:
     PackPool(const PackPool&) = delete;
     PackPool& operator=(const PackPool&) = delete;
     int workers() const { return static_cast<int>(threads_.size()); }
-    // palette_lens may be NULL; desc[n], staging[n * kPackSlotBytes]
-    void start(const uint16_t* blocks, const uint32_t* palette_lens, uint64_t n, uint32_t* desc, uint8_t* staging);
+    // palette_lens may be NULL; desc[n], staging[n * kPackSlotBytes].  keep_of_16 < 16: of every 16 consecutive chunks only the first
+    // keep_of_16 are packed, the others are left where they are (kPackInPlace) for the device to fetch -- the share of the work PCIe
+    // takes off the host cores when there are few of them (the caller's array must be device-addressable for that).
+    void start(const uint16_t* blocks, const uint32_t* palette_lens, uint64_t n, uint32_t* desc, uint8_t* staging, uint32_t keep_of_16 = 16);
     // chunks [0, returned) are packed (monotonic; == n once the job is complete)
     uint64_t packed_upto();
     void help();   // the calling thread packs blocks too until none is left to hand out
@@ -51,7 +54,7 @@ private:
         uint32_t* desc = nullptr;
         uint8_t* staging = nullptr;
         uint64_t n = 0, n_blocks = 0;
-        uint32_t generation = 0;
+        uint32_t generation = 0, keep_of_16 = 16;
     };
     void run();
     void work(const Job& job);

@@ -391,7 +391,8 @@ __device__ __forceinline__ uint32_t ldcv_u32(const uint32_t* p) {
 }
 __global__ void __launch_bounds__(kUnpackChunksPerCta * 32) unpack_host_chunks_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, uint16_t* uid, uint8_t* bvalid,
                                                                                        uint16_t* voxels, const int4* host_pos, const uint32_t* host_slots,
-                                                                                       const uint32_t* host_desc, const uint8_t* host_packed, uint32_t n) {
+                                                                                       const uint32_t* host_desc, const uint8_t* host_packed, const uint8_t* host_blocks,
+                                                                                       uint32_t n) {
     __shared__ uint32_t s_slot[kUnpackChunksPerCta], s_desc[kUnpackChunksPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
@@ -414,7 +415,8 @@ __global__ void __launch_bounds__(kUnpackChunksPerCta * 32) unpack_host_chunks_k
     if (i >= n) return;
     const uint32_t d = s_desc[warp], form = d & 7u;
     uint4* tile = reinterpret_cast<uint4*>(voxels + static_cast<size_t>(s_slot[warp]) * kChunkVoxels);  // 512 x 16 bytes
-    const uint8_t* src = host_packed + static_cast<size_t>(i) * 8192;
+    // (form 6: the host did not touch the chunk -- its 8 KiB are read where the caller holds them, host_blocks = the caller's array)
+    const uint8_t* src = (form == 6u ? host_blocks : host_packed) + static_cast<size_t>(i) * 8192;
     if (form <= 1u) {
         const uint32_t w = form == 0u ? 0u : (d >> 16) * 0x00010001u;
 #pragma unroll

@@ -208,7 +208,10 @@ int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
  * into the voxel store (and leaves the chunk summaries a generator would have left for air / one-id chunks), the ordinary mesh
  * kernel follows; three pieces per call, packing of piece k + 1 under the GPU work of piece k.  On the bench region 33.5 MB of voxels
  * become 1.3 MB on the bus and the call takes 0.21 ms instead of 0.51 ms.  Results are identical to the other paths (the chunks
- * are resident afterwards, bit for bit); DSP_E2E_PACK=0 switches the packed upload off, dsp_host_upload_stats reports what it did. */
+ * are resident afterwards, bit for bit).  With eight worker threads or fewer and `blocks` in device-addressable memory the chunks
+ * are shared out between the host cores and the bus (of every 16, 8 or 12 are packed, the others are fetched by the unpack kernel
+ * as they are): eight ranks on a 32-CPU box, all reading host memory at once, pack slower than PCIe copies.  DSP_E2E_PACK=0 switches
+ * the packed upload off, =2 packs everything whatever the core count; dsp_host_upload_stats reports what a call did. */
 int dsp_mesh_host_chunks_ex(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode,
                             uint64_t arena_offset, uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes,
                             void* host_vertices, uint64_t host_capacity);

@@ -90,7 +90,7 @@ def test_host_chunks_every_path_equals_the_oracle(uv_default, path, with_palette
     pal = np.where((ids == 0).all(axis=1), 1, 3).astype(np.uint32) if with_palette_lens else None
     keep, host = pinned_copy(ids) if "pageable" not in path else (None, ids.copy())
     # (DSP_E2E_PULL 2: pull whatever the share of all-air chunks -- the default wants a tenth; DSP_E2E_PACK 0: no packed upload)
-    with env(DSP_E2E_PULL="0" if path == "copy engine" else "2", DSP_E2E_PACK="1" if path.startswith("packed") else "0"):
+    with env(DSP_E2E_PULL="0" if path == "copy engine" else "2", DSP_E2E_PACK="2" if path.startswith("packed") else "0"):
         with capi.Context(0, n + 64, 1 << 30) as c:
             c.set_uv_table(uv_default)
             entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
@@ -121,7 +121,7 @@ def test_host_chunks_every_path_equals_the_oracle(uv_default, path, with_palette
     del keep
 
 
-@pytest.mark.parametrize("packed", ["1", "0"])
+@pytest.mark.parametrize("packed", ["2", "0"])
 def test_palette_length_one_means_the_voxels_are_never_fetched(uv_default, packed):
     """chunk_mesh.rs:18-20: palette.len() == 1 => None.  The slot is zero-filled on the device: whatever was resident at that
     position before is gone, and what the (unread) host array holds does not matter."""
@@ -178,7 +178,7 @@ def test_pull_path_small_and_ragged_batches_with_vertices_to_host(uv_default, n)
     del keep
 
 
-@pytest.mark.parametrize("packed", ["1", "0"])
+@pytest.mark.parametrize("packed", ["2", "0"])
 def test_pull_path_rejects_duplicates_and_rolls_back(uv_default, packed):
     pos, ids = world()
     pos, ids = pos[:600].copy(), ids[:600]
@@ -209,7 +209,7 @@ def test_quad_modes_pull_equals_copy_engine_and_the_extension_oracle(uv_default,
     pal = np.where((ids == 0).all(axis=1), 1, 3).astype(np.uint32)
     keep, host = pinned_copy(ids)
     got = {}
-    for label, e, pk in (("pull", "2", "0"), ("copy engine", "0", "0"), ("packed", "2", "1")):
+    for label, e, pk in (("pull", "2", "0"), ("copy engine", "0", "0"), ("packed", "2", "2")):
         with env(DSP_E2E_PULL=e, DSP_E2E_PACK=pk):
             with capi.Context(0, n + 64, 1 << 30) as c:
                 c.set_uv_table(uv_default)

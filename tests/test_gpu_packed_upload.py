@@ -54,7 +54,7 @@ def test_every_form_lands_bit_exact_and_meshes_like_the_oracle(pinned, with_lens
     counts, want = oracle_streams(pos, ids, uv)
     pal = np.where((ids == 0).all(axis=1), 1, 5).astype(np.uint32) if with_lens else None
     keep, host = pinned_copy(ids) if pinned else (None, ids.copy())
-    with capi.Context(0, n + 8, 2 << 30) as c:
+    with env(DSP_E2E_PACK="2"), capi.Context(0, n + 8, 2 << 30) as c:  # (2: also on a box with fewer than seven CPUs)
         c.set_uv_table(uv)
         entries = np.zeros(n, dtype=capi.MESH_ENTRY_DTYPE)
         slots = np.zeros(n, dtype=np.uint32)
@@ -93,7 +93,7 @@ def test_ragged_sizes_thread_counts_and_recycled_slots(uv_default, n, threads):
     pos, ids, _ = every_form_world(1000, seed=n)
     ids = np.minimum(ids, 2)  # (ids of the default uv table)
     pos, ids = pos[:n], ids[:n]
-    with env(DSP_HOST_THREADS=threads, DSP_E2E_PACK_PIECES=str(1 + n % 4)), capi.Context(0, n + 300, 1 << 30) as c:
+    with env(DSP_HOST_THREADS=threads, DSP_E2E_PACK="2", DSP_E2E_PACK_PIECES=str(1 + n % 4)), capi.Context(0, n + 300, 1 << 30) as c:
         c.set_uv_table(uv_default)
         # scatter the free slots: load something, unload every other chunk of it -- the call's slots are not consecutive
         pre = np.stack([np.arange(300) + 1000, np.zeros(300), np.zeros(300)], axis=1).astype(np.int32)
@@ -120,7 +120,7 @@ def test_small_calls_readback_calls_and_the_switch_take_the_other_paths(uv_defau
     pos, ids, _ = every_form_world(400)
     ids = np.minimum(ids, 2)
     keep, host = pinned_copy(ids)
-    with capi.Context(0, 512, 1 << 30) as c:
+    with env(DSP_E2E_PACK="2"), capi.Context(0, 512, 1 << 30) as c:
         c.set_uv_table(uv_default)
         entries = np.zeros(400, dtype=capi.MESH_ENTRY_DTYPE)
         c.mesh_host_chunks_ex_ptr(255, pos, host.ctypes.data, None, entries[:255])
@@ -134,4 +134,17 @@ def test_small_calls_readback_calls_and_the_switch_take_the_other_paths(uv_defau
         c.set_uv_table(uv_default)
         c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries)
         assert sum(c.host_upload_stats().values()) == 0
+    # few worker threads and a device-addressable array: the chunks are shared out between the cores and the bus (half of them are
+    # fetched as they are); same result
+    counts, want = oracle_streams(pos, ids, uv_default)
+    for threads, raw_min in (("3", 150), ("7", 60)):
+        with env(DSP_E2E_PACK="1", DSP_HOST_THREADS=threads), capi.Context(0, 512, 1 << 30) as c:
+            c.set_uv_table(uv_default)
+            slots = np.zeros(400, dtype=np.uint32)
+            c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries, slots_out=slots)
+            st = c.host_upload_stats()
+            assert sum(st[k] for k in capi.PACK_FORMS) == 400 and st["raw"] >= raw_min, st
+            assert [c.download_vertices(e).tobytes() for e in entries] == want
+            for i in range(400):
+                assert np.array_equal(c.download_chunk(int(slots[i]))[0], ids[i])
     del keep
