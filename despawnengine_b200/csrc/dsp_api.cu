@@ -1229,8 +1229,17 @@ int dsp_mesh_range(dsp_ctx* ctx, uint32_t first_slot, uint64_t n, uint32_t mode,
 // ever read by the host: pageable memory works as well as pinned.  Same contract as the other host-chunk paths (a failing call
 // leaves no trace).  *handled = false: the call is not one for this path (nothing has been done).
 static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode,
-                                   uint64_t arena_offset, uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, bool* handled) {
+                                   uint64_t arena_offset, uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes, void* host_vertices,
+                                   uint64_t host_capacity, bool* handled) {
     *handled = false;
+    // vertices to the host as well (dsp_mesh_host_chunks_to_host): only into pinned memory, where the device-driven download applies
+    uint8_t* zero_copy_dst = nullptr;
+    if (host_vertices != nullptr) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, host_vertices) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr) zero_copy_dst = static_cast<uint8_t*>(attr.devicePointer);
+        else { cudaGetLastError(); return DSP_OK; }
+    }
+    const bool readback = zero_copy_dst != nullptr;
     if (!ctx->e2e_pack || n < 256 || n > (1u << 17) || (mode & (DSP_MESH_ORDERED | DSP_MESH_HALO))) return DSP_OK;
     if (!ctx->pack_pool) {
         int workers = ctx->host_threads;
@@ -1283,11 +1292,15 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     pool.start(blocks, palette_lens, n, h_desc, ctx->h_pack, keep_of_16);  // the workers are off; this thread resolves positions to slots meanwhile
     tr("packing started");
     std::vector<uint32_t> fresh_slots;
+    unsigned long long* d_cursors = nullptr;  // (download) the arena cursor behind every piece
+    int last_piece = -1;
+    const uint64_t room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
     auto bail = [&](int code) {
         const std::string msg = ctx->err;
         pool.finish();  // nobody may still be reading the caller's voxels or writing the staging buffers
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
         release_fresh_slots(ctx, fresh_slots);
         stage_release(ctx);
         ctx->err = msg;
@@ -1297,6 +1310,10 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
         return bail(fail(ctx, DSP_ERR_CUDA, "control block reset failed: %s", cudaGetErrorString(cudaGetLastError())));
     ctx->ctl_clean = false;  // the pieces share the cursor and leave the block as it is
     ctx->result_in_tail = false;
+    if (readback) {
+        if ((rc = ensure_scratch(ctx, dsp_ctx::kMaxSub * sizeof(unsigned long long))) != DSP_OK) return bail(rc);
+        d_cursors = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
+    }
     // the side stream must not overtake earlier work of the main stream that still reads the voxel store
     if (cudaEventRecord(ctx->ev_done, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0) != cudaSuccess)
         return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed"));
@@ -1304,7 +1321,9 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     // pieces: a small first one (the GPU starts while most of the packing is still to do), the rest even
     std::vector<uint64_t> piece_begin;
     {
-        const int pieces = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(ctx->e2e_pack_pieces), std::max<uint64_t>(1, n / 256)));
+        // (unit quads on their way to the host are 12x the voxels' bytes: the download bounds the call and wants finer pieces to hide behind)
+        const uint64_t want = readback && !(mode & DSP_MESH_GREEDY) ? std::max(8, ctx->e2e_pack_pieces) : ctx->e2e_pack_pieces;
+        const int pieces = static_cast<int>(std::min<uint64_t>(want, std::max<uint64_t>(1, n / 256)));
         piece_begin.push_back(0);
         if (pieces > 1) {
             const uint64_t head = ((n / (2 * static_cast<uint64_t>(pieces))) + 15) & ~uint64_t(15);
@@ -1351,6 +1370,19 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
         tev_mark();
         if ((rc = launch_mesh(ctx, m, consecutive ? nullptr : ctx->d_slots + i0, h_slots[i0], mode, arena_offset, i0, static_cast<int>(j), false, false, nullptr)) != DSP_OK) return bail(rc);
         tev_mark();
+        if (readback) {
+            // this piece's vertices = the arena bytes between the cursor behind the previous piece and the cursor now: the device records
+            // the cursor, a copy kernel on the third stream, ordered behind the piece by an event, stores the window into host memory
+            dsp::publish_u64_kernel<<<1, 1, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long*>(ctx->d_ctl + 16), d_cursors + j);
+            if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_meshed[j], ctx->stream) != cudaSuccess ||
+                cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_meshed[j], 0) != cudaSuccess)
+                return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed in the download pipeline"));
+            dsp::copy_window_to_host_kernel<<<ctx->num_sms * 2, 256, 0, ctx->d2h_stream>>>(ctx->d_arena + arena_offset, zero_copy_dst, last_piece >= 0 ? d_cursors + last_piece : nullptr,
+                                                                                           d_cursors + j, std::min<uint64_t>(room, host_capacity));
+            if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "copy_window_to_host_kernel launch failed"));
+            ctx->launches += 2;
+            last_piece = static_cast<int>(j);
+        }
         tr("piece enqueued");
     }
     pool.finish();
@@ -1369,12 +1401,15 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     tr("all enqueued");
     rc = finish_mesh(ctx, out_entries, &total, 0);
     if (out_total_bytes) *out_total_bytes = total;
+    if (readback) cudaStreamSynchronize(ctx->d2h_stream);
     if (rc != DSP_OK) {  // arena too small: the call did not happen -- the slots it created are given back (the bytes needed stay in *out_total_bytes)
         const std::string msg = ctx->err;
         release_fresh_slots(ctx, fresh_slots);
         ctx->err = msg;
         return rc;
     }
+    if (readback && total > host_capacity)
+        rc = fail(ctx, DSP_ERR_BAD_ARG, "host vertex buffer too small: %llu bytes needed, %llu given (what fits was copied)", (unsigned long long)total, (unsigned long long)host_capacity);
     tr("finished");
     if (trace) {
         for (size_t k = 1; k < tev.size(); ++k) {
@@ -1399,11 +1434,6 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     if (rc != DSP_OK) return rc;
     const bool readback = host_vertices != nullptr;
     std::memset(ctx->upload_stats, 0, sizeof(ctx->upload_stats));
-    if (!readback && n) {  // bulk calls: pack on the host, expand on the device (the bus carries a fraction of the voxels' bytes)
-        bool handled = false;
-        rc = mesh_host_chunks_packed(ctx, n, pos, blocks, palette_lens, mode, arena_offset, out_slots, out_entries, out_total_bytes, &handled);
-        if (handled || rc != DSP_OK) return rc;
-    }
     // Entry table in pinned host memory: the entries of every sub-batch but the last leave on the download stream as soon as the
     // sub-batch is meshed (the D2H engine is idle while the voxels come up), so only the last piece's few KB remain for the tail.
     bool early_entries = false;
@@ -1415,6 +1445,11 @@ static int mesh_host_chunks_impl(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
     if ((readback || early_entries) && !ctx->d2h_stream) {
         DSP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
         for (int i = 0; i < dsp_ctx::kMaxSub; ++i) DSP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_meshed[i], cudaEventDisableTiming));
+    }
+    if (n) {  // bulk calls: pack on the host, expand on the device (the bus carries a fraction of the voxels' bytes)
+        bool handled = false;
+        rc = mesh_host_chunks_packed(ctx, n, pos, blocks, palette_lens, mode, arena_offset, out_slots, out_entries, out_total_bytes, host_vertices, host_capacity, &handled);
+        if (handled || rc != DSP_OK) return rc;
     }
     if (mode & (DSP_MESH_ORDERED | DSP_MESH_HALO)) {  // these need the whole batch resident first: plain load, then mesh
         std::vector<uint32_t> slots(n);

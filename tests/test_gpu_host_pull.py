@@ -163,7 +163,7 @@ def test_pull_path_small_and_ragged_batches_with_vertices_to_host(uv_default, n)
     pos_all, ids_all = world()
     pos, ids = pos_all[:n], ids_all[:n]
     keep, host = pinned_copy(ids) if n else (None, np.zeros((0, 4096), dtype=np.uint16))
-    with env(DSP_E2E_PULL="2"), capi.Context(0, 2048, 1 << 30) as c:  # (2: the kernel pull also in front of a download, where the default prefers the copy engine)
+    with env(DSP_E2E_PULL="2", DSP_E2E_PACK="0"), capi.Context(0, 2048, 1 << 30) as c:  # (2: the kernel pull also in front of a download, where the default prefers the copy engine)
         c.set_uv_table(uv_default)
         entries = np.zeros(max(n, 1), dtype=capi.MESH_ENTRY_DTYPE)[:n]
         mirror = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()

@@ -125,11 +125,27 @@ def test_small_calls_readback_calls_and_the_switch_take_the_other_paths(uv_defau
         entries = np.zeros(400, dtype=capi.MESH_ENTRY_DTYPE)
         c.mesh_host_chunks_ex_ptr(255, pos, host.ctypes.data, None, entries[:255])
         assert sum(c.host_upload_stats().values()) == 0  # below 256 chunks the workers' wake-up costs more than the bus
-        mirror = torch.empty(192 << 20, dtype=torch.uint8).pin_memory()
-        c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries, host_vertices_ptr=mirror.data_ptr(), host_capacity=192 << 20)
-        assert sum(c.host_upload_stats().values()) == 0  # vertices to the host: the download bounds the call, not the upload
         c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries)
         assert c.host_upload_stats()["host_threads"] >= 1
+        # vertices to the host as well: packed upload + device-driven download when the destination is pinned ...
+        counts, want = oracle_streams(pos, ids, uv_default)
+        mirror = torch.empty(192 << 20, dtype=torch.uint8).pin_memory()
+        total = c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries, arena_offset=1280, host_vertices_ptr=mirror.data_ptr(), host_capacity=192 << 20)
+        assert sum(c.host_upload_stats()[k] for k in capi.PACK_FORMS) == 400 and total == sum(align128(int(k) * 20) for k in counts)
+        m = mirror.numpy()
+        for e, w in zip(entries, want):
+            o = int(e["offset_bytes"]) - 1280
+            assert m[o:o + len(w)].tobytes() == w
+        with pytest.raises(capi.DspError) as ei:  # too small a destination is reported, as on the other paths
+            c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries, host_vertices_ptr=mirror.data_ptr(), host_capacity=1 << 20)
+        assert ei.value.status == capi.ERR_BAD_ARG
+        # ... and the copy-engine pipeline when it is pageable
+        pageable = np.zeros(192 << 20, dtype=np.uint8)
+        c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries, host_vertices_ptr=pageable.ctypes.data, host_capacity=192 << 20)
+        assert sum(c.host_upload_stats().values()) == 0
+        for e, w in list(zip(entries, want))[::9]:
+            o = int(e["offset_bytes"])
+            assert pageable[o:o + len(w)].tobytes() == w
     with env(DSP_E2E_PACK="0"), capi.Context(0, 512, 1 << 30) as c:
         c.set_uv_table(uv_default)
         c.mesh_host_chunks_ex_ptr(400, pos, host.ctypes.data, None, entries)
