@@ -27,7 +27,9 @@ def timed(ctx, pal, label):
     out[label + "_faces"] = int(ent_np["vertex_count"].astype(np.int64).sum()) // 6
     if os.environ.get("DSP_TRACE_ONE"):
         os.environ["DSP_TRACE"] = "1"
-        fn()
+        for _ in range(int(os.environ["DSP_TRACE_ONE"])):
+            fn()
+            print("[trace] ----", file=sys.stderr, flush=True)
         os.environ.pop("DSP_TRACE")
 
 
