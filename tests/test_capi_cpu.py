@@ -30,6 +30,13 @@ def test_header_and_binding_declare_the_same_symbols():
     assert declared_functions() == sorted(capi.SYMBOLS)
 
 
+def test_integration_md_binds_every_declared_symbol():
+    """INTEGRATION.md's Rust `extern "C"` block is the binding a maintainer of the reference would paste: it must name every entry point."""
+    text = open(os.path.join(os.path.dirname(HEADER), "..", "INTEGRATION.md")).read()
+    bound = set(re.findall(r"pub fn (dsp_[a-z_0-9]+)\(", text))
+    assert bound == set(declared_functions()), sorted(set(declared_functions()) ^ bound)
+
+
 def test_library_exports_every_declared_symbol():
     L = capi.lib()
     for name in declared_functions():
