@@ -200,8 +200,8 @@ int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
  * 8 KiB tile over PCIe with the bulk (TMA) copy that otherwise reads the voxel store, meshes it and files it in the store on the
  * way -- two launches per call, nothing staged, nothing copied twice.  Otherwise (pageable memory, no palette lengths) the
  * copy-engine pipeline described above is used.  Both give identical results.
- * PACKED UPLOAD (the default for calls of 256 .. 131,072 chunks without host_vertices and without DSP_MESH_ORDERED / DSP_MESH_HALO,
- * with or without palette lengths, pinned or pageable `blocks`): PCIe, not the GPU, bounds these calls, and the host has the voxels
+ * PACKED UPLOAD (the default for calls of 256 .. 131,072 chunks without DSP_MESH_ORDERED / DSP_MESH_HALO, with or without palette
+ * lengths, pinned or pageable `blocks`; with host_vertices only when that buffer is pinned, where the download is device-driven): PCIe, not the GPU, bounds these calls, and the host has the voxels
  * in memory anyway -- so a few host worker threads (the CPUs the calling thread may run on, minus one, at most 15;
  * DSP_HOST_THREADS) first reduce every chunk to the smallest lossless form that holds it: nothing at all for a chunk of one id
  * (air included), 2 / 4 / 8 bits per voxel when its ids fit, the 8 KiB as they are otherwise.  A small kernel expands the forms
@@ -211,7 +211,10 @@ int dsp_mesh_host_chunks_to_host(dsp_ctx* ctx, uint64_t n, const int32_t* pos, c
  * are resident afterwards, bit for bit).  With eight worker threads or fewer and `blocks` in device-addressable memory the chunks
  * are shared out between the host cores and the bus (of every 16, 8 or 12 are packed, the others are fetched by the unpack kernel
  * as they are): eight ranks on a 32-CPU box, all reading host memory at once, pack slower than PCIe copies.  DSP_E2E_PACK=0 switches
- * the packed upload off, =2 packs everything whatever the core count; dsp_host_upload_stats reports what a call did. */
+ * the packed upload off, =2 packs everything whatever the core count; dsp_host_upload_stats reports what a call did.  The worker
+ * threads belong to the context: created by its first such call, awake (spinning) for about a millisecond after a call so that
+ * back-to-back calls find them ready, asleep after that, joined by dsp_destroy.  A process that runs several contexts side by side
+ * should give each its own CPUs (sched_setaffinity before the first call) or set DSP_HOST_THREADS. */
 int dsp_mesh_host_chunks_ex(dsp_ctx* ctx, uint64_t n, const int32_t* pos, const uint16_t* blocks, const uint32_t* palette_lens, uint32_t mode,
                             uint64_t arena_offset, uint32_t* out_slots, dsp_mesh_entry* out_entries, uint64_t* out_total_bytes,
                             void* host_vertices, uint64_t host_capacity);
