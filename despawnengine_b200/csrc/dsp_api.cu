@@ -55,6 +55,7 @@ struct dsp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // H2D of dsp_mesh_host_chunks, overlapped with meshing on `stream`
+    cudaStream_t copy_stream2 = nullptr; // second side stream: the unpack kernels of a persistent-launch call alternate between the two
     cudaStream_t d2h_stream = nullptr;   // vertices -> host of dsp_mesh_host_chunks_to_host (created on first use)
     cudaEvent_t ev_meshed[64] = {};
     static constexpr int kMaxSub = 64;   // sub-batches of one pipelined call
@@ -67,6 +68,7 @@ struct dsp_ctx {
     bool mesh_variant_forced = false;  // DSP_MESH_VARIANT was given
     unsigned mesh_prefetch_mult = 2;  // L2 prefetch distance in units of the grid size (0 = off)
     int mesh_ctas_per_sm[4][4] = {};  // [variant][halo], filled on first launch
+    bool mesh_live_ready[4] = {};   // the LIVE instantiation of a kernel shape has its shared-memory attribute set
     int quad_ctas_per_sm[8] = {};     // [halo + 2 greedy + 4 indexed]
 
     uint16_t* d_voxels = nullptr;
@@ -120,6 +122,8 @@ struct dsp_ctx {
     uint64_t upload_stats[8] = {};  // dsp_host_upload_stats
     int e2e_pack_keep = 0;    // DSP_E2E_PACK_KEEP=1..16: of every 16 chunks, how many the host packs (0: from the number of workers)
     int e2e_pack_pieces = 3;  // DSP_E2E_PACK_PIECES: launches per call (pack / unpack + mesh pipeline)
+    int e2e_pack_persist = 1; // parity-mode calls use ONE mesh launch that takes chunks as the unpack kernels release them (DSP_E2E_PACK_PERSIST=0: a mesh launch per piece, as the other modes)
+    int e2e_pack_persist_pieces = 6;  // DSP_E2E_PACK_PERSIST_PIECES: unpack launches of such a call
     int quad_ctas_cap = 0;  // DSP_QUAD_CTAS: upper bound on the quad kernels' CTAs per SM (0: whatever fits)
     unsigned long long* d_phase = nullptr;  // debug phase timers (16 counters)
     size_t scratch_bytes = 0;
@@ -531,7 +535,17 @@ int launch_mesh_t(dsp_ctx* ctx, const dsp::MeshParams& p, int variant) {
         DSP_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         if (occ < 1) return fail(ctx, DSP_ERR_INTERNAL, "mesh kernel does not fit on an SM (smem %d)", smem);
     }
-    const uint64_t resident_ctas = static_cast<uint64_t>(ctx->num_sms) * occ;
+    if (p.released != nullptr) {  // the launch runs beside the upload of its batch: the instantiation that waits for released pieces
+        if (HALO) return fail(ctx, DSP_ERR_INTERNAL, "a launch beside its upload is chunk-local");
+        kern = dsp::mesh_chunks_bump_kernel<Cfg, false, true>;
+        if (!ctx->mesh_live_ready[variant]) {
+            DSP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            ctx->mesh_live_ready[variant] = true;
+        }
+    }
+    // (a launch that runs beside the upload of its own batch leaves one CTA slot per SM free: the unpack kernels it waits for must
+    // find room next to its resident, possibly spinning CTAs)
+    const uint64_t resident_ctas = static_cast<uint64_t>(ctx->num_sms) * (p.released != nullptr ? std::max(1, occ - 1) : occ);
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n, resident_ctas));
     dsp::MeshParams pp = p;
     pp.phase_cycles = ctx->d_phase;
@@ -618,11 +632,13 @@ int check_mesh_args(dsp_ctx* ctx, uint64_t n, uint32_t mode, uint64_t arena_offs
 
 // One mesh launch over `n` chunks whose entries start at entry index `entry0`; `sub` picks the ticket counter.
 int launch_mesh(dsp_ctx* ctx, uint64_t n, const uint32_t* d_list, uint32_t first_slot, uint32_t mode, uint64_t arena_offset, uint64_t entry0, int sub, bool self_reset = false,
-                bool work_list = false, const uint16_t* host_tiles = nullptr) {
+                bool work_list = false, const uint16_t* host_tiles = nullptr, const uint32_t* released = nullptr, uint32_t piece_chunks = 0) {
     const bool halo = (mode & DSP_MESH_HALO) != 0;
     dsp::MeshParams p{};
     p.voxels = ctx->d_voxels;
     p.host_tiles = host_tiles;  // the chunks of this launch are pulled out of (pinned) host memory by the kernel itself
+    p.released = released;      // the launch runs beside the upload of its batch (packed upload, chunk-local parity mode only)
+    p.piece_chunks = piece_chunks;
     p.voxels_out = ctx->d_voxels;
     p.chunk_pos = ctx->d_pos;
     p.slot_list = d_list;
@@ -896,7 +912,7 @@ int finish_mesh(dsp_ctx* ctx, dsp_mesh_entry* out_entries, uint64_t* out_total, 
         total = *reinterpret_cast<uint64_t*>(ctx->h_pinned + 16);
     }
     if (out_total) *out_total = total;
-    if (status & dsp::kStatusSpin) return fail(ctx, DSP_ERR_INTERNAL, "mesh kernel look-back timed out");
+    if (status & dsp::kStatusSpin) return fail(ctx, DSP_ERR_INTERNAL, "the mesh launch that runs beside the upload of its batch timed out waiting for chunks to be released");
     if (status & dsp::kStatusSeam)
         return fail(ctx, DSP_ERR_INTERNAL, "a region seam timed out: the neighbour's border layers (or its ack) for epoch %u never arrived -- every side of a seam "
                     "must call dsp_seam_exchange_async once per epoch, before its halo-mode mesh call", ctx->seam_epoch);
@@ -958,6 +974,8 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if (const char* s = getenv("DSP_HOST_THREADS")) ctx->host_threads = std::min(63, std::max(-1, atoi(s)));
     if (const char* s = getenv("DSP_E2E_PACK_KEEP")) ctx->e2e_pack_keep = std::min(16, std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_E2E_PACK_PIECES")) ctx->e2e_pack_pieces = std::min(16, std::max(1, atoi(s)));
+    if (const char* s = getenv("DSP_E2E_PACK_PERSIST")) ctx->e2e_pack_persist = atoi(s);
+    if (const char* s = getenv("DSP_E2E_PACK_PERSIST_PIECES")) ctx->e2e_pack_persist_pieces = std::min(32, std::max(1, atoi(s)));
     if (const char* s = getenv("DSP_QUAD_CTAS")) ctx->quad_ctas_cap = atoi(s);
     if (const char* s = getenv("DSP_MESH_PREFETCH")) ctx->mesh_prefetch_mult = static_cast<unsigned>(std::max(0, atoi(s)));
     if (const char* s = getenv("DSP_MESH_VARIANT")) { const int v = atoi(s); if (v >= 0 && v < kMeshVariants) { ctx->mesh_variant = v; ctx->mesh_variant_forced = true; } }
@@ -987,6 +1005,7 @@ int dsp_create_ex(int device, uint64_t max_chunks, uint64_t arena_bytes, uint32_
     if ((e = cudaMalloc(&ctx->d_phase, kPhaseWords * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc(phase)", e);
     cudaMemset(ctx->d_phase, 0, kPhaseWords * sizeof(unsigned long long));
     if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->copy_stream2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i)
         if ((e = cudaEventCreateWithFlags(&ctx->ev_sub[i], cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
@@ -1012,6 +1031,7 @@ int dsp_destroy(dsp_ctx* ctx) {
     if (ctx->arena_vmm_size) free_exportable_arena(ctx);
     cudaFree(ctx->d_voxels); cudaFree(ctx->d_pos); cudaFree(ctx->d_nbr); cudaFree(ctx->d_halo); cudaFree(ctx->d_arena); cudaFree(ctx->d_entries);
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_stream2) { cudaStreamSynchronize(ctx->copy_stream2); cudaStreamDestroy(ctx->copy_stream2); }
     if (ctx->d2h_stream) { cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); }
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_meshed[i]) cudaEventDestroy(ctx->ev_meshed[i]);
     for (int i = 0; i < dsp_ctx::kMaxSub; ++i) if (ctx->ev_sub[i]) cudaEventDestroy(ctx->ev_sub[i]);
@@ -1407,14 +1427,19 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     dsp_host::PackPool& pool = *ctx->pack_pool;
     pool.start(blocks, palette_lens, n, h_desc, ctx->h_pack, keep_of_16);  // the workers are off; this thread resolves positions to slots meanwhile
     tr("packing started");
+    bool persist_launched_flag = false;
     std::vector<uint32_t> fresh_slots;
     unsigned long long* d_cursors = nullptr;  // (download) the arena cursor behind every piece
     int last_piece = -1;
     const uint64_t room = (ctx->arena_limit ? ctx->arena_limit : ctx->arena_bytes) - arena_offset;
+    bool* const persist_launched_p = &persist_launched_flag;
     auto bail = [&](int code) {
         const std::string msg = ctx->err;
         pool.finish();  // nobody may still be reading the caller's voxels or writing the staging buffers
+        if (*persist_launched_p)  // a mesh launch is waiting for the rest of the batch: let it run out (the call fails, its output is void)
+            dsp::release_all_pieces_kernel<<<1, 32, 0, ctx->copy_stream>>>(ctx->d_tickets + 32 * (dsp_ctx::kMaxSub - 1));
         cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->copy_stream2);
         cudaStreamSynchronize(ctx->stream);
         if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
         release_fresh_slots(ctx, fresh_slots);
@@ -1431,13 +1456,29 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
         d_cursors = reinterpret_cast<unsigned long long*>(ctx->d_scratch);
     }
     // the side stream must not overtake earlier work of the main stream that still reads the voxel store
-    if (cudaEventRecord(ctx->ev_done, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0) != cudaSuccess)
+    if (cudaEventRecord(ctx->ev_done, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done, 0) != cudaSuccess ||
+        cudaStreamWaitEvent(ctx->copy_stream2, ctx->ev_done, 0) != cudaSuccess)
         return bail(fail(ctx, DSP_ERR_CUDA, "event record / wait failed"));
     new_stamp(ctx);
     tr("streams set up");
+    // Chunk-local parity calls without a download: ONE mesh launch for the whole batch, started behind the first unpack kernel.  Its
+    // CTAs take tickets in order and wait (thread 0, bounded) until the piece a ticket belongs to has been released: the last warp
+    // of every unpack kernel sets the piece's word.  A mesh launch per piece costs ~15 us of ramp, tail and control-block epilogue
+    // each time -- three of them took 118-124 us for work that is 72 us in one.  The launch leaves one CTA slot per SM free so that
+    // the unpack kernels always find room beside its waiting CTAs; the unpack kernels (a handful of PCIe round trips each, ~13 us
+    // whatever their size) alternate between two side streams so that their latencies overlap.  Pieces are of equal size here.
+    const bool persist = ctx->e2e_pack_persist != 0 && !readback && mode == 0u;
+    uint32_t* const d_released = ctx->d_tickets + 32 * (dsp_ctx::kMaxSub - 1);  // 32 words, one per piece (a ticket line no piece uses; zeroed with the others above)
+    uint32_t* const d_done_warps = ctx->d_tickets + 32 * (dsp_ctx::kMaxSub - 2);  // 32 counters
+    uint64_t persist_piece_chunks = 0;
     // pieces: a small first one (the GPU starts while most of the packing is still to do), the rest even
     std::vector<uint64_t> piece_begin;
-    {
+    if (persist) {
+        const uint64_t pieces = std::min<uint64_t>(static_cast<uint64_t>(std::min(32, ctx->e2e_pack_persist_pieces)), std::max<uint64_t>(1, n / 256));
+        persist_piece_chunks = (((n + pieces - 1) / pieces) + 15) & ~uint64_t(15);
+        for (uint64_t b = 0; b < n; b += persist_piece_chunks) piece_begin.push_back(b);
+        piece_begin.push_back(n);
+    } else {
         // (unit quads on their way to the host are 12x the voxels' bytes: the download bounds the call and wants finer pieces to hide behind)
         const uint64_t want = readback && !(mode & DSP_MESH_GREEDY) ? std::max(8, ctx->e2e_pack_pieces) : ctx->e2e_pack_pieces;
         const int pieces = static_cast<int>(std::min<uint64_t>(want, std::max<uint64_t>(1, n / 256)));
@@ -1455,6 +1496,12 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     if (trace && tev_pool.empty()) { tev_pool.resize(40); for (cudaEvent_t& e : tev_pool) cudaEventCreate(&e); }
     auto tev_mark = [&] { if (trace && tev.size() < tev_pool.size()) { cudaEvent_t e = tev_pool[tev.size()]; cudaEventRecord(e, ctx->stream); tev.push_back(e); } };
     tev_mark();
+    bool all_consecutive = true;
+    if (persist) {  // the one launch needs to know up front whether the batch is a run of consecutive slots
+        if ((rc = resolve_positions(ctx, pos, 0, n, h_slots, h_pos, fresh_slots)) != DSP_OK) return bail(rc);
+        resolved = n;
+        for (uint64_t i = 1; i < n && all_consecutive; ++i) all_consecutive = h_slots[i] == h_slots[i - 1] + 1;
+    }
     for (size_t j = 0; j + 1 < piece_begin.size(); ++j) {
         const uint64_t i0 = piece_begin[j], i1 = piece_begin[j + 1], m = i1 - i0;
         if (m == 0) continue;
@@ -1474,9 +1521,23 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
         tr("piece packed");
         // the expansion of piece j runs on the side stream, next to the mesh kernel of piece j - 1 (it is a handful of PCIe round
         // trips, not bandwidth); the mesh kernel of piece j waits for it through an event
-        dsp::unpack_host_chunks_kernel<<<static_cast<unsigned>((m + dsp::kUnpackChunksPerCta - 1) / dsp::kUnpackChunksPerCta), dsp::kUnpackChunksPerCta * 32, 0, ctx->copy_stream>>>(
+        dsp::unpack_host_chunks_kernel<<<static_cast<unsigned>((m + dsp::kUnpackChunksPerCta - 1) / dsp::kUnpackChunksPerCta), dsp::kUnpackChunksPerCta * 32, 0,
+                                         (persist && (j & 1)) ? ctx->copy_stream2 : ctx->copy_stream>>>(
             ctx->d_pos, ctx->d_slots + i0, ctx->d_summary, ctx->d_uid, ctx->d_bvalid, ctx->d_voxels, h_pos + i0, h_slots + i0, h_desc + i0, ctx->h_pack + i0 * dsp_host::kPackSlotBytes,
-            dev_blocks != nullptr ? dev_blocks + i0 * dsp::kChunkBytes : nullptr, static_cast<uint32_t>(m));
+            dev_blocks != nullptr ? dev_blocks + i0 * dsp::kChunkBytes : nullptr, static_cast<uint32_t>(m), persist ? d_done_warps + j : nullptr, persist ? d_released + j : nullptr);
+        if (persist) {
+            if (cudaGetLastError() != cudaSuccess) return bail(fail(ctx, DSP_ERR_CUDA, "unpack kernel launch failed"));
+            ctx->bmask_stale = true;
+            ctx->launches++;
+            tr("unpack launched");
+            if (!persist_launched_flag) {
+                persist_launched_flag = true;  // (set first: a launch that fails half way must still be released by bail)
+                if ((rc = launch_mesh(ctx, n, all_consecutive ? nullptr : ctx->d_slots, h_slots[0], mode, arena_offset, 0, 0, false, false, nullptr, d_released,
+                                      static_cast<uint32_t>(persist_piece_chunks))) != DSP_OK) return bail(rc);
+            }
+            tr("piece enqueued");
+            continue;
+        }
         if (cudaGetLastError() != cudaSuccess || cudaEventRecord(ctx->ev_sub[j], ctx->copy_stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, ctx->ev_sub[j], 0) != cudaSuccess)
             return bail(fail(ctx, DSP_ERR_CUDA, "unpack kernel launch failed"));
         ctx->bmask_stale = true;

@@ -101,6 +101,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// device-scope acquire / release: a word one kernel publishes for another kernel running beside it on the same GPU
+__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes to global memory (observed through an acquire) before an async-proxy (bulk copy) read of them
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // L2-coherent 128-bit load (no L1, no read-only path): data another GPU wrote into this GPU's memory during the kernel
 __device__ __forceinline__ uint4 ld_cg_u4(const uint4* p) {
     uint4 v;

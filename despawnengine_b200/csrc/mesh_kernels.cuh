@@ -77,6 +77,13 @@ struct MeshParams {
     // the chunk is resident afterwards like any other.  nullptr: tiles come from the voxel store.
     const uint16_t* host_tiles;
     uint16_t* voxels_out;
+    // Persistent launch over a batch that is still being uploaded (packed upload of host chunks): the batch arrives in pieces of
+    // piece_chunks chunks; released[j] != 0 once piece j is in the voxel store -- tiles, summaries, positions and slot-list entries
+    // written by an unpack kernel that ran beside this launch and set the word behind its last write.  Thread 0 waits (bounded)
+    // before it uses a ticket of a piece it has not seen released; the per-chunk metadata is then read past the non-coherent L1
+    // path (it was NOT constant for the lifetime of this kernel).  nullptr: everything was there before the launch.
+    const uint32_t* released;
+    uint32_t piece_chunks;
     // DSP_MESH_ORDERED: count_chunks_scan_kernel has already written every chunk's entry (slots packed in call order); the mesh
     // kernel takes each chunk's offset from its entry instead of claiming one, and writes neither entries nor the total.
     bool preset;
@@ -444,8 +451,9 @@ __global__ void __launch_bounds__(kCountThreads, 2) count_chunks_scan_kernel(con
     if (threadIdx.x == 0) *p.total_bytes = carry;
 }
 
-// Per-CTA working set of the mesh kernel.
-template <class Cfg, bool HALO>
+// Per-CTA working set of the mesh kernel.  LIVE: the launch runs beside the upload of its own batch (MeshParams::released) -- a separate
+// instantiation, so that the kernel every other call uses carries none of the waiting or the coherent metadata loads.
+template <class Cfg, bool HALO, bool LIVE = false>
 struct MeshCta {
     static constexpr int NSTAGE = Cfg::NSTAGE;
     static constexpr uint32_t kRecCap = Cfg::kRecCap;
@@ -463,6 +471,7 @@ struct MeshCta {
     // halo mode: the neighbour masks of the chunk that comes next, fetched in two stages during the current chunk
     uint32_t pf_code = kNbrNone, pf_val = 0u;
     bool pf_ready = false;
+    uint32_t released_seen = 0;  // thread 0: bit j = piece j of the batch has been seen released (see MeshParams::released)
 
     __device__ __forceinline__ MeshCta(const MeshParams& params, uint8_t* smem) : p(params) {
         s_vox = reinterpret_cast<uint16_t*>(smem + Cfg::kVox);
@@ -477,7 +486,13 @@ struct MeshCta {
         r = tid; y = r & 15; z = r >> 4;
     }
 
-    __device__ __forceinline__ uint32_t slot_of(uint32_t chunk) const { return p.slot_list ? __ldg(p.slot_list + work_index(p, chunk)) : p.first_slot + chunk; }
+    // per-chunk metadata: read-only for the launch (__ldg) unless the launch runs beside the upload of its own batch (see MeshParams::released)
+    template <class T>
+    __device__ __forceinline__ T meta(const T* ptr) const {
+        if constexpr (LIVE) return __ldcg(ptr);
+        else return __ldg(ptr);
+    }
+    __device__ __forceinline__ uint32_t slot_of(uint32_t chunk) const { return p.slot_list ? meta(p.slot_list + work_index(p, chunk)) : p.first_slot + chunk; }
 
     // stage A / stage B of the neighbour-mask prefetch for ticket `nxt`, whose slot thread 0 left in s_next[2 + ...] when it issued the tile
     __device__ __forceinline__ void prefetch_codes(uint32_t nxt, int nxt_buf) {
@@ -492,13 +507,34 @@ struct MeshCta {
     // thread 0 only: the first ticket from `t` on that needs the CTA.  Where the chunk summaries are at hand (parity mode, no
     // pre-pass) an all-air chunk -- the reference's palette.len() == 1 early-out, chunk_mesh.rs:18-20 -- ends right here: empty
     // entry, next ticket.  Its tile is never read and the CTA spends no iteration (two barriers, a tile wait) on it.
-    __device__ __forceinline__ uint32_t claim_ticket(uint32_t t) const {
-        if (p.summary == nullptr || !p.summary_air_skip) return t;
-        while (t < p.n && (__ldg(p.summary + slot_of(t)) & kSummaryAir)) {
-            if (!p.preset) *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
-            t = gridDim.x + atomicAdd(p.ticket, 1u);
+    __device__ __forceinline__ uint32_t claim_ticket(uint32_t t) {
+        if constexpr (!LIVE) {
+            if (p.summary == nullptr || !p.summary_air_skip) return t;
+            while (t < p.n && (__ldg(p.summary + slot_of(t)) & kSummaryAir)) {
+                if (!p.preset) *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
+                t = gridDim.x + atomicAdd(p.ticket, 1u);
+            }
+            return t;
+        } else {
+            for (;;) {
+                if (t >= p.n) return t;
+                const uint32_t piece = t / p.piece_chunks;  // (at most 32 pieces)
+                if (!((released_seen >> piece) & 1u)) {
+                    // the chunk is still on its way (host packers -> unpack kernel -> the word read here).  Bounded like every spin in
+                    // this library: a host that never releases the rest of its batch becomes an error code, and this CTA takes no more tickets.
+                    uint32_t spins = 0;
+                    while (ld_acquire_gpu_u32(p.released + piece) == 0u) {
+                        __nanosleep(100);
+                        if (++spins > (1u << 23)) { atomicOr(p.status, kStatusSpin); return p.n; }
+                    }
+                    released_seen |= 1u << piece;
+                    fence_proxy_async_global();  // the tile about to be fetched by the async proxy was written through the generic one
+                }
+                if (p.summary == nullptr || !p.summary_air_skip || !(meta(p.summary + slot_of(t)) & kSummaryAir)) return t;
+                if (!p.preset) *entry_of(p, t) = MeshEntry{p.arena_offset, 0u, 0u};
+                t = gridDim.x + atomicAdd(p.ticket, 1u);
+            }
         }
-        return t;
     }
 
     // thread 0 only: 8 KiB voxel tile of `chunk` -> voxel buffer `buf`, completion on s_bar[buf]
@@ -508,8 +544,8 @@ struct MeshCta {
         // A chunk known to be one solid block id throughout needs no tile: every row mask is 0xFFFF and every voxel is that id.
         // count_phase rebuilds the tile in shared memory (two STS.128 per thread); the barrier phase completes without bytes.
         uint32_t uni = 0u;
-        if (p.summary != nullptr && p.uid != nullptr && (__ldg(p.summary + slot) & kSummarySolid)) {
-            const uint32_t id = __ldg(p.uid + slot);
+        if (p.summary != nullptr && p.uid != nullptr && (meta(p.summary + slot) & kSummarySolid)) {
+            const uint32_t id = meta(p.uid + slot);
             if (id != kUidMixed) uni = 0x10000u | id;
         }
         s_next[4 + buf] = uni;
@@ -686,7 +722,7 @@ struct MeshCta {
         tick(0);
         // issued first so that its global-memory latency hides behind the record phase (it used to sit right after the
         // barrier, where ncu showed a quarter of all stall samples)
-        const int4 cp = __ldg(&p.chunk_pos[slot_of(chunk)]);
+        const int4 cp = meta(&p.chunk_pos[slot_of(chunk)]);
         write_records(fc, 0);
         tick(1);
         between();
@@ -733,7 +769,7 @@ struct MeshCta {
 // chunk's stream is byte-exact and the entry table says where it landed; only the ORDER of the slots in the arena follows
 // completion order instead of call order.  DSP_MESH_ORDERED runs count_chunks_scan_kernel first and this kernel with p.preset:
 // same emission, offsets taken from the entries.
-template <class Cfg, bool HALO>
+template <class Cfg, bool HALO, bool LIVE = false>
 __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(const MeshParams p_in) {
     // Back-to-back mesh calls (a frame loop; bench.py's steps): the next launch's CTAs take their SM slots while this launch's
     // last CTAs drain, and wait here -- before the first global access -- until it has completed (control block reset included).
@@ -742,7 +778,7 @@ __global__ void __launch_bounds__(256, Cfg::kCtasPerSm) mesh_chunks_bump_kernel(
     MeshParams p = p_in;
     adopt_work_list(p);  // device-built work list (written by an earlier kernel of the same stream)
     extern __shared__ __align__(128) uint8_t smem[];
-    MeshCta<Cfg, HALO> c(p, smem);
+    MeshCta<Cfg, HALO, LIVE> c(p, smem);
     const int tid = c.tid;
     if (tid == 0) {
         mbar_init(&c.s_bar[0], 1);

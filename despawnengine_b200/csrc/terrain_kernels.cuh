@@ -392,7 +392,7 @@ __device__ __forceinline__ uint32_t ldcv_u32(const uint32_t* p) {
 __global__ void __launch_bounds__(kUnpackChunksPerCta * 32) unpack_host_chunks_kernel(int4* chunk_pos, uint32_t* slot_list_out, uint8_t* summary, uint16_t* uid, uint8_t* bvalid,
                                                                                        uint16_t* voxels, const int4* host_pos, const uint32_t* host_slots,
                                                                                        const uint32_t* host_desc, const uint8_t* host_packed, const uint8_t* host_blocks,
-                                                                                       uint32_t n) {
+                                                                                       uint32_t n, uint32_t* done_warps, uint32_t* released_flag) {
     __shared__ uint32_t s_slot[kUnpackChunksPerCta], s_desc[kUnpackChunksPerCta];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
@@ -412,7 +412,17 @@ __global__ void __launch_bounds__(kUnpackChunksPerCta * 32) unpack_host_chunks_k
     }
     __syncthreads();
     const uint32_t i = blockIdx.x * kUnpackChunksPerCta + warp;
-    if (i >= n) return;
+    // released_flag != nullptr: a mesh launch running beside this kernel waits for the piece (MeshParams::released).  Every warp counts
+    // itself out behind its last store; the last one of the grid sets the word.
+    auto count_out = [&] {
+        if (released_flag == nullptr) return;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence();
+            if (atomicAdd(done_warps, 1u) + 1u == gridDim.x * kUnpackChunksPerCta) { __threadfence(); st_release_gpu_u32(released_flag, 1u); }
+        }
+    };
+    if (i >= n) { count_out(); return; }
     const uint32_t d = s_desc[warp], form = d & 7u;
     uint4* tile = reinterpret_cast<uint4*>(voxels + static_cast<size_t>(s_slot[warp]) * kChunkVoxels);  // 512 x 16 bytes
     // (form 6: the host did not touch the chunk -- its 8 KiB are read where the caller holds them, host_blocks = the caller's array)
@@ -462,6 +472,7 @@ __global__ void __launch_bounds__(kUnpackChunksPerCta * 32) unpack_host_chunks_k
 #pragma unroll 4
         for (int j = 0; j < 16; ++j) tile[lane + 32 * j] = ldcv_u4(reinterpret_cast<const uint4*>(src) + lane + 32 * j);
     }
+    count_out();
 }
 
 __global__ void scatter_pos_kernel(int4* chunk_pos, uint8_t* summary, uint8_t* bvalid, const uint32_t* slots, const int4* src, uint32_t n) {
@@ -757,6 +768,8 @@ __global__ void publish_u64_kernel(const unsigned long long* src, unsigned long 
     *host_dst = *src;
     __threadfence_system();
 }
+// A failing call lets a mesh launch that waits for the rest of its batch run out: every piece is declared released.
+__global__ void release_all_pieces_kernel(uint32_t* released) { st_release_gpu_u32(released + threadIdx.x, 1u); }
 // dsp_mesh_host_chunks_to_host, device-driven: the arena bytes [*lo_p, *hi_p) of a sub-batch -- bounds that only the device knows
 // when the launch is enqueued (they are the cursor after the previous and after this sub-batch) -- stored straight into
 // pinned host memory over PCIe (UVA), 16 bytes per thread and iteration.  No host round trip sits between the sub-batches.
