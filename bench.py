@@ -747,7 +747,7 @@ def main():
                             "host worker threads (host_threads; this rank's share of the CPUs local to the GPU) reduce every chunk to the smallest lossless form that holds it -- "
                             "nothing for all-air (by palette length, chunk_mesh.rs:18-20, which the CPU arm takes too) and one-id chunks, 2 / 4 / 8 bits per voxel where the ids "
                             "fit, raw otherwise -- in pinned staging; unpack_host_chunks_kernel reads that over PCIe (h2d_bytes_per_step: what the device actually read) and "
-                            "expands it into the voxel store, the mesh kernel follows, three pieces per call; chunks are resident afterwards bit for bit; vertices stay in HBM "
+                            "expands it into the voxel store in six pieces, ONE mesh launch started behind the first piece takes the chunks as the pieces are released; chunks are resident afterwards bit for bit; vertices stay in HBM "
                             "(the reference's result is a device buffer too, chunk_mesh.rs:111-124; dsp_arena_export_fd hands that buffer to the renderer)"},
             "e2e_without_palette_lens": {"value": nopal_value, "unit": "chunks/s", "h2d_bytes_per_step": up_nopal["device_read_bytes"] if packed else h2d, "d2h_bytes_per_step": d2h_entries,
                                          "steps": e2e_steps, "ms_per_step": nopal_ms,
