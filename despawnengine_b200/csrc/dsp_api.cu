@@ -1467,7 +1467,8 @@ static int mesh_host_chunks_packed(dsp_ctx* ctx, uint64_t n, const int32_t* pos,
     // each time -- three of them took 118-124 us for work that is 72 us in one.  The launch leaves one CTA slot per SM free so that
     // the unpack kernels always find room beside its waiting CTAs; the unpack kernels (a handful of PCIe round trips each, ~13 us
     // whatever their size) alternate between two side streams so that their latencies overlap.  Pieces are of equal size here.
-    const bool persist = ctx->e2e_pack_persist != 0 && !readback && mode == 0u;
+    // (batches beyond 16,384 chunks keep a launch per piece: its fixed cost no longer shows there, and that launch runs three CTAs per SM)
+    const bool persist = ctx->e2e_pack_persist != 0 && !readback && mode == 0u && (n <= 16384 || ctx->e2e_pack_persist > 1);
     uint32_t* const d_released = ctx->d_tickets + 32 * (dsp_ctx::kMaxSub - 1);  // 32 words, one per piece (a ticket line no piece uses; zeroed with the others above)
     uint32_t* const d_done_warps = ctx->d_tickets + 32 * (dsp_ctx::kMaxSub - 2);  // 32 counters
     uint64_t persist_piece_chunks = 0;
